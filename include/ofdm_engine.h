@@ -1,0 +1,172 @@
+/*
+ * ofdm_engine.h -- C ABI of the B200-native OFDM baseband engine (libofdm_b200.so).
+ *
+ * Drop-in boundary for the modem hot path of jkelleyrtp/ofdm. The reference has NO existing FFI
+ * (no extern, no build.rs); each entry point below names the reference function(s) it replaces.
+ * A thin Rust `ofdm-sys` shim (rust/ofdm-sys) binds exactly these symbols and keeps
+ *   pub fn encode(data:&[u8], guard_bands:Option<bool>, modulation:Option<ModulationScheme>) -> Vec<Complex64>
+ *                                                                        (src/transmitter.rs:10-15)
+ *   pub fn decode(samples:Vec<Complex64>, guard_bands:Option<bool>, modulation:Option<ModulationScheme>)
+ *                                                      -> anyhow::Result<Vec<u8>>   (src/receiver.rs:8-13)
+ * as the host surface.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every buffer; the engine owns its handle + scratch.
+ *  - IQ is fc32: interleaved float re, im (the reference's wire format, src/utils.rs:228-254).
+ *  - `mem` says where ALL buffer arguments of that call live: OFDM_MEM_HOST or OFDM_MEM_DEVICE.
+ *    With OFDM_MEM_HOST the call copies in/out itself (pinned memory recommended: ofdm_host_alloc) and is
+ *    synchronous. With OFDM_MEM_DEVICE the call only enqueues kernels on `stream` (a cudaStream_t, may be
+ *    NULL) and returns; results are valid after the stream is synchronised.
+ *  - return value: 0 ok, <0 engine/CUDA error (text via ofdm_last_error). Per-stream problems never fail
+ *    the call; they are reported in `status[]` (the reference panics / returns Err instead:
+ *    src/receiver.rs:25,27-29,87-89).
+ *  - There is no CPU fallback: without a CUDA device ofdm_engine_create fails.
+ *  - A handle is not thread-safe; use one handle per GPU / host thread. No global state.
+ */
+#ifndef OFDM_ENGINE_H
+#define OFDM_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDM_ABI_VERSION 1
+
+typedef struct ofdm_engine ofdm_engine;
+typedef struct { float re, im; } ofdm_fc32;
+
+/* ModulationScheme, src/transmitter.rs:98-104 (Qam is an empty arm there; 64QAM here, docs/SPEC.md) */
+enum { OFDM_MOD_BPSK = 0, OFDM_MOD_QPSK = 1, OFDM_MOD_QAM64 = 2 };
+enum { OFDM_SYNC_REFERENCE = 0, OFDM_SYNC_SCHMIDL_COX = 1 };      /* src/receiver.rs:20-21 | SPEC 4 */
+enum { OFDM_CFO_REFERENCE = 0, OFDM_CFO_ANGLE_OF_SUM = 1 };       /* src/receiver.rs:231-240 | SPEC 5 */
+enum { OFDM_PHASE_REFERENCE = 0, OFDM_PHASE_ANGLE_OF_SUM = 1 };   /* src/receiver.rs:126,137 | SPEC 6 */
+enum { OFDM_MEM_HOST = 0, OFDM_MEM_DEVICE = 1 };
+
+/* per-stream status */
+enum {
+    OFDM_OK = 0,
+    OFDM_TOO_SHORT = 1,    /* src/receiver.rs:27-29 "Input not long enough" */
+    OFDM_NO_SYNC = 2,      /* Schmidl-Cox metric never crossed the threshold */
+    OFDM_BAD_HEADER = 3,   /* header length does not fit the received symbols / out_stride (src/receiver.rs:86-93 has no check) */
+    OFDM_NEG_OFFSET = 4    /* src/receiver.rs:25 panics on a negative offset */
+};
+
+/* call-level errors */
+enum {
+    OFDM_E_INVALID = -1,   /* bad argument / unsupported configuration */
+    OFDM_E_CUDA = -2,      /* a CUDA runtime call failed */
+    OFDM_E_NOMEM = -3,
+    OFDM_E_NODEVICE = -4   /* no CUDA device: there is no CPU fallback */
+};
+
+typedef struct {
+    uint32_t struct_size;  /* = sizeof(ofdm_cfg) */
+    uint32_t nfft;         /* 64 (src/receiver.rs:99) */
+    uint32_t cp;           /* 16 */
+    uint32_t modulation;   /* decode!/encode! `modulation`, default Bpsk (src/transmitter.rs:17) */
+    uint32_t guard_bands;  /* decode!/encode! `guard_bands`, default false (src/transmitter.rs:16) */
+    uint32_t fec;          /* 0 none; 1 Hamming(7,4) fused where the reference applies RS (examples/lab3c_image.rs:19-21) */
+    uint32_t sync_mode;
+    uint32_t cfo_mode;
+    uint32_t phase_mode;
+    uint32_t sync_window;  /* lags searched for the frame start; 0 = whole capture like the reference */
+    /* optional table overrides (NULL = the reference's generators, src/transmitter.rs:60-96) */
+    const ofdm_fc32 *locking;   /* 80 */
+    const ofdm_fc32 *preamble;  /* 80 */
+    const ofdm_fc32 *training;  /* 64, frequency domain */
+} ofdm_cfg;
+
+/* optional per-stream diagnostics of ofdm_rx_decode_batch; every pointer may be NULL.
+ * These are the reference's npy tap points (src/receiver.rs:41,52,58,76). Same `mem` as the call. */
+typedef struct {
+    int32_t   *offset;        /* [n_streams]  src/receiver.rs:21 */
+    float     *f_delta;       /* [n_streams]  src/receiver.rs:39 */
+    ofdm_fc32 *h_k;           /* [n_streams][64]  src/receiver.rs:56 */
+    uint32_t  *n_data_syms;   /* [n_streams]  data OFDM symbols demodulated */
+    ofdm_fc32 *points;        /* [n_streams][points_stride] equalised + phase-corrected data points (src/receiver.rs:76) */
+    uint32_t   points_stride;
+} ofdm_rx_diag;
+
+/* parameters of the synthetic channel harness (src/channel.rs:33-74) */
+typedef struct {
+    float    snr_db;          /* src/channel.rs:40, default 30 */
+    float    cfo_max;         /* per-stream f ~ U(0, cfo_max) rad/sample; <0: none (src/channel.rs:54) */
+    uint32_t lead_min;        /* per-stream noise-only lead-in, U{lead_min..lead_max} samples */
+    uint32_t lead_max;
+    uint32_t multipath;       /* 1: the 12 taps of src/channel.rs:26-31 */
+    uint32_t noise_mode;      /* 0: reference-faithful uniform noise (src/channel.rs:66-71); 1: Gaussian AWGN */
+    uint64_t seed;
+} ofdm_channel_params;
+
+uint32_t ofdm_abi_version(void);
+void     ofdm_cfg_default(ofdm_cfg *cfg);
+const char *ofdm_status_name(int32_t status);
+
+/* engine life cycle */
+int  ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine **out);
+void ofdm_engine_destroy(ofdm_engine *h);
+const char *ofdm_last_error(const ofdm_engine *h);        /* h may be NULL: error of the last failed create */
+int  ofdm_get_tables(const ofdm_engine *h, ofdm_fc32 *locking80, ofdm_fc32 *preamble80, ofdm_fc32 *training64);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
+int  ofdm_host_alloc(size_t bytes, void **out);
+void ofdm_host_free(void *p);
+
+/* sizes -- src/transmitter.rs:49-54 (block count), docs/SPEC.md 3 (Hamming lengths) */
+uint32_t ofdm_coded_len(const ofdm_cfg *cfg, uint32_t payload_len);       /* bytes handed to `encode` */
+uint32_t ofdm_frame_data_syms(const ofdm_cfg *cfg, uint32_t payload_len); /* S */
+uint32_t ofdm_frame_len(const ofdm_cfg *cfg, uint32_t payload_len);       /* (10+S)*80 samples */
+uint32_t ofdm_max_payload(const ofdm_cfg *cfg, uint32_t n_data_syms);     /* largest payload that fits S symbols */
+
+/*
+ * TX: replaces `encode` (src/transmitter.rs:11-58) for a batch of frames.
+ * payload[s*payload_stride ..][payload_len[s]] -> iq_out[s*iq_stride ..][frame_len]; samples past the
+ * frame up to iq_stride are zero-filled. frame_len_out (optional) receives each frame's length.
+ */
+int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, const uint32_t *payload_len,
+                         uint32_t payload_stride, uint32_t n_streams,
+                         ofdm_fc32 *iq_out, uint32_t iq_stride, uint32_t *frame_len_out,
+                         int mem, void *stream);
+
+/*
+ * RX: replaces `decode` (src/receiver.rs:9-96) for a batch of captures: sync, CFO estimate + derotation,
+ * channel estimate, CP strip, FFT, equalise, pilot phase, demap, header parse, (Hamming decode).
+ * iq[s*iq_stride ..][n_samples[s]] -> out[s*out_stride ..][out_len[s]], status[s].
+ * max_n_samples: upper bound of n_samples[] (0 = iq_stride); only used to size the launch.
+ */
+int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples,
+                         uint32_t n_streams, uint32_t iq_stride, uint32_t max_n_samples,
+                         uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
+                         const ofdm_rx_diag *diag, int mem, void *stream);
+
+/*
+ * Channel harness: replaces `channel` (src/channel.rs:33-74) with a seeded, batched device version.
+ * tx[s*tx_stride ..][tx_len[s]] -> rx[s*rx_stride ..][rx_len[s]], rx_len = lead + tx_len + 63.
+ * lead_out / cfo_out (optional) receive the per-stream draws.
+ */
+int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t *tx_len, uint32_t tx_stride,
+                             uint32_t n_streams, const ofdm_channel_params *p,
+                             ofdm_fc32 *rx, uint32_t rx_stride, uint32_t *rx_len,
+                             uint32_t *lead_out, float *cfo_out, int mem, void *stream);
+
+/*
+ * BER: replaces utils::Analysis::new (src/utils.rs:45-68) for a batch and accumulates into
+ * counters[4] = { bit_errs, byte_errs, bits_compared, frames_failed }. A stream whose status != OK or
+ * whose length differs from ref_len counts as failed with all its reference bits in error.
+ * The counters are what a multi-GPU run sum-reduces (NCCL, 4 x u64) -- the only collective of the path.
+ */
+int ofdm_ber_accumulate(ofdm_engine *h, const uint8_t *ref, const uint32_t *ref_len, uint32_t ref_stride,
+                        const uint8_t *got, const uint32_t *got_len, uint32_t got_stride,
+                        const int32_t *status, uint32_t n_streams, uint64_t *counters,
+                        int mem, void *stream);
+
+/* how many kernels this handle has launched so far (bench.py's gpu_launches) */
+uint64_t ofdm_kernel_launches(const ofdm_engine *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

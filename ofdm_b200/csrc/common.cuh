@@ -1,0 +1,160 @@
+// common.cuh -- device helpers shared by the OFDM kernels (sm_100a).
+//
+// FFT design: one 64-point transform is done by 8 lanes x 8 points. Lane l holds x[l + 8j] (j = 0..7),
+// which is exactly what a coalesced 8-byte-per-lane load of 64 consecutive fc32 samples delivers.
+//   1. radix-8 DFT over j in registers            -> Y_l[ka]
+//   2. twiddle W64^(l*ka) (lane constants)
+//   3. 8x8 transpose across the 8 lanes through a padded, conflict-free shared-memory tile
+//   4. radix-8 DFT over l in registers            -> lane ka holds X[ka + 8 kb] (kb = 0..7)
+// A warp therefore transforms 4 OFDM symbols at a time. No cuFFT anywhere.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ofdm {
+
+constexpr int kNfft = 64;
+constexpr int kCp = 16;
+constexpr int kSym = 80;           // samples per OFDM symbol
+constexpr int kHeadSyms = 10;      // lock + 4 preamble + 5 training rows
+constexpr int kHeaderBits = 128;   // bincode u128
+
+// transpose scratch: 8 rows (ka) x 10 float2 (8 used + 2 pad => row stride 20 words: LDS.128 of the 8 lanes of a
+// group hit 8 disjoint 4-bank groups), + 8 float2 pad per group (group stride 176 words = 16 mod 32: the two
+// groups of a half-warp STS.64 into disjoint bank halves).
+constexpr int kTrRow = 10;
+constexpr int kTrGroup = 8 * kTrRow + 8;   // 88 float2 per 8-lane group
+constexpr int kTrWarp = 4 * kTrGroup;      // 352 float2 per warp
+
+__device__ __forceinline__ void cmul(float &ar, float &ai, float br, float bi)
+{
+    float r = ar * br - ai * bi;
+    float i = ar * bi + ai * br;
+    ar = r; ai = i;
+}
+
+// forward radix-8 DFT (W8 = exp(-j pi/4)), in place, natural order in and out.
+// The inverse transform is obtained by calling it with re/im swapped (ifft(x) = swap(fft(swap(x))) / N).
+__device__ __forceinline__ void dft8(float (&re)[8], float (&im)[8])
+{
+    constexpr float kR = 0.70710678118654752440f;
+    // DIF stage 1: e[n] = x[n] + x[n+4]; o[n] = (x[n] - x[n+4]) * W8^n
+    float er[4], ei[4], orr[4], oi[4];
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        er[n] = re[n] + re[n + 4]; ei[n] = im[n] + im[n + 4];
+        orr[n] = re[n] - re[n + 4]; oi[n] = im[n] - im[n + 4];
+    }
+    {   // W8^1 = (1 - j)/sqrt2 : (a + jb) -> ((a + b) + j(b - a))/sqrt2
+        float a = orr[1], b = oi[1];
+        orr[1] = (a + b) * kR; oi[1] = (b - a) * kR;
+        // W8^2 = -j : (a + jb) -> b - ja
+        a = orr[2]; b = oi[2];
+        orr[2] = b; oi[2] = -a;
+        // W8^3 = (-1 - j)/sqrt2 : (a + jb) -> ((b - a) + j(-a - b))/sqrt2
+        a = orr[3]; b = oi[3];
+        orr[3] = (b - a) * kR; oi[3] = -(a + b) * kR;
+    }
+    // two 4-point DFTs: Y0 = (y0+y2)+(y1+y3), Y2 = (y0+y2)-(y1+y3), Y1 = (y0-y2) - j(y1-y3), Y3 = (y0-y2) + j(y1-y3)
+    {
+        float s0r = er[0] + er[2], s0i = ei[0] + ei[2], d0r = er[0] - er[2], d0i = ei[0] - ei[2];
+        float s1r = er[1] + er[3], s1i = ei[1] + ei[3], d1r = er[1] - er[3], d1i = ei[1] - ei[3];
+        re[0] = s0r + s1r; im[0] = s0i + s1i;
+        re[4] = s0r - s1r; im[4] = s0i - s1i;
+        re[2] = d0r + d1i; im[2] = d0i - d1r;
+        re[6] = d0r - d1i; im[6] = d0i + d1r;
+    }
+    {
+        float s0r = orr[0] + orr[2], s0i = oi[0] + oi[2], d0r = orr[0] - orr[2], d0i = oi[0] - oi[2];
+        float s1r = orr[1] + orr[3], s1i = oi[1] + oi[3], d1r = orr[1] - orr[3], d1i = oi[1] - oi[3];
+        re[1] = s0r + s1r; im[1] = s0i + s1i;
+        re[5] = s0r - s1r; im[5] = s0i - s1i;
+        re[3] = d0r + d1i; im[3] = d0i - d1r;
+        re[7] = d0r - d1i; im[7] = d0i + d1r;
+    }
+}
+
+// lane twiddles W64^(l*ka), ka = 0..7
+__device__ __forceinline__ void fft64_lane_twiddles(int l, float (&twr)[8], float (&twi)[8])
+{
+#pragma unroll
+    for (int ka = 0; ka < 8; ka++) {
+        float s, c;
+        sincospif(-(float)(l * ka) * (1.0f / 32.0f), &s, &c);
+        twr[ka] = c; twi[ka] = s;
+    }
+}
+
+// 64-point forward FFT over an 8-lane group. In: lane l holds x[l + 8j] at index j.
+// Out: lane ka holds X[ka + 8kb] at index kb. `tr` points at this group's kTrGroup-float2 scratch.
+// All 32 lanes of the warp must call it together (two __syncwarp inside).
+__device__ __forceinline__ void fft64_group(float (&re)[8], float (&im)[8], const float (&twr)[8], const float (&twi)[8],
+                                            float2 *tr, int l)
+{
+    dft8(re, im);
+#pragma unroll
+    for (int ka = 1; ka < 8; ka++) cmul(re[ka], im[ka], twr[ka], twi[ka]);
+    __syncwarp();                                     // previous readers of the scratch are done
+#pragma unroll
+    for (int ka = 0; ka < 8; ka++) tr[ka * kTrRow + l] = make_float2(re[ka], im[ka]);
+    __syncwarp();
+    const float4 *row = reinterpret_cast<const float4 *>(tr + l * kTrRow);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        float4 v = row[q];
+        re[2 * q] = v.x; im[2 * q] = v.y; re[2 * q + 1] = v.z; im[2 * q + 1] = v.w;
+    }
+    dft8(re, im);
+}
+
+// ---- carrier map (src/transmitter.rs:150-161, src/receiver.rs:119-134) ------------------------------------------
+__host__ __device__ __forceinline__ bool is_null_bin(int k) { return k >= 59 || k <= 5 || k == 32; }
+__host__ __device__ __forceinline__ bool is_pilot_bin(int k) { return k == 6 || k == 25 || k == 39 || k == 58; }
+// rank of data bin k among the data bins in ascending order, or -1
+template <bool GUARD>
+__host__ __device__ __forceinline__ int data_rank(int k)
+{
+    if (!GUARD) return k;
+    if (is_null_bin(k) || is_pilot_bin(k)) return -1;
+    return k - 7 - (k > 25) - (k > 32) - (k > 39);
+}
+
+// ---- Hamming(7,4), docs/SPEC.md section 3 ------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned ham74_encode_nibble(unsigned d)
+{
+    unsigned d1 = d & 1, d2 = (d >> 1) & 1, d3 = (d >> 2) & 1, d4 = (d >> 3) & 1;
+    unsigned p1 = d1 ^ d2 ^ d4, p2 = d1 ^ d3 ^ d4, p3 = d2 ^ d3 ^ d4;
+    return p1 | (p2 << 1) | (d1 << 2) | (p3 << 3) | (d2 << 4) | (d3 << 5) | (d4 << 6);
+}
+__host__ __device__ __forceinline__ unsigned ham74_decode_word(unsigned c)
+{
+    unsigned s1 = (c ^ (c >> 2) ^ (c >> 4) ^ (c >> 6)) & 1;
+    unsigned s2 = ((c >> 1) ^ (c >> 2) ^ (c >> 5) ^ (c >> 6)) & 1;
+    unsigned s3 = ((c >> 3) ^ (c >> 4) ^ (c >> 5) ^ (c >> 6)) & 1;
+    unsigned s = s1 | (s2 << 1) | (s3 << 2);
+    c ^= (1u << s) >> 1;
+    return ((c >> 2) & 1) | ((c >> 3) & 0xEu);
+}
+
+// ---- Philox4x32-10 (counter-based RNG for the synthetic channel) -------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__host__ __device__ __forceinline__ float u01_from_u32(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// angle (in units of pi, [-1, 1)) of a 0.64 fixed-point turn count
+__device__ __forceinline__ float turns_to_pi_units(uint64_t turns) { return (float)(int32_t)(turns >> 32) * (1.0f / 2147483648.0f); }
+
+}  // namespace ofdm

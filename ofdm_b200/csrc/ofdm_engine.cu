@@ -1,0 +1,539 @@
+// ofdm_engine.cu -- C ABI (include/ofdm_engine.h) over the sm_100a kernels. No torch types, no CPU fallback.
+#include "../../include/ofdm_engine.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "rx_kernels.cuh"
+#include "tables.h"
+#include "tx_kernels.cuh"
+
+using namespace ofdm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct ofdm_engine {
+    ofdm_cfg cfg;
+    int device = 0;
+    std::string err;
+    uint64_t launches = 0;
+    RxTables *d_tables = nullptr;
+    ofdm_fc32 lock[80], pre[80], train[64];
+    DevBuf state;                       // StreamState[n_streams]
+    DevBuf scratch_u32;                 // frame_len / stream_max
+    DevBuf scratch_f32;                 // channel accumulators
+    DevBuf counters;                    // 4 x u64
+    // host-mode staging
+    DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
+    cudaStream_t own_stream = nullptr;
+    int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
+};
+
+#define ENG_FAIL(h, code, ...)                                   \
+    do {                                                         \
+        char _b[512];                                            \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                    \
+        (h)->err = _b;                                           \
+        return (code);                                           \
+    } while (0)
+
+#define CU(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) ENG_FAIL(h, OFDM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- kernel dispatch ---------------------------------------------------------------------------------------------
+typedef void (*DecodeKernel)(const RxArgs);
+typedef void (*AcquireKernel)(const RxArgs);
+typedef void (*TxKernel)(const TxArgs);
+
+template <int MOD, bool GUARD, bool FEC, int PHASE>
+static DecodeKernel pick_decode_pts(bool points)
+{
+    return points ? (DecodeKernel)rx_decode_kernel<MOD, GUARD, FEC, PHASE, true> : (DecodeKernel)rx_decode_kernel<MOD, GUARD, FEC, PHASE, false>;
+}
+template <int MOD, bool GUARD, bool FEC>
+static DecodeKernel pick_decode_phase(int phase, bool points)
+{
+    return phase ? pick_decode_pts<MOD, GUARD, FEC, 1>(points) : pick_decode_pts<MOD, GUARD, FEC, 0>(points);
+}
+template <int MOD>
+static DecodeKernel pick_decode_mod(bool guard, bool fec, int phase, bool points)
+{
+    if (guard) return fec ? pick_decode_phase<MOD, true, true>(phase, points) : pick_decode_phase<MOD, true, false>(phase, points);
+    return fec ? pick_decode_phase<MOD, false, true>(phase, points) : pick_decode_phase<MOD, false, false>(phase, points);
+}
+static DecodeKernel pick_decode(const ofdm_cfg &c, bool points)
+{
+    switch (c.modulation) {
+    case 0: return pick_decode_mod<0>(c.guard_bands, c.fec, c.phase_mode, points);
+    case 1: return pick_decode_mod<1>(c.guard_bands, c.fec, c.phase_mode, points);
+    default: return pick_decode_mod<2>(c.guard_bands, c.fec, c.phase_mode, points);
+    }
+}
+
+template <int MOD, bool GUARD>
+static AcquireKernel pick_acquire_phase(int phase)
+{
+    return phase ? (AcquireKernel)rx_acquire_kernel<MOD, GUARD, 1> : (AcquireKernel)rx_acquire_kernel<MOD, GUARD, 0>;
+}
+static AcquireKernel pick_acquire(const ofdm_cfg &c)
+{
+    switch (c.modulation) {
+    case 0: return c.guard_bands ? pick_acquire_phase<0, true>(c.phase_mode) : pick_acquire_phase<0, false>(c.phase_mode);
+    case 1: return c.guard_bands ? pick_acquire_phase<1, true>(c.phase_mode) : pick_acquire_phase<1, false>(c.phase_mode);
+    default: return c.guard_bands ? pick_acquire_phase<2, true>(c.phase_mode) : pick_acquire_phase<2, false>(c.phase_mode);
+    }
+}
+
+template <int MOD>
+static TxKernel pick_tx_mod(bool guard, bool fec)
+{
+    if (guard) return fec ? (TxKernel)tx_symbols_kernel<MOD, true, true> : (TxKernel)tx_symbols_kernel<MOD, true, false>;
+    return fec ? (TxKernel)tx_symbols_kernel<MOD, false, true> : (TxKernel)tx_symbols_kernel<MOD, false, false>;
+}
+static TxKernel pick_tx(const ofdm_cfg &c)
+{
+    switch (c.modulation) {
+    case 0: return pick_tx_mod<0>(c.guard_bands, c.fec);
+    case 1: return pick_tx_mod<1>(c.guard_bands, c.fec);
+    default: return pick_tx_mod<2>(c.guard_bands, c.fec);
+    }
+}
+
+// ---- sizes -------------------------------------------------------------------------------------------------------
+static int cfg_bpc(const ofdm_cfg *c) { return c->modulation == 0 ? 1 : (c->modulation == 1 ? 2 : 6); }
+static int cfg_dcar(const ofdm_cfg *c) { return c->guard_bands ? 48 : 64; }
+
+extern "C" uint32_t ofdm_abi_version(void) { return OFDM_ABI_VERSION; }
+
+extern "C" void ofdm_cfg_default(ofdm_cfg *cfg)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = sizeof *cfg;
+    cfg->nfft = 64; cfg->cp = 16;
+    cfg->modulation = OFDM_MOD_BPSK;        // src/transmitter.rs:17
+    cfg->guard_bands = 0;                   // src/transmitter.rs:16
+}
+
+extern "C" const char *ofdm_status_name(int32_t s)
+{
+    switch (s) {
+    case OFDM_OK: return "OK";
+    case OFDM_TOO_SHORT: return "TOO_SHORT";
+    case OFDM_NO_SYNC: return "NO_SYNC";
+    case OFDM_BAD_HEADER: return "BAD_HEADER";
+    case OFDM_NEG_OFFSET: return "NEG_OFFSET";
+    default: return "UNKNOWN";
+    }
+}
+
+extern "C" uint32_t ofdm_coded_len(const ofdm_cfg *cfg, uint32_t payload_len)
+{
+    return cfg->fec ? (uint32_t)((14ull * payload_len + 7) / 8) : payload_len;
+}
+extern "C" uint32_t ofdm_frame_data_syms(const ofdm_cfg *cfg, uint32_t payload_len)
+{
+    uint64_t nbits = 128 + 8ull * ofdm_coded_len(cfg, payload_len);
+    uint64_t ncar = (nbits + cfg_bpc(cfg) - 1) / cfg_bpc(cfg);
+    return (uint32_t)((ncar + cfg_dcar(cfg) - 1) / cfg_dcar(cfg));
+}
+extern "C" uint32_t ofdm_frame_len(const ofdm_cfg *cfg, uint32_t payload_len)
+{
+    return (10 + ofdm_frame_data_syms(cfg, payload_len)) * 80;
+}
+extern "C" uint32_t ofdm_max_payload(const ofdm_cfg *cfg, uint32_t n_data_syms)
+{
+    uint64_t bits = (uint64_t)n_data_syms * cfg_bpc(cfg) * cfg_dcar(cfg);
+    if (bits < 128) return 0;
+    uint64_t coded = (bits - 128) / 8;
+    return (uint32_t)(cfg->fec ? (8 * coded) / 14 : coded);
+}
+
+// ---- life cycle --------------------------------------------------------------------------------------------------
+static int validate_cfg(const ofdm_cfg *c, std::string &err)
+{
+    if (!c || c->struct_size != sizeof(ofdm_cfg)) { err = "ofdm_cfg.struct_size mismatch"; return OFDM_E_INVALID; }
+    if (c->nfft != 64 || c->cp != 16) { err = "only nfft=64, cp=16 (the reference's layout) is implemented"; return OFDM_E_INVALID; }
+    if (c->modulation > 2 || c->guard_bands > 1 || c->fec > 1 || c->sync_mode > 1 || c->cfo_mode > 1 || c->phase_mode > 1) {
+        err = "ofdm_cfg field out of range";
+        return OFDM_E_INVALID;
+    }
+    return 0;
+}
+
+extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine **out)
+{
+    if (!out) return OFDM_E_INVALID;
+    *out = nullptr;
+    int rc = validate_cfg(cfg, g_create_error);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return OFDM_E_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return OFDM_E_INVALID; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return OFDM_E_CUDA; }
+
+    ofdm_engine *h = new ofdm_engine();
+    h->cfg = *cfg;
+    h->device = device;
+    h->bpc = cfg_bpc(cfg);
+    h->dcar = cfg_dcar(cfg);
+    h->bps_sym = h->bpc * h->dcar;
+    h->tile_shift = 0;
+    if (cfg->fec) {                          // tile boundaries on Hamming byte boundaries: BPS*s == 128 (mod 14)
+        int s0 = -1;
+        for (int s = 0; s < 7; s++) if (((h->bps_sym * s - 128) % 14 + 14) % 14 == 0) { s0 = s; break; }
+        if (s0 < 0) { g_create_error = "no Hamming-aligned tiling for this carrier layout"; delete h; return OFDM_E_INVALID; }
+        h->tile_shift = (7 - s0) % 7;
+    }
+
+    // tables (src/transmitter.rs:60-96) in f64, then fc32
+    std::vector<ofdm_host::cd> lock(80), pre(80), train(64), tsym(64);
+    ofdm_host::locking_signal(lock.data(), 80);
+    ofdm_host::preamble(pre.data(), 80);
+    ofdm_host::training_signals(train.data(), 64);
+    if (cfg->locking) for (int i = 0; i < 80; i++) lock[i] = { cfg->locking[i].re, cfg->locking[i].im };
+    if (cfg->preamble) for (int i = 0; i < 80; i++) pre[i] = { cfg->preamble[i].re, cfg->preamble[i].im };
+    if (cfg->training) for (int i = 0; i < 64; i++) train[i] = { cfg->training[i].re, cfg->training[i].im };
+    h->cfg.locking = h->cfg.preamble = h->cfg.training = nullptr;
+    RxTables *t = new RxTables();
+    for (int i = 0; i < 80; i++) {
+        h->lock[i] = { (float)lock[i].re, (float)lock[i].im };
+        h->pre[i] = { (float)pre[i].re, (float)pre[i].im };
+        t->lock[i] = make_float2((float)lock[i].re, (float)lock[i].im);
+        t->head[i] = t->lock[i];
+        for (int r = 0; r < 4; r++) t->head[80 * (1 + r) + i] = make_float2((float)pre[i].re, (float)pre[i].im);
+    }
+    ofdm_host::idft(train.data(), tsym.data(), 64);
+    for (int i = 0; i < 64; i++) {
+        h->train[i] = { (float)train[i].re, (float)train[i].im };
+        double n2 = train[i].re * train[i].re + train[i].im * train[i].im;
+        t->inv_training[i] = make_float2((float)(train[i].re / n2), (float)(-train[i].im / n2));
+    }
+    for (int r = 0; r < 5; r++)
+        for (int i = 0; i < 80; i++) {
+            const ofdm_host::cd &v = tsym[i < 16 ? 48 + i : i - 16];        // prefix_block, src/transmitter.rs:168-181
+            t->head[400 + 80 * r + i] = make_float2((float)v.re, (float)v.im);
+        }
+    float mx = 0.0f;
+    for (int i = 0; i < 800; i++) { mx = fmaxf(mx, t->head[i].x); mx = fmaxf(mx, t->head[i].y); }
+    t->head_max = mx;
+
+    bool ok = cudaMalloc(&h->d_tables, sizeof(RxTables)) == cudaSuccess &&
+              cudaMemcpy(h->d_tables, t, sizeof(RxTables), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              h->counters.ensure(4 * sizeof(uint64_t)) == cudaSuccess;
+    delete t;
+    if (!ok) {
+        g_create_error = std::string("engine allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        ofdm_engine_destroy(h);
+        return OFDM_E_CUDA;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" void ofdm_engine_destroy(ofdm_engine *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->d_tables) cudaFree(h->d_tables);
+    DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
+                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h };
+    for (DevBuf *b : bufs) b->release();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" const char *ofdm_last_error(const ofdm_engine *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int ofdm_get_tables(const ofdm_engine *h, ofdm_fc32 *locking80, ofdm_fc32 *preamble80, ofdm_fc32 *training64)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (locking80) memcpy(locking80, h->lock, sizeof h->lock);
+    if (preamble80) memcpy(preamble80, h->pre, sizeof h->pre);
+    if (training64) memcpy(training64, h->train, sizeof h->train);
+    return 0;
+}
+
+extern "C" int ofdm_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return OFDM_E_INVALID;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? 0 : OFDM_E_NOMEM;
+}
+extern "C" void ofdm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" uint64_t ofdm_kernel_launches(const ofdm_engine *h) { return h ? h->launches : 0; }
+
+// ---- TX ----------------------------------------------------------------------------------------------------------
+static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *payload_len, uint32_t payload_stride,
+                     uint32_t n_streams, ofdm_fc32 *iq, uint32_t iq_stride, uint32_t *frame_len_out, cudaStream_t st)
+{
+    CU(h, h->scratch_u32.ensure(2 * sizeof(uint32_t) * (size_t)n_streams));
+    uint32_t *d_flen = h->scratch_u32.as<uint32_t>();
+    int *d_max = reinterpret_cast<int *>(d_flen + n_streams);
+    CU(h, cudaMemsetAsync(d_flen, 0, 2 * sizeof(uint32_t) * (size_t)n_streams, st));
+    TxArgs a{};
+    a.payload = payload; a.payload_len = payload_len; a.payload_stride = payload_stride; a.n_streams = n_streams;
+    a.iq = reinterpret_cast<float2 *>(iq); a.iq_stride = iq_stride; a.frame_len = d_flen; a.stream_max = d_max; a.tables = h->d_tables;
+    uint32_t max_syms = iq_stride / 80;
+    uint32_t gx = (max_syms + 31) / 32;
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    pick_tx(h->cfg)<<<dim3(gx, n_streams), 256, 0, st>>>(a);
+    uint32_t gf = (iq_stride + 256 * 8 - 1) / (256 * 8);
+    if (gf < 1) gf = 1;
+    tx_finalize_kernel<<<dim3(gf, n_streams), 256, 0, st>>>(a, d_flen);
+    h->launches += 2;
+    CU(h, cudaGetLastError());
+    if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, const uint32_t *payload_len,
+                                    uint32_t payload_stride, uint32_t n_streams,
+                                    ofdm_fc32 *iq_out, uint32_t iq_stride, uint32_t *frame_len_out,
+                                    int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!payload || !payload_len || !iq_out || n_streams == 0 || iq_stride < 880) ENG_FAIL(h, OFDM_E_INVALID, "tx: bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    if (mem == OFDM_MEM_DEVICE) return tx_device(h, payload, payload_len, payload_stride, n_streams, iq_out, iq_stride, frame_len_out, (cudaStream_t)stream);
+
+    for (uint32_t s = 0; s < n_streams; s++) {
+        if (payload_len[s] > payload_stride) ENG_FAIL(h, OFDM_E_INVALID, "tx: payload_len[%u] exceeds payload_stride", s);
+        if (ofdm_frame_len(&h->cfg, payload_len[s]) > iq_stride) ENG_FAIL(h, OFDM_E_INVALID, "tx: frame %u does not fit iq_stride", s);
+    }
+    cudaStream_t st = h->own_stream;
+    size_t pb = (size_t)n_streams * payload_stride, ib = (size_t)n_streams * iq_stride * sizeof(float2);
+    CU(h, h->s_bytes.ensure(pb));
+    CU(h, h->s_len.ensure(2 * sizeof(uint32_t) * (size_t)n_streams));
+    CU(h, h->s_iq.ensure(ib));
+    uint32_t *d_len = h->s_len.as<uint32_t>(), *d_flen = d_len + n_streams;
+    CU(h, cudaMemcpyAsync(h->s_bytes.p, payload, pb, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_len, payload_len, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
+    int rc = tx_device(h, h->s_bytes.as<uint8_t>(), d_len, payload_stride, n_streams, h->s_iq.as<ofdm_fc32>(), iq_stride, d_flen, st);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(iq_out, h->s_iq.p, ib, cudaMemcpyDeviceToHost, st));
+    if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- RX ----------------------------------------------------------------------------------------------------------
+static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples, uint32_t n_streams, uint32_t iq_stride,
+                     uint32_t max_n_samples, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
+                     const ofdm_rx_diag *diag, cudaStream_t st)
+{
+    CU(h, h->state.ensure(sizeof(StreamState) * (size_t)n_streams));
+    RxArgs a{};
+    a.iq = reinterpret_cast<const float2 *>(iq); a.n_samples = n_samples; a.iq_stride = iq_stride; a.n_streams = n_streams;
+    a.state = h->state.as<StreamState>(); a.tables = h->d_tables;
+    a.out = out; a.out_stride = out_stride; a.out_len = out_len; a.status = status;
+    a.sync_window = h->cfg.sync_window; a.tile_shift = h->tile_shift;
+    a.sync_mode = (int)h->cfg.sync_mode; a.cfo_mode = (int)h->cfg.cfo_mode; a.fec = (int)h->cfg.fec;
+    bool points = false;
+    if (diag) {
+        a.d_offset = diag->offset; a.d_f_delta = diag->f_delta; a.d_h = reinterpret_cast<float2 *>(diag->h_k);
+        a.d_nsyms = diag->n_data_syms; a.d_points = reinterpret_cast<float2 *>(diag->points); a.points_stride = diag->points_stride;
+        points = diag->points != nullptr && diag->points_stride > 0;
+    }
+    pick_acquire(h->cfg)<<<n_streams, kAcqThreads, 0, st>>>(a);
+    uint32_t mx = max_n_samples ? max_n_samples : iq_stride;
+    if (mx > iq_stride) mx = iq_stride;
+    long rows = ((long)mx + 79) / 80, S = rows - 10;
+    h->launches += 1;
+    if (S > 0) {
+        uint32_t tiles = (uint32_t)((S + h->tile_shift + kTileSyms - 1) / kTileSyms);
+        pick_decode(h->cfg, points)<<<dim3(tiles, n_streams), kDecThreads, 0, st>>>(a);
+        h->launches += 1;
+    }
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples,
+                                    uint32_t n_streams, uint32_t iq_stride, uint32_t max_n_samples,
+                                    uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
+                                    const ofdm_rx_diag *diag, int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!iq || !n_samples || !out || !out_len || !status || n_streams == 0 || iq_stride == 0)
+        ENG_FAIL(h, OFDM_E_INVALID, "rx: bad arguments");
+    if (n_streams > 65535) ENG_FAIL(h, OFDM_E_INVALID, "rx: at most 65535 streams per call");
+    CU(h, cudaSetDevice(h->device));
+    if (mem == OFDM_MEM_DEVICE)
+        return rx_device(h, iq, n_samples, n_streams, iq_stride, max_n_samples, out, out_stride, out_len, status, diag, (cudaStream_t)stream);
+
+    uint32_t mx = 0;
+    for (uint32_t s = 0; s < n_streams; s++) {
+        if (n_samples[s] > iq_stride) ENG_FAIL(h, OFDM_E_INVALID, "rx: n_samples[%u] exceeds iq_stride", s);
+        if (n_samples[s] > mx) mx = n_samples[s];
+    }
+    cudaStream_t st = h->own_stream;
+    size_t ib = (size_t)n_streams * iq_stride * sizeof(float2), ob = (size_t)n_streams * out_stride;
+    CU(h, h->s_iq.ensure(ib));
+    CU(h, h->s_bytes.ensure(ob));
+    CU(h, h->s_len.ensure(2 * sizeof(uint32_t) * (size_t)n_streams));
+    CU(h, h->s_status.ensure(sizeof(int32_t) * (size_t)n_streams));
+    uint32_t *d_ns = h->s_len.as<uint32_t>(), *d_ol = d_ns + n_streams;
+    ofdm_rx_diag dd{};
+    if (diag) {
+        CU(h, h->s_aux.ensure(3 * sizeof(uint32_t) * (size_t)n_streams));
+        uint32_t *aux = h->s_aux.as<uint32_t>();
+        if (diag->offset) dd.offset = reinterpret_cast<int32_t *>(aux);
+        if (diag->f_delta) dd.f_delta = reinterpret_cast<float *>(aux + n_streams);
+        if (diag->n_data_syms) dd.n_data_syms = aux + 2 * (size_t)n_streams;
+        if (diag->h_k) { CU(h, h->s_h.ensure(sizeof(float2) * 64 * (size_t)n_streams)); dd.h_k = h->s_h.as<ofdm_fc32>(); }
+        if (diag->points && diag->points_stride) {
+            CU(h, h->s_points.ensure(sizeof(float2) * (size_t)diag->points_stride * n_streams));
+            CU(h, cudaMemsetAsync(h->s_points.p, 0, sizeof(float2) * (size_t)diag->points_stride * n_streams, st));
+            dd.points = h->s_points.as<ofdm_fc32>(); dd.points_stride = diag->points_stride;
+        }
+    }
+    CU(h, cudaMemcpyAsync(h->s_iq.p, iq, ib, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_ns, n_samples, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
+    int rc = rx_device(h, h->s_iq.as<ofdm_fc32>(), d_ns, n_streams, iq_stride, mx, h->s_bytes.as<uint8_t>(), out_stride, d_ol,
+                       h->s_status.as<int32_t>(), diag ? &dd : nullptr, st);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(out, h->s_bytes.p, ob, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(out_len, d_ol, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+    if (diag) {
+        if (dd.offset) CU(h, cudaMemcpyAsync(diag->offset, dd.offset, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+        if (dd.f_delta) CU(h, cudaMemcpyAsync(diag->f_delta, dd.f_delta, sizeof(float) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+        if (dd.n_data_syms) CU(h, cudaMemcpyAsync(diag->n_data_syms, dd.n_data_syms, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+        if (dd.h_k) CU(h, cudaMemcpyAsync(diag->h_k, dd.h_k, sizeof(float2) * 64 * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+        if (dd.points) CU(h, cudaMemcpyAsync(diag->points, dd.points, sizeof(float2) * (size_t)diag->points_stride * n_streams, cudaMemcpyDeviceToHost, st));
+    }
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- channel harness ---------------------------------------------------------------------------------------------
+static int channel_device(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t *tx_len, uint32_t tx_stride, uint32_t n_streams,
+                          const ofdm_channel_params *p, ofdm_fc32 *rx, uint32_t rx_stride, uint32_t *rx_len,
+                          uint32_t *lead_out, float *cfo_out, cudaStream_t st)
+{
+    CU(h, h->scratch_f32.ensure(5 * sizeof(float) * (size_t)n_streams));
+    CU(h, cudaMemsetAsync(h->scratch_f32.p, 0, 5 * sizeof(float) * (size_t)n_streams, st));
+    ChanArgs a{};
+    a.tx = reinterpret_cast<const float2 *>(tx); a.tx_len = tx_len; a.tx_stride = tx_stride; a.n_streams = n_streams;
+    a.rx = reinterpret_cast<float2 *>(rx); a.rx_stride = rx_stride; a.rx_len = rx_len; a.lead_out = lead_out; a.cfo_out = cfo_out;
+    a.accum = h->scratch_f32.as<float>();
+    a.snr_lin = powf(10.0f, p->snr_db / 10.0f);
+    a.cfo_max = p->cfo_max; a.lead_min = p->lead_min; a.lead_max = p->lead_max; a.multipath = p->multipath; a.noise_mode = p->noise_mode;
+    a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
+    uint32_t gx = (rx_stride + 256 * 8 - 1) / (256 * 8);
+    if (gx < 1) gx = 1;
+    channel_conv_kernel<<<dim3(gx, n_streams), 256, 0, st>>>(a);
+    channel_noise_kernel<<<dim3(gx, n_streams), 256, 0, st>>>(a);
+    h->launches += 2;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t *tx_len, uint32_t tx_stride,
+                                        uint32_t n_streams, const ofdm_channel_params *p,
+                                        ofdm_fc32 *rx, uint32_t rx_stride, uint32_t *rx_len,
+                                        uint32_t *lead_out, float *cfo_out, int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!tx || !tx_len || !p || !rx || !rx_len || n_streams == 0) ENG_FAIL(h, OFDM_E_INVALID, "channel: bad arguments");
+    if (n_streams > 65535) ENG_FAIL(h, OFDM_E_INVALID, "channel: at most 65535 streams per call");
+    CU(h, cudaSetDevice(h->device));
+    if (mem == OFDM_MEM_DEVICE)
+        return channel_device(h, tx, tx_len, tx_stride, n_streams, p, rx, rx_stride, rx_len, lead_out, cfo_out, (cudaStream_t)stream);
+    cudaStream_t st = h->own_stream;
+    size_t tb = (size_t)n_streams * tx_stride * sizeof(float2), rb = (size_t)n_streams * rx_stride * sizeof(float2);
+    CU(h, h->s_iq.ensure(tb));
+    CU(h, h->s_iq2.ensure(rb));
+    CU(h, h->s_len.ensure(4 * sizeof(uint32_t) * (size_t)n_streams));
+    uint32_t *d_tl = h->s_len.as<uint32_t>(), *d_rl = d_tl + n_streams, *d_lead = d_rl + n_streams;
+    float *d_cfo = reinterpret_cast<float *>(d_lead + n_streams);
+    CU(h, cudaMemcpyAsync(h->s_iq.p, tx, tb, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_tl, tx_len, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
+    int rc = channel_device(h, h->s_iq.as<ofdm_fc32>(), d_tl, tx_stride, n_streams, p, h->s_iq2.as<ofdm_fc32>(), rx_stride, d_rl, d_lead, d_cfo, st);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(rx, h->s_iq2.p, rb, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(rx_len, d_rl, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+    if (lead_out) CU(h, cudaMemcpyAsync(lead_out, d_lead, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+    if (cfo_out) CU(h, cudaMemcpyAsync(cfo_out, d_cfo, sizeof(float) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- BER ---------------------------------------------------------------------------------------------------------
+extern "C" int ofdm_ber_accumulate(ofdm_engine *h, const uint8_t *ref, const uint32_t *ref_len, uint32_t ref_stride,
+                                   const uint8_t *got, const uint32_t *got_len, uint32_t got_stride,
+                                   const int32_t *status, uint32_t n_streams, uint64_t *counters,
+                                   int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!ref || !ref_len || !got || !got_len || !status || !counters || n_streams == 0) ENG_FAIL(h, OFDM_E_INVALID, "ber: bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    BerArgs a{};
+    a.ref_stride = ref_stride; a.got_stride = got_stride; a.n_streams = n_streams;
+    if (mem == OFDM_MEM_DEVICE) {
+        a.ref = ref; a.ref_len = ref_len; a.got = got; a.got_len = got_len; a.status = status;
+        a.counters = reinterpret_cast<unsigned long long *>(counters);
+        ber_kernel<<<n_streams, 256, 0, (cudaStream_t)stream>>>(a);
+        h->launches += 1;
+        CU(h, cudaGetLastError());
+        return 0;
+    }
+    cudaStream_t st = h->own_stream;
+    size_t rb = (size_t)n_streams * ref_stride, gb = (size_t)n_streams * got_stride;
+    CU(h, h->s_bytes.ensure(rb));
+    CU(h, h->s_bytes2.ensure(gb));
+    CU(h, h->s_len2.ensure(3 * sizeof(uint32_t) * (size_t)n_streams));
+    uint32_t *d_rl = h->s_len2.as<uint32_t>(), *d_gl = d_rl + n_streams;
+    int32_t *d_st = reinterpret_cast<int32_t *>(d_gl + n_streams);
+    CU(h, cudaMemcpyAsync(h->s_bytes.p, ref, rb, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->s_bytes2.p, got, gb, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_rl, ref_len, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_gl, got_len, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_st, status, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(uint64_t), st));
+    a.ref = h->s_bytes.as<uint8_t>(); a.ref_len = d_rl; a.got = h->s_bytes2.as<uint8_t>(); a.got_len = d_gl; a.status = d_st;
+    a.counters = h->counters.as<unsigned long long>();
+    ber_kernel<<<n_streams, 256, 0, st>>>(a);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+    uint64_t tmp[4];
+    CU(h, cudaMemcpyAsync(tmp, h->counters.p, sizeof tmp, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; i++) counters[i] += tmp[i];
+    return 0;
+}

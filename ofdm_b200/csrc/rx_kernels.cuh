@@ -1,0 +1,566 @@
+// rx_kernels.cuh -- receive path kernels (replace `decode`, src/receiver.rs:9-96).
+//
+//   rx_acquire_kernel : one CTA per stream. Frame sync (reference ramp correlation or sliding Schmidl-Cox on
+//                       warp-shuffle prefix sums over smem-staged IQ), CFO estimate, channel estimate from the 5
+//                       training symbols, header symbol decode -> StreamState (offset, phase step, 1/h_k, lengths).
+//   rx_decode_kernel  : the HBM-bound hot kernel. One CTA = 7 warps x 32 OFDM symbols of one stream; per symbol
+//                       (8 lanes): coalesced CP-stripped load -> CFO derotation -> register/smem radix-8x8 FFT ->
+//                       one-tap equalise -> pilot phase -> hard demap -> (smem) -> Hamming(7,4) LUT decode -> bytes.
+//                       The IQ is read exactly once; nothing but the decoded payload is written.
+#pragma once
+
+#include "common.cuh"
+
+namespace ofdm {
+
+enum { ST_OK = 0, ST_TOO_SHORT = 1, ST_NO_SYNC = 2, ST_BAD_HEADER = 3, ST_NEG_OFFSET = 4 };
+
+struct __align__(16) StreamState {
+    int32_t  status;
+    int32_t  offset;      // src/receiver.rs:21
+    uint32_t n_syms;      // data symbols the header asks for (<= symbols received)
+    uint32_t out_len;     // decoded payload bytes
+    uint64_t fstep;       // -f_delta / 2pi as a 0.64 fixed-point turn count (wrapping)
+    float    f_delta;     // src/receiver.rs:39
+    uint32_t plen;        // Header.packet_length (coded bytes)
+    uint32_t n_syms_rx;   // data symbols present in the capture
+    uint32_t pad[3];
+    float2   g[64];       // 1 / h_k
+    float2   h[64];       // h_k, src/receiver.rs:56
+};
+
+struct RxTables {          // device copy of the engine's tables
+    float2 lock[80];       // locking_signal (src/transmitter.rs:60-72)
+    float2 inv_training[64];  // 1 / training_signals (src/transmitter.rs:88-96)
+    float2 head[800];      // un-normalised lock | preamble x4 | (CP + IFFT(training)) x5
+    float  head_max;       // max positive component of head
+};
+
+struct RxArgs {
+    const float2   *iq;
+    const uint32_t *n_samples;
+    uint32_t        iq_stride;
+    uint32_t        n_streams;
+    StreamState    *state;
+    const RxTables *tables;
+    uint8_t        *out;
+    uint32_t        out_stride;
+    uint32_t       *out_len;
+    int32_t        *status;
+    uint32_t        sync_window;
+    int32_t         tile_shift;     // symbols by which tile boundaries are shifted so they fall on Hamming byte boundaries
+    int32_t         sync_mode, cfo_mode, fec;   // run-time switches of the (cold) acquisition kernel
+    // diag (optional)
+    int32_t  *d_offset;
+    float    *d_f_delta;
+    float2   *d_h;
+    uint32_t *d_nsyms;
+    float2   *d_points;
+    uint32_t  points_stride;
+};
+
+template <int MOD> struct ModTraits;
+template <> struct ModTraits<0> { static constexpr int kBpc = 1; };
+template <> struct ModTraits<1> { static constexpr int kBpc = 2; };
+template <> struct ModTraits<2> { static constexpr int kBpc = 6; };
+
+// per-lane constants of the symbol pipeline (constant for all symbols of one stream)
+struct RxLane {
+    float twr[8], twi[8];   // FFT twiddles W64^(l*ka)
+    float wr[8], wi[8];     // derotation inside a symbol: exp(-j f (l + 8j))
+    float gr[8], gi[8];     // equaliser 1/h at bins l + 8kb
+};
+
+__device__ __forceinline__ void phasor_from_turns(uint64_t turns, float &c, float &s)
+{
+    sincospif(turns_to_pi_units(turns), &s, &c);
+}
+
+__device__ __forceinline__ void rx_lane_init(RxLane &L, const StreamState *st, int l)
+{
+    fft64_lane_twiddles(l, L.twr, L.twi);
+    const uint64_t fstep = st->fstep;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        phasor_from_turns(fstep * (uint64_t)(l + 8 * j), L.wr[j], L.wi[j]);
+        float2 g = st->g[l + 8 * j];
+        L.gr[j] = g.x; L.gi[j] = g.y;
+    }
+}
+
+// hard decision of one data point -> BPC bits (src/receiver.rs:155-178; 64QAM docs/SPEC.md 2)
+template <int MOD>
+__device__ __forceinline__ uint32_t demap_point(float re, float im)
+{
+    if (MOD == 0) return re > 0.0f ? 1u : 0u;
+    if (MOD == 1) {
+        bool lb = re >= 0.0f;
+        bool rb = lb ? (im >= 0.0f) : (re < 0.0f && im > 0.0f);
+        return (lb ? 1u : 0u) | (rb ? 2u : 0u);
+    }
+    // floor(3.5 v + 4) lands in the mantissa of 2^23 + i (round-down FMA), clamp to [0, 7]
+    float ti = __fmaf_rd(re, 3.5f, 8388612.0f);
+    float tq = __fmaf_rd(im, 3.5f, 8388612.0f);
+    ti = fminf(fmaxf(ti, 8388608.0f), 8388615.0f);
+    tq = fminf(fmaxf(tq, 8388608.0f), 8388615.0f);
+    uint32_t x = (__float_as_uint(ti) & 7u) | ((__float_as_uint(tq) & 7u) << 3);
+    return x ^ ((x >> 1) & 0x1Bu);      // per-axis Gray: i ^ (i >> 1)
+}
+
+// One OFDM symbol per 8-lane group: load (CP stripped), derotate, FFT, equalise, pilot phase.
+// x0 = pointer to the first post-offset sample of the stream; n_avail = samples from x0 to the end of the capture.
+// On return (zr, zi)[kb] is the equalised + phase-corrected value of bin l + 8kb.
+template <bool GUARD, int PHASE>
+__device__ __forceinline__ void rx_symbol(const float2 *__restrict__ x0, uint32_t n_avail, uint32_t sym, bool valid,
+                                          const RxLane &L, float br, float bi, float2 *tr, int l,
+                                          float (&zr)[8], float (&zi)[8])
+{
+    const uint32_t n0 = (kHeadSyms + sym) * kSym + kCp + l;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t n = n0 + 8 * j;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (valid && n < n_avail) v = __ldg(x0 + n);     // zero-padded tail row, src/receiver.rs:206-210
+        zr[j] = v.x; zi[j] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) cmul(zr[j], zi[j], L.wr[j], L.wi[j]);      // src/receiver.rs:44-50 (intra-symbol part)
+    fft64_group(zr, zi, L.twr, L.twi, tr, l);                              // src/receiver.rs:99-104
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) cmul(zr[kb], zi[kb], L.gr[kb], L.gi[kb]);   // src/receiver.rs:67-70
+    float rr = br, ri = bi;                                                // common rotation of the data bins
+    if (GUARD) {
+        // pilots: bins 6, 25, 39, 58 = (lane, kb) (6,0) (1,3) (7,4) (2,7)   src/receiver.rs:125-128
+        float pr = 0.0f, pi = 0.0f;
+        if (l == 6) { pr = zr[0]; pi = zi[0]; }
+        if (l == 1) { pr = zr[3]; pi = zi[3]; }
+        if (l == 7) { pr = zr[4]; pi = zi[4]; }
+        if (l == 2) { pr = zr[7]; pi = zi[7]; }
+        if (PHASE == 1) {
+            // angle of the pilot sum: the per-symbol base phasor cancels, rot = conj(sum)/|sum|
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+                pr += __shfl_xor_sync(0xffffffffu, pr, m);
+                pi += __shfl_xor_sync(0xffffffffu, pi, m);
+            }
+            float inv = rsqrtf(fmaxf(pr * pr + pi * pi, 1e-30f));
+            rr = pr * inv; ri = -pi * inv;
+        } else {
+            // reference: mean of the four pilot angles (after the full derotation), src/receiver.rs:126,137
+            cmul(pr, pi, br, bi);
+            const bool pilot_lane = (l == 6) | (l == 1) | (l == 7) | (l == 2);
+            float ang = pilot_lane ? atan2f(pi, pr) : 0.0f;
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) ang += __shfl_xor_sync(0xffffffffu, ang, m);
+            float s, c;
+            sincosf(-0.25f * ang, &s, &c);
+            rr = c; ri = s;
+            cmul(rr, ri, br, bi);
+        }
+    }
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) cmul(zr[kb], zi[kb], rr, ri);           // src/receiver.rs:140-144
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// hot kernel
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDecWarps = 7;
+constexpr int kDecThreads = kDecWarps * 32;      // 224
+constexpr int kTileSyms = kDecWarps * 32;        // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
+
+template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
+__global__ void __launch_bounds__(kDecThreads) rx_decode_kernel(const RxArgs a)
+{
+    constexpr int BPC = ModTraits<MOD>::kBpc;
+    constexpr int D = GUARD ? 48 : 64;
+    constexpr int BPS = BPC * D;                 // bits per OFDM symbol
+    constexpr int NB = FEC ? 14 : 8;             // stream bits per output byte
+
+    __shared__ __align__(16) float2 s_tr[kDecWarps * kTrWarp];
+    __shared__ __align__(16) uint8_t s_car[kTileSyms * D + 32];   // one byte (BPC valid bits) per data carrier
+    __shared__ uint8_t s_ham[128];
+
+    const uint32_t stream = blockIdx.y;
+    const StreamState *st = a.state + stream;
+    if (st->status != ST_OK) return;
+    const int S = (int)st->n_syms;
+    int t0 = (int)blockIdx.x * kTileSyms - a.tile_shift;
+    int t1 = t0 + kTileSyms;
+    if (t0 < 0) t0 = 0;
+    if (t1 > S) t1 = S;
+    if (t0 >= t1) return;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
+    if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
+
+    const uint32_t n_samples = a.n_samples[stream];
+    const uint32_t offset = (uint32_t)st->offset;
+    const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
+    const uint32_t n_avail = n_samples - offset;
+
+    RxLane L;
+    rx_lane_init(L, st, l);
+    int8_t rank[8];
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) rank[kb] = (int8_t)data_rank<GUARD>(l + 8 * kb);
+
+    float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
+    const uint64_t fstep = st->fstep;
+    // base phasor of this group's first symbol, then a x4-symbol recurrence (8 steps: negligible drift)
+    const int s_first = t0 + warp * 32 + g;
+    float br, bi, dr, di;
+    phasor_from_turns(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp), br, bi);
+    phasor_from_turns(fstep * (uint64_t)(4 * kSym), dr, di);
+
+#pragma unroll 1
+    for (int it = 0; it < 8; it++) {
+        const int s = s_first + 4 * it;
+        const bool valid = s < t1;
+        float zr[8], zi[8];
+        rx_symbol<GUARD, PHASE>(x0, n_avail, (uint32_t)s, valid, L, br, bi, tr, l, zr, zi);
+        cmul(br, bi, dr, di);
+        if (valid) {
+            const int row = (s - t0) * D;
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                if (rank[kb] >= 0) {
+                    s_car[row + rank[kb]] = (uint8_t)demap_point<MOD>(zr[kb], zi[kb]);
+                    if (POINTS) {
+                        size_t p = (size_t)s * D + rank[kb];
+                        if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr[kb], zi[kb]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- tile bits -> output bytes (header strip src/receiver.rs:86-93, Hamming docs/SPEC.md 3) ------------------
+    const long bit0 = (long)t0 * BPS;                       // first stream bit held by this tile
+    const long bit1 = (long)t1 * BPS;
+    long j0 = bit0 <= kHeaderBits ? 0 : (bit0 - kHeaderBits + NB - 1) / NB;
+    long j1 = (bit1 - kHeaderBits) / NB;                    // bytes fully inside the tile
+    if (j1 > (long)st->out_len) j1 = (long)st->out_len;
+    uint8_t *out = a.out + (size_t)stream * a.out_stride;
+    for (long j = j0 + tid; j < j1; j += kDecThreads) {
+        const int p = (int)(kHeaderBits + j * NB - bit0);   // tile-local bit position
+        const int c = p / BPC, sh = p - c * BPC;
+        constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < NC; i++) v |= (uint32_t)s_car[c + i] << (BPC * i);
+        v >>= sh;
+        uint32_t byte;
+        if (FEC) byte = (uint32_t)s_ham[v & 127u] | ((uint32_t)s_ham[(v >> 7) & 127u] << 4);
+        else byte = v & 255u;
+        out[j] = (uint8_t)byte;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// acquisition kernel
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kAcqThreads = 256;
+constexpr int kAcqChunk = 1024;                  // Schmidl-Cox lags per smem-staged chunk
+
+__device__ __forceinline__ float2 ld_sample(const float2 *__restrict__ x, long n, long n_samples)
+{
+    return (n >= 0 && n < n_samples) ? __ldg(x + n) : make_float2(0.0f, 0.0f);
+}
+
+// block-wide arg-max with "first strict maximum" semantics (larger value wins, ties -> smaller index)
+__device__ __forceinline__ void block_argmax(float &val, int &idx, float *s_val, int *s_idx)
+{
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, val, m);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, m);
+        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { s_val[warp] = val; s_idx[warp] = idx; }
+    __syncthreads();
+    if (warp == 0) {
+        float v = lane < (kAcqThreads / 32) ? s_val[lane] : -1.0f;
+        int i = lane < (kAcqThreads / 32) ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, v, m);
+            int oi = __shfl_xor_sync(0xffffffffu, i, m);
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+        if (lane == 0) { s_val[0] = v; s_idx[0] = i; }
+    }
+    __syncthreads();
+    val = s_val[0]; idx = s_idx[0];
+    __syncthreads();
+}
+
+// |c[k]|^2 of the ramp correlation c[k] = sum_{n<80} a[n+k] lock[n] (lock is real) -- src/signals/mod.rs:186-217 direct form
+__device__ __forceinline__ float ramp_corr_sq(const float2 *__restrict__ x, long k, long n_samples, const float *s_lock)
+{
+    float cr = 0.0f, ci = 0.0f;
+    if (k >= 0 && k + kSym <= n_samples) {
+#pragma unroll 8
+        for (int n = 0; n < kSym; n++) { float2 v = __ldg(x + k + n); cr = fmaf(v.x, s_lock[n], cr); ci = fmaf(v.y, s_lock[n], ci); }
+    } else {
+        for (int n = 0; n < kSym; n++) { float2 v = ld_sample(x, k + n, n_samples); cr = fmaf(v.x, s_lock[n], cr); ci = fmaf(v.y, s_lock[n], ci); }
+    }
+    return cr * cr + ci * ci;
+}
+
+// arg-max of the ramp correlation over lags [k_lo, k_hi]
+__device__ __forceinline__ int ramp_argmax(const float2 *__restrict__ x, long n_samples, long k_lo, long k_hi,
+                                           const float *s_lock, float *s_val, int *s_idx)
+{
+    float best = 0.0f;
+    int bidx = 0x7fffffff;
+    for (long k = k_lo + threadIdx.x; k <= k_hi; k += kAcqThreads) {
+        float v = ramp_corr_sq(x, k, n_samples, s_lock);
+        if (v > best) { best = v; bidx = (int)k; }         // per-thread lags ascend: strict > keeps the first
+    }
+    block_argmax(best, bidx, s_val, s_idx);
+    return best > 0.0f ? bidx : (int)k_lo;
+}
+
+template <int MOD, bool GUARD, int PHASE>
+__global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
+{
+    const int SYNC = a.sync_mode, CFO = a.cfo_mode;
+    const bool FEC = a.fec != 0;
+    constexpr int BPC = ModTraits<MOD>::kBpc;
+    constexpr int D = GUARD ? 48 : 64;
+    constexpr int BPS = BPC * D;
+    constexpr int HDR_SYMS = (kHeaderBits + BPS - 1) / BPS;         // 1..3
+
+    __shared__ float s_lock[kSym];
+    __shared__ float s_val[kAcqThreads / 32];
+    __shared__ int s_idx[kAcqThreads / 32];
+    __shared__ int s_d0;
+    __shared__ double s_red[2 * (kAcqThreads / 32)];
+    __shared__ __align__(16) float2 s_tr[kTrWarp];
+    __shared__ uint8_t s_car[HDR_SYMS * D + 32];
+    // Schmidl-Cox staging: prefix sums of q[n] = conj(a[n]) a[n+80] and e[n] = |a[n]|^2
+    __shared__ float2 s_q[kAcqChunk + kSym + 1];
+    __shared__ float s_e[kAcqChunk + 2 * kSym + 1];
+
+    const uint32_t stream = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    StreamState *st = a.state + stream;
+    const long M = (long)a.n_samples[stream];
+    const float2 *x = a.iq + (size_t)stream * a.iq_stride;
+
+    if (tid < kSym) s_lock[tid] = a.tables->lock[tid].x;
+    if (tid == 0) s_d0 = 0x7fffffff;
+    __syncthreads();
+
+    long W = a.sync_window > 0 ? (long)a.sync_window : M;
+    if (W > M) W = M;
+    int status = ST_OK;
+    long offset = 0;
+
+    if (SYNC == 0) {
+        offset = (long)ramp_argmax(x, M, -(kSym - 1), W - 1, s_lock, s_val, s_idx) - 1;     // src/receiver.rs:21: lag - 1
+    } else {
+        // sliding Schmidl-Cox (docs/SPEC.md 4): P(d) = Q[d+80] - Q[d], R(d) = E[d+160] - E[d+80]
+        long d_end = W;
+        if (d_end > M - 2 * kSym + 1) d_end = M - 2 * kSym + 1;
+        for (long base = 0; base < d_end; base += kAcqChunk) {
+            // exclusive prefix sums over this chunk (+ halo), built from per-thread serial runs + a warp-shuffle scan
+            constexpr int NQ = kAcqChunk + kSym;          // q needed for n in [base, base + chunk + 80)
+            constexpr int NE = kAcqChunk + 2 * kSym;      // e needed for n in [base, base + chunk + 160)
+            constexpr int RUN = (NE + kAcqThreads - 1) / kAcqThreads;   // consecutive samples per thread
+            float qr[RUN], qi[RUN], ee[RUN];
+            float tqr = 0.0f, tqi = 0.0f, te = 0.0f;
+#pragma unroll
+            for (int r = 0; r < RUN; r++) {
+                long n = base + (long)tid * RUN + r;
+                float2 v0 = ld_sample(x, n, M), v1 = ld_sample(x, n + kSym, M);
+                // conj(v0) * v1
+                float pr = v0.x * v1.x + v0.y * v1.y, pi = v0.x * v1.y - v0.y * v1.x;
+                qr[r] = tqr; qi[r] = tqi; ee[r] = te;                   // exclusive within the run
+                tqr += pr; tqi += pi; te += v0.x * v0.x + v0.y * v0.y;
+            }
+            // scan of the per-thread totals: warp shuffle, then across warps through smem
+            float sqr = tqr, sqi = tqi, se = te;
+#pragma unroll
+            for (int m = 1; m < 32; m <<= 1) {
+                float a0 = __shfl_up_sync(0xffffffffu, sqr, m), a1 = __shfl_up_sync(0xffffffffu, sqi, m), a2 = __shfl_up_sync(0xffffffffu, se, m);
+                if (lane >= m) { sqr += a0; sqi += a1; se += a2; }
+            }
+            __shared__ float s_wtot[3 * (kAcqThreads / 32)];
+            __syncthreads();
+            if (lane == 31) { s_wtot[warp] = sqr; s_wtot[8 + warp] = sqi; s_wtot[16 + warp] = se; }
+            __syncthreads();
+            float oqr = sqr - tqr, oqi = sqi - tqi, oe = se - te;       // exclusive offset of this thread inside its warp
+            for (int w2 = 0; w2 < warp; w2++) { oqr += s_wtot[w2]; oqi += s_wtot[8 + w2]; oe += s_wtot[16 + w2]; }
+#pragma unroll
+            for (int r = 0; r < RUN; r++) {
+                int i = tid * RUN + r;
+                if (i <= NQ) s_q[i] = make_float2(qr[r] + oqr, qi[r] + oqi);
+                if (i <= NE) s_e[i] = ee[r] + oe;
+            }
+            __syncthreads();
+            int found = 0x7fffffff;
+            for (int i = tid; i < kAcqChunk && base + i < d_end; i += kAcqThreads) {
+                float2 qa = s_q[i], qb = s_q[i + kSym];
+                float pr = qb.x - qa.x, pi = qb.y - qa.y;
+                float rr = s_e[i + 2 * kSym] - s_e[i + kSym];
+                if (pr * pr + pi * pi > 0.5f * rr * rr) { found = i; break; }
+            }
+            if (found != 0x7fffffff) atomicMin(&s_d0, (int)(base + found));
+            __syncthreads();
+            if (s_d0 != 0x7fffffff) break;
+        }
+        if (s_d0 == 0x7fffffff) {
+            status = ST_NO_SYNC;
+        } else {
+            long d0 = s_d0, k_lo = d0 - 176, k_hi = d0 + 16;
+            if (k_lo < -(kSym - 1)) k_lo = -(kSym - 1);
+            offset = (long)ramp_argmax(x, M, k_lo, k_hi, s_lock, s_val, s_idx) - 1;
+        }
+    }
+    if (status == ST_OK && offset < 0) status = ST_NEG_OFFSET;                       // src/receiver.rs:25
+    if (status == ST_OK && (offset > M || M - offset < 800)) status = ST_TOO_SHORT;  // src/receiver.rs:27-29
+
+    if (status != ST_OK) {
+        if (tid == 0) {
+            st->status = status; st->offset = (int32_t)offset; st->n_syms = 0; st->out_len = 0; st->f_delta = 0.0f; st->fstep = 0;
+            a.status[stream] = status; a.out_len[stream] = 0;
+            if (a.d_offset) a.d_offset[stream] = (int32_t)offset;
+            if (a.d_f_delta) a.d_f_delta[stream] = 0.0f;
+            if (a.d_nsyms) a.d_nsyms[stream] = 0;
+        }
+        return;
+    }
+
+    const float2 *x0 = x + offset;
+    const long n_avail = M - offset;
+
+    // ---- CFO estimate in f64 (80 or 160 terms per stream; src/receiver.rs:231-240) -------------------------------
+    double acc0 = 0.0, acc1 = 0.0;
+    if (tid < kSym) {
+        float2 r2 = x0[2 * kSym + tid], r3 = x0[3 * kSym + tid], r4 = x0[4 * kSym + tid];
+        if (CFO == 0) {
+            // angle(r / l), naive complex division like num::Complex
+            double lr = r3.x, li = r3.y, rr = r4.x, ri = r4.y, nn = lr * lr + li * li;
+            acc0 = atan2((ri * lr - rr * li) / nn, (rr * lr + ri * li) / nn);
+        } else {
+            acc0 = (double)r2.x * r3.x + (double)r2.y * r3.y + (double)r3.x * r4.x + (double)r3.y * r4.y;
+            acc1 = (double)r2.x * r3.y - (double)r2.y * r3.x + (double)r3.x * r4.y - (double)r3.y * r4.x;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, m);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, m);
+    }
+    if (lane == 0) { s_red[warp] = acc0; s_red[8 + warp] = acc1; }
+    __syncthreads();
+    double f_delta;
+    {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w2 = 0; w2 < kAcqThreads / 32; w2++) { t0 += s_red[w2]; t1 += s_red[8 + w2]; }
+        if (CFO == 0) f_delta = fabs((t0 / 80.0) / 80.0);
+        else f_delta = atan2(t1, t0) / 80.0;
+    }
+    const uint64_t fstep = (uint64_t)(int64_t)llrint(-f_delta * (0.15915494309189533577 * 18446744073709551616.0));
+    if (tid == 0) { st->fstep = fstep; st->f_delta = (float)f_delta; st->offset = (int32_t)offset; }
+    __syncthreads();
+
+    // ---- channel estimate (src/receiver.rs:212-229) and header symbols: warp 0 -----------------------------------
+    if (warp == 0) {
+        const int g = lane >> 3, l = lane & 7;
+        float2 *tr = s_tr + g * kTrGroup;
+        float twr[8], twi[8];
+        fft64_lane_twiddles(l, twr, twi);
+        float hr[8], hi[8];
+#pragma unroll
+        for (int kb = 0; kb < 8; kb++) { hr[kb] = 0.0f; hi[kb] = 0.0f; }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            const int row = 5 + 4 * pass + g;                 // training rows 5..9
+            const bool valid = row < 10;
+            float zr[8], zi[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t n = row * kSym + kCp + l + 8 * j;
+                float2 v = valid ? x0[n] : make_float2(0.0f, 0.0f);
+                float c, s;
+                phasor_from_turns(fstep * (uint64_t)n, c, s);
+                cmul(v.x, v.y, c, s);
+                zr[j] = v.x; zi[j] = v.y;
+            }
+            fft64_group(zr, zi, twr, twi, tr, l);
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                float2 it = a.tables->inv_training[l + 8 * kb];
+                cmul(zr[kb], zi[kb], it.x, it.y);
+                hr[kb] += zr[kb]; hi[kb] += zi[kb];
+            }
+        }
+#pragma unroll
+        for (int kb = 0; kb < 8; kb++) {
+            hr[kb] += __shfl_xor_sync(0xffffffffu, hr[kb], 8);  hi[kb] += __shfl_xor_sync(0xffffffffu, hi[kb], 8);
+            hr[kb] += __shfl_xor_sync(0xffffffffu, hr[kb], 16); hi[kb] += __shfl_xor_sync(0xffffffffu, hi[kb], 16);
+            hr[kb] *= 0.2f; hi[kb] *= 0.2f;
+            if (g == 0) {
+                float inv = 1.0f / (hr[kb] * hr[kb] + hi[kb] * hi[kb]);
+                st->h[l + 8 * kb] = make_float2(hr[kb], hi[kb]);
+                st->g[l + 8 * kb] = make_float2(hr[kb] * inv, -hi[kb] * inv);
+                if (a.d_h) a.d_h[(size_t)stream * 64 + l + 8 * kb] = make_float2(hr[kb], hi[kb]);
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+
+        // header symbols (src/receiver.rs:86-89): the first HDR_SYMS data symbols, one per 8-lane group
+        RxLane L;
+        rx_lane_init(L, st, l);
+        const bool valid = g < HDR_SYMS;
+        float br, bi;
+        phasor_from_turns(fstep * (uint64_t)((kHeadSyms + g) * kSym + kCp), br, bi);
+        float zr[8], zi[8];
+        rx_symbol<GUARD, PHASE>(x0, (uint32_t)(n_avail > 0xffffffffL ? 0xffffffffL : n_avail), (uint32_t)g, valid, L, br, bi, tr, l, zr, zi);
+        if (valid) {
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                int rk = data_rank<GUARD>(l + 8 * kb);
+                if (rk >= 0) s_car[g * D + rk] = (uint8_t)demap_point<MOD>(zr[kb], zi[kb]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            uint64_t lo = 0, hi64 = 0;
+            for (int b = 0; b < 128; b++) {
+                int c = b / BPC, sh = b - c * BPC;
+                uint64_t bit = (s_car[c] >> sh) & 1u;
+                if (b < 64) lo |= bit << b; else hi64 |= bit << (b - 64);
+            }
+            const long rows = (n_avail + kSym - 1) / kSym;                // src/receiver.rs:192-203
+            const long s_rx = rows - kHeadSyms;
+            const long avail_bytes = (s_rx * BPS) / 8 - 16;
+            int stt = ST_OK;
+            uint32_t n_syms = 0, out_len = 0;
+            if (hi64 != 0 || (long)lo > avail_bytes || avail_bytes < 0) {
+                stt = ST_BAD_HEADER;
+            } else {
+                const uint64_t plen = lo;
+                const uint64_t nbits = kHeaderBits + 8 * plen;
+                const uint64_t ncar = (nbits + BPC - 1) / BPC;
+                n_syms = (uint32_t)((ncar + D - 1) / D);
+                out_len = (uint32_t)(FEC ? (8 * plen) / 14 : plen);
+                if (out_len > a.out_stride) { stt = ST_BAD_HEADER; n_syms = 0; out_len = 0; }
+            }
+            st->status = stt; st->n_syms = n_syms; st->out_len = out_len; st->plen = (uint32_t)lo; st->n_syms_rx = (uint32_t)s_rx;
+            a.status[stream] = stt; a.out_len[stream] = out_len;
+            if (a.d_offset) a.d_offset[stream] = (int32_t)offset;
+            if (a.d_f_delta) a.d_f_delta[stream] = (float)f_delta;
+            if (a.d_nsyms) a.d_nsyms[stream] = (uint32_t)s_rx;
+        }
+    }
+}
+
+}  // namespace ofdm
