@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- RX hot-path throughput on B200 (BASELINE.json metric: RX Msamples/s & decoded Gbit/s, % HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload "4096x64QAM_long", BASELINE.json configs[1]): per GPU 4096 independent streams, each one a
+capture holding a 64QAM + guard-band + Hamming(7,4) frame of S=2038 data symbols (163 840 samples) behind a random
+noise-only lead-in, through the 12-tap multipath + CFO + AWGN channel at 30 dB; sliding Schmidl-Cox sync + the full
+RX chain. The IQ is synthesised ON THE DEVICE by the engine's own TX + channel kernels before the timed region.
+A "step" = one ofdm_rx_decode_batch over all streams of the rank. Weak scaling: every rank owns its own 4096 streams,
+no data-path collective; the BER counters are sum-reduced once over NCCL after the timed region.
+
+  value : whole-job Msamples/s, inputs resident in HBM, CUDA events on the launch stream, max over ranks.
+  e2e   : same metric through the C ABI with HOST (pinned) buffers: H2D of the IQ and D2H of the payload inside.
+  roofline : decode kernel, algorithmic bytes (8 B/sample in + payload bytes out) / its CUDA-event duration.
+  cpu_baseline : the CPU oracle (C port of the reference algorithm; the Rust reference cannot be built here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--syms", type=int, default=2038, help="data OFDM symbols per frame")
+    ap.add_argument("--snr", type=float, default=30.0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+LEAD_MIN, LEAD_MAX = 8, 1031
+SYNC_WINDOW = 2048
+SEED = 0x0FD64
+
+
+def workload_cfg():
+    import ofdm_b200 as ob
+    return ob.Config(modulation=ob.MOD_QAM64, guard_bands=True, fec=True, sync_mode=ob.SYNC_SCHMIDL_COX,
+                     cfo_mode=ob.CFO_ANGLE_OF_SUM, phase_mode=ob.PHASE_ANGLE_OF_SUM, sync_window=SYNC_WINDOW)
+
+
+def oracle_cfg():
+    from oracle import oracle as oo
+    return oo.make_cfg(True, oo.QAM64, True, oo.SYNC_SCHMIDL_COX, oo.CFO_ANGLE_OF_SUM, oo.PHASE_ANGLE_OF_SUM, SYNC_WINDOW)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def read_traffic(workload: str):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            t = json.load(f)
+        e = t.get(workload)
+        if e:
+            return e.get("dram_bytes_per_launch")
+    return None
+
+
+def cpu_sample(iq_host: np.ndarray, n_samples: np.ndarray, out_stride: int, target_s: float, threads: int):
+    """Time the oracle on a bounded sample of the same workload. Returns (msamples_per_s, n_streams_used, seconds)."""
+    from oracle import oracle as oo
+    cfg = oracle_cfg()
+    n_avail = iq_host.shape[0]
+    k = min(n_avail, max(threads, 1))
+    t0 = time.perf_counter()
+    oo.decode_batch_fc32(iq_host[:k].view(np.float32).reshape(k, iq_host.shape[1], 2), n_samples[:k], cfg, out_stride, threads)
+    dt = time.perf_counter() - t0
+    per_stream_batch = dt                               # seconds for `threads` streams in parallel
+    reps = max(1, int(target_s / max(per_stream_batch, 1e-3)))
+    k2 = min(n_avail, k * reps)
+    t0 = time.perf_counter()
+    out, out_len, status, _ = oo.decode_batch_fc32(iq_host[:k2].view(np.float32).reshape(k2, iq_host.shape[1], 2), n_samples[:k2],
+                                                   cfg, out_stride, threads)
+    dt = time.perf_counter() - t0
+    return float(n_samples[:k2].sum()) / dt / 1e6, k2, dt, (out, out_len, status)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0                                     # rank 0 alone runs the CPU arm
+        return reference_arm(args)
+
+    import torch
+    import ofdm_b200 as ob
+
+    cfg = workload_cfg()
+    S = args.syms
+    payload_len = cfg.max_payload(S)
+    assert cfg.frame_data_syms(payload_len) == S, (cfg.frame_data_syms(payload_len), S)
+    frame_len = cfg.frame_len(payload_len)
+    n_streams = args.streams
+    iq_stride = (frame_len + LEAD_MAX + 63 + 31) // 32 * 32
+    out_stride = (payload_len + 15) // 16 * 16
+    workload = f"{n_streams}x64QAM_S{S}"
+    config = {"workload": workload, "streams_per_gpu": n_streams, "data_syms_per_frame": S, "frame_samples": frame_len,
+              "payload_bytes": payload_len, "modulation": "64QAM", "guard_bands": True, "fec": "hamming(7,4)",
+              "sync": "schmidl_cox(window=%d)" % SYNC_WINDOW, "cfo": "angle_of_sum", "snr_db": args.snr,
+              "lead_in": [LEAD_MIN, LEAD_MAX], "l2": "inputs (%.2f GB/GPU) larger than L2" % (n_streams * iq_stride * 8 / 1e9)}
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; the engine has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthesise the workload on the device (untimed) ----------------------------------------------------
+    eng = ob.Engine(cfg, local_rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    payload = torch.randint(0, 256, (n_streams, out_stride), dtype=torch.uint8, device=dev, generator=g)
+    plen = torch.full((n_streams,), payload_len, dtype=torch.int32, device=dev)
+    tx = torch.empty((n_streams, frame_len, 2), dtype=torch.float32, device=dev)
+    flen = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    eng.tx_encode_device(payload.data_ptr(), plen.data_ptr(), out_stride, n_streams, tx.data_ptr(), frame_len, flen.data_ptr(), stream)
+    rx = torch.empty((n_streams, iq_stride, 2), dtype=torch.float32, device=dev)
+    rx_len = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    chan = ob.ChannelParams(snr_db=args.snr, cfo_max=0.9 * np.pi / 80, lead_min=LEAD_MIN, lead_max=LEAD_MAX, multipath=True,
+                            noise_mode=1, seed=SEED + 1000 * rank)
+    eng.channel_device(tx.data_ptr(), flen.data_ptr(), frame_len, n_streams, chan, rx.data_ptr(), iq_stride, rx_len.data_ptr(), 0, 0, stream)
+    torch.cuda.synchronize()
+    del tx
+    torch.cuda.empty_cache()
+    total_samples = int(rx_len.sum().item())
+    max_n = int(rx_len.max().item())
+
+    out = torch.zeros((n_streams, out_stride), dtype=torch.uint8, device=dev)
+    out_len = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+    status = torch.zeros(n_streams, dtype=torch.int32, device=dev)
+
+    def step():
+        eng.rx_decode_device(rx.data_ptr(), rx_len.data_ptr(), n_streams, iq_stride, max_n, out.data_ptr(), out_stride,
+                             out_len.data_ptr(), status.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, inputs resident in HBM -------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = eng.kernel_launches
+    eng.profile_begin(args.steps)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    gpu_launches = eng.kernel_launches - launches0
+    acq_ms, dec_ms = eng.profile_read(args.steps)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # ---- correctness of what was timed: BER vs the transmitted payload, counters sum-reduced over NCCL ---------
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    eng.ber_device(payload.data_ptr(), plen.data_ptr(), out_stride, out.data_ptr(), out_len.data_ptr(), out_stride,
+                   status.data_ptr(), n_streams, counters.data_ptr(), stream)
+    tot = torch.tensor([total_samples], dtype=torch.int64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)      # the path's only collective (4 x u64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    c = [int(x) for x in counters.tolist()]
+    job_samples = int(tot.item())
+    value = job_samples / (ms_step * 1e-3) / 1e6
+    decoded_gbit = world * n_streams * payload_len * 8 / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (rank 0's launches) --------------------------------------------------
+    peak, peak_src = read_peaks()
+    alg_bytes = 8 * total_samples + n_streams * payload_len
+    dec_avg_ms = float(np.mean(dec_ms)) if len(dec_ms) else float("nan")
+    achieved = alg_bytes / (dec_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "rx_decode_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": read_traffic(workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(dec_avg_ms, 4),
+                "acquire_kernel_ms": round(float(np.mean(acq_ms)), 4) if len(acq_ms) else None,
+                "kernel_share_of_step": round(dec_avg_ms / (ms_total / args.steps), 4)}
+
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ---------------------------
+    e2e = None
+    rx_host = None
+    if not args.no_e2e:
+        rx_host = torch.empty((n_streams, iq_stride, 2), dtype=torch.float32, pin_memory=True)
+        rx_host.copy_(rx)
+        n_host = rx_len.cpu().numpy().astype(np.uint32)
+        out_host = torch.zeros((n_streams, out_stride), dtype=torch.uint8, pin_memory=True)
+        ol_host = np.zeros(n_streams, np.uint32)
+        st_host = np.zeros(n_streams, np.int32)
+        import ctypes as C
+
+        def e2e_step():
+            eng._check(eng.lib.ofdm_rx_decode_batch(eng._h, rx_host.data_ptr(), n_host.ctypes.data, n_streams, iq_stride, max_n,
+                                                    out_host.data_ptr(), out_stride, ol_host.ctypes.data, st_host.ctypes.data,
+                                                    None, ob.engine.MEM_HOST, None), "ofdm_rx_decode_batch(host)")
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        same = bool((out_host.to(dev) == out).all().item())
+        e2e = {"value": round(job_samples / dt / 1e6, 1), "unit": "Msamples/s", "h2d_bytes_per_step": int(n_streams * iq_stride * 8 + n_streams * 4),
+               "d2h_bytes_per_step": int(n_streams * out_stride + n_streams * 8), "ms_per_step": round(dt * 1e3, 3),
+               "decoded_gbit_per_s": round(world * n_streams * payload_len * 8 / dt / 1e9, 2),
+               "h2d_gb_per_s_per_gpu": round(n_streams * iq_stride * 8 / dt / 1e9, 1), "steps": args.e2e_steps,
+               "matches_device_path": same}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as oo
+        threads = oo.max_threads()
+        k = min(n_streams, 4 * threads + 64)
+        iq_h = rx[:k].cpu().numpy().view(np.complex64).reshape(k, iq_stride)
+        ns_h = rx_len[:k].cpu().numpy().astype(np.uint32)
+        v1, k1, dt1, _ = cpu_sample(iq_h, ns_h, out_stride, args.cpu_seconds / 2, 1)
+        vN, kN, dtN, res = cpu_sample(iq_h, ns_h, out_stride, args.cpu_seconds / 2, threads)
+        o_out, o_len, o_st = res
+        gpu_out = out[:kN].cpu().numpy()
+        agree = bool((o_st == 0).all() and (o_len == payload_len).all() and (o_out[:, :payload_len] == gpu_out[:, :payload_len]).all())
+        cpu_baseline = {"value": round(vN, 2), "unit": "Msamples/s", "cores": threads, "kind": "port",
+                        "sample": f"{kN} of the {n_streams} streams ({dtN:.1f} s on {threads} threads; f64 C oracle, FFT plans reused)",
+                        "single_core": {"value": round(v1, 2), "sample": f"{k1} streams, {dt1:.1f} s"},
+                        "gpu_bytes_equal_oracle_on_sample": agree}
+
+    if rank == 0:
+        line = {"metric": "rx_msamples_per_s", "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "decoded_gbit_per_s": round(decoded_gbit, 1), "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+                "gpu_launches": int(gpu_launches), "clocks": clocks,
+                "ber": {"bit_errs": c[0], "byte_errs": c[1], "bits_compared": c[2], "frames_failed": c[3]}}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm with all host threads, no GPU and none of the engine's code.
+
+    The Rust crate cannot be built here (no rustc/cargo, out-of-tree dependencies), so this times the f64 C oracle port
+    of the same algorithm. Each step decodes a bounded sample (2 streams per host thread) of the same workload,
+    synthesised on the CPU by the oracle's own TX + channel.
+    """
+    from oracle import oracle as oo
+    threads = oo.max_threads()
+    cfg = oracle_cfg()
+    S = args.syms
+    # largest payload that fits S data symbols (same arithmetic as ofdm_max_payload)
+    coded = (S * 288 - 128) // 8
+    payload_len = (8 * coded) // 14
+    frame_len = (10 + S) * 80
+    iq_stride = (frame_len + LEAD_MAX + 63 + 31) // 32 * 32
+    out_stride = (payload_len + 15) // 16 * 16
+    k = max(threads, 1) * 2
+    rng = np.random.default_rng(SEED)
+    iq = np.zeros((k, iq_stride), np.complex64)
+    ns = np.zeros(k, np.uint32)
+    pays = []
+    base_tx = None
+    for i in range(k):
+        pay = rng.integers(0, 256, payload_len, dtype=np.uint8)
+        pays.append(pay)
+        tx = oo.tx(pay, cfg)
+        assert tx.size == frame_len
+        ch = oo.channel(tx, args.snr, float(rng.uniform(0, 0.9 * np.pi / 80)), 1, SEED + i)
+        lead = int(rng.integers(LEAD_MIN, LEAD_MAX + 1))
+        sigma = np.sqrt(0.5 * np.mean(np.abs(ch) ** 2) / 10 ** (args.snr / 10))
+        noise = sigma * (rng.standard_normal(lead) + 1j * rng.standard_normal(lead))
+        cap = np.concatenate([noise, ch])
+        iq[i, : cap.size] = cap
+        ns[i] = cap.size
+    f32 = iq.view(np.float32).reshape(k, iq_stride, 2)
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        oo.decode_batch_fc32(f32, ns, cfg, out_stride, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out, out_len, status, _ = oo.decode_batch_fc32(f32, ns, cfg, out_stride, threads)
+    dt = (time.perf_counter() - t0) / steps
+    ok = all(status[i] == 0 and out_len[i] == payload_len and (out[i, :payload_len] == pays[i]).all() for i in range(k))
+    v = float(ns.sum()) / dt / 1e6
+    gbit = float(out_len[status == 0].sum()) * 8 / dt / 1e9
+    config = {"workload": f"{args.streams}x64QAM_S{S}", "streams_per_gpu": args.streams, "data_syms_per_frame": S,
+              "frame_samples": frame_len, "payload_bytes": payload_len, "modulation": "64QAM", "guard_bands": True,
+              "fec": "hamming(7,4)", "sync": "schmidl_cox(window=%d)" % SYNC_WINDOW, "cfo": "angle_of_sum", "snr_db": args.snr,
+              "lead_in": [LEAD_MIN, LEAD_MAX]}
+    cpu = {"value": round(v, 2), "unit": "Msamples/s", "cores": threads, "kind": "port",
+           "sample": f"{k} streams of the workload per step (f64 C port of the reference algorithm, {threads} host threads, FFT plans reused)",
+           "payloads_recovered": bool(ok)}
+    line = {"impl": "reference", "metric": "rx_msamples_per_s", "value": round(v, 2), "unit": "Msamples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "decoded_gbit_per_s": round(gbit, 4),
+            "cpu_baseline": cpu, "e2e": {"value": round(v, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -163,6 +163,14 @@ int ofdm_ber_accumulate(ofdm_engine *h, const uint8_t *ref, const uint32_t *ref_
                         const int32_t *status, uint32_t n_streams, uint64_t *counters,
                         int mem, void *stream);
 
+/*
+ * Per-kernel device timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE) for the roofline report: after
+ * ofdm_profile_begin(h, n) the next n calls record CUDA events on their stream around the acquisition and the
+ * decode kernel; ofdm_profile_read waits for them and returns the durations (ms) of each call.
+ */
+int ofdm_profile_begin(ofdm_engine *h, uint32_t max_calls);
+int ofdm_profile_read(ofdm_engine *h, float *acquire_ms, float *decode_ms, uint32_t *n_calls);
+
 /* how many kernels this handle has launched so far (bench.py's gpu_launches) */
 uint64_t ofdm_kernel_launches(const ofdm_engine *h);
 

@@ -51,8 +51,12 @@ struct ofdm_engine {
     DevBuf counters;                    // 4 x u64
     // host-mode staging
     DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
     int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
+    // per-kernel timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE): 3 events per call (start, after acquire, end)
+    std::vector<cudaEvent_t> prof_ev;
+    uint32_t prof_cap = 0, prof_n = 0;
 };
 
 #define ENG_FAIL(h, code, ...)                                   \
@@ -253,6 +257,11 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     bool ok = cudaMalloc(&h->d_tables, sizeof(RxTables)) == cudaSuccess &&
               cudaMemcpy(h->d_tables, t, sizeof(RxTables), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_copied[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_copied[1], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_done[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_done[1], cudaEventDisableTiming) == cudaSuccess &&
               h->counters.ensure(4 * sizeof(uint64_t)) == cudaSuccess;
     delete t;
     if (!ok) {
@@ -273,6 +282,9 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
                        &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h };
     for (DevBuf *b : bufs) b->release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
 }
 
@@ -354,12 +366,16 @@ extern "C" int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, cons
 // ---- RX ----------------------------------------------------------------------------------------------------------
 static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples, uint32_t n_streams, uint32_t iq_stride,
                      uint32_t max_n_samples, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
-                     const ofdm_rx_diag *diag, cudaStream_t st)
+                     const ofdm_rx_diag *diag, cudaStream_t st, size_t state_offset = 0, size_t state_total = 0)
 {
-    CU(h, h->state.ensure(sizeof(StreamState) * (size_t)n_streams));
+    if (state_total < n_streams) state_total = n_streams;
+    if (state_offset == 0) CU(h, h->state.ensure(sizeof(StreamState) * state_total));
+    const bool prof = h->prof_n < h->prof_cap;
+    cudaEvent_t *pe = prof ? &h->prof_ev[3 * (size_t)h->prof_n] : nullptr;
+    if (prof) { h->prof_n++; CU(h, cudaEventRecord(pe[0], st)); }
     RxArgs a{};
     a.iq = reinterpret_cast<const float2 *>(iq); a.n_samples = n_samples; a.iq_stride = iq_stride; a.n_streams = n_streams;
-    a.state = h->state.as<StreamState>(); a.tables = h->d_tables;
+    a.state = h->state.as<StreamState>() + state_offset; a.tables = h->d_tables;
     a.out = out; a.out_stride = out_stride; a.out_len = out_len; a.status = status;
     a.sync_window = h->cfg.sync_window; a.tile_shift = h->tile_shift;
     a.sync_mode = (int)h->cfg.sync_mode; a.cfo_mode = (int)h->cfg.cfo_mode; a.fec = (int)h->cfg.fec;
@@ -370,6 +386,7 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         points = diag->points != nullptr && diag->points_stride > 0;
     }
     pick_acquire(h->cfg)<<<n_streams, kAcqThreads, 0, st>>>(a);
+    if (prof) CU(h, cudaEventRecord(pe[1], st));
     uint32_t mx = max_n_samples ? max_n_samples : iq_stride;
     if (mx > iq_stride) mx = iq_stride;
     long rows = ((long)mx + 79) / 80, S = rows - 10;
@@ -379,7 +396,42 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         pick_decode(h->cfg, points)<<<dim3(tiles, n_streams), kDecThreads, 0, st>>>(a);
         h->launches += 1;
     }
+    if (prof) CU(h, cudaEventRecord(pe[2], st));
     CU(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofdm_profile_begin(ofdm_engine *h, uint32_t max_calls)
+{
+    if (!h) return OFDM_E_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    while (h->prof_ev.size() < 3 * (size_t)max_calls) {
+        cudaEvent_t e;
+        CU(h, cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_cap = max_calls;
+    h->prof_n = 0;
+    return 0;
+}
+
+extern "C" int ofdm_profile_read(ofdm_engine *h, float *acquire_ms, float *decode_ms, uint32_t *n_calls)
+{
+    if (!h || !n_calls) return OFDM_E_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    uint32_t n = h->prof_n;
+    for (uint32_t i = 0; i < n; i++) {
+        cudaEvent_t *pe = &h->prof_ev[3 * (size_t)i];
+        CU(h, cudaEventSynchronize(pe[2]));
+        float a = 0, d = 0;
+        CU(h, cudaEventElapsedTime(&a, pe[0], pe[1]));
+        CU(h, cudaEventElapsedTime(&d, pe[1], pe[2]));
+        if (acquire_ms) acquire_ms[i] = a;
+        if (decode_ms) decode_ms[i] = d;
+    }
+    *n_calls = n;
+    h->prof_cap = 0;
+    h->prof_n = 0;
     return 0;
 }
 
@@ -401,12 +453,21 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
         if (n_samples[s] > iq_stride) ENG_FAIL(h, OFDM_E_INVALID, "rx: n_samples[%u] exceeds iq_stride", s);
         if (n_samples[s] > mx) mx = n_samples[s];
     }
-    cudaStream_t st = h->own_stream;
-    size_t ib = (size_t)n_streams * iq_stride * sizeof(float2), ob = (size_t)n_streams * out_stride;
-    CU(h, h->s_iq.ensure(ib));
+    // Host path: the capture is streamed through two device staging buffers in chunks of whole streams; the H2D copy of
+    // chunk c+1 (copy_stream) overlaps the kernels of chunk c (own_stream). Outputs are gathered on the device and
+    // copied back once.
+    cudaStream_t st = h->own_stream, cs = h->copy_stream;
+    const size_t stream_bytes = (size_t)iq_stride * sizeof(float2);
+    uint32_t chunk = (uint32_t)((256u << 20) / stream_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_streams) chunk = n_streams;
+    const size_t ob = (size_t)n_streams * out_stride;
+    CU(h, h->s_iq.ensure(chunk * stream_bytes));
+    CU(h, h->s_iq2.ensure(chunk * stream_bytes));
     CU(h, h->s_bytes.ensure(ob));
     CU(h, h->s_len.ensure(2 * sizeof(uint32_t) * (size_t)n_streams));
     CU(h, h->s_status.ensure(sizeof(int32_t) * (size_t)n_streams));
+    CU(h, h->state.ensure(sizeof(StreamState) * (size_t)n_streams));
     uint32_t *d_ns = h->s_len.as<uint32_t>(), *d_ol = d_ns + n_streams;
     ofdm_rx_diag dd{};
     if (diag) {
@@ -422,11 +483,27 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
             dd.points = h->s_points.as<ofdm_fc32>(); dd.points_stride = diag->points_stride;
         }
     }
-    CU(h, cudaMemcpyAsync(h->s_iq.p, iq, ib, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(d_ns, n_samples, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
-    int rc = rx_device(h, h->s_iq.as<ofdm_fc32>(), d_ns, n_streams, iq_stride, mx, h->s_bytes.as<uint8_t>(), out_stride, d_ol,
-                       h->s_status.as<int32_t>(), diag ? &dd : nullptr, st);
-    if (rc) return rc;
+    DevBuf *stage[2] = { &h->s_iq, &h->s_iq2 };
+    uint32_t ci = 0;
+    for (uint32_t s0 = 0; s0 < n_streams; s0 += chunk, ci++) {
+        const uint32_t ns = n_streams - s0 < chunk ? n_streams - s0 : chunk;
+        const int b = ci & 1;
+        if (ci >= 2) CU(h, cudaStreamWaitEvent(cs, h->ev_done[b], 0));           // staging buffer free again
+        CU(h, cudaMemcpyAsync(stage[b]->p, iq + (size_t)s0 * iq_stride, ns * stream_bytes, cudaMemcpyHostToDevice, cs));
+        CU(h, cudaEventRecord(h->ev_copied[b], cs));
+        CU(h, cudaStreamWaitEvent(st, h->ev_copied[b], 0));
+        ofdm_rx_diag dc = dd;
+        if (dc.offset) dc.offset += s0;
+        if (dc.f_delta) dc.f_delta += s0;
+        if (dc.n_data_syms) dc.n_data_syms += s0;
+        if (dc.h_k) dc.h_k += (size_t)s0 * 64;
+        if (dc.points) dc.points += (size_t)s0 * dc.points_stride;
+        int rc = rx_device(h, stage[b]->as<ofdm_fc32>(), d_ns + s0, ns, iq_stride, mx, h->s_bytes.as<uint8_t>() + (size_t)s0 * out_stride,
+                           out_stride, d_ol + s0, h->s_status.as<int32_t>() + s0, diag ? &dc : nullptr, st, s0, n_streams);
+        if (rc) return rc;
+        CU(h, cudaEventRecord(h->ev_done[b], st));
+    }
     CU(h, cudaMemcpyAsync(out, h->s_bytes.p, ob, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(out_len, d_ol, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));

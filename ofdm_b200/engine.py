@@ -26,7 +26,7 @@ EXPORTS = [
     "ofdm_abi_version", "ofdm_cfg_default", "ofdm_status_name", "ofdm_engine_create", "ofdm_engine_destroy",
     "ofdm_last_error", "ofdm_get_tables", "ofdm_host_alloc", "ofdm_host_free", "ofdm_coded_len",
     "ofdm_frame_data_syms", "ofdm_frame_len", "ofdm_max_payload", "ofdm_tx_encode_batch", "ofdm_rx_decode_batch",
-    "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches",
+    "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches", "ofdm_profile_begin", "ofdm_profile_read",
 ]
 
 
@@ -97,6 +97,10 @@ def load_library(build: bool = False) -> C.CDLL:
     L.ofdm_channel_apply_batch.restype = i32
     L.ofdm_ber_accumulate.argtypes = [vp, vp, vp, u32, vp, vp, u32, vp, u32, vp, i32, vp]
     L.ofdm_ber_accumulate.restype = i32
+    L.ofdm_profile_begin.argtypes = [vp, u32]
+    L.ofdm_profile_begin.restype = i32
+    L.ofdm_profile_read.argtypes = [vp, vp, vp, vp]
+    L.ofdm_profile_read.restype = i32
     L.ofdm_kernel_launches.argtypes = [vp]
     L.ofdm_kernel_launches.restype = u64
     _lib = L
@@ -213,6 +217,17 @@ class Engine:
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.ofdm_kernel_launches(self._h))
+
+    def profile_begin(self, max_calls: int):
+        self._check(self.lib.ofdm_profile_begin(self._h, max_calls), "ofdm_profile_begin")
+
+    def profile_read(self, max_calls: int):
+        """Returns (acquire_ms[], decode_ms[]) of the rx_decode_device calls since profile_begin."""
+        a = np.zeros(max_calls, np.float32)
+        d = np.zeros(max_calls, np.float32)
+        n = C.c_uint32(0)
+        self._check(self.lib.ofdm_profile_read(self._h, _ptr(a), _ptr(d), C.byref(n)), "ofdm_profile_read")
+        return a[: n.value], d[: n.value]
 
     def tables(self):
         lock = np.zeros(80, np.complex64)

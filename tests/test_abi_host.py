@@ -1,0 +1,109 @@
+"""C-ABI library loads and exports what include/ofdm_engine.h declares; host-side logic (no GPU compute)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "ofdm_engine.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ofdm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(engine_lib):
+    from ofdm_b200 import engine
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(engine_lib, n), f"{n} declared in include/ofdm_engine.h but not exported"
+    assert sorted(engine.EXPORTS) == names
+    assert engine_lib.ofdm_abi_version() == 1
+
+
+def test_no_torch_in_abi_signatures():
+    text = open(os.path.join(ROOT, "include", "ofdm_engine.h")).read()
+    assert "torch" not in text.lower() and "at::" not in text and "std::" not in text
+
+
+def test_cfg_struct_layout(engine_lib):
+    from ofdm_b200 import engine
+    c = engine.CCfg()
+    engine_lib.ofdm_cfg_default(C.byref(c))
+    assert c.struct_size == C.sizeof(engine.CCfg) == 64
+    assert (c.nfft, c.cp, c.modulation, c.guard_bands) == (64, 16, 0, 0)       # reference defaults
+    assert engine_lib.ofdm_status_name(1) == b"TOO_SHORT"
+
+
+def test_sizes_match_oracle(engine_lib, oo):
+    import ofdm_b200 as ob
+    for mod in (0, 1, 2):
+        for guard in (False, True):
+            for fec in (False, True):
+                cfg = ob.Config(modulation=mod, guard_bands=guard, fec=fec)
+                ocfg = oo.make_cfg(guard, mod, fec)
+                for n in (0, 1, 8, 100, 576, 765, 41915):
+                    assert cfg.frame_len(n) == oo.lib().oo_tx_len(n, C.byref(ocfg))
+                    assert cfg.coded_len(n) == (oo.lib().oo_hamming74_encoded_len(n) if fec else n)
+                for S in (1, 3, 17, 29, 131, 2038):
+                    p = cfg.max_payload(S)
+                    if p > 0:
+                        assert cfg.frame_data_syms(p) <= S < cfg.frame_data_syms(p + 2) + 1
+    assert ob.Config(modulation=2, guard_bands=True, fec=True).frame_len(576) == 3120
+
+
+def test_engine_create_fails_loudly_without_gpu(engine_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import ofdm_b200 as ob
+    with pytest.raises(ob.EngineError, match="no CPU fallback"):
+        ob.Engine(ob.Config())
+    with pytest.raises(ob.EngineError):
+        ob.encode(b"alskdjas", True, None)
+
+
+def test_engine_rejects_bad_cfg(engine_lib):
+    from ofdm_b200 import engine
+    c = engine.CCfg()
+    engine_lib.ofdm_cfg_default(C.byref(c))
+    c.nfft = 1024
+    h = C.c_void_p()
+    assert engine_lib.ofdm_engine_create(C.byref(c), 0, C.byref(h)) == -1
+    assert b"nfft" in engine_lib.ofdm_last_error(None)
+
+
+def test_header_and_wire_format():
+    import ofdm_b200 as ob
+    assert ob.Header(100).serialize() == (100).to_bytes(16, "little") and len(ob.Header(1).serialize()) == 16
+    assert ob.Header.deserialize(ob.Header(12345).serialize()).packet_length == 12345
+    sig = np.arange(10) + 1j * np.arange(10)
+    b = ob.sig_to_bytes(sig)
+    assert len(b) == 80
+    np.testing.assert_array_equal(ob.bytes_to_sig(b + b"\x01\x02"), sig)           # chunks_exact drops the tail
+    assert int(ob.ModulationScheme.Qam) == 2
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ofdm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                t = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in t.replace("the oracle has its own copy", ""), f"{f} mentions the oracle"
+
+
+def test_shard_helpers():
+    from ofdm_b200 import dist
+    for n in (1, 7, 4096, 4097):
+        for w in (1, 2, 3, 8):
+            spans = [dist.stream_shard(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sh = dist.capture_shards(10_000_000, 8, 163840)
+    assert sh[0][0] == 0 and sh[-1][1] == 10_000_000
+    assert all(a[1] - b[0] == 2 * 80 + 163840 for a, b in zip(sh, sh[1:]))
+    assert dist.err_rate([3, 2, 300, 0]) == 0.01

@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle on identical inputs.
+
+Bars (north star): Hamming / QAM bit mapping / frame + packet indexing bit-exact given the same hard decisions;
+equalised constellation points within 1e-4 relative (fp32 engine vs f64 oracle); offset identical; f_delta within 1e-6.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_POINTS = 1e-4        # north star tolerance for equalised constellation points
+ABS_TOL_FDELTA = 1e-6        # rad/sample
+MODES = [(0, 0, 0), (1, 1, 1), (1, 0, 0), (0, 1, 1)]      # (sync, cfo, phase)
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import ofdm_b200
+    return ofdm_b200
+
+
+def _mk(ob, oo, mod, guard, fec, sync, cfo, phase, window=None):
+    window = (0 if sync == 0 else 1024) if window is None else window
+    cfg = ob.Config(modulation=mod, guard_bands=guard, fec=fec, sync_mode=sync, cfo_mode=cfo, phase_mode=phase, sync_window=window)
+    return ob.Engine(cfg, 0), cfg, oo.make_cfg(guard, mod, fec, sync, cfo, phase, window)
+
+
+def _batch(caps):
+    n = np.array([c.size for c in caps], np.uint32)
+    iq = np.zeros((len(caps), int(n.max())), np.complex64)
+    for i, c in enumerate(caps):
+        iq[i, : c.size] = c
+    return iq, n
+
+
+def _near_boundary(points, mod, tol):
+    """True where a hard decision of the point could flip under a perturbation of `tol` (relative to scale 1)."""
+    re, im = points.real, points.imag
+    if mod == 0:
+        return np.abs(re) < tol
+    if mod == 1:
+        return (np.abs(re) < tol) | (np.abs(im) < tol)
+    fr = lambda v: np.abs((3.5 * v + 4.0) - np.round(3.5 * v + 4.0)) < 3.5 * tol
+    return fr(re) | fr(im)
+
+
+@pytest.mark.parametrize("mod,guard,fec", list(itertools.product((0, 1, 2), (False, True), (False, True))))
+@pytest.mark.parametrize("modes", MODES)
+def test_tx_rx_parity_matrix(ob, oo, mod, guard, fec, modes):
+    sync, cfo, phase = modes
+    eng, cfg, ocfg = _mk(ob, oo, mod, guard, fec, sync, cfo, phase)
+    rng = np.random.default_rng(1000 * mod + 100 * guard + 10 * fec + sync)
+    pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (576, 0, 1, 100, 333)]   # ragged + empty
+    iq, flen = eng.tx_encode(pays)
+    caps = []
+    for i, p in enumerate(pays):
+        ref = oo.tx(p, ocfg)
+        assert ref.size == flen[i]
+        np.testing.assert_allclose(iq[i, : flen[i]], ref, atol=2e-6)           # TX parity (fp32 IFFT vs f64)
+        assert not iq[i, flen[i]:].any()                                        # zero fill past the frame
+        caps.append(oo.channel(ref, 40.0, 0.02 + 0.003 * i, 1, 100 + i))
+    batch, n = _batch(caps)
+    res = eng.rx_decode(batch, n, points=True)
+    for i, p in enumerate(pays):
+        ref = oo.decode(batch[i, : n[i]].astype(np.complex128), ocfg)
+        assert ref.status == res.status[i] == 0
+        assert ref.offset == res.offset[i] == 8
+        assert abs(ref.f_delta - res.f_delta[i]) < ABS_TOL_FDELTA
+        np.testing.assert_allclose(res.h_k[i], ref.h_k, atol=REL_TOL_POINTS * np.abs(ref.h_k).max())
+        npts = cfg.frame_data_syms(len(p)) * cfg.data_carriers
+        scale = max(1.0, np.abs(ref.points[:npts]).max())
+        assert np.abs(res.points[i, :npts] - ref.points[:npts]).max() <= REL_TOL_POINTS * scale
+        assert res.data[i] == ref.data.tobytes() == p                           # bit exact, ragged lengths
+        assert res.out_len[i] == len(p)
+    eng.close()
+
+
+def test_low_snr_decisions_identical_away_from_boundaries(ob, oo):
+    """At 20 dB (many symbol errors) the engine's hard decisions equal the oracle's wherever the oracle's point is
+    not within 1e-4 of a decision boundary; with identical decisions the bytes are identical."""
+    eng, cfg, ocfg = _mk(ob, oo, 2, True, False, 0, 0, 0)
+    rng = np.random.default_rng(4)
+    pays = [rng.integers(0, 256, 2000, dtype=np.uint8).tobytes() for _ in range(4)]
+    caps = [oo.channel(oo.tx(p, ocfg), 20.0, 0.02, 1, 7 + i) for i, p in enumerate(pays)]
+    batch, n = _batch(caps)
+    res = eng.rx_decode(batch, n, points=True)
+    n_err = 0
+    for i, p in enumerate(pays):
+        ref = oo.decode(batch[i, : n[i]].astype(np.complex128), ocfg)
+        if ref.status != 0:
+            assert res.status[i] == ref.status
+            continue
+        assert res.status[i] == 0 and res.out_len[i] == ref.data.size
+        npts = cfg.frame_data_syms(len(p)) * 48
+        gb = np.unpackbits(np.frombuffer(res.data[i], np.uint8), bitorder="little")
+        rb = np.unpackbits(ref.data, bitorder="little")
+        n_err += int((rb != np.unpackbits(np.frombuffer(p, np.uint8), bitorder="little")).sum())
+        diff = np.flatnonzero(gb != rb)
+        risky = _near_boundary(ref.points[:npts], 2, 1e-4)
+        for b in diff:                                  # payload bit b -> stream bit 128 + b -> carrier
+            assert risky[(128 + b) // 6], f"stream {i}: bit {b} differs away from any decision boundary"
+    assert n_err > 0                                    # the channel really produced bit errors
+
+
+def test_long_frame_hot_kernel_tiling(ob, oo):
+    """Frames spanning many 224-symbol tiles, Hamming tile alignment, every modulation."""
+    for mod, guard, fec in ((2, True, True), (2, True, False), (1, True, True), (0, False, True), (2, False, True)):
+        eng, cfg, ocfg = _mk(ob, oo, mod, guard, fec, 1, 1, 1, 2048)
+        rng = np.random.default_rng(mod)
+        S = 700 if mod == 2 else 500
+        lens = [cfg.max_payload(S), cfg.max_payload(S) - 1, cfg.max_payload(225), cfg.max_payload(224), cfg.max_payload(217) + 1, 5]
+        pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+        caps = []
+        for i, p in enumerate(pays):
+            lead = int(rng.integers(0, 900))
+            c = oo.channel(oo.tx(p, ocfg), 45.0, 0.025, 1, i)
+            caps.append(np.concatenate([0.002 * (rng.standard_normal(lead) + 1j * rng.standard_normal(lead)), c]))
+        batch, n = _batch(caps)
+        res = eng.rx_decode(batch, n, diag=True)
+        for i, p in enumerate(pays):
+            ref = oo.decode(batch[i, : n[i]].astype(np.complex128), ocfg, want_points=False)
+            assert ref.status == res.status[i] == 0 and ref.offset == res.offset[i]
+            assert res.data[i] == ref.data.tobytes() == p, (mod, guard, fec, i)
+        eng.close()
+
+
+def test_status_paths_and_mixed_batch(ob, oo):
+    """TOO_SHORT / NEG_OFFSET / BAD_HEADER / NO_SYNC never abort the batch; good streams still decode."""
+    rng = np.random.default_rng(8)
+    pay = rng.integers(0, 256, 40, dtype=np.uint8).tobytes()
+    for sync in (0, 1):
+        eng, cfg, ocfg = _mk(ob, oo, 0, True, False, sync, 0, 0)
+        tx = oo.tx(pay, ocfg)
+        noise = 0.01 * (rng.standard_normal(4000) + 1j * rng.standard_normal(4000))
+        caps = [
+            tx,                                                   # no delay: lag 0 -> offset -1 (reference panics)
+            np.concatenate([[0], tx]),                            # offset 0
+            np.concatenate([np.zeros(5), tx[:700]]),              # too short
+            np.concatenate([[0], tx[:1200]]),                     # header length does not fit
+            np.concatenate([[0], tx, 0.001 * np.ones(37)]),       # partial (zero padded) tail row
+            noise,                                                # nothing there
+            oo.channel(tx, 30.0, 0.01, 0, 3),
+        ]
+        batch, n = _batch(caps)
+        res = eng.rx_decode(batch, n, diag=True)
+        for i in range(len(caps)):
+            ref = oo.decode(batch[i, : n[i]].astype(np.complex128), ocfg, want_points=False)
+            assert res.status[i] == ref.status, (sync, i, res.status[i], ref.status)
+            if ref.status == 0:
+                assert res.offset[i] == ref.offset and res.data[i] == ref.data.tobytes() == pay
+            else:
+                assert res.out_len[i] == 0 and res.data[i] == b""
+        if sync == 0:
+            assert list(res.status[:6]) == [ob.NEG_OFFSET, ob.OK, ob.TOO_SHORT, ob.BAD_HEADER, ob.OK, res.status[5]]
+        else:
+            assert res.status[5] == ob.NO_SYNC
+        eng.close()
+
+
+def test_out_stride_too_small_is_bad_header(ob, oo):
+    eng, cfg, ocfg = _mk(ob, oo, 1, True, False, 0, 0, 0)
+    cap = oo.channel(oo.tx(bytes(100), ocfg), 30.0, 0.0, 0, 1)
+    batch, n = _batch([cap])
+    assert eng.rx_decode(batch, n, out_stride=64).status[0] == ob.BAD_HEADER
+    assert eng.rx_decode(batch, n, out_stride=100).status[0] == ob.OK
+    eng.close()
+
+
+def test_golden_vectors(ob, oo, golden):
+    for name in golden["names"]:
+        mod, guard, fec, sync, cfo, phase, win = [int(v) for v in golden[f"{name}.cfg"]]
+        eng, cfg, _ = _mk(ob, oo, mod, bool(guard), bool(fec), sync, cfo, phase, win)
+        pay = golden[f"{name}.payload"].tobytes()
+        iq, flen = eng.tx_encode([pay])
+        np.testing.assert_allclose(iq[0, : flen[0]], golden[f"{name}.tx"], atol=2e-6)
+        cap = golden[f"{name}.capture"]
+        res = eng.rx_decode(cap[None, :], points=True)
+        assert res.status[0] == 0 and res.offset[0] == int(golden[f"{name}.offset"])
+        assert abs(res.f_delta[0] - float(golden[f"{name}.f_delta"])) < ABS_TOL_FDELTA
+        pts = golden[f"{name}.points"]
+        npts = cfg.frame_data_syms(len(pay)) * cfg.data_carriers
+        assert np.abs(res.points[0, :npts] - pts[:npts]).max() <= REL_TOL_POINTS * max(1.0, np.abs(pts[:npts]).max())
+        assert res.data[0] == golden[f"{name}.data"].tobytes() == pay
+        lock, pre, tr = eng.tables()
+        np.testing.assert_allclose(lock, golden["tables.lock"], atol=1e-7)
+        np.testing.assert_allclose(pre, golden["tables.preamble"], atol=1e-7)
+        np.testing.assert_allclose(tr, golden["tables.training"], atol=1e-7)
+        eng.close()
+
+
+def test_ber_counters_match_analysis(ob, oo):
+    eng = ob.Engine(ob.Config(), 0)
+    rng = np.random.default_rng(3)
+    ref = rng.integers(0, 256, (9, 500), dtype=np.uint8)
+    got = ref.copy()
+    flips = rng.random(got.shape) < 0.01
+    got[flips] ^= rng.integers(1, 256, int(flips.sum()), dtype=np.uint8)
+    lens = np.array([500, 0, 1, 499, 500, 123, 500, 500, 77], np.uint32)
+    glen = lens.copy()
+    status = np.zeros(9, np.int32)
+    status[6] = 2                                              # failed stream
+    glen[7] = 499                                              # length mismatch = failed
+    c = eng.ber(ref, lens, got, glen, status)
+    want = np.zeros(4, np.int64)
+    for i in range(9):
+        n = int(lens[i])
+        if status[i] != 0 or glen[i] != n:
+            want += [8 * n, n, 8 * n, 1]
+        elif n:
+            e, be, _ = oo.analysis(ref[i, :n], got[i, :n])
+            want += [e, be, 8 * n, 0]
+    assert c.tolist() == want.tolist()
+    eng.close()
+
+
+def test_channel_harness_statistics(ob, oo):
+    """The device channel is a seeded restatement of src/channel.rs: taps, lead-in, CFO and SNR are checked statistically;
+    the oracle then decodes what it produced."""
+    eng, cfg, ocfg = _mk(ob, oo, 2, True, True, 1, 1, 1, 2048)
+    rng = np.random.default_rng(5)
+    pays = [rng.integers(0, 256, 576, dtype=np.uint8).tobytes() for _ in range(32)]
+    iq, flen = eng.tx_encode(pays)
+    # noiseless, no CFO: exactly the 12-tap convolution
+    rx0, rl0, lead0, _ = eng.channel(iq, flen, ob.ChannelParams(snr_db=200.0, cfo_max=-1.0, lead_min=3, lead_max=3, seed=1))
+    ref0 = oo.convolve(iq[0, : flen[0]].astype(np.complex128), np.r_[np.zeros(7), [-0.0, -0.1912, 0.9316, 0.2821, -0.1990, 0.1630, -0.1017, 0.0544, -0.0261, 0.0090, 0.0, -0.0034]])
+    assert rl0[0] == flen[0] + 63 + 3 and lead0[0] == 3
+    np.testing.assert_allclose(rx0[0, 3: 3 + ref0.size - 7 + 0][: flen[0] + 18], ref0[: flen[0] + 18], atol=1e-5)
+    # full channel
+    prm = ob.ChannelParams(snr_db=35.0, cfo_max=0.9 * np.pi / 80, lead_min=8, lead_max=1031, noise_mode=1, seed=99)
+    rx, rl, lead, cfo = eng.channel(iq, flen, prm)
+    assert (rl == flen + 63 + lead).all() and lead.min() >= 8 and lead.max() <= 1031 and len(set(lead.tolist())) > 16
+    assert (cfo >= 0).all() and (cfo < 0.9 * np.pi / 80).all()
+    res = eng.rx_decode(rx, rl, out_stride=640, diag=True)
+    for i, p in enumerate(pays):
+        ref = oo.decode(rx[i, : rl[i]].astype(np.complex128), ocfg, want_points=False, out_cap=640)
+        assert ref.status == res.status[i] == 0
+        assert ref.offset == res.offset[i] == lead[i] + 8
+        assert abs(res.f_delta[i] - cfo[i]) < 2e-4                                  # estimator accuracy at 35 dB
+        assert res.data[i] == ref.data.tobytes() == p
+    # measured SNR of the noise-only lead-in vs the frame
+    i = int(np.argmax(lead))
+    pn = np.mean(np.abs(rx[i, : lead[i]]) ** 2)
+    ps = np.mean(np.abs(rx[i, lead[i]: rl[i]]) ** 2)
+    assert 10 * np.log10(ps / pn) == pytest.approx(35.0, abs=1.5)
+    eng.close()
+
+
+def test_host_and_device_paths_agree(ob, oo):
+    import torch
+    eng, cfg, ocfg = _mk(ob, oo, 2, True, True, 1, 1, 1, 2048)
+    rng = np.random.default_rng(6)
+    pays = [rng.integers(0, 256, 3000, dtype=np.uint8).tobytes() for _ in range(40)]
+    iq, flen = eng.tx_encode(pays)
+    rx, rl, _, _ = eng.channel(iq, flen, ob.ChannelParams(snr_db=40.0, cfo_max=0.03, lead_min=8, lead_max=500, noise_mode=1, seed=4))
+    host = eng.rx_decode(rx, rl, out_stride=3008)
+    d_iq = torch.from_numpy(rx.view(np.float32).reshape(40, rx.shape[1], 2)).cuda()
+    d_n = torch.from_numpy(rl.astype(np.int32)).cuda()
+    d_out = torch.zeros((40, 3008), dtype=torch.uint8, device="cuda")
+    d_ol = torch.zeros(40, dtype=torch.int32, device="cuda")
+    d_st = torch.zeros(40, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.rx_decode_device(d_iq.data_ptr(), d_n.data_ptr(), 40, rx.shape[1], int(rl.max()), d_out.data_ptr(), 3008, d_ol.data_ptr(), d_st.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert (d_st.cpu().numpy() == host.status).all() and (host.status == 0).all()
+    assert (d_out.cpu().numpy() == host.out).all()
+    assert all(host.data[i] == pays[i] for i in range(40))
+    eng.close()

@@ -1,0 +1,186 @@
+"""The reference's own known-answer tests, run against the oracle."""
+import numpy as np
+import pytest
+
+
+def test_demodulate_works(oo):
+    # src/lib.rs:37-51: modulate(b"alskdjas", Qpsk) |> demodulate(Qpsk) == input
+    text = b"alskdjas"
+    assert oo.demodulate(oo.modulate(text, oo.QPSK), oo.QPSK).tobytes() == text
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2])
+def test_mod_demod_roundtrip_all_schemes(oo, scheme):
+    data = bytes(range(256)) * 3                      # 768 bytes: multiple of 6 -> whole 8-symbol groups for 64QAM
+    syms = oo.modulate(data, scheme)
+    assert oo.demodulate(syms, scheme).tobytes() == data
+
+
+def test_encoding_works(oo):
+    # src/lib.rs:53-57: encode(b"alskdjas", Some(true), None) does not panic; BPSK default
+    x = oo.encode(b"alskdjas", True, oo.BPSK)
+    assert x.size == (10 + 4) * 80                    # (16+8)*8 = 192 symbols / 48 = 4 blocks
+    assert np.isfinite(x.view(np.float64)).all()
+    assert max(x.real.max(), x.imag.max()) == pytest.approx(1.0)      # normalize, src/transmitter.rs:183-194
+
+
+def test_get_bit_at_and_bools(oo):
+    # src/utils.rs:281-292, 321-327: LSB first
+    L = oo.lib()
+    import ctypes as C
+    for n in range(256):
+        b = (C.c_uint8 * 8)()
+        L.oo_to_bools(C.c_uint8(n), b)
+        assert [int(x) for x in b] == [(n >> i) & 1 for i in range(8)]
+        assert L.oo_bools_to_u8(b) == n
+    assert oo.modulate(bytes([127]), oo.BPSK).real.tolist() == [1, 1, 1, 1, 1, 1, 1, -1]
+
+
+def test_analysis_semantics(oo):
+    # src/utils.rs:45-68 (the code, not the stale test at :294-316): err_rate = bit errs / (8 * len)
+    assert oo.analysis([1, 0, 1, 0], [1, 0, 1, 0]) == (0, 0, 0.0)
+    assert oo.analysis([1, 0, 0, 0], [1, 0, 1, 0]) == (1, 1, 1 / 32)
+    assert oo.analysis([0, 0, 0, 0], [1, 0, 1, 0]) == (2, 2, 2 / 32)
+    assert oo.analysis([0xFF], [0x00]) == (8, 1, 1.0)
+
+
+def test_mean_works(oo):
+    # src/signals/mod.rs:385-394
+    import ctypes as C
+    x = np.array([1 + 1j, 1 + 2j, 1 + 3j])
+
+    class Z(C.Structure):
+        _fields_ = [("re", C.c_double), ("im", C.c_double)]
+    oo.lib().oo_mean.restype = Z
+    oo.lib().oo_mean.argtypes = [C.c_void_p, C.c_size_t]
+    m = oo.lib().oo_mean(x.ctypes.data, 3)
+    assert (m.re, m.im) == (1.0, 2.0)
+
+
+def test_xcorr_fft_lags(oo):
+    # src/signals/mod.rs:420-441: the non-negative lags of the two examples are [14,23,12] and [2,1,0,1,2,1,0,0]
+    idx, c = oo.xcorr_fft([1, 2, 3], [4, 5])
+    assert c.size == 5
+    np.testing.assert_allclose(c[2:].real, [14, 23, 12], atol=1e-12)
+    assert idx == 3                                   # lag 1
+    idx, c = oo.xcorr_fft([1, 1, 0, 0, 1, 1, 0, 0], [1, 1, 0, 0])
+    np.testing.assert_allclose(c[7:].real, [2, 1, 0, 1, 2, 1, 0, 0], atol=1e-12)
+    assert idx == 7                                   # first strict maximum = lag 0
+
+
+def test_xcorr_matches_direct_and_offset_rule(oo):
+    # src/receiver.rs:20-21: offset = idxmax - (len-1)/2 - 1 = lag - 1
+    rng = np.random.default_rng(1)
+    lock = oo.locking_signal()
+    a = 0.01 * (rng.standard_normal(700) + 1j * rng.standard_normal(700))
+    a[123:203] += lock
+    idx, c = oo.xcorr_fft(a, lock)
+    direct = np.array([np.sum(a[k:k + 80] * lock.real[: max(0, min(80, 700 - k))]) for k in range(700)])
+    np.testing.assert_allclose(c[699:], direct, atol=1e-10)
+    assert idx - (((c.size - 1) // 2) + 1) == 123 - 1
+
+
+def test_fft_shift_semantics(oo):
+    # src/signals/mod.rs:61-77, demos :331-367
+    assert oo.fft_shift([1, 2, 3, 4, 5, 6, 7]).real.tolist() == [5, 6, 7, 1, 2, 3, 4]
+    assert oo.fft_shift([1, 2, 3, 4, 5, 6]).real.tolist() == [4, 5, 6, 1, 2, 3]
+    x = np.arange(1, 8)
+    assert oo.ifft_shift(oo.fft_shift(x)).real.tolist() == x.tolist()
+
+
+def test_angle(oo):
+    # src/receiver.rs:253-256: angle(1 - 1j) "should be -0.7854"
+    assert oo.angle(1 - 1j) == pytest.approx(-0.7854, abs(1e-4))
+    z = (1.562529741252829 - 1.660641994738211j) / (-2.2353334900267217 + 0.45001690562988267j)
+    assert np.isfinite(oo.angle(z))
+
+
+def test_channel_response_listing(oo):
+    # src/channel.rs:99-177: MATLAB response of the multipath channel, 79 = 16 + 63 values, i.e. to 16 x (1 - 1j)
+    # (MATLAB used the un-rounded taps -> agreement to ~1e-3)
+    h = np.zeros(64)
+    h[7:19] = [-0.0, -0.1912, 0.9316, 0.2821, -0.1990, 0.1630, -0.1017, 0.0544, -0.0261, 0.0090, 0.0, -0.0034]
+    r = oo.convolve(np.full(16, 1 - 1j), h)
+    want = [0, 0, 0, 0, 0, 0, 0, 0, -0.1912, 0.7404, 1.0225, 0.8234, 0.9864, 0.8847, 0.9391, 0.9130, 0.9220, 0.9220,
+            0.9186, 0.9186, 0.9186, 0.9186, 0.9186, 0.9186, 1.1098, 0.1782, -0.1039, 0.0952, -0.0678, 0.0339, -0.0205,
+            0.0056, -0.0034, -0.0034] + [0.0] * 45
+    assert r.size == 16 + 63 == len(want)
+    np.testing.assert_allclose(r.real, want, atol=1.5e-3)
+    np.testing.assert_allclose(r.imag, -np.array(want), atol=1.5e-3)
+
+
+def test_fft_definition(oo):
+    # src/signals/mod.rs:27-58: forward unscaled, inverse scaled by 1/N; stands in for rustfft (DFT definition)
+    rng = np.random.default_rng(0)
+    for n in (8, 64, 80, 159, 1024):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        np.testing.assert_allclose(oo.fft(x), np.fft.fft(x), atol=1e-11)
+        np.testing.assert_allclose(oo.fft(x, True), np.fft.ifft(x), atol=1e-13)
+    # src/signals/mod.rs:463-471 fft_test input
+    sig = np.array([-1, 1, 1, -1, 1, -1, 1, -1], float)
+    np.testing.assert_allclose(oo.fft(sig, True), np.fft.ifft(sig), atol=1e-15)
+
+
+def test_header_is_16_le_bytes(oo):
+    # src/packets/mod.rs:20-32 + bincode fixint: u128 LE
+    x = oo.encode(b"\x00" * 300, False, oo.BPSK)
+    pts = np.fft.fft(x[800:880][16:])                 # first data symbol, no channel
+    bits = (pts.real > 0).astype(np.uint8)
+    assert np.packbits(bits, bitorder="little").tobytes() == (300).to_bytes(8, "little")
+
+
+def test_locking_signal_and_tables(oo):
+    # src/transmitter.rs:60-72: v[i] = 0.5*(i/160 + 0.5), fft_shift (halves swapped at 40)
+    lock = oo.locking_signal()
+    v = 0.5 * (np.arange(80) / 160 + 0.5)
+    np.testing.assert_array_equal(lock.real, np.concatenate([v[40:], v[:40]]))
+    assert (lock.imag == 0).all()
+    pre, tr = oo.preamble(), oo.training_signals()
+    assert np.abs(pre.real).max() < 0.25 and np.abs(pre.imag).max() < 0.25      # (U(-1,1) + jU(-1,1)) * 0.25
+    assert np.abs(tr.real).max() < 1.0 and tr.size == 64
+    # same StdRng stream prefix for LEN=64 and LEN=80 (src/receiver.rs:216 uses 80, src/transmitter.rs:33 uses 64)
+    np.testing.assert_array_equal(oo.training_signals(80)[:64], tr)
+    # deterministic and seed dependent
+    a, b = oo.stdrng_uniform_pm1(100, 160), oo.stdrng_uniform_pm1(50, 160)
+    np.testing.assert_array_equal(a[0::2] * 0.25, pre.real)
+    np.testing.assert_array_equal(b[:128:2], tr.real)
+    assert not np.array_equal(a, b) and (np.abs(a) < 1).all()
+    assert abs(a.mean()) < 0.2 and 0.2 < a.std() < 0.8
+
+
+def test_fc32_wire_format(oo):
+    # src/utils.rs:228-254: interleaved native-endian f32 re, im
+    x = np.arange(10) + 1j * np.arange(10, 20)
+    f = oo.sig_to_fc32(x)
+    assert f.dtype == np.float32 and f.tolist() == [v for k in range(10) for v in (k, 10 + k)]
+    np.testing.assert_array_equal(oo.fc32_to_sig(f), x)
+
+
+def test_hamming74(oo):
+    rng = np.random.default_rng(2)
+    data = rng.integers(0, 256, 333, dtype=np.uint8)
+    coded = oo.hamming74_encode(data)
+    assert coded.size == (14 * 333 + 7) // 8
+    np.testing.assert_array_equal(oo.hamming74_decode(coded), data)
+    # every single-bit error inside a codeword is corrected
+    bits = np.unpackbits(coded, bitorder="little")
+    for cw in range(0, 14 * 333 // 7, 37):
+        for b in range(7):
+            e = bits.copy()
+            e[7 * cw + b] ^= 1
+            np.testing.assert_array_equal(oo.hamming74_decode(np.packbits(e, bitorder="little")), data)
+    # 576 B -> 1008 B (SURVEY T-SPEC-2)
+    assert oo.hamming74_encode(np.zeros(576, np.uint8)).size == 1008
+
+
+def test_qam64_mapping_is_gray(oo):
+    pts = oo.modulate(bytes(range(256)) * 3, oo.QAM64)
+    levels = np.unique(np.round(pts.real * 7).astype(int))
+    assert levels.tolist() == [-7, -5, -3, -1, 1, 3, 5, 7]
+    # neighbouring levels differ in exactly one bit
+    code_of = {}
+    for b in range(8):
+        p = oo.modulate(bytes([b, 0, 0, 0, 0, 0]), oo.QAM64)[0]
+        code_of[int(round(p.real * 7))] = b
+    lv = sorted(code_of)
+    assert all(bin(code_of[a] ^ code_of[b]).count("1") == 1 for a, b in zip(lv, lv[1:]))
