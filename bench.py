@@ -35,12 +35,12 @@ import numpy as np  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--syms", type=int, default=2038, help="data OFDM symbols per frame")
-    ap.add_argument("--snr", type=float, default=30.0)
+    ap.add_argument("--snr", type=float, default=40.0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -65,51 +65,62 @@ def oracle_cfg():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML every ~5 ms DURING the timed region (the recipe's clocks line)."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.lines = []
-        self.proc = None
+        self.sm, self.pw, self.reasons = [], [], set()
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.t = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = nv
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:           # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:       # noqa: BLE001
+                self.err = repr(e)
+                break
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "error": self.err}
+        self._stop.set()
+        self.t.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "power_w_max": max(self.pw) if self.pw else None, "samples": len(self.sm), "reasons": sorted(self.reasons)}
 
 
 def read_peaks():
@@ -132,22 +143,21 @@ def read_traffic(workload: str):
 
 
 def cpu_sample(iq_host: np.ndarray, n_samples: np.ndarray, out_stride: int, target_s: float, threads: int):
-    """Time the oracle on a bounded sample of the same workload. Returns (msamples_per_s, n_streams_used, seconds)."""
+    """Time the oracle on a bounded sample of the same workload: the k streams are decoded repeatedly until about
+    `target_s` seconds of wall time are spent. Returns (msamples_per_s, k, seconds, reps, last results)."""
     from oracle import oracle as oo
     cfg = oracle_cfg()
-    n_avail = iq_host.shape[0]
-    k = min(n_avail, max(threads, 1))
-    t0 = time.perf_counter()
-    oo.decode_batch_fc32(iq_host[:k].view(np.float32).reshape(k, iq_host.shape[1], 2), n_samples[:k], cfg, out_stride, threads)
-    dt = time.perf_counter() - t0
-    per_stream_batch = dt                               # seconds for `threads` streams in parallel
-    reps = max(1, int(target_s / max(per_stream_batch, 1e-3)))
-    k2 = min(n_avail, k * reps)
-    t0 = time.perf_counter()
-    out, out_len, status, _ = oo.decode_batch_fc32(iq_host[:k2].view(np.float32).reshape(k2, iq_host.shape[1], 2), n_samples[:k2],
-                                                   cfg, out_stride, threads)
-    dt = time.perf_counter() - t0
-    return float(n_samples[:k2].sum()) / dt / 1e6, k2, dt, (out, out_len, status)
+    k = iq_host.shape[0]
+    f32 = iq_host.view(np.float32).reshape(k, iq_host.shape[1], 2)
+    res = oo.decode_batch_fc32(f32, n_samples, cfg, out_stride, threads)          # warm-up (FFT plan, page faults)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        res = oo.decode_batch_fc32(f32, n_samples, cfg, out_stride, threads)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= target_s:
+            break
+    return float(n_samples.sum()) * reps / dt / 1e6, k, dt, reps, res[:3]
 
 
 def main():
@@ -313,18 +323,20 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as oo
         threads = oo.max_threads()
-        k = min(n_streams, 4 * threads + 64)
+        k = min(n_streams, 2 * threads)
         iq_h = rx[:k].cpu().numpy().view(np.complex64).reshape(k, iq_stride)
         ns_h = rx_len[:k].cpu().numpy().astype(np.uint32)
-        v1, k1, dt1, _ = cpu_sample(iq_h, ns_h, out_stride, args.cpu_seconds / 2, 1)
-        vN, kN, dtN, res = cpu_sample(iq_h, ns_h, out_stride, args.cpu_seconds / 2, threads)
+        v1, k1, dt1, r1, _ = cpu_sample(iq_h[:2], ns_h[:2], out_stride, args.cpu_seconds / 2, 1)
+        vN, kN, dtN, rN, res = cpu_sample(iq_h, ns_h, out_stride, args.cpu_seconds / 2, threads)
         o_out, o_len, o_st = res
         gpu_out = out[:kN].cpu().numpy()
-        agree = bool((o_st == 0).all() and (o_len == payload_len).all() and (o_out[:, :payload_len] == gpu_out[:, :payload_len]).all())
+        gpu_st = status[:kN].cpu().numpy()
+        differ = int((o_out[:, :payload_len] != gpu_out[:, :payload_len]).sum()) + int((o_st != gpu_st).sum())
         cpu_baseline = {"value": round(vN, 2), "unit": "Msamples/s", "cores": threads, "kind": "port",
-                        "sample": f"{kN} of the {n_streams} streams ({dtN:.1f} s on {threads} threads; f64 C oracle, FFT plans reused)",
-                        "single_core": {"value": round(v1, 2), "sample": f"{k1} streams, {dt1:.1f} s"},
-                        "gpu_bytes_equal_oracle_on_sample": agree}
+                        "sample": f"{kN} of the {n_streams} streams x {rN} passes ({dtN:.1f} s on {threads} threads; f64 C port of the "
+                                  "reference algorithm, FFT plans reused = upper bound on the Rust crate's speed)",
+                        "single_core": {"value": round(v1, 2), "sample": f"{k1} streams x {r1} passes, {dt1:.1f} s on 1 thread"},
+                        "bytes_differing_from_gpu_on_sample": differ}
 
     if rank == 0:
         line = {"metric": "rx_msamples_per_s", "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,

@@ -78,12 +78,12 @@ def test_tx_rx_parity_matrix(ob, oo, mod, guard, fec, modes):
 
 
 def test_low_snr_decisions_identical_away_from_boundaries(ob, oo):
-    """At 20 dB (many symbol errors) the engine's hard decisions equal the oracle's wherever the oracle's point is
+    """At 27 dB (many symbol errors) the engine's hard decisions equal the oracle's wherever the oracle's point is
     not within 1e-4 of a decision boundary; with identical decisions the bytes are identical."""
     eng, cfg, ocfg = _mk(ob, oo, 2, True, False, 0, 0, 0)
     rng = np.random.default_rng(4)
-    pays = [rng.integers(0, 256, 2000, dtype=np.uint8).tobytes() for _ in range(4)]
-    caps = [oo.channel(oo.tx(p, ocfg), 20.0, 0.02, 1, 7 + i) for i, p in enumerate(pays)]
+    pays = [rng.integers(0, 256, 2000, dtype=np.uint8).tobytes() for _ in range(24)]
+    caps = [oo.channel(oo.tx(p, ocfg), 27.0, 0.02, 1, 7 + i) for i, p in enumerate(pays)]
     batch, n = _batch(caps)
     res = eng.rx_decode(batch, n, points=True)
     n_err = 0
@@ -96,7 +96,8 @@ def test_low_snr_decisions_identical_away_from_boundaries(ob, oo):
         npts = cfg.frame_data_syms(len(p)) * 48
         gb = np.unpackbits(np.frombuffer(res.data[i], np.uint8), bitorder="little")
         rb = np.unpackbits(ref.data, bitorder="little")
-        n_err += int((rb != np.unpackbits(np.frombuffer(p, np.uint8), bitorder="little")).sum())
+        if ref.data.size == len(p):                     # (a corrupted header can still give a valid, shorter length)
+            n_err += int((rb != np.unpackbits(np.frombuffer(p, np.uint8), bitorder="little")).sum())
         diff = np.flatnonzero(gb != rb)
         risky = _near_boundary(ref.points[:npts], 2, 1e-4)
         for b in diff:                                  # payload bit b -> stream bit 128 + b -> carrier
