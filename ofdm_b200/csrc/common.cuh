@@ -75,14 +75,33 @@ __device__ __forceinline__ void dft8(float (&re)[8], float (&im)[8])
     }
 }
 
-// lane twiddles W64^(l*ka), ka = 0..7
+// W64^k = exp(-2 pi j k / 64), k = 0..63 (f64 values rounded to f32)
+__constant__ float2 c_w64[64] = {
+    {1.0f, 0.0f}, {0.9951847266721969f, -0.0980171403295606f}, {0.9807852804032304f, -0.19509032201612825f}, {0.9569403357322088f, -0.29028467725446233f},
+    {0.9238795325112867f, -0.3826834323650898f}, {0.881921264348355f, -0.47139673682599764f}, {0.8314696123025452f, -0.5555702330196022f}, {0.773010453362737f, -0.6343932841636455f},
+    {0.7071067811865476f, -0.7071067811865475f}, {0.6343932841636455f, -0.773010453362737f}, {0.5555702330196023f, -0.8314696123025452f}, {0.4713967368259978f, -0.8819212643483549f},
+    {0.38268343236508984f, -0.9238795325112867f}, {0.29028467725446233f, -0.9569403357322089f}, {0.19509032201612833f, -0.9807852804032304f}, {0.09801714032956077f, -0.9951847266721968f},
+    {0.0f, -1.0f}, {-0.09801714032956065f, -0.9951847266721969f}, {-0.1950903220161282f, -0.9807852804032304f}, {-0.29028467725446216f, -0.9569403357322089f},
+    {-0.3826834323650897f, -0.9238795325112867f}, {-0.4713967368259977f, -0.881921264348355f}, {-0.555570233019602f, -0.8314696123025455f}, {-0.6343932841636454f, -0.7730104533627371f},
+    {-0.7071067811865475f, -0.7071067811865476f}, {-0.773010453362737f, -0.6343932841636455f}, {-0.8314696123025453f, -0.5555702330196022f}, {-0.8819212643483549f, -0.47139673682599786f},
+    {-0.9238795325112867f, -0.3826834323650899f}, {-0.9569403357322088f, -0.2902846772544624f}, {-0.9807852804032304f, -0.1950903220161286f}, {-0.9951847266721968f, -0.09801714032956083f},
+    {-1.0f, 0.0f}, {-0.9951847266721969f, 0.09801714032956059f}, {-0.9807852804032304f, 0.19509032201612836f}, {-0.9569403357322089f, 0.2902846772544621f},
+    {-0.9238795325112868f, 0.38268343236508967f}, {-0.881921264348355f, 0.47139673682599764f}, {-0.8314696123025455f, 0.555570233019602f}, {-0.7730104533627371f, 0.6343932841636453f},
+    {-0.7071067811865477f, 0.7071067811865475f}, {-0.6343932841636459f, 0.7730104533627367f}, {-0.5555702330196022f, 0.8314696123025452f}, {-0.47139673682599786f, 0.8819212643483549f},
+    {-0.38268343236509034f, 0.9238795325112865f}, {-0.29028467725446244f, 0.9569403357322088f}, {-0.19509032201612866f, 0.9807852804032303f}, {-0.09801714032956045f, 0.9951847266721969f},
+    {0.0f, 1.0f}, {0.09801714032956009f, 0.9951847266721969f}, {0.1950903220161283f, 0.9807852804032304f}, {0.29028467725446205f, 0.9569403357322089f},
+    {0.38268343236509f, 0.9238795325112866f}, {0.4713967368259976f, 0.881921264348355f}, {0.5555702330196018f, 0.8314696123025455f}, {0.6343932841636456f, 0.7730104533627369f},
+    {0.7071067811865474f, 0.7071067811865477f}, {0.7730104533627367f, 0.6343932841636459f}, {0.8314696123025452f, 0.5555702330196022f}, {0.8819212643483548f, 0.4713967368259979f},
+    {0.9238795325112865f, 0.3826834323650904f}, {0.9569403357322088f, 0.2902846772544625f}, {0.9807852804032303f, 0.19509032201612872f}, {0.9951847266721969f, 0.0980171403295605f},
+};
+
+// lane twiddles W64^(l*ka), ka = 0..7 (table look-up: 8 distinct addresses per warp instruction)
 __device__ __forceinline__ void fft64_lane_twiddles(int l, float (&twr)[8], float (&twi)[8])
 {
 #pragma unroll
     for (int ka = 0; ka < 8; ka++) {
-        float s, c;
-        sincospif(-(float)(l * ka) * (1.0f / 32.0f), &s, &c);
-        twr[ka] = c; twi[ka] = s;
+        float2 w = c_w64[(l * ka) & 63];
+        twr[ka] = w.x; twi[ka] = w.y;
     }
 }
 

@@ -80,9 +80,17 @@ __device__ __forceinline__ void rx_lane_init(RxLane &L, const StreamState *st, i
 {
     fft64_lane_twiddles(l, L.twr, L.twi);
     const uint64_t fstep = st->fstep;
+    // exp(-j f (l + 8j)) = exp(-j f l) * exp(-j f 8)^j : two exact phasors + a 7-step recurrence (error ~ 7 ulp)
+    float sr, si;
+    phasor_from_turns(fstep * (uint64_t)l, L.wr[0], L.wi[0]);
+    phasor_from_turns(fstep * 8ull, sr, si);
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+        L.wr[j] = L.wr[j - 1]; L.wi[j] = L.wi[j - 1];
+        cmul(L.wr[j], L.wi[j], sr, si);
+    }
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        phasor_from_turns(fstep * (uint64_t)(l + 8 * j), L.wr[j], L.wi[j]);
         float2 g = st->g[l + 8 * j];
         L.gr[j] = g.x; L.gi[j] = g.y;
     }
@@ -107,6 +115,25 @@ __device__ __forceinline__ uint32_t demap_point(float re, float im)
     return x ^ ((x >> 1) & 0x1Bu);      // per-axis Gray: i ^ (i >> 1)
 }
 
+// 64QAM demap for the hot kernel: 4 FMA-pipe ops + 1 shift-add + 1 smem table look-up.
+//   t = sat((3.5 v + 4) / 8) in [0, 1];  2^23 + floor(8 t) by a round-down FMA -> level index 0..8 in the mantissa;
+//   x = ui + (uq << 4) = 0xFB000000 + ii + 16 iq indexes a 256-byte table holding gray(min(ii,7)) | gray(min(iq,7)) << 3.
+constexpr uint32_t kQamLutBias = 0xFB000000u;
+__device__ __forceinline__ uint8_t qam64_lut_entry(int t)
+{
+    int ii = t & 15, iq = t >> 4;
+    ii = ii > 7 ? 7 : ii; iq = iq > 7 ? 7 : iq;
+    return (uint8_t)((ii ^ (ii >> 1)) | ((iq ^ (iq >> 1)) << 3));
+}
+__device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, const uint8_t *lut_biased)
+{
+    float ti = __saturatef(fmaf(re, 0.4375f, 0.5f));
+    float tq = __saturatef(fmaf(im, 0.4375f, 0.5f));
+    uint32_t ui = __float_as_uint(__fmaf_rd(ti, 8.0f, 8388608.0f));
+    uint32_t uq = __float_as_uint(__fmaf_rd(tq, 8.0f, 8388608.0f));
+    return lut_biased[ui + (uq << 4)];
+}
+
 // One OFDM symbol per 8-lane group: load (CP stripped), derotate, FFT, equalise, pilot phase.
 // x0 = pointer to the first post-offset sample of the stream; n_avail = samples from x0 to the end of the capture.
 // On return (zr, zi)[kb] is the equalised + phase-corrected value of bin l + 8kb.
@@ -116,12 +143,17 @@ __device__ __forceinline__ void rx_symbol(const float2 *__restrict__ x0, uint32_
                                           float (&zr)[8], float (&zi)[8])
 {
     const uint32_t n0 = (kHeadSyms + sym) * kSym + kCp + l;
+    const float2 *p = x0 + n0;
+    if (valid && n0 + 56 < n_avail) {                    // whole symbol inside the capture: 8 loads, immediate offsets
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        uint32_t n = n0 + 8 * j;
-        float2 v = make_float2(0.0f, 0.0f);
-        if (valid && n < n_avail) v = __ldg(x0 + n);     // zero-padded tail row, src/receiver.rs:206-210
-        zr[j] = v.x; zi[j] = v.y;
+        for (int j = 0; j < 8; j++) { float2 v = __ldg(p + 8 * j); zr[j] = v.x; zi[j] = v.y; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float2 v = make_float2(0.0f, 0.0f);
+            if (valid && n0 + 8 * j < n_avail) v = __ldg(p + 8 * j);     // zero-padded tail row, src/receiver.rs:206-210
+            zr[j] = v.x; zi[j] = v.y;
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) cmul(zr[j], zi[j], L.wr[j], L.wi[j]);      // src/receiver.rs:44-50 (intra-symbol part)
@@ -165,12 +197,13 @@ __device__ __forceinline__ void rx_symbol(const float2 *__restrict__ x0, uint32_
 // ------------------------------------------------------------------------------------------------------------------
 // hot kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDecWarps = 7;
-constexpr int kDecThreads = kDecWarps * 32;      // 224
-constexpr int kTileSyms = kDecWarps * 32;        // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
+constexpr int kDecWarps = 8;
+constexpr int kDecThreads = kDecWarps * 32;      // 256
+constexpr int kDecIters = 7;                     // 4 symbols per warp iteration -> 28 symbols per warp
+constexpr int kTileSyms = kDecWarps * 4 * kDecIters;   // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
-__global__ void __launch_bounds__(kDecThreads) rx_decode_kernel(const RxArgs a)
+__global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs a)
 {
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 48 : 64;
@@ -178,8 +211,9 @@ __global__ void __launch_bounds__(kDecThreads) rx_decode_kernel(const RxArgs a)
     constexpr int NB = FEC ? 14 : 8;             // stream bits per output byte
 
     __shared__ __align__(16) float2 s_tr[kDecWarps * kTrWarp];
-    __shared__ __align__(16) uint8_t s_car[kTileSyms * D + 32];   // one byte (BPC valid bits) per data carrier
+    __shared__ __align__(16) uint8_t s_car[kTileSyms * D + 64];   // one byte (BPC valid bits) per data carrier
     __shared__ uint8_t s_ham[128];
+    __shared__ uint8_t s_qam[256];
 
     const uint32_t stream = blockIdx.y;
     const StreamState *st = a.state + stream;
@@ -193,6 +227,8 @@ __global__ void __launch_bounds__(kDecThreads) rx_decode_kernel(const RxArgs a)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
+    if (MOD == 2) s_qam[tid] = qam64_lut_entry(tid);
+    __syncthreads();
 
     const uint32_t n_samples = a.n_samples[stream];
     const uint32_t offset = (uint32_t)st->offset;
@@ -201,38 +237,39 @@ __global__ void __launch_bounds__(kDecThreads) rx_decode_kernel(const RxArgs a)
 
     RxLane L;
     rx_lane_init(L, st, l);
-    int8_t rank[8];
+    // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins go to the sink)
+    int off[8];
 #pragma unroll
-    for (int kb = 0; kb < 8; kb++) rank[kb] = (int8_t)data_rank<GUARD>(l + 8 * kb);
+    for (int kb = 0; kb < 8; kb++) { int r = data_rank<GUARD>(l + 8 * kb); off[kb] = r; }
 
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
+    const uint8_t *qam_biased = s_qam - kQamLutBias;
     const uint64_t fstep = st->fstep;
-    // base phasor of this group's first symbol, then a x4-symbol recurrence (8 steps: negligible drift)
-    const int s_first = t0 + warp * 32 + g;
+    // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
+    const int s_first = t0 + warp * (4 * kDecIters) + g;
     float br, bi, dr, di;
     phasor_from_turns(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp), br, bi);
     phasor_from_turns(fstep * (uint64_t)(4 * kSym), dr, di);
+    uint8_t *rowp = s_car + (s_first - t0) * D;
 
 #pragma unroll 1
-    for (int it = 0; it < 8; it++) {
+    for (int it = 0; it < kDecIters; it++) {
         const int s = s_first + 4 * it;
         const bool valid = s < t1;
         float zr[8], zi[8];
         rx_symbol<GUARD, PHASE>(x0, n_avail, (uint32_t)s, valid, L, br, bi, tr, l, zr, zi);
         cmul(br, bi, dr, di);
-        if (valid) {
-            const int row = (s - t0) * D;
+        // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
 #pragma unroll
-            for (int kb = 0; kb < 8; kb++) {
-                if (rank[kb] >= 0) {
-                    s_car[row + rank[kb]] = (uint8_t)demap_point<MOD>(zr[kb], zi[kb]);
-                    if (POINTS) {
-                        size_t p = (size_t)s * D + rank[kb];
-                        if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr[kb], zi[kb]);
-                    }
-                }
+        for (int kb = 0; kb < 8; kb++) {
+            uint32_t v = MOD == 2 ? demap_qam64_lut(zr[kb], zi[kb], qam_biased) : demap_point<MOD>(zr[kb], zi[kb]);
+            if (!GUARD || off[kb] >= 0) rowp[off[kb]] = (uint8_t)v;
+            if (POINTS && valid && (!GUARD || off[kb] >= 0)) {
+                size_t p = (size_t)s * D + off[kb];
+                if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr[kb], zi[kb]);
             }
         }
+        rowp += 4 * D;
     }
     __syncthreads();
 
@@ -243,18 +280,52 @@ __global__ void __launch_bounds__(kDecThreads) rx_decode_kernel(const RxArgs a)
     long j1 = (bit1 - kHeaderBits) / NB;                    // bytes fully inside the tile
     if (j1 > (long)st->out_len) j1 = (long)st->out_len;
     uint8_t *out = a.out + (size_t)stream * a.out_stride;
-    for (long j = j0 + tid; j < j1; j += kDecThreads) {
-        const int p = (int)(kHeaderBits + j * NB - bit0);   // tile-local bit position
-        const int c = p / BPC, sh = p - c * BPC;
-        constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
-        uint32_t v = 0;
+    const int pbase = (int)(kHeaderBits + j0 * NB - bit0);  // tile-local bit position of byte j0
+    const int nbytes = (int)(j1 - j0);
+    if (MOD == 2) {
+        // 3 output bytes per thread: 42 (Hamming) or 24 stream bits = 7 or 4 six-bit carriers (+1 for the bit shift)
+        constexpr int NC = (3 * NB + 5) / 6 + 1;
+        for (int u = 3 * tid; u < nbytes; u += 3 * kDecThreads) {
+            const int p = pbase + u * NB;
+            const int c = p / 6, sh = p - 6 * c;
+            const uint8_t *cp = s_car + c;
+            uint32_t lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
+            uint32_t hi = 0;
+            if (NC > 5) {
+                uint32_t b5 = cp[5];
+                lo |= b5 << 30;
+                hi = (b5 >> 2) | (cp[6] << 4) | (cp[7] << 10);
+            }
+            lo = __funnelshift_r(lo, hi, sh);
+            hi >>= sh;
+            uint32_t w0, w1, w2;
+            if (FEC) {
+                w0 = lo & 0x3FFFu; w1 = (lo >> 14) & 0x3FFFu; w2 = __funnelshift_r(lo, hi, 28) & 0x3FFFu;
+                w0 = s_ham[w0 & 127u] | (s_ham[w0 >> 7] << 4);
+                w1 = s_ham[w1 & 127u] | (s_ham[w1 >> 7] << 4);
+                w2 = s_ham[w2 & 127u] | (s_ham[w2 >> 7] << 4);
+            } else {
+                w0 = lo & 255u; w1 = (lo >> 8) & 255u; w2 = (lo >> 16) & 255u;
+            }
+            uint8_t *o = out + j0 + u;
+            o[0] = (uint8_t)w0;
+            if (u + 1 < nbytes) o[1] = (uint8_t)w1;
+            if (u + 2 < nbytes) o[2] = (uint8_t)w2;
+        }
+    } else {
+        for (int u = tid; u < nbytes; u += kDecThreads) {
+            const int p = pbase + u * NB;
+            const int c = p / BPC, sh = p - c * BPC;
+            constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
+            uint32_t v = 0;
 #pragma unroll
-        for (int i = 0; i < NC; i++) v |= (uint32_t)s_car[c + i] << (BPC * i);
-        v >>= sh;
-        uint32_t byte;
-        if (FEC) byte = (uint32_t)s_ham[v & 127u] | ((uint32_t)s_ham[(v >> 7) & 127u] << 4);
-        else byte = v & 255u;
-        out[j] = (uint8_t)byte;
+            for (int i = 0; i < NC; i++) v |= (uint32_t)s_car[c + i] << (BPC * i);
+            v >>= sh;
+            uint32_t byte;
+            if (FEC) byte = (uint32_t)s_ham[v & 127u] | ((uint32_t)s_ham[(v >> 7) & 127u] << 4);
+            else byte = v & 255u;
+            out[j0 + u] = (uint8_t)byte;
+        }
     }
 }
 
