@@ -76,7 +76,7 @@ __device__ __forceinline__ void dft8(float (&re)[8], float (&im)[8])
 }
 
 // W64^k = exp(-2 pi j k / 64), k = 0..63 (f64 values rounded to f32)
-__constant__ float2 c_w64[64] = {
+static const float2 h_w64[64] = {
     {1.0f, 0.0f}, {0.9951847266721969f, -0.0980171403295606f}, {0.9807852804032304f, -0.19509032201612825f}, {0.9569403357322088f, -0.29028467725446233f},
     {0.9238795325112867f, -0.3826834323650898f}, {0.881921264348355f, -0.47139673682599764f}, {0.8314696123025452f, -0.5555702330196022f}, {0.773010453362737f, -0.6343932841636455f},
     {0.7071067811865476f, -0.7071067811865475f}, {0.6343932841636455f, -0.773010453362737f}, {0.5555702330196023f, -0.8314696123025452f}, {0.4713967368259978f, -0.8819212643483549f},
@@ -95,12 +95,16 @@ __constant__ float2 c_w64[64] = {
     {0.9238795325112865f, 0.3826834323650904f}, {0.9569403357322088f, 0.2902846772544625f}, {0.9807852804032303f, 0.19509032201612872f}, {0.9951847266721969f, 0.0980171403295605f},
 };
 
-// lane twiddles W64^(l*ka), ka = 0..7 (table look-up: 8 distinct addresses per warp instruction)
-__device__ __forceinline__ void fft64_lane_twiddles(int l, float (&twr)[8], float (&twi)[8])
+// global-memory copy of the table (filled once per engine): lane-dependent indices on __constant__ memory would be
+// serialised by the constant cache, a plain cached global load is not
+struct W64Table { float2 w[64]; };
+
+// lane twiddles W64^(l*ka), ka = 0..7
+__device__ __forceinline__ void fft64_lane_twiddles(const float2 *__restrict__ w64, int l, float (&twr)[8], float (&twi)[8])
 {
 #pragma unroll
     for (int ka = 0; ka < 8; ka++) {
-        float2 w = c_w64[(l * ka) & 63];
+        float2 w = __ldg(w64 + ((l * ka) & 63));
         twr[ka] = w.x; twi[ka] = w.y;
     }
 }

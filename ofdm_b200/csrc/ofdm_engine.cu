@@ -253,6 +253,7 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     float mx = 0.0f;
     for (int i = 0; i < 800; i++) { mx = fmaxf(mx, t->head[i].x); mx = fmaxf(mx, t->head[i].y); }
     t->head_max = mx;
+    for (int i = 0; i < 64; i++) t->w64[i] = h_w64[i];
 
     bool ok = cudaMalloc(&h->d_tables, sizeof(RxTables)) == cudaSuccess &&
               cudaMemcpy(h->d_tables, t, sizeof(RxTables), cudaMemcpyHostToDevice) == cudaSuccess &&

@@ -33,6 +33,7 @@ struct RxTables {          // device copy of the engine's tables
     float2 lock[80];       // locking_signal (src/transmitter.rs:60-72)
     float2 inv_training[64];  // 1 / training_signals (src/transmitter.rs:88-96)
     float2 head[800];      // un-normalised lock | preamble x4 | (CP + IFFT(training)) x5
+    float2 w64[64];        // W64^k twiddles
     float  head_max;       // max positive component of head
 };
 
@@ -76,9 +77,9 @@ __device__ __forceinline__ void phasor_from_turns(uint64_t turns, float &c, floa
     sincospif(turns_to_pi_units(turns), &s, &c);
 }
 
-__device__ __forceinline__ void rx_lane_init(RxLane &L, const StreamState *st, int l)
+__device__ __forceinline__ void rx_lane_init(RxLane &L, const StreamState *st, const float2 *__restrict__ w64, int l)
 {
-    fft64_lane_twiddles(l, L.twr, L.twi);
+    fft64_lane_twiddles(w64, l, L.twr, L.twi);
     const uint64_t fstep = st->fstep;
     // exp(-j f (l + 8j)) = exp(-j f l) * exp(-j f 8)^j : two exact phasors + a 7-step recurrence (error ~ 7 ulp)
     float sr, si;
@@ -94,6 +95,14 @@ __device__ __forceinline__ void rx_lane_init(RxLane &L, const StreamState *st, i
         float2 g = st->g[l + 8 * j];
         L.gr[j] = g.x; L.gi[j] = g.y;
     }
+}
+
+// predicated byte store to shared memory (keeps the producing arithmetic branch-free: null / pilot bins are computed
+// like data bins and simply not stored)
+__device__ __forceinline__ void st_shared_u8_if_nonneg(uint8_t *p, uint32_t v, int cond)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %2, 0;\n\t@q st.shared.u8 [%0], %1;\n\t}"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v), "r"(cond) : "memory");
 }
 
 // hard decision of one data point -> BPC bits (src/receiver.rs:155-178; 64QAM docs/SPEC.md 2)
@@ -125,13 +134,15 @@ __device__ __forceinline__ uint8_t qam64_lut_entry(int t)
     ii = ii > 7 ? 7 : ii; iq = iq > 7 ? 7 : iq;
     return (uint8_t)((ii ^ (ii >> 1)) | ((iq ^ (iq >> 1)) << 3));
 }
-__device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, const uint8_t *lut_biased)
+__device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, uint32_t lut_biased_saddr)
 {
     float ti = __saturatef(fmaf(re, 0.4375f, 0.5f));
     float tq = __saturatef(fmaf(im, 0.4375f, 0.5f));
     uint32_t ui = __float_as_uint(__fmaf_rd(ti, 8.0f, 8388608.0f));
     uint32_t uq = __float_as_uint(__fmaf_rd(tq, 8.0f, 8388608.0f));
-    return lut_biased[ui + (uq << 4)];
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_biased_saddr + ui + (uq << 4)));
+    return v;
 }
 
 // One OFDM symbol per 8-lane group: load (CP stripped), derotate, FFT, equalise, pilot phase.
@@ -236,14 +247,14 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     const uint32_t n_avail = n_samples - offset;
 
     RxLane L;
-    rx_lane_init(L, st, l);
+    rx_lane_init(L, st, a.tables->w64, l);
     // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins go to the sink)
     int off[8];
 #pragma unroll
     for (int kb = 0; kb < 8; kb++) { int r = data_rank<GUARD>(l + 8 * kb); off[kb] = r; }
 
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
-    const uint8_t *qam_biased = s_qam - kQamLutBias;
+    const uint32_t qam_biased = (uint32_t)__cvta_generic_to_shared(s_qam) - kQamLutBias;
     const uint64_t fstep = st->fstep;
     // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
     const int s_first = t0 + warp * (4 * kDecIters) + g;
@@ -263,7 +274,8 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
 #pragma unroll
         for (int kb = 0; kb < 8; kb++) {
             uint32_t v = MOD == 2 ? demap_qam64_lut(zr[kb], zi[kb], qam_biased) : demap_point<MOD>(zr[kb], zi[kb]);
-            if (!GUARD || off[kb] >= 0) rowp[off[kb]] = (uint8_t)v;
+            if (!GUARD) rowp[off[kb]] = (uint8_t)v;
+            else st_shared_u8_if_nonneg(rowp + off[kb], v, off[kb]);
             if (POINTS && valid && (!GUARD || off[kb] >= 0)) {
                 size_t p = (size_t)s * D + off[kb];
                 if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr[kb], zi[kb]);
@@ -546,7 +558,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
         const int g = lane >> 3, l = lane & 7;
         float2 *tr = s_tr + g * kTrGroup;
         float twr[8], twi[8];
-        fft64_lane_twiddles(l, twr, twi);
+        fft64_lane_twiddles(a.tables->w64, l, twr, twi);
         float hr[8], hi[8];
 #pragma unroll
         for (int kb = 0; kb < 8; kb++) { hr[kb] = 0.0f; hi[kb] = 0.0f; }
@@ -589,7 +601,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
 
         // header symbols (src/receiver.rs:86-89): the first HDR_SYMS data symbols, one per 8-lane group
         RxLane L;
-        rx_lane_init(L, st, l);
+        rx_lane_init(L, st, a.tables->w64, l);
         const bool valid = g < HDR_SYMS;
         float br, bi;
         phasor_from_turns(fstep * (uint64_t)((kHeadSyms + g) * kSym + kCp), br, bi);

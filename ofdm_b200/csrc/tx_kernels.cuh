@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) tx_symbols_kernel(const TxArgs a)
     const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
     float2 *out = a.iq + (size_t)stream * a.iq_stride;
     float twr[8], twi[8];
-    fft64_lane_twiddles(l, twr, twi);
+    fft64_lane_twiddles(a.tables->w64, l, twr, twi);
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
 
     float mx = 0.0f;
