@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,7 @@ struct ofdm_engine {
     // per-kernel timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE): 3 events per call (start, after acquire, end)
     std::vector<cudaEvent_t> prof_ev;
     uint32_t prof_cap = 0, prof_n = 0;
+    std::set<const void *> smem_configured;   // kernels whose dynamic shared memory limit has been raised
 };
 
 #define ENG_FAIL(h, code, ...)                                   \
@@ -394,7 +396,11 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
     h->launches += 1;
     if (S > 0) {
         uint32_t tiles = (uint32_t)((S + h->tile_shift + kTileSyms - 1) / kTileSyms);
-        pick_decode(h->cfg, points)<<<dim3(tiles, n_streams), kDecThreads, 0, st>>>(a);
+        DecodeKernel k = pick_decode(h->cfg, points);
+        const size_t smem = h->cfg.guard_bands ? rx_decode_smem_bytes<true>() : rx_decode_smem_bytes<false>();
+        if (h->smem_configured.insert((const void *)k).second)
+            CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<dim3(tiles, n_streams), kDecThreads, smem, st>>>(a);
         h->launches += 1;
     }
     if (prof) CU(h, cudaEventRecord(pe[2], st));

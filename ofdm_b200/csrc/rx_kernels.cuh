@@ -145,13 +145,10 @@ __device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, uint32_t
     return v;
 }
 
-// One OFDM symbol per 8-lane group: load (CP stripped), derotate, FFT, equalise, pilot phase.
+// CP-stripped samples of one OFDM symbol, lane l gets x[l + 8j]: direct (coalesced 8-byte) global loads.
 // x0 = pointer to the first post-offset sample of the stream; n_avail = samples from x0 to the end of the capture.
-// On return (zr, zi)[kb] is the equalised + phase-corrected value of bin l + 8kb.
-template <bool GUARD, int PHASE>
-__device__ __forceinline__ void rx_symbol(const float2 *__restrict__ x0, uint32_t n_avail, uint32_t sym, bool valid,
-                                          const RxLane &L, float br, float bi, float2 *tr, int l,
-                                          float (&zr)[8], float (&zi)[8])
+__device__ __forceinline__ void rx_load_symbol(const float2 *__restrict__ x0, uint32_t n_avail, uint32_t sym, bool valid, int l,
+                                               float (&zr)[8], float (&zi)[8])
 {
     const uint32_t n0 = (kHeadSyms + sym) * kSym + kCp + l;
     const float2 *p = x0 + n0;
@@ -166,8 +163,13 @@ __device__ __forceinline__ void rx_symbol(const float2 *__restrict__ x0, uint32_
             zr[j] = v.x; zi[j] = v.y;
         }
     }
-#pragma unroll
-    for (int j = 0; j < 8; j++) cmul(zr[j], zi[j], L.wr[j], L.wi[j]);      // src/receiver.rs:44-50 (intra-symbol part)
+}
+
+// One OFDM symbol per 8-lane group, samples already in (zr, zi): derotate, FFT, equalise, pilot phase.
+// On return (zr, zi)[kb] is the equalised + phase-corrected value of bin l + 8kb.
+template <bool GUARD, int PHASE>
+__device__ __forceinline__ void rx_symbol(const RxLane &L, float br, float bi, float2 *tr, int l, float (&zr)[8], float (&zi)[8])
+{
     fft64_group(zr, zi, L.twr, L.twi, tr, l);                              // src/receiver.rs:99-104
 #pragma unroll
     for (int kb = 0; kb < 8; kb++) cmul(zr[kb], zi[kb], L.gr[kb], L.gi[kb]);   // src/receiver.rs:67-70
@@ -212,6 +214,12 @@ constexpr int kDecWarps = 8;
 constexpr int kDecThreads = kDecWarps * 32;      // 256
 constexpr int kDecIters = 7;                     // 4 symbols per warp iteration -> 28 symbols per warp
 constexpr int kTileSyms = kDecWarps * 4 * kDecIters;   // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
+template <bool GUARD> constexpr size_t rx_decode_smem_bytes()
+{
+    return sizeof(float2) * (kDecWarps * 4 * 72 + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * kDecWarps;
+}
+constexpr int kStageBytes = 528;                 // 64 samples + up to 1 leading + 1 trailing alignment sample
+constexpr int kStageGroup = 72;                  // float2 per staging slot: 576 B = 144 words = 16 mod 32 (conflict-free LDS.64 across the 2 groups of a half-warp)
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
 __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs a)
@@ -221,10 +229,14 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     constexpr int BPS = BPC * D;                 // bits per OFDM symbol
     constexpr int NB = FEC ? 14 : 8;             // stream bits per output byte
 
-    __shared__ __align__(16) float2 s_tr[kDecWarps * kTrWarp];
-    __shared__ __align__(16) uint8_t s_car[kTileSyms * D + 64];   // one byte (BPC valid bits) per data carrier
-    __shared__ uint8_t s_ham[128];
-    __shared__ uint8_t s_qam[256];
+    // dynamic shared memory (> 48 KB for the 64-carrier layout): staging | transpose scratch | carrier bytes | LUTs | mbarriers
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float2 *s_stage = reinterpret_cast<float2 *>(smem_raw);
+    float2 *s_tr = s_stage + kDecWarps * 4 * kStageGroup;
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_tr + kDecWarps * kTrWarp);       // one byte (BPC valid bits) per data carrier
+    uint8_t *s_ham = s_car + (kTileSyms * D + 64);
+    uint8_t *s_qam = s_ham + 128;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_qam + 256);
 
     const uint32_t stream = blockIdx.y;
     const StreamState *st = a.state + stream;
@@ -246,18 +258,37 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
     const uint32_t n_avail = n_samples - offset;
 
-    RxLane L;
-    rx_lane_init(L, st, a.tables->w64, l);
-    // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins go to the sink)
-    int off[8];
-#pragma unroll
-    for (int kb = 0; kb < 8; kb++) { int r = data_rank<GUARD>(l + 8 * kb); off[kb] = r; }
-
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
     const uint32_t qam_biased = (uint32_t)__cvta_generic_to_shared(s_qam) - kQamLutBias;
     const uint64_t fstep = st->fstep;
-    // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
     const int s_first = t0 + warp * (4 * kDecIters) + g;
+
+    // ---- TMA prefetch: one bulk copy per symbol (the 64 CP-stripped samples, widened to 16-byte alignment) lands in this
+    // warp's staging slot one iteration ahead; completion is signalled on the warp's mbarrier.
+    float2 *stage = s_stage + warp * (4 * kStageGroup) + g * kStageGroup;
+    uint64_t *bar = s_bar + warp;
+    const uintptr_t xaddr = reinterpret_cast<uintptr_t>(x0 + (kHeadSyms * kSym + kCp));   // sample 0 of data symbol 0
+    const int shift = (int)((xaddr >> 3) & 1);                    // symbol starts are 8-byte aligned; 80-sample stride keeps the parity
+    auto issue = [&](int s) {
+        // fast path: the symbol and its 2 alignment samples are inside the capture
+        const bool fast = s < t1 && (uint32_t)((kHeadSyms + s) * kSym + kCp + kNfft + 2) <= n_avail;
+        const uint32_t m = __ballot_sync(0xffffffffu, fast && l == 0);
+        if (fast && l == 0)
+            tma_bulk_g2s(stage, reinterpret_cast<const void *>((xaddr + (uintptr_t)s * (kSym * 8)) & ~(uintptr_t)15), kStageBytes, bar);
+        if (lane == 0) mbar_arrive_expect_tx(bar, kStageBytes * __popc(m));
+        return fast;
+    };
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    bool fast = issue(s_first);
+
+    RxLane L;
+    rx_lane_init(L, st, a.tables->w64, l);
+    // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins are not stored)
+    int off[8];
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) { int r = data_rank<GUARD>(l + 8 * kb); off[kb] = r; }
+    // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
     float br, bi, dr, di;
     phasor_from_turns(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp), br, bi);
     phasor_from_turns(fstep * (uint64_t)(4 * kSym), dr, di);
@@ -266,9 +297,19 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
 #pragma unroll 1
     for (int it = 0; it < kDecIters; it++) {
         const int s = s_first + 4 * it;
-        const bool valid = s < t1;
         float zr[8], zi[8];
-        rx_symbol<GUARD, PHASE>(x0, n_avail, (uint32_t)s, valid, L, br, bi, tr, l, zr, zi);
+        mbar_wait(bar, it & 1);
+        if (fast) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { float2 v = stage[shift + l + 8 * j]; zr[j] = v.x; zi[j] = v.y; }
+        } else {
+            rx_load_symbol(x0, n_avail, (uint32_t)s, s < t1, l, zr, zi);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) cmul(zr[j], zi[j], L.wr[j], L.wi[j]);      // src/receiver.rs:44-50 (intra-symbol part)
+        __syncwarp();                                                          // staging slot consumed by every lane
+        if (it + 1 < kDecIters) fast = issue(s + 4);
+        rx_symbol<GUARD, PHASE>(L, br, bi, tr, l, zr, zi);
         cmul(br, bi, dr, di);
         // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
 #pragma unroll
@@ -276,7 +317,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
             uint32_t v = MOD == 2 ? demap_qam64_lut(zr[kb], zi[kb], qam_biased) : demap_point<MOD>(zr[kb], zi[kb]);
             if (!GUARD) rowp[off[kb]] = (uint8_t)v;
             else st_shared_u8_if_nonneg(rowp + off[kb], v, off[kb]);
-            if (POINTS && valid && (!GUARD || off[kb] >= 0)) {
+            if (POINTS && s < t1 && (!GUARD || off[kb] >= 0)) {
                 size_t p = (size_t)s * D + off[kb];
                 if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr[kb], zi[kb]);
             }
@@ -606,7 +647,10 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
         float br, bi;
         phasor_from_turns(fstep * (uint64_t)((kHeadSyms + g) * kSym + kCp), br, bi);
         float zr[8], zi[8];
-        rx_symbol<GUARD, PHASE>(x0, (uint32_t)(n_avail > 0xffffffffL ? 0xffffffffL : n_avail), (uint32_t)g, valid, L, br, bi, tr, l, zr, zi);
+        rx_load_symbol(x0, (uint32_t)(n_avail > 0xffffffffL ? 0xffffffffL : n_avail), (uint32_t)g, valid, l, zr, zi);
+#pragma unroll
+        for (int j = 0; j < 8; j++) cmul(zr[j], zi[j], L.wr[j], L.wi[j]);      // src/receiver.rs:44-50 (intra-symbol part)
+        rx_symbol<GUARD, PHASE>(L, br, bi, tr, l, zr, zi);
         if (valid) {
 #pragma unroll
             for (int kb = 0; kb < 8; kb++) {
