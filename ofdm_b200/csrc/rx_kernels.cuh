@@ -207,6 +207,78 @@ __device__ __forceinline__ void rx_symbol(const RxLane &L, float br, float bi, f
     for (int kb = 0; kb < 8; kb++) cmul(zr[kb], zi[kb], rr, ri);           // src/receiver.rs:140-144
 }
 
+// ---- packed-complex (FFMA2 / FADD2) versions used by the hot kernel ---------------------------------------------------
+struct RxLaneP {
+    cpx tw[8];   // FFT twiddles W64^(l*ka)
+    cpx w[8];    // derotation inside a symbol: exp(-j f (l + 8j))
+    cpx g[8];    // equaliser 1/h at bins l + 8kb
+};
+
+__device__ __forceinline__ cpx phasor_from_turns_p(uint64_t turns)
+{
+    float c, s;
+    phasor_from_turns(turns, c, s);
+    return c_make(c, s);
+}
+
+__device__ __forceinline__ void rx_lane_init_p(RxLaneP &L, const StreamState *st, const float2 *__restrict__ w64, int l)
+{
+#pragma unroll
+    for (int ka = 0; ka < 8; ka++) L.tw[ka] = c_from(__ldg(w64 + ((l * ka) & 63)));
+    const uint64_t fstep = st->fstep;
+    // exp(-j f (l + 8j)) = exp(-j f l) * exp(-j f 8)^j : two exact phasors + a 7-step recurrence (error ~ 7 ulp)
+    L.w[0] = phasor_from_turns_p(fstep * (uint64_t)l);
+    const cpx step = phasor_from_turns_p(fstep * 8ull);
+#pragma unroll
+    for (int j = 1; j < 8; j++) L.w[j] = c_mul(L.w[j - 1], step);
+#pragma unroll
+    for (int j = 0; j < 8; j++) L.g[j] = c_from(st->g[l + 8 * j]);
+}
+
+// One OFDM symbol per 8-lane group, derotated samples in z: FFT, equalise, pilot phase.
+// On return z[kb] is the equalised + phase-corrected value of bin l + 8kb.
+template <bool GUARD, int PHASE>
+__device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, cpx base, float2 *tr, int l, cpx (&z)[8])
+{
+    fft64_group_p(z, L.tw, tr, l);                                         // src/receiver.rs:99-104
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) z[kb] = c_mul(z[kb], L.g[kb]);          // src/receiver.rs:67-70
+    cpx rot = base;                                                        // common rotation of the data bins
+    if (GUARD) {
+        // pilots: bins 6, 25, 39, 58 = (lane, kb) (6,0) (1,3) (7,4) (2,7)   src/receiver.rs:125-128
+        cpx p = c_make(0.0f, 0.0f);
+        if (l == 6) p = z[0];
+        if (l == 1) p = z[3];
+        if (l == 7) p = z[4];
+        if (l == 2) p = z[7];
+        if (PHASE == 1) {
+            // angle of the pilot sum: the per-symbol base phasor cancels, rot = conj(sum)/|sum|
+            float pr, pi;
+            c_split(p, pr, pi);
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+                pr += __shfl_xor_sync(0xffffffffu, pr, m);
+                pi += __shfl_xor_sync(0xffffffffu, pi, m);
+            }
+            float inv = rsqrtf(fmaxf(pr * pr + pi * pi, 1e-30f));
+            rot = c_make(pr * inv, -pi * inv);
+        } else {
+            // reference: mean of the four pilot angles (after the full derotation), src/receiver.rs:126,137
+            float pr, pi;
+            c_split(c_mul(p, base), pr, pi);
+            const bool pilot_lane = (l == 6) | (l == 1) | (l == 7) | (l == 2);
+            float ang = pilot_lane ? atan2f(pi, pr) : 0.0f;
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) ang += __shfl_xor_sync(0xffffffffu, ang, m);
+            float sn, cs;
+            sincosf(-0.25f * ang, &sn, &cs);
+            rot = c_mul(c_make(cs, sn), base);
+        }
+    }
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) z[kb] = c_mul(z[kb], rot);              // src/receiver.rs:140-144
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // hot kernel
 // ------------------------------------------------------------------------------------------------------------------
@@ -214,9 +286,10 @@ constexpr int kDecWarps = 8;
 constexpr int kDecThreads = kDecWarps * 32;      // 256
 constexpr int kDecIters = 7;                     // 4 symbols per warp iteration -> 28 symbols per warp
 constexpr int kTileSyms = kDecWarps * 4 * kDecIters;   // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
+constexpr int kStageSlots = 1;                   // prefetch distance in warp iterations (staging slots per warp)
 template <bool GUARD> constexpr size_t rx_decode_smem_bytes()
 {
-    return sizeof(float2) * (kDecWarps * 4 * 72 + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * kDecWarps;
+    return sizeof(float2) * (kDecWarps * kStageSlots * 4 * 72 + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 16 * kDecWarps;
 }
 constexpr int kStageBytes = 528;                 // 64 samples + up to 1 leading + 1 trailing alignment sample
 constexpr int kStageGroup = 72;                  // float2 per staging slot: 576 B = 144 words = 16 mod 32 (conflict-free LDS.64 across the 2 groups of a half-warp)
@@ -232,7 +305,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     // dynamic shared memory (> 48 KB for the 64-carrier layout): staging | transpose scratch | carrier bytes | LUTs | mbarriers
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float2 *s_stage = reinterpret_cast<float2 *>(smem_raw);
-    float2 *s_tr = s_stage + kDecWarps * 4 * kStageGroup;
+    float2 *s_tr = s_stage + kDecWarps * kStageSlots * 4 * kStageGroup;
     uint8_t *s_car = reinterpret_cast<uint8_t *>(s_tr + kDecWarps * kTrWarp);       // one byte (BPC valid bits) per data carrier
     uint8_t *s_ham = s_car + (kTileSyms * D + 64);
     uint8_t *s_qam = s_ham + 128;
@@ -263,63 +336,81 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     const uint64_t fstep = st->fstep;
     const int s_first = t0 + warp * (4 * kDecIters) + g;
 
-    // ---- TMA prefetch: one bulk copy per symbol (the 64 CP-stripped samples, widened to 16-byte alignment) lands in this
-    // warp's staging slot one iteration ahead; completion is signalled on the warp's mbarrier.
-    float2 *stage = s_stage + warp * (4 * kStageGroup) + g * kStageGroup;
-    uint64_t *bar = s_bar + warp;
+    // ---- TMA prefetch: one bulk copy per symbol (the 64 CP-stripped samples, widened to 16-byte alignment) lands in one of
+    // this warp's two staging slots two iterations ahead; completion is signalled on the slot's mbarrier. Lane 0 issues the
+    // (up to) four copies of a warp iteration: symbols below `s_fast` are valid and lie, with their two alignment samples,
+    // inside the capture; the others take the bounds-checked direct-load path.
     const uintptr_t xaddr = reinterpret_cast<uintptr_t>(x0 + (kHeadSyms * kSym + kCp));   // sample 0 of data symbol 0
-    const int shift = (int)((xaddr >> 3) & 1);                    // symbol starts are 8-byte aligned; 80-sample stride keeps the parity
-    auto issue = [&](int s) {
-        // fast path: the symbol and its 2 alignment samples are inside the capture
-        const bool fast = s < t1 && (uint32_t)((kHeadSyms + s) * kSym + kCp + kNfft + 2) <= n_avail;
-        const uint32_t m = __ballot_sync(0xffffffffu, fast && l == 0);
-        if (fast && l == 0)
-            tma_bulk_g2s(stage, reinterpret_cast<const void *>((xaddr + (uintptr_t)s * (kSym * 8)) & ~(uintptr_t)15), kStageBytes, bar);
-        if (lane == 0) mbar_arrive_expect_tx(bar, kStageBytes * __popc(m));
-        return fast;
+    const int shift = (int)((xaddr >> 3) & 1);                    // symbol starts are 8-byte aligned; the 80-sample stride keeps the parity
+    int s_fast = n_avail >= (uint32_t)(kHeadSyms * kSym + kCp + kNfft + 2) ? (int)((n_avail - (kHeadSyms * kSym + kCp + kNfft + 2)) / kSym) + 1 : 0;
+    if (s_fast > t1) s_fast = t1;
+    const int s_warp = t0 + warp * (4 * kDecIters);               // first symbol of this warp
+    float2 *stage_w = s_stage + warp * (kStageSlots * 4 * kStageGroup);     // [slot][group][kStageGroup]
+    uint64_t *bar_w = s_bar + 2 * warp;
+    auto issue = [&](int it) {                                    // group leaders copy, lane 0 arms the barrier
+        const int sb = s_warp + 4 * it;
+        const int slot = it % kStageSlots;
+        uint64_t *bar = bar_w + slot;
+        if (l == 0 && sb + g < s_fast) {
+            const uintptr_t src = (xaddr + (uintptr_t)(sb + g) * (kSym * 8)) & ~(uintptr_t)15;
+            tma_bulk_g2s(stage_w + slot * (4 * kStageGroup) + g * kStageGroup, reinterpret_cast<const void *>(src), kStageBytes, bar);
+        }
+        if (lane == 0) {
+            int nf = s_fast - sb;
+            nf = nf < 0 ? 0 : (nf > 4 ? 4 : nf);
+            mbar_arrive_expect_tx(bar, kStageBytes * nf);
+        }
     };
-    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (lane == 0) { mbar_init(bar_w, 1); mbar_init(bar_w + 1, 1); mbar_fence_init(); }
     __syncwarp();
-    bool fast = issue(s_first);
+#pragma unroll
+    for (int q = 0; q < kStageSlots; q++) issue(q);
+    __syncwarp();
+    const float2 *stage_g = stage_w + g * kStageGroup + shift + l;
 
-    RxLane L;
-    rx_lane_init(L, st, a.tables->w64, l);
+    RxLaneP L;
+    rx_lane_init_p(L, st, a.tables->w64, l);
     // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins are not stored)
     int off[8];
 #pragma unroll
     for (int kb = 0; kb < 8; kb++) { int r = data_rank<GUARD>(l + 8 * kb); off[kb] = r; }
     // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
-    float br, bi, dr, di;
-    phasor_from_turns(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp), br, bi);
-    phasor_from_turns(fstep * (uint64_t)(4 * kSym), dr, di);
+    cpx base = phasor_from_turns_p(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp));
+    const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)(4 * kSym));
     uint8_t *rowp = s_car + (s_first - t0) * D;
 
 #pragma unroll 1
     for (int it = 0; it < kDecIters; it++) {
         const int s = s_first + 4 * it;
-        float zr[8], zi[8];
-        mbar_wait(bar, it & 1);
-        if (fast) {
+        cpx z[8];
+        mbar_wait(bar_w + it % kStageSlots, (it / kStageSlots) & 1);
+        if (s < s_fast) {
+            const unsigned long long *sp = reinterpret_cast<const unsigned long long *>(stage_g + (it % kStageSlots) * (4 * kStageGroup));
 #pragma unroll
-            for (int j = 0; j < 8; j++) { float2 v = stage[shift + l + 8 * j]; zr[j] = v.x; zi[j] = v.y; }
+            for (int j = 0; j < 8; j++) z[j].v = sp[8 * j];
         } else {
+            float zr[8], zi[8];
             rx_load_symbol(x0, n_avail, (uint32_t)s, s < t1, l, zr, zi);
+#pragma unroll
+            for (int j = 0; j < 8; j++) z[j] = c_make(zr[j], zi[j]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) cmul(zr[j], zi[j], L.wr[j], L.wi[j]);      // src/receiver.rs:44-50 (intra-symbol part)
+        for (int j = 0; j < 8; j++) z[j] = c_mul(z[j], L.w[j]);                // src/receiver.rs:44-50 (intra-symbol part)
         __syncwarp();                                                          // staging slot consumed by every lane
-        if (it + 1 < kDecIters) fast = issue(s + 4);
-        rx_symbol<GUARD, PHASE>(L, br, bi, tr, l, zr, zi);
-        cmul(br, bi, dr, di);
+        if (it + kStageSlots < kDecIters) issue(it + kStageSlots);
+        rx_symbol_p<GUARD, PHASE>(L, base, tr, l, z);
+        base = c_mul(base, dbase);
         // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
 #pragma unroll
         for (int kb = 0; kb < 8; kb++) {
-            uint32_t v = MOD == 2 ? demap_qam64_lut(zr[kb], zi[kb], qam_biased) : demap_point<MOD>(zr[kb], zi[kb]);
+            float zr, zi;
+            c_split(z[kb], zr, zi);
+            uint32_t v = MOD == 2 ? demap_qam64_lut(zr, zi, qam_biased) : demap_point<MOD>(zr, zi);
             if (!GUARD) rowp[off[kb]] = (uint8_t)v;
             else st_shared_u8_if_nonneg(rowp + off[kb], v, off[kb]);
             if (POINTS && s < t1 && (!GUARD || off[kb] >= 0)) {
                 size_t p = (size_t)s * D + off[kb];
-                if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr[kb], zi[kb]);
+                if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
             }
         }
         rowp += 4 * D;
