@@ -396,6 +396,13 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
     h->launches += 1;
     if (S > 0) {
         uint32_t tiles = (uint32_t)((S + h->tile_shift + kTileSyms - 1) / kTileSyms);
+        // several consecutive tiles per CTA (lane constants and the prefetch pipeline are reused across them), but keep
+        // >= ~16 waves of CTAs (148 SMs x 3 CTAs) so the tail stays small
+        uint32_t tpc = (uint32_t)(((uint64_t)tiles * n_streams) / (16u * 148u * 3u));
+        if (tpc < 1) tpc = 1;
+        if (tpc > tiles) tpc = tiles;
+        a.tiles_per_cta = (int)tpc;
+        tiles = (tiles + tpc - 1) / tpc;
         DecodeKernel k = pick_decode(h->cfg, points);
         const size_t smem = h->cfg.guard_bands ? rx_decode_smem_bytes<true>() : rx_decode_smem_bytes<false>();
         if (h->smem_configured.insert((const void *)k).second)

@@ -51,6 +51,7 @@ struct RxArgs {
     uint32_t        sync_window;
     int32_t         tile_shift;     // symbols by which tile boundaries are shifted so they fall on Hamming byte boundaries
     int32_t         sync_mode, cfo_mode, fec;   // run-time switches of the (cold) acquisition kernel
+    int32_t         tiles_per_cta;  // consecutive tiles of one stream handled by one CTA of the decode kernel
     // diag (optional)
     int32_t  *d_offset;
     float    *d_f_delta;
@@ -286,13 +287,12 @@ constexpr int kDecWarps = 8;
 constexpr int kDecThreads = kDecWarps * 32;      // 256
 constexpr int kDecIters = 7;                     // 4 symbols per warp iteration -> 28 symbols per warp
 constexpr int kTileSyms = kDecWarps * 4 * kDecIters;   // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
-constexpr int kStageSlots = 1;                   // prefetch distance in warp iterations (staging slots per warp)
+constexpr int kStageBytes = 4 * kSym * 8 + 16;       // 4 consecutive OFDM symbols (CPs included) + 1 leading / 1 trailing alignment sample
+constexpr int kStageGroup = (kStageBytes + 15) / 16 * 2 / 4 + 1;   // float2 per warp staging slot / 4
 template <bool GUARD> constexpr size_t rx_decode_smem_bytes()
 {
-    return sizeof(float2) * (kDecWarps * kStageSlots * 4 * 72 + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 16 * kDecWarps;
+    return sizeof(float2) * (kDecWarps * 4 * kStageGroup + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * kDecWarps;
 }
-constexpr int kStageBytes = 528;                 // 64 samples + up to 1 leading + 1 trailing alignment sample
-constexpr int kStageGroup = 72;                  // float2 per staging slot: 576 B = 144 words = 16 mod 32 (conflict-free LDS.64 across the 2 groups of a half-warp)
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
 __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs a)
@@ -305,171 +305,188 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     // dynamic shared memory (> 48 KB for the 64-carrier layout): staging | transpose scratch | carrier bytes | LUTs | mbarriers
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float2 *s_stage = reinterpret_cast<float2 *>(smem_raw);
-    float2 *s_tr = s_stage + kDecWarps * kStageSlots * 4 * kStageGroup;
+    float2 *s_tr = s_stage + kDecWarps * 4 * kStageGroup;
     uint8_t *s_car = reinterpret_cast<uint8_t *>(s_tr + kDecWarps * kTrWarp);       // one byte (BPC valid bits) per data carrier
     uint8_t *s_ham = s_car + (kTileSyms * D + 64);
     uint8_t *s_qam = s_ham + 128;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_qam + 256);
 
+    // A CTA owns `tiles_per_cta` consecutive 224-symbol tiles of one stream. Tile k covers symbols
+    // [k*224 - tile_shift, (k+1)*224 - tile_shift) n [0, S): every inner boundary falls on a Hamming byte boundary.
     const uint32_t stream = blockIdx.y;
     const StreamState *st = a.state + stream;
     if (st->status != ST_OK) return;
     const int S = (int)st->n_syms;
-    int t0 = (int)blockIdx.x * kTileSyms - a.tile_shift;
-    int t1 = t0 + kTileSyms;
-    if (t0 < 0) t0 = 0;
-    if (t1 > S) t1 = S;
-    if (t0 >= t1) return;
+    const int tile_first = (int)blockIdx.x * a.tiles_per_cta;
+    int tile_end = tile_first + a.tiles_per_cta;
+    {
+        const int n_tiles = (S + a.tile_shift + kTileSyms - 1) / kTileSyms;
+        if (tile_end > n_tiles) tile_end = n_tiles;
+    }
+    if (tile_first >= tile_end) return;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
     if (MOD == 2) s_qam[tid] = qam64_lut_entry(tid);
-    __syncthreads();
 
     const uint32_t n_samples = a.n_samples[stream];
     const uint32_t offset = (uint32_t)st->offset;
     const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
     const uint32_t n_avail = n_samples - offset;
-
+    const uint64_t fstep = st->fstep;
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
     const uint32_t qam_biased = (uint32_t)__cvta_generic_to_shared(s_qam) - kQamLutBias;
-    const uint64_t fstep = st->fstep;
-    const int s_first = t0 + warp * (4 * kDecIters) + g;
 
-    // ---- TMA prefetch: one bulk copy per symbol (the 64 CP-stripped samples, widened to 16-byte alignment) lands in one of
-    // this warp's two staging slots two iterations ahead; completion is signalled on the slot's mbarrier. Lane 0 issues the
-    // (up to) four copies of a warp iteration: symbols below `s_fast` are valid and lie, with their two alignment samples,
-    // inside the capture; the others take the bounds-checked direct-load path.
+    // ---- TMA prefetch: one bulk copy per OFDM symbol (its 64 CP-stripped samples, widened to 16-byte alignment) lands in
+    // this warp's staging slot one warp-iteration ahead -- also across tile boundaries, so only the very first iteration of
+    // a CTA sees the DRAM latency. Completion is signalled on the warp's mbarrier. Symbols below `s_fast` lie, with their
+    // two alignment samples, inside the capture; the (rare) others take the bounds-checked direct-load path.
     const uintptr_t xaddr = reinterpret_cast<uintptr_t>(x0 + (kHeadSyms * kSym + kCp));   // sample 0 of data symbol 0
-    const int shift = (int)((xaddr >> 3) & 1);                    // symbol starts are 8-byte aligned; the 80-sample stride keeps the parity
+    const int shift = (int)((xaddr >> 3) & 1);      // symbol starts are 8-byte aligned; the 80-sample stride keeps the parity
     int s_fast = n_avail >= (uint32_t)(kHeadSyms * kSym + kCp + kNfft + 2) ? (int)((n_avail - (kHeadSyms * kSym + kCp + kNfft + 2)) / kSym) + 1 : 0;
-    if (s_fast > t1) s_fast = t1;
-    const int s_warp = t0 + warp * (4 * kDecIters);               // first symbol of this warp
-    float2 *stage_w = s_stage + warp * (kStageSlots * 4 * kStageGroup);     // [slot][group][kStageGroup]
-    uint64_t *bar_w = s_bar + 2 * warp;
-    auto issue = [&](int it) {                                    // group leaders copy, lane 0 arms the barrier
-        const int sb = s_warp + 4 * it;
-        const int slot = it % kStageSlots;
-        uint64_t *bar = bar_w + slot;
-        if (l == 0 && sb + g < s_fast) {
-            const uintptr_t src = (xaddr + (uintptr_t)(sb + g) * (kSym * 8)) & ~(uintptr_t)15;
-            tma_bulk_g2s(stage_w + slot * (4 * kStageGroup) + g * kStageGroup, reinterpret_cast<const void *>(src), kStageBytes, bar);
-        }
+    if (s_fast > S) s_fast = S;
+    float2 *stage_w = s_stage + warp * (4 * kStageGroup);          // [group][kStageGroup]
+    uint64_t *bar = s_bar + warp;
+    const unsigned long long *stage_rd = reinterpret_cast<const unsigned long long *>(stage_w + shift + g * kSym + kCp + l);
+    auto tile_t0 = [&](int tile) { int t = tile * kTileSyms - a.tile_shift; return t < 0 ? 0 : t; };
+    auto tile_t1 = [&](int tile) { int t = (tile + 1) * kTileSyms - a.tile_shift; return t > S ? S : t; };
+    // one copy for the 4 symbols sb .. sb+3 of a warp iteration when all of them are below lim; lane 0 only
+    auto issue = [&](int sb, int lim) {
         if (lane == 0) {
-            int nf = s_fast - sb;
-            nf = nf < 0 ? 0 : (nf > 4 ? 4 : nf);
-            mbar_arrive_expect_tx(bar, kStageBytes * nf);
+            const bool full = sb + 4 <= lim;
+            if (full) {
+                const uintptr_t src = (xaddr - kCp * 8 + (uintptr_t)sb * (kSym * 8)) & ~(uintptr_t)15;
+                tma_bulk_g2s(stage_w, reinterpret_cast<const void *>(src), kStageBytes, bar);
+            }
+            mbar_arrive_expect_tx(bar, full ? kStageBytes : 0);
         }
     };
-    if (lane == 0) { mbar_init(bar_w, 1); mbar_init(bar_w + 1, 1); mbar_fence_init(); }
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncwarp();
-#pragma unroll
-    for (int q = 0; q < kStageSlots; q++) issue(q);
-    __syncwarp();
-    const float2 *stage_g = stage_w + g * kStageGroup + shift + l;
+    {
+        const int t1 = tile_t1(tile_first);
+        issue(tile_t0(tile_first) + warp * (4 * kDecIters), s_fast < t1 ? s_fast : t1);
+    }
 
     RxLaneP L;
     rx_lane_init_p(L, st, a.tables->w64, l);
     // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins are not stored)
     int off[8];
 #pragma unroll
-    for (int kb = 0; kb < 8; kb++) { int r = data_rank<GUARD>(l + 8 * kb); off[kb] = r; }
-    // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
-    cpx base = phasor_from_turns_p(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp));
+    for (int kb = 0; kb < 8; kb++) off[kb] = data_rank<GUARD>(l + 8 * kb);
     const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)(4 * kSym));
-    uint8_t *rowp = s_car + (s_first - t0) * D;
+    uint8_t *out = a.out + (size_t)stream * a.out_stride;
+    uint32_t phase = 0;                                             // mbarrier phase parity
+    __syncthreads();                                                // LUTs visible
 
 #pragma unroll 1
-    for (int it = 0; it < kDecIters; it++) {
-        const int s = s_first + 4 * it;
-        cpx z[8];
-        mbar_wait(bar_w + it % kStageSlots, (it / kStageSlots) & 1);
-        if (s < s_fast) {
-            const unsigned long long *sp = reinterpret_cast<const unsigned long long *>(stage_g + (it % kStageSlots) * (4 * kStageGroup));
-#pragma unroll
-            for (int j = 0; j < 8; j++) z[j].v = sp[8 * j];
-        } else {
-            float zr[8], zi[8];
-            rx_load_symbol(x0, n_avail, (uint32_t)s, s < t1, l, zr, zi);
-#pragma unroll
-            for (int j = 0; j < 8; j++) z[j] = c_make(zr[j], zi[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) z[j] = c_mul(z[j], L.w[j]);                // src/receiver.rs:44-50 (intra-symbol part)
-        __syncwarp();                                                          // staging slot consumed by every lane
-        if (it + kStageSlots < kDecIters) issue(it + kStageSlots);
-        rx_symbol_p<GUARD, PHASE>(L, base, tr, l, z);
-        base = c_mul(base, dbase);
-        // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
-#pragma unroll
-        for (int kb = 0; kb < 8; kb++) {
-            float zr, zi;
-            c_split(z[kb], zr, zi);
-            uint32_t v = MOD == 2 ? demap_qam64_lut(zr, zi, qam_biased) : demap_point<MOD>(zr, zi);
-            if (!GUARD) rowp[off[kb]] = (uint8_t)v;
-            else st_shared_u8_if_nonneg(rowp + off[kb], v, off[kb]);
-            if (POINTS && s < t1 && (!GUARD || off[kb] >= 0)) {
-                size_t p = (size_t)s * D + off[kb];
-                if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
-            }
-        }
-        rowp += 4 * D;
-    }
-    __syncthreads();
+    for (int tile = tile_first; tile < tile_end; tile++) {
+        const int t0 = tile_t0(tile), t1 = tile_t1(tile);
+        const int lim = s_fast < t1 ? s_fast : t1;                  // symbols of this tile served by the TMA path
+        const int s_warp = t0 + warp * (4 * kDecIters);             // first symbol of this warp
+        const int s_first = s_warp + g;
+        // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
+        cpx base = phasor_from_turns_p(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp));
+        uint8_t *rowp = s_car + (s_first - t0) * D;
 
-    // ---- tile bits -> output bytes (header strip src/receiver.rs:86-93, Hamming docs/SPEC.md 3) ------------------
-    const long bit0 = (long)t0 * BPS;                       // first stream bit held by this tile
-    const long bit1 = (long)t1 * BPS;
-    long j0 = bit0 <= kHeaderBits ? 0 : (bit0 - kHeaderBits + NB - 1) / NB;
-    long j1 = (bit1 - kHeaderBits) / NB;                    // bytes fully inside the tile
-    if (j1 > (long)st->out_len) j1 = (long)st->out_len;
-    uint8_t *out = a.out + (size_t)stream * a.out_stride;
-    const int pbase = (int)(kHeaderBits + j0 * NB - bit0);  // tile-local bit position of byte j0
-    const int nbytes = (int)(j1 - j0);
-    if (MOD == 2) {
-        // 3 output bytes per thread: 42 (Hamming) or 24 stream bits = 7 or 4 six-bit carriers (+1 for the bit shift)
-        constexpr int NC = (3 * NB + 5) / 6 + 1;
-        for (int u = 3 * tid; u < nbytes; u += 3 * kDecThreads) {
-            const int p = pbase + u * NB;
-            const int c = p / 6, sh = p - 6 * c;
-            const uint8_t *cp = s_car + c;
-            uint32_t lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
-            uint32_t hi = 0;
-            if (NC > 5) {
-                uint32_t b5 = cp[5];
-                lo |= b5 << 30;
-                hi = (b5 >> 2) | (cp[6] << 4) | (cp[7] << 10);
-            }
-            lo = __funnelshift_r(lo, hi, sh);
-            hi >>= sh;
-            uint32_t w0, w1, w2;
-            if (FEC) {
-                w0 = lo & 0x3FFFu; w1 = (lo >> 14) & 0x3FFFu; w2 = __funnelshift_r(lo, hi, 28) & 0x3FFFu;
-                w0 = s_ham[w0 & 127u] | (s_ham[w0 >> 7] << 4);
-                w1 = s_ham[w1 & 127u] | (s_ham[w1 >> 7] << 4);
-                w2 = s_ham[w2 & 127u] | (s_ham[w2 >> 7] << 4);
-            } else {
-                w0 = lo & 255u; w1 = (lo >> 8) & 255u; w2 = (lo >> 16) & 255u;
-            }
-            uint8_t *o = out + j0 + u;
-            o[0] = (uint8_t)w0;
-            if (u + 1 < nbytes) o[1] = (uint8_t)w1;
-            if (u + 2 < nbytes) o[2] = (uint8_t)w2;
-        }
-    } else {
-        for (int u = tid; u < nbytes; u += kDecThreads) {
-            const int p = pbase + u * NB;
-            const int c = p / BPC, sh = p - c * BPC;
-            constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
-            uint32_t v = 0;
+#pragma unroll 1
+        for (int it = 0; it < kDecIters; it++) {
+            const int s = s_first + 4 * it;
+            cpx z[8];
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            if (s_warp + 4 * it + 4 <= lim) {
 #pragma unroll
-            for (int i = 0; i < NC; i++) v |= (uint32_t)s_car[c + i] << (BPC * i);
-            v >>= sh;
-            uint32_t byte;
-            if (FEC) byte = (uint32_t)s_ham[v & 127u] | ((uint32_t)s_ham[(v >> 7) & 127u] << 4);
-            else byte = v & 255u;
-            out[j0 + u] = (uint8_t)byte;
+                for (int j = 0; j < 8; j++) z[j].v = stage_rd[8 * j];
+            } else {
+                float zr[8], zi[8];
+                rx_load_symbol(x0, n_avail, (uint32_t)s, s < t1, l, zr, zi);
+#pragma unroll
+                for (int j = 0; j < 8; j++) z[j] = c_make(zr[j], zi[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) z[j] = c_mul(z[j], L.w[j]);            // src/receiver.rs:44-50 (intra-symbol part)
+            __syncwarp();                                                      // staging slot consumed by every lane
+            if (it + 1 < kDecIters) {
+                issue(s_warp + 4 * (it + 1), lim);
+            } else if (tile + 1 < tile_end) {                                  // first iteration of the next tile
+                const int n1 = tile_t1(tile + 1);
+                issue(t1 + warp * (4 * kDecIters), s_fast < n1 ? s_fast : n1);
+            }
+            rx_symbol_p<GUARD, PHASE>(L, base, tr, l, z);
+            base = c_mul(base, dbase);
+            // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                float zr, zi;
+                c_split(z[kb], zr, zi);
+                uint32_t v = MOD == 2 ? demap_qam64_lut(zr, zi, qam_biased) : demap_point<MOD>(zr, zi);
+                // bins l + 8kb for kb in {1, 2, 5, 6} are data carriers on every lane
+                if (!GUARD || kb == 1 || kb == 2 || kb == 5 || kb == 6) rowp[off[kb]] = (uint8_t)v;
+                else st_shared_u8_if_nonneg(rowp + off[kb], v, off[kb]);
+                if (POINTS && s < t1 && (!GUARD || off[kb] >= 0)) {
+                    size_t p = (size_t)s * D + off[kb];
+                    if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
+                }
+            }
+            rowp += 4 * D;
         }
+        __syncthreads();
+
+        // ---- tile bits -> output bytes (header strip src/receiver.rs:86-93, Hamming docs/SPEC.md 3) --------------
+        const long bit0 = (long)t0 * BPS;                       // first stream bit held by this tile
+        const long bit1 = (long)t1 * BPS;
+        long j0 = bit0 <= kHeaderBits ? 0 : (bit0 - kHeaderBits + NB - 1) / NB;
+        long j1 = (bit1 - kHeaderBits) / NB;                    // bytes fully inside the tile
+        if (j1 > (long)st->out_len) j1 = (long)st->out_len;
+        const int pbase = (int)(kHeaderBits + j0 * NB - bit0);  // tile-local bit position of byte j0
+        const int nbytes = (int)(j1 - j0);
+        if (MOD == 2) {
+            // 3 output bytes per thread: 42 (Hamming) or 24 stream bits = 7 or 4 six-bit carriers (+1 for the bit shift)
+            constexpr int NC = (3 * NB + 5) / 6 + 1;
+            for (int u = 3 * tid; u < nbytes; u += 3 * kDecThreads) {
+                const int p = pbase + u * NB;
+                const int c = p / 6, sh = p - 6 * c;
+                const uint8_t *cp = s_car + c;
+                uint32_t lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
+                uint32_t hi = 0;
+                if (NC > 5) {
+                    uint32_t b5 = cp[5];
+                    lo |= b5 << 30;
+                    hi = (b5 >> 2) | (cp[6] << 4) | (cp[7] << 10);
+                }
+                lo = __funnelshift_r(lo, hi, sh);
+                hi >>= sh;
+                uint32_t w0, w1, w2;
+                if (FEC) {
+                    w0 = lo & 0x3FFFu; w1 = (lo >> 14) & 0x3FFFu; w2 = __funnelshift_r(lo, hi, 28) & 0x3FFFu;
+                    w0 = s_ham[w0 & 127u] | (s_ham[w0 >> 7] << 4);
+                    w1 = s_ham[w1 & 127u] | (s_ham[w1 >> 7] << 4);
+                    w2 = s_ham[w2 & 127u] | (s_ham[w2 >> 7] << 4);
+                } else {
+                    w0 = lo & 255u; w1 = (lo >> 8) & 255u; w2 = (lo >> 16) & 255u;
+                }
+                uint8_t *o = out + j0 + u;
+                o[0] = (uint8_t)w0;
+                if (u + 1 < nbytes) o[1] = (uint8_t)w1;
+                if (u + 2 < nbytes) o[2] = (uint8_t)w2;
+            }
+        } else {
+            for (int u = tid; u < nbytes; u += kDecThreads) {
+                const int p = pbase + u * NB;
+                const int c = p / BPC, sh = p - c * BPC;
+                constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
+                uint32_t v = 0;
+#pragma unroll
+                for (int i = 0; i < NC; i++) v |= (uint32_t)s_car[c + i] << (BPC * i);
+                v >>= sh;
+                uint32_t byte;
+                if (FEC) byte = (uint32_t)s_ham[v & 127u] | ((uint32_t)s_ham[(v >> 7) & 127u] << 4);
+                else byte = v & 255u;
+                out[j0 + u] = (uint8_t)byte;
+            }
+        }
+        if (tile + 1 < tile_end) __syncthreads();               // s_car is rewritten by the next tile
     }
 }
 
