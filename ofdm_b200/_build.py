@@ -44,3 +44,19 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(r.stderr)
     return LIB_PATH
+
+
+HOST_DIR = os.path.join(_HERE, "host")
+LAB3C = os.path.join(HOST_DIR, "lab3c")
+
+
+def build_host_example(force: bool = False) -> str:
+    """g++ the C++ host mirror's lab3c example against libofdm_b200.so (rpath $ORIGIN/..)."""
+    srcs = [os.path.join(HOST_DIR, "lab3c.cpp"), os.path.join(HOST_DIR, "ofdm.hpp"), LIB_PATH]
+    if not force and os.path.exists(LAB3C) and all(os.path.getmtime(LAB3C) >= os.path.getmtime(x) for x in srcs):
+        return LAB3C
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", LAB3C, srcs[0], "-L" + _HERE, "-lofdm_b200", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return LAB3C

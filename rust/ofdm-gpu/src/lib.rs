@@ -1,0 +1,114 @@
+//! Drop-in for the reference crate's modem entry points (src/transmitter.rs:10-15, src/receiver.rs:8-13): same
+//! signatures, engine behind them. The reference's `pub use transmitter::*; pub use receiver::*;` (src/lib.rs:14-21)
+//! is replaced by `pub use ofdm_gpu::{encode, decode, ModulationScheme};` -- examples and tests compile unchanged.
+//! NOT compiled in this repository's build image (no rustc); see INTEGRATION.md.
+use anyhow::{anyhow, Result};
+use num::complex::Complex64;
+use ofdm_sys as sys;
+use std::{ffi::CStr, ptr};
+
+#[derive(Clone, Copy, Debug, PartialEq)]
+pub enum ModulationScheme {
+    Bpsk,
+    Qpsk,
+    Qam,
+}
+
+pub struct Engine {
+    h: *mut sys::ofdm_engine,
+    cfg: sys::ofdm_cfg,
+}
+
+impl Engine {
+    pub fn new(guard_bands: bool, modulation: ModulationScheme, fec: bool, device: i32) -> Result<Self> {
+        unsafe {
+            let mut cfg: sys::ofdm_cfg = std::mem::zeroed();
+            sys::ofdm_cfg_default(&mut cfg);
+            cfg.guard_bands = guard_bands as u32;
+            cfg.modulation = modulation as u32;
+            cfg.fec = fec as u32;
+            let mut h = ptr::null_mut();
+            if sys::ofdm_engine_create(&cfg, device, &mut h) != 0 {
+                return Err(anyhow!("{}", CStr::from_ptr(sys::ofdm_last_error(ptr::null())).to_string_lossy()));
+            }
+            Ok(Engine { h, cfg })
+        }
+    }
+
+    /// Batched `encode`: one frame per payload.
+    pub fn encode_batch(&mut self, payloads: &[&[u8]]) -> Result<Vec<Vec<Complex64>>> {
+        let n = payloads.len() as u32;
+        let lens: Vec<u32> = payloads.iter().map(|p| p.len() as u32).collect();
+        let pstride = lens.iter().copied().max().unwrap_or(1).max(1);
+        let istride = lens.iter().map(|&l| unsafe { sys::ofdm_frame_len(&self.cfg, l) }).max().unwrap_or(880);
+        let mut pay = vec![0u8; (n * pstride) as usize];
+        for (i, p) in payloads.iter().enumerate() {
+            pay[i * pstride as usize..i * pstride as usize + p.len()].copy_from_slice(p);
+        }
+        let mut iq = vec![sys::ofdm_fc32::default(); (n * istride) as usize];
+        let mut flen = vec![0u32; n as usize];
+        let rc = unsafe {
+            sys::ofdm_tx_encode_batch(self.h, pay.as_ptr(), lens.as_ptr(), pstride, n, iq.as_mut_ptr(), istride, flen.as_mut_ptr(),
+                                      sys::OFDM_MEM_HOST, ptr::null_mut())
+        };
+        self.check(rc)?;
+        Ok((0..n as usize)
+            .map(|i| iq[i * istride as usize..i * istride as usize + flen[i] as usize].iter().map(|s| Complex64::new(s.re as f64, s.im as f64)).collect())
+            .collect())
+    }
+
+    /// Batched `decode`: `Err` per stream where the reference returns Err / panics.
+    pub fn decode_batch(&mut self, captures: &[&[Complex64]]) -> Result<Vec<Result<Vec<u8>>>> {
+        let n = captures.len() as u32;
+        let ns: Vec<u32> = captures.iter().map(|c| c.len() as u32).collect();
+        let istride = ns.iter().copied().max().unwrap_or(1).max(1);
+        let mut iq = vec![sys::ofdm_fc32::default(); (n * istride) as usize];
+        for (i, c) in captures.iter().enumerate() {
+            for (k, s) in c.iter().enumerate() {
+                iq[i * istride as usize + k] = sys::ofdm_fc32 { re: s.re as f32, im: s.im as f32 }; // sig_to_bytes, src/utils.rs:228-236
+            }
+        }
+        let ostride = (istride / 80 + 1) * 48 + 16;
+        let mut out = vec![0u8; (n * ostride) as usize];
+        let mut olen = vec![0u32; n as usize];
+        let mut status = vec![0i32; n as usize];
+        let rc = unsafe {
+            sys::ofdm_rx_decode_batch(self.h, iq.as_ptr(), ns.as_ptr(), n, istride, istride, out.as_mut_ptr(), ostride, olen.as_mut_ptr(),
+                                      status.as_mut_ptr(), ptr::null(), sys::OFDM_MEM_HOST, ptr::null_mut())
+        };
+        self.check(rc)?;
+        Ok((0..n as usize)
+            .map(|i| match status[i] {
+                sys::OFDM_OK => Ok(out[i * ostride as usize..i * ostride as usize + olen[i] as usize].to_vec()),
+                sys::OFDM_TOO_SHORT => Err(anyhow!("Input not long enough, bailing early")), // src/receiver.rs:28
+                s => Err(anyhow!("{}", unsafe { CStr::from_ptr(sys::ofdm_status_name(s)) }.to_string_lossy())),
+            })
+            .collect())
+    }
+
+    fn check(&self, rc: i32) -> Result<()> {
+        if rc == 0 {
+            Ok(())
+        } else {
+            Err(anyhow!("{}", unsafe { CStr::from_ptr(sys::ofdm_last_error(self.h)) }.to_string_lossy()))
+        }
+    }
+}
+
+impl Drop for Engine {
+    fn drop(&mut self) {
+        unsafe { sys::ofdm_engine_destroy(self.h) }
+    }
+}
+
+/// src/transmitter.rs:10-15 -- same signature (the `#[optargs::optfn]` attribute can be kept on this function).
+pub fn encode(data: &[u8], guard_bands: Option<bool>, modulation: Option<ModulationScheme>) -> Vec<Complex64> {
+    let mut e = Engine::new(guard_bands.unwrap_or(false), modulation.unwrap_or(ModulationScheme::Bpsk), false, 0).expect("engine");
+    e.encode_batch(&[data]).expect("encode").pop().unwrap()
+}
+
+/// src/receiver.rs:8-13 -- same signature and error behaviour.
+pub fn decode(samples: Vec<Complex64>, guard_bands: Option<bool>, modulation: Option<ModulationScheme>) -> Result<Vec<u8>> {
+    let mut e = Engine::new(guard_bands.unwrap_or(false), modulation.unwrap_or(ModulationScheme::Bpsk), false, 0)?;
+    e.decode_batch(&[&samples])?.pop().unwrap()
+}

@@ -107,3 +107,22 @@ def test_shard_helpers():
     assert sh[0][0] == 0 and sh[-1][1] == 10_000_000
     assert all(a[1] - b[0] == 2 * 80 + 163840 for a, b in zip(sh, sh[1:]))
     assert dist.err_rate([3, 2, 300, 0]) == 0.01
+
+
+def test_rust_shim_declares_every_symbol():
+    """rust/ofdm-sys/src/lib.rs (not compilable here: no rustc) must bind exactly the header's functions."""
+    text = open(os.path.join(ROOT, "rust", "ofdm-sys", "src", "lib.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (ofdm_[a-z0-9_]+)\(", text)))
+    assert rust == declared_functions()
+    # struct field order of ofdm_cfg
+    hdr = open(os.path.join(ROOT, "include", "ofdm_engine.h")).read()
+    c_fields = re.findall(r"\b(?:uint32_t|const ofdm_fc32 \*)\s*(\w+);", hdr[hdr.index("typedef struct {\n    uint32_t struct_size"):hdr.index("} ofdm_cfg;")])
+    r_fields = re.findall(r"pub (\w+):", text[text.index("pub struct ofdm_cfg"):text.index("pub struct ofdm_rx_diag")])
+    assert c_fields == r_fields
+
+
+def test_cpp_host_example_builds():
+    from ofdm_b200 import _build
+    _build.build_engine()
+    exe = _build.build_host_example()
+    assert os.access(exe, os.X_OK)

@@ -115,3 +115,25 @@ def test_config1_dancing_bytes_loopback(golden):
             assert st == ref.status
             if ref.status == 0 and oo.analysis(pay, ref.data)[0] == 0:          # where the oracle decodes error-free
                 assert got == pay
+
+
+def test_cpp_host_lab3c_file_roundtrip(tmp_path):
+    """The C++ host mirror (ofdm_b200/host): lab3c --transmit -> fc32 file -> channel -> lab3c --receive --start/--stop."""
+    import subprocess
+    from ofdm_b200 import _build
+    from oracle import oracle as oo
+    import ofdm_b200 as ob
+    exe = _build.build_host_example()
+    pay = bytes(range(256)) * 2 + b"lab3c"
+    (tmp_path / "in.bin").write_bytes(pay)
+    subprocess.run([exe, "--transmit", str(tmp_path / "tx.dat"), "--payload", str(tmp_path / "in.bin"), "--qpsk", "--guard"], check=True)
+    tx = ob.bytes_to_sig((tmp_path / "tx.dat").read_bytes())
+    np.testing.assert_allclose(tx, oo.encode(pay, True, oo.QPSK), atol=2e-6)
+    cap = np.concatenate([np.zeros(100), oo.channel(tx, 30.0, 0.02, 0, 3), np.zeros(50)])
+    (tmp_path / "rx.dat").write_bytes(ob.sig_to_bytes(cap))
+    subprocess.run([exe, "--receive", str(tmp_path / "rx.dat"), "--out", str(tmp_path / "out.bin"), "--start", "100", "--stop", str(100 + tx.size + 63),
+                    "--qpsk", "--guard"], check=True)
+    assert (tmp_path / "out.bin").read_bytes() == pay
+    r = subprocess.run([exe, "--receive", str(tmp_path / "rx.dat"), "--out", str(tmp_path / "o2.bin"), "--stop", "500", "--qpsk", "--guard"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Input not long enough" in r.stderr
