@@ -7,9 +7,15 @@ rep, lib, kern = sys.argv[1:4]
 units = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hdr = rows[1]
-data = rows[2:]
-iex, ismp, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
+sections, cur_sec = [], None           # one section per profiled kernel: ["Kernel Name", name], header row, instruction rows
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur_sec = {"name": r[1], "hdr": None, "data": []}
+        sections.append(cur_sec)
+    elif cur_sec is not None and cur_sec["hdr"] is None:
+        cur_sec["hdr"] = r
+    elif cur_sec is not None:
+        cur_sec["data"].append(r)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -28,7 +34,11 @@ for l in dis[start + 1:]:
     m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", l)
     if m:
         lines.append((cur, m.group(1)))
-assert len(lines) == len(data), (len(lines), len(data))
+sec = next((x for x in sections if len(x["data"]) == len(lines)), None)
+assert sec is not None, (len(lines), [(x["name"][:40], len(x["data"])) for x in sections])
+hdr, data = sec["hdr"], sec["data"]
+iex, ismp, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
+print("kernel:", sec["name"])
 agg, smp = collections.Counter(), collections.Counter()
 tot = 0
 for (loc, _), r in zip(lines, data):
