@@ -32,6 +32,14 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+def host_threads() -> int:
+    """All the host threads this process may use (torchrun pins OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,7 +330,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as oo
-        threads = oo.max_threads()
+        threads = host_threads()
         k = min(n_streams, 2 * threads)
         iq_h = rx[:k].cpu().numpy().view(np.complex64).reshape(k, iq_stride)
         ns_h = rx_len[:k].cpu().numpy().astype(np.uint32)
@@ -360,7 +368,7 @@ def reference_arm(args):
     synthesised on the CPU by the oracle's own TX + channel.
     """
     from oracle import oracle as oo
-    threads = oo.max_threads()
+    threads = host_threads()
     cfg = oracle_cfg()
     S = args.syms
     # largest payload that fits S data symbols (same arithmetic as ofdm_max_payload)
