@@ -222,16 +222,23 @@ __device__ __forceinline__ cpx phasor_from_turns_p(uint64_t turns)
     return c_make(c, s);
 }
 
-__device__ __forceinline__ void rx_lane_init_p(RxLaneP &L, const StreamState *st, const float2 *__restrict__ w64, int l)
+// `rot` (0 or 1): register j of this lane holds sample chunk (j + rot) & 7, i.e. x[l + 8((j + rot) & 7)]. A cyclic shift of
+// the radix-8 input only multiplies output ka by W8^(rot*ka) (shift theorem), which is folded into the lane twiddles:
+// W64^(l*ka) * W8^(rot*ka) = W64^((l + 8 rot) ka). Odd 8-lane groups use rot = 1 so that the two groups of a half-warp read
+// their staged symbols (640 B apart = same banks) from different banks.
+__device__ __forceinline__ void rx_lane_init_p(RxLaneP &L, const StreamState *st, const float2 *__restrict__ w64, int l, int rot)
 {
 #pragma unroll
-    for (int ka = 0; ka < 8; ka++) L.tw[ka] = c_from(__ldg(w64 + ((l * ka) & 63)));
+    for (int ka = 0; ka < 8; ka++) L.tw[ka] = c_from(__ldg(w64 + (((l + 8 * rot) * ka) & 63)));
     const uint64_t fstep = st->fstep;
-    // exp(-j f (l + 8j)) = exp(-j f l) * exp(-j f 8)^j : two exact phasors + a 7-step recurrence (error ~ 7 ulp)
-    L.w[0] = phasor_from_turns_p(fstep * (uint64_t)l);
+    // exp(-j f (l + 8m)) = exp(-j f l) * exp(-j f 8)^m : exact phasors for m = rot and the step, then a recurrence (error ~ 7 ulp)
     const cpx step = phasor_from_turns_p(fstep * 8ull);
+    cpx w = phasor_from_turns_p(fstep * (uint64_t)(l + 8 * rot));
 #pragma unroll
-    for (int j = 1; j < 8; j++) L.w[j] = c_mul(L.w[j - 1], step);
+    for (int j = 0; j < 8; j++) {
+        L.w[j] = w;                                        // chunk (j + rot) & 7
+        if (j + 1 < 8) w = (rot && j == 6) ? phasor_from_turns_p(fstep * (uint64_t)l) : c_mul(w, step);
+    }
 #pragma unroll
     for (int j = 0; j < 8; j++) L.g[j] = c_from(st->g[l + 8 * j]);
 }
@@ -347,7 +354,8 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     if (s_fast > S) s_fast = S;
     float2 *stage_w = s_stage + warp * (4 * kStageGroup);          // [group][kStageGroup]
     uint64_t *bar = s_bar + warp;
-    const unsigned long long *stage_rd = reinterpret_cast<const unsigned long long *>(stage_w + shift + g * kSym + kCp + l);
+    const unsigned long long *stage_rd = reinterpret_cast<const unsigned long long *>(stage_w + shift + g * kSym + kCp + l + 8 * (g & 1));
+    const unsigned long long *stage_rd7 = stage_rd + ((g & 1) ? -8 : 56);                       // chunk (7 + rot) & 7
     auto tile_t0 = [&](int tile) { int t = tile * kTileSyms - a.tile_shift; return t < 0 ? 0 : t; };
     auto tile_t1 = [&](int tile) { int t = (tile + 1) * kTileSyms - a.tile_shift; return t > S ? S : t; };
     // one copy for the 4 symbols sb .. sb+3 of a warp iteration when all of them are below lim; lane 0 only
@@ -368,8 +376,9 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
         issue(tile_t0(tile_first) + warp * (4 * kDecIters), s_fast < t1 ? s_fast : t1);
     }
 
+    const int rot = g & 1;                                          // see rx_lane_init_p
     RxLaneP L;
-    rx_lane_init_p(L, st, a.tables->w64, l);
+    rx_lane_init_p(L, st, a.tables->w64, l, rot);
     // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins are not stored)
     int off[8];
 #pragma unroll
@@ -397,12 +406,13 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
             phase ^= 1;
             if (s_warp + 4 * it + 4 <= lim) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) z[j].v = stage_rd[8 * j];
+                for (int j = 0; j < 7; j++) z[j].v = stage_rd[8 * j];          // chunk j + rot
+                z[7].v = stage_rd7[0];                                          // chunk (7 + rot) & 7
             } else {
                 float zr[8], zi[8];
                 rx_load_symbol(x0, n_avail, (uint32_t)s, s < t1, l, zr, zi);
 #pragma unroll
-                for (int j = 0; j < 8; j++) z[j] = c_make(zr[j], zi[j]);
+                for (int j = 0; j < 8; j++) z[j] = rot ? c_make(zr[(j + 1) & 7], zi[(j + 1) & 7]) : c_make(zr[j], zi[j]);
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) z[j] = c_mul(z[j], L.w[j]);            // src/receiver.rs:44-50 (intra-symbol part)
