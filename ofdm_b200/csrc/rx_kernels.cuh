@@ -254,13 +254,13 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, cpx base, float2 *
     cpx rot = base;                                                        // common rotation of the data bins
     if (GUARD) {
         // pilots: bins 6, 25, 39, 58 = (lane, kb) (6,0) (1,3) (7,4) (2,7)   src/receiver.rs:125-128
-        cpx p = c_make(0.0f, 0.0f);
-        if (l == 6) p = z[0];
-        if (l == 1) p = z[3];
-        if (l == 7) p = z[4];
-        if (l == 2) p = z[7];
         if (PHASE == 1) {
             // angle of the pilot sum: the per-symbol base phasor cancels, rot = conj(sum)/|sum|
+            cpx p = c_make(0.0f, 0.0f);
+            if (l == 6) p = z[0];
+            if (l == 1) p = z[3];
+            if (l == 7) p = z[4];
+            if (l == 2) p = z[7];
             float pr, pi;
             c_split(p, pr, pi);
 #pragma unroll
@@ -272,6 +272,11 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, cpx base, float2 *
             rot = c_make(pr * inv, -pi * inv);
         } else {
             // reference: mean of the four pilot angles (after the full derotation), src/receiver.rs:126,137
+            cpx p = c_make(0.0f, 0.0f);
+            if (l == 6) p = z[0];
+            if (l == 1) p = z[3];
+            if (l == 7) p = z[4];
+            if (l == 2) p = z[7];
             float pr, pi;
             c_split(c_mul(p, base), pr, pi);
             const bool pilot_lane = (l == 6) | (l == 1) | (l == 7) | (l == 2);
@@ -383,6 +388,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     int off[8];
 #pragma unroll
     for (int kb = 0; kb < 8; kb++) off[kb] = data_rank<GUARD>(l + 8 * kb);
+    const int d3 = 24 - (l >= 2), d4 = 31 - (l >= 1);               // rank(l + 24) - (l - 7), rank(l + 32) - (l - 7)
     const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)(4 * kSym));
     uint8_t *out = a.out + (size_t)stream * a.out_stride;
     uint32_t phase = 0;                                             // mbarrier phase parity
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
         const int s_first = s_warp + g;
         // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
         cpx base = phasor_from_turns_p(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp));
-        uint8_t *rowp = s_car + (s_first - t0) * D;
+        uint8_t *rowp = s_car + (s_first - t0) * D + (GUARD ? l - 7 : l);       // row of this group's symbol, biased by the lane
 
 #pragma unroll 1
         for (int it = 0; it < kDecIters; it++) {
@@ -431,9 +437,14 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
                 float zr, zi;
                 c_split(z[kb], zr, zi);
                 uint32_t v = MOD == 2 ? demap_qam64_lut(zr, zi, qam_biased) : demap_point<MOD>(zr, zi);
-                // bins l + 8kb for kb in {1, 2, 5, 6} are data carriers on every lane
-                if (!GUARD || kb == 1 || kb == 2 || kb == 5 || kb == 6) rowp[off[kb]] = (uint8_t)v;
-                else st_shared_u8_if_nonneg(rowp + off[kb], v, off[kb]);
+                // carrier rank of bin l + 8kb is affine in kb except at the pilot / DC crossings (kb = 3, 4): immediate
+                // offsets from one row pointer; kb in {1, 2, 5, 6} are data carriers on every lane
+                if (!GUARD) rowp[8 * kb] = (uint8_t)v;
+                else if (kb == 1 || kb == 2) rowp[8 * kb] = (uint8_t)v;
+                else if (kb == 5 || kb == 6) rowp[8 * kb - 3] = (uint8_t)v;
+                else if (kb == 3) st_shared_u8_if_nonneg(rowp + d3, v, off[3]);
+                else if (kb == 4) st_shared_u8_if_nonneg(rowp + d4, v, off[4]);
+                else st_shared_u8_if_nonneg(rowp + (kb == 0 ? 0 : 53), v, off[kb]);
                 if (POINTS && s < t1 && (!GUARD || off[kb] >= 0)) {
                     size_t p = (size_t)s * D + off[kb];
                     if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
