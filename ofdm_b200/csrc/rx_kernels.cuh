@@ -212,7 +212,6 @@ __device__ __forceinline__ void rx_symbol(const RxLane &L, float br, float bi, f
 struct RxLaneP {
     cpx tw[8];   // FFT twiddles W64^(l*ka)
     cpx w[8];    // derotation inside a symbol: exp(-j f (l + 8j))
-    cpx g[8];    // equaliser 1/h at bins l + 8kb
 };
 
 __device__ __forceinline__ cpx phasor_from_turns_p(uint64_t turns)
@@ -239,18 +238,21 @@ __device__ __forceinline__ void rx_lane_init_p(RxLaneP &L, const StreamState *st
         L.w[j] = w;                                        // chunk (j + rot) & 7
         if (j + 1 < 8) w = (rot && j == 6) ? phasor_from_turns_p(fstep * (uint64_t)l) : c_mul(w, step);
     }
-#pragma unroll
-    for (int j = 0; j < 8; j++) L.g[j] = c_from(st->g[l + 8 * j]);
 }
 
 // One OFDM symbol per 8-lane group, derotated samples in z: FFT, equalise, pilot phase.
 // On return z[kb] is the equalised + phase-corrected value of bin l + 8kb.
 template <bool GUARD, int PHASE>
-__device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, cpx base, float2 *tr, int l, cpx (&z)[8])
+__device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *__restrict__ g_row, cpx base, float2 *tr, int l, cpx (&z)[8])
 {
     fft64_group_p(z, L.tw, tr, l);                                         // src/receiver.rs:99-104
 #pragma unroll
-    for (int kb = 0; kb < 8; kb++) z[kb] = c_mul(z[kb], L.g[kb]);          // src/receiver.rs:67-70
+    for (int q = 0; q < 4; q++) {                                          // src/receiver.rs:67-70; 1/h_k of this lane's bins from smem
+        const ulonglong2 gg = g_row[q];
+        cpx g0, g1;
+        g0.v = gg.x; g1.v = gg.y;
+        z[2 * q] = c_mul(z[2 * q], g0); z[2 * q + 1] = c_mul(z[2 * q + 1], g1);
+    }
     cpx rot = base;                                                        // common rotation of the data bins
     if (GUARD) {
         // pilots: bins 6, 25, 39, 58 = (lane, kb) (6,0) (1,3) (7,4) (2,7)   src/receiver.rs:125-128
@@ -303,11 +305,11 @@ constexpr int kStageBytes = 4 * kSym * 8 + 16;       // 4 consecutive OFDM symbo
 constexpr int kStageGroup = (kStageBytes + 15) / 16 * 2 / 4 + 1;   // float2 per warp staging slot / 4
 template <bool GUARD> constexpr size_t rx_decode_smem_bytes()
 {
-    return sizeof(float2) * (kDecWarps * 4 * kStageGroup + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * kDecWarps;
+    return sizeof(float2) * (kDecWarps * 4 * kStageGroup + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * kDecWarps + 8 * kTrRow * sizeof(float2);
 }
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
-__global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs a)
+__global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(const RxArgs a)
 {
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 48 : 64;
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     uint8_t *s_ham = s_car + (kTileSyms * D + 64);
     uint8_t *s_qam = s_ham + 128;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_qam + 256);
+    float2 *s_g = reinterpret_cast<float2 *>(s_bar + kDecWarps);                    // [lane l][kTrRow]: 1/h at bins l + 8kb, padded rows
 
     // A CTA owns `tiles_per_cta` consecutive 224-symbol tiles of one stream. Tile k covers symbols
     // [k*224 - tile_shift, (k+1)*224 - tile_shift) n [0, S): every inner boundary falls on a Hamming byte boundary.
@@ -340,6 +343,8 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
     if (MOD == 2) s_qam[tid] = qam64_lut_entry(tid);
+    if (tid < 64) s_g[(tid & 7) * kTrRow + (tid >> 3)] = st->g[tid];
+    const ulonglong2 *g_row = reinterpret_cast<const ulonglong2 *>(s_g + (threadIdx.x & 7) * kTrRow);
 
     const uint32_t n_samples = a.n_samples[stream];
     const uint32_t offset = (uint32_t)st->offset;
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(kDecThreads, 3) rx_decode_kernel(const RxArgs 
                 const int n1 = tile_t1(tile + 1);
                 issue(t1 + warp * (4 * kDecIters), s_fast < n1 ? s_fast : n1);
             }
-            rx_symbol_p<GUARD, PHASE>(L, base, tr, l, z);
+            rx_symbol_p<GUARD, PHASE>(L, g_row, base, tr, l, z);
             base = c_mul(base, dbase);
             // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
 #pragma unroll
