@@ -153,6 +153,22 @@ int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t
                              uint32_t *lead_out, float *cfo_out, int mem, void *stream);
 
 /*
+ * Preamble search over ONE long capture: replaces `samples.xcorr_fft(locking_signal)` on a whole radio buffer
+ * (src/receiver.rs:20-21, src/signals/mod.rs:186-217; examples/jetson_rx.rs:46-57,84 is the 2 M-sample case) with a single
+ * 8 B/sample pass of the sliding Schmidl-Cox metric (docs/SPEC.md 4): every frame start is reported once as
+ * (offset by the lag-1 rule, CFO estimate, metric). n_samples < 2^32. peaks[0 .. *n_peaks) is in ascending offset order;
+ * with OFDM_MEM_DEVICE entries whose metric < 0 are unusable detections (frame head cut by the capture end) and
+ * *n_peaks counts them too; with OFDM_MEM_HOST they are removed. More than max_peaks detections are truncated.
+ */
+typedef struct {
+    uint64_t offset;
+    float    f_delta;
+    float    metric;
+} ofdm_peak;
+int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, ofdm_peak *peaks, uint32_t max_peaks,
+                     uint32_t *n_peaks, int mem, void *stream);
+
+/*
  * BER: replaces utils::Analysis::new (src/utils.rs:45-68) for a batch and accumulates into
  * counters[4] = { bit_errs, byte_errs, bits_compared, frames_failed }. A stream whose status != OK or
  * whose length differs from ref_len counts as failed with all its reference bits in error.

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "rx_kernels.cuh"
 #include "tables.h"
+#include "sync_kernels.cuh"
 #include "tx_kernels.cuh"
 
 using namespace ofdm;
@@ -50,6 +51,7 @@ struct ofdm_engine {
     DevBuf scratch_u32;                 // frame_len / stream_max
     DevBuf scratch_f32;                 // channel accumulators
     DevBuf counters;                    // 4 x u64
+    DevBuf sync_scratch;                // candidate list + counters of ofdm_sync_search
     // host-mode staging
     DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
@@ -282,7 +284,7 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     cudaSetDevice(h->device);
     if (h->d_tables) cudaFree(h->d_tables);
     DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
-                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h };
+                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch };
     for (DevBuf *b : bufs) b->release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -582,6 +584,61 @@ extern "C" int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, con
     if (lead_out) CU(h, cudaMemcpyAsync(lead_out, d_lead, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
     if (cfo_out) CU(h, cudaMemcpyAsync(cfo_out, d_cfo, sizeof(float) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- capture search ----------------------------------------------------------------------------------------------
+static int sync_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak *peaks, uint32_t max_peaks, uint32_t *n_peaks, cudaStream_t st)
+{
+    static_assert(sizeof(SyncPeak) == sizeof(ofdm_peak), "peak layout");
+    CU(h, h->sync_scratch.ensure(sizeof(uint32_t) * (kSyncCandCap + 8)));
+    SyncArgs a{};
+    a.iq = reinterpret_cast<const float2 *>(iq); a.n = n;
+    a.cand = h->sync_scratch.as<uint32_t>(); a.counters = a.cand + kSyncCandCap;
+    a.tables = h->d_tables; a.peaks = reinterpret_cast<SyncPeak *>(peaks); a.max_peaks = max_peaks;
+    CU(h, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), st));
+    if (n >= 2 * kSym) {
+        const uint64_t lags = n - 2 * kSym + 1;
+        const uint32_t grid = (uint32_t)((lags + kScanD - 1) / kScanD);
+        if (h->smem_configured.insert((const void *)sync_scan_kernel).second)
+            CU(h, cudaFuncSetAttribute((const void *)sync_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_scan_smem_bytes()));
+        sync_scan_kernel<<<grid, kScanRows, sync_scan_smem_bytes(), st>>>(a);
+        sync_select_kernel<<<1, 1024, 0, st>>>(a);
+        const uint32_t rg = max_peaks < (uint32_t)kSyncCandCap ? max_peaks : (uint32_t)kSyncCandCap;
+        if (rg) sync_refine_kernel<<<rg, kAcqThreads, 0, st>>>(a);
+        h->launches += 3;
+    }
+    CU(h, cudaGetLastError());
+    // *n_peaks = min(accepted, max_peaks); a candidate overflow is reported through ofdm_sync_candidates()
+    CU(h, cudaMemcpyAsync(n_peaks, a.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, ofdm_peak *peaks, uint32_t max_peaks,
+                                uint32_t *n_peaks, int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!iq || !peaks || !n_peaks || max_peaks == 0) ENG_FAIL(h, OFDM_E_INVALID, "sync: bad arguments");
+    if (n_samples >= 0xFFFFFFFFull) ENG_FAIL(h, OFDM_E_INVALID, "sync: captures are limited to 2^32 - 2 samples per call");
+    CU(h, cudaSetDevice(h->device));
+    if (mem == OFDM_MEM_DEVICE) return sync_device(h, iq, n_samples, peaks, max_peaks, n_peaks, (cudaStream_t)stream);
+    cudaStream_t st = h->own_stream;
+    CU(h, h->s_iq.ensure(n_samples * sizeof(float2) + 16));
+    CU(h, h->s_points.ensure(sizeof(ofdm_peak) * (size_t)max_peaks + 16));
+    CU(h, h->s_len.ensure(16));
+    CU(h, cudaMemcpyAsync(h->s_iq.p, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, st));
+    int rc = sync_device(h, h->s_iq.as<ofdm_fc32>(), n_samples, h->s_points.as<ofdm_peak>(), max_peaks, h->s_len.as<uint32_t>(), st);
+    if (rc) return rc;
+    uint32_t cnt[2] = { 0, 0 };
+    CU(h, cudaMemcpyAsync(cnt, h->sync_scratch.as<uint32_t>() + kSyncCandCap, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    if (cnt[0] > (uint32_t)kSyncCandCap) ENG_FAIL(h, OFDM_E_INVALID, "sync: %u threshold crossings exceed the candidate capacity %d; split the capture", cnt[0], kSyncCandCap);
+    uint32_t m = cnt[1] < max_peaks ? cnt[1] : max_peaks;
+    std::vector<ofdm_peak> tmp(m);
+    if (m) CU(h, cudaMemcpy(tmp.data(), h->s_points.p, sizeof(ofdm_peak) * m, cudaMemcpyDeviceToHost));
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < m; i++) if (tmp[i].metric >= 0.0f) peaks[k++] = tmp[i];
+    *n_peaks = k;
     return 0;
 }
 

@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
     if (SYNC == 0) {
         offset = (long)ramp_argmax(x, M, -(kSym - 1), W - 1, s_lock, s_val, s_idx) - 1;     // src/receiver.rs:21: lag - 1
     } else {
-        // sliding Schmidl-Cox (docs/SPEC.md 4): P(d) = Q[d+80] - Q[d], R(d) = E[d+160] - E[d+80]
+        // sliding Schmidl-Cox (docs/SPEC.md 4): P(d) = Q[d+80] - Q[d], R1(d) = E[d+80] - E[d], R2(d) = E[d+160] - E[d+80]
         long d_end = W;
         if (d_end > M - 2 * kSym + 1) d_end = M - 2 * kSym + 1;
         for (long base = 0; base < d_end; base += kAcqChunk) {
@@ -665,8 +665,8 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
             for (int i = tid; i < kAcqChunk && base + i < d_end; i += kAcqThreads) {
                 float2 qa = s_q[i], qb = s_q[i + kSym];
                 float pr = qb.x - qa.x, pi = qb.y - qa.y;
-                float rr = s_e[i + 2 * kSym] - s_e[i + kSym];
-                if (pr * pr + pi * pi > 0.5f * rr * rr) { found = i; break; }
+                float r1 = s_e[i + kSym] - s_e[i], r2 = s_e[i + 2 * kSym] - s_e[i + kSym];
+                if (pr * pr + pi * pi > 0.5f * r1 * r2) { found = i; break; }
             }
             if (found != 0x7fffffff) atomicMin(&s_d0, (int)(base + found));
             __syncthreads();

@@ -27,6 +27,7 @@ EXPORTS = [
     "ofdm_last_error", "ofdm_get_tables", "ofdm_host_alloc", "ofdm_host_free", "ofdm_coded_len",
     "ofdm_frame_data_syms", "ofdm_frame_len", "ofdm_max_payload", "ofdm_tx_encode_batch", "ofdm_rx_decode_batch",
     "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches", "ofdm_profile_begin", "ofdm_profile_read",
+    "ofdm_sync_search",
 ]
 
 
@@ -56,6 +57,8 @@ class CChannelParams(C.Structure):
         ("multipath", C.c_uint32), ("noise_mode", C.c_uint32), ("seed", C.c_uint64),
     ]
 
+
+PEAK_DTYPE = np.dtype([("offset", np.uint64), ("f_delta", np.float32), ("metric", np.float32)])      # = ofdm_peak
 
 _lib = None
 
@@ -101,6 +104,8 @@ def load_library(build: bool = False) -> C.CDLL:
     L.ofdm_profile_begin.restype = i32
     L.ofdm_profile_read.argtypes = [vp, vp, vp, vp]
     L.ofdm_profile_read.restype = i32
+    L.ofdm_sync_search.argtypes = [vp, vp, u64, vp, u32, vp, i32, vp]
+    L.ofdm_sync_search.restype = i32
     L.ofdm_kernel_launches.argtypes = [vp]
     L.ofdm_kernel_launches.restype = u64
     _lib = L
@@ -309,6 +314,19 @@ class Engine:
                                                       rx_stride, _ptr(rx_len), _ptr(lead), _ptr(cfo), MEM_HOST, None),
                     "ofdm_channel_apply_batch")
         return rx, rx_len, lead, cfo
+
+    def sync_search(self, iq: np.ndarray, max_peaks: int = 4096) -> np.ndarray:
+        """Preamble search over one long capture (complex64). Returns a structured array (offset, f_delta, metric)."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        peaks = np.zeros(max_peaks, PEAK_DTYPE)
+        n = C.c_uint32(0)
+        self._check(self.lib.ofdm_sync_search(self._h, _ptr(iq), iq.size, _ptr(peaks), max_peaks, C.byref(n), MEM_HOST, None),
+                    "ofdm_sync_search")
+        return peaks[: n.value].copy()
+
+    def sync_search_device(self, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, stream=0):
+        self._check(self.lib.ofdm_sync_search(self._h, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, MEM_DEVICE, stream or None),
+                    "ofdm_sync_search")
 
     def ber(self, ref: np.ndarray, ref_len, got: np.ndarray, got_len, status) -> np.ndarray:
         """Batch utils::Analysis (src/utils.rs:45-68) -> [bit_errs, byte_errs, bits_compared, frames_failed]."""

@@ -683,20 +683,22 @@ static int find_offset(const oo_c64 *a, size_t n, const oo_cfg *cfg, long *offse
     /* Schmidl-Cox, docs/SPEC.md section 4 */
     long d0 = -1;
     oo_c64 P = c_make(0.0, 0.0);
-    double R = 0.0;
+    double R1 = 0.0, R2 = 0.0;
     for (long d = 0; d < W && (size_t)(d + 160) <= n; d++) {
         if (d == 0 || (d & 1023) == 0) {           /* exact re-sum periodically: no drift */
-            P = c_make(0.0, 0.0); R = 0.0;
+            P = c_make(0.0, 0.0); R1 = 0.0; R2 = 0.0;
             for (int m = 0; m < NSYM; m++) {
                 P = c_add(P, c_mul(c_conj(a[d + m]), a[d + m + NSYM]));
-                R += c_norm_sqr(a[d + m + NSYM]);
+                R1 += c_norm_sqr(a[d + m]);
+                R2 += c_norm_sqr(a[d + m + NSYM]);
             }
         } else {
             P = c_sub(P, c_mul(c_conj(a[d - 1]), a[d - 1 + NSYM]));
             P = c_add(P, c_mul(c_conj(a[d - 1 + NSYM]), a[d - 1 + 2 * NSYM]));
-            R += c_norm_sqr(a[d - 1 + 2 * NSYM]) - c_norm_sqr(a[d - 1 + NSYM]);
+            R1 += c_norm_sqr(a[d - 1 + NSYM]) - c_norm_sqr(a[d - 1]);
+            R2 += c_norm_sqr(a[d - 1 + 2 * NSYM]) - c_norm_sqr(a[d - 1 + NSYM]);
         }
-        if (c_norm_sqr(P) > 0.5 * R * R) { d0 = d; break; }
+        if (c_norm_sqr(P) > 0.5 * R1 * R2) { d0 = d; break; }
     }
     if (d0 < 0) return OO_NO_SYNC;
     long k_lo = d0 - 176, k_hi = d0 + 16;
@@ -817,6 +819,73 @@ int oo_decode(const oo_c64 *samples, size_t n, const oo_cfg *cfg,
     free(bytes);
     diag->status = OO_OK;
     return OO_OK;
+}
+
+/* docs/SPEC.md section 4 (capture search). The reference's equivalent is the whole-capture xcorr_fft of
+ * src/receiver.rs:20-21, which finds only the single strongest frame of a buffer (examples/jetson_rx.rs:84). */
+size_t oo_sync_search(const oo_c64 *a, size_t n, oo_peak *peaks, size_t max_peaks)
+{
+    if (n < 2 * NSYM) return 0;
+    oo_c64 lock[NSYM];
+    oo_locking_signal(lock, NSYM);
+    size_t np = 0;
+    long d_last = (long)n - 2 * NSYM;
+    long last_acc = -800;
+    int prev_above = 0;
+    oo_c64 P = c_make(0.0, 0.0);
+    double R1 = 0.0, R2 = 0.0;
+    for (long d = 0; d <= d_last; d++) {
+        if ((d & 1023) == 0) {                    /* exact re-sum periodically: no drift */
+            P = c_make(0.0, 0.0); R1 = 0.0; R2 = 0.0;
+            for (int m = 0; m < NSYM; m++) {
+                P = c_add(P, c_mul(c_conj(a[d + m]), a[d + m + NSYM]));
+                R1 += c_norm_sqr(a[d + m]);
+                R2 += c_norm_sqr(a[d + m + NSYM]);
+            }
+        } else {
+            P = c_sub(P, c_mul(c_conj(a[d - 1]), a[d - 1 + NSYM]));
+            P = c_add(P, c_mul(c_conj(a[d - 1 + NSYM]), a[d - 1 + 2 * NSYM]));
+            R1 += c_norm_sqr(a[d - 1 + NSYM]) - c_norm_sqr(a[d - 1]);
+            R2 += c_norm_sqr(a[d - 1 + 2 * NSYM]) - c_norm_sqr(a[d - 1 + NSYM]);
+        }
+        int above = c_norm_sqr(P) > 0.5 * R1 * R2;
+        if (above && !prev_above && d >= last_acc + 800) {
+            last_acc = d;
+            long k_lo = d - 176, k_hi = d + 16;
+            if (k_lo < -(NSYM - 1)) k_lo = -(NSYM - 1);
+            long offset = ramp_argmax(a, n, k_lo, k_hi, lock) - 1;
+            if (offset >= 0 && (size_t)offset + 800 <= n && np < max_peaks) {
+                const oo_c64 *x = a + offset;
+                oo_c64 s = c_make(0.0, 0.0);
+                for (int i = 0; i < NSYM; i++) {
+                    s = c_add(s, c_mul(c_conj(x[2 * NSYM + i]), x[3 * NSYM + i]));
+                    s = c_add(s, c_mul(c_conj(x[3 * NSYM + i]), x[4 * NSYM + i]));
+                }
+                oo_c64 p0 = c_make(0.0, 0.0);
+                double r1 = 0.0, r2 = 0.0;
+                for (int m = 0; m < NSYM; m++) {
+                    p0 = c_add(p0, c_mul(c_conj(a[d + m]), a[d + m + NSYM]));
+                    r1 += c_norm_sqr(a[d + m]);
+                    r2 += c_norm_sqr(a[d + m + NSYM]);
+                }
+                peaks[np].offset = (uint64_t)offset;
+                peaks[np].f_delta = oo_angle(s) / 80.0;
+                peaks[np].metric = c_norm_sqr(p0) / (r1 * r2);
+                np++;
+            }
+        }
+        prev_above = above;
+    }
+    return np;
+}
+
+size_t oo_sync_search_fc32(const float *iq, size_t n, oo_peak *peaks, size_t max_peaks)
+{
+    oo_c64 *x = (oo_c64 *)malloc(sizeof(oo_c64) * (n + 1));
+    oo_fc32_to_sig(iq, n, x);
+    size_t r = oo_sync_search(x, n, peaks, max_peaks);
+    free(x);
+    return r;
 }
 
 int oo_max_threads(void)

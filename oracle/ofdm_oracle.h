@@ -106,6 +106,12 @@ int oo_decode(const oo_c64 *samples, size_t n, const oo_cfg *cfg,
               uint8_t *out, size_t out_cap, size_t *out_len,
               oo_c64 *points, size_t points_cap, oo_diag *diag);
 
+/* preamble search over one long capture (docs/SPEC.md section 4: sliding Schmidl-Cox rising edges, 800-sample hold-off,
+ * ramp-correlation refinement with the lag-1 rule, angle-of-sum CFO). Returns the number of peaks written. */
+typedef struct { uint64_t offset; double f_delta; double metric; } oo_peak;
+size_t oo_sync_search(const oo_c64 *a, size_t n, oo_peak *peaks, size_t max_peaks);
+size_t oo_sync_search_fc32(const float *iq, size_t n, oo_peak *peaks, size_t max_peaks);
+
 /* fc32 batch front end used by the CPU baseline: threads = OpenMP threads (0 = default). */
 int oo_decode_batch_fc32(const float *iq, const uint32_t *n_samples, uint32_t n_streams, size_t iq_stride,
                          const oo_cfg *cfg, uint8_t *out, size_t out_stride, uint32_t *out_len,

@@ -107,6 +107,8 @@ def lib() -> C.CDLL:
     L.oo_decode_batch_fc32.argtypes = [vp, vp, C.c_uint32, sz, C.POINTER(OoCfg), vp, sz, vp, vp, vp, i32]
     L.oo_decode_batch_fc32.restype = i32
     L.oo_max_threads.restype = i32
+    L.oo_sync_search_fc32.argtypes = [vp, sz, vp, sz]
+    L.oo_sync_search_fc32.restype = sz
     L.oo_angle.argtypes = [C.c_double * 2]
     _lib = L
     return L
@@ -317,3 +319,14 @@ def decode_batch_fc32(iq: np.ndarray, n_samples: np.ndarray, cfg: OoCfg, out_str
 
 def max_threads() -> int:
     return int(lib().oo_max_threads())
+
+
+PEAK_DTYPE = np.dtype([("offset", np.uint64), ("f_delta", np.float64), ("metric", np.float64)])
+
+
+def sync_search(iq_c64: np.ndarray, max_peaks: int = 4096) -> np.ndarray:
+    """Capture search (docs/SPEC.md 4). iq_c64: complex64 capture. Returns a structured array (offset, f_delta, metric)."""
+    x = np.ascontiguousarray(iq_c64, dtype=np.complex64)
+    peaks = np.zeros(max_peaks, PEAK_DTYPE)
+    n = lib().oo_sync_search_fc32(_p(x), x.size, _p(peaks), max_peaks)
+    return peaks[:n].copy()

@@ -72,6 +72,14 @@ pub struct ofdm_channel_params {
     pub seed: u64,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct ofdm_peak {
+    pub offset: u64,
+    pub f_delta: f32,
+    pub metric: f32,
+}
+
 extern "C" {
     pub fn ofdm_abi_version() -> u32;
     pub fn ofdm_cfg_default(cfg: *mut ofdm_cfg);
@@ -97,6 +105,8 @@ extern "C" {
     pub fn ofdm_ber_accumulate(h: *mut ofdm_engine, reference: *const u8, ref_len: *const u32, ref_stride: u32, got: *const u8,
                                got_len: *const u32, got_stride: u32, status: *const i32, n_streams: u32, counters: *mut u64,
                                mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn ofdm_sync_search(h: *mut ofdm_engine, iq: *const ofdm_fc32, n_samples: u64, peaks: *mut ofdm_peak, max_peaks: u32,
+                            n_peaks: *mut u32, mem: c_int, stream: *mut c_void) -> c_int;
     pub fn ofdm_profile_begin(h: *mut ofdm_engine, max_calls: u32) -> c_int;
     pub fn ofdm_profile_read(h: *mut ofdm_engine, acquire_ms: *mut f32, decode_ms: *mut f32, n_calls: *mut u32) -> c_int;
     pub fn ofdm_kernel_launches(h: *const ofdm_engine) -> u64;

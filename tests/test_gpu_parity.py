@@ -270,3 +270,63 @@ def test_host_and_device_paths_agree(ob, oo):
     assert all((d_o[i, : d_l[i]] == host.out[i, : d_l[i]]).all() for i in range(40))     # bytes past out_len are unspecified
     assert all(host.data[i] == pays[i] for i in range(40))
     eng.close()
+
+
+def _capture_with_frames(oo, rng, n, stride, first, payload_len=300, sigma=0.01, mod=2):
+    cfg = oo.make_cfg(True, mod, True)
+    cap = (sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    truth = []
+    p = first
+    while p + oo.lib().oo_tx_len(payload_len, __import__("ctypes").byref(cfg)) + 200 < n:
+        pay = rng.integers(0, 256, payload_len, dtype=np.uint8)
+        tx = oo.tx(pay, cfg)
+        f = float(rng.uniform(-0.035, 0.035))
+        cap[p: p + tx.size] += (tx * np.exp(1j * f * np.arange(tx.size))).astype(np.complex64)
+        truth.append((p, f))
+        p += stride
+    return cap, truth
+
+
+def test_capture_sync_search_matches_oracle(ob, oo):
+    """BASELINE.json configs[2] in small: frames every 100 003 samples (prime stride: all alignments) in a noise floor,
+    each with its own CFO. Every inserted offset is found exactly (lag - 1 rule), CFO within 1e-4 rad/sample, and the
+    engine's peak list equals the oracle's."""
+    eng = ob.Engine(ob.Config(modulation=2, guard_bands=True, fec=True), 0)
+    rng = np.random.default_rng(33)
+    cap, truth = _capture_with_frames(oo, rng, 3_000_000, 100_003, 777)
+    got = eng.sync_search(cap)
+    ref = oo.sync_search(cap)
+    assert len(got) == len(ref) == len(truth) >= 29
+    for (p, f), g, r in zip(truth, got, ref):
+        assert int(g["offset"]) == int(r["offset"]) == p - 1            # no channel: lock peak at lag p, offset = lag - 1
+        assert abs(float(g["f_delta"]) - float(r["f_delta"])) < 1e-6
+        assert abs(float(g["f_delta"]) - f) < 1e-4
+        assert float(g["metric"]) == pytest.approx(float(r["metric"]), rel=1e-4) and float(g["metric"]) > 0.5
+    # ascending order, and the found offsets decode
+    assert (np.diff(got["offset"].astype(np.int64)) > 0).all()
+    eng.close()
+
+
+def test_capture_sync_search_edges(ob, oo):
+    eng = ob.Engine(ob.Config(modulation=0, guard_bands=True), 0)
+    rng = np.random.default_rng(34)
+    noise = (0.01 * (rng.standard_normal(200_000) + 1j * rng.standard_normal(200_000))).astype(np.complex64)
+    assert len(eng.sync_search(noise)) == len(oo.sync_search(noise)) == 0          # nothing there
+    assert len(eng.sync_search(noise[:100])) == 0                                  # shorter than two preamble periods
+    assert len(eng.sync_search(np.zeros(5000, np.complex64))) == 0                 # all zero: 0 > 0 is false
+    # frames at the very start (offset would be -1 -> dropped), through the lab channel, and cut by the capture end
+    cfg = oo.make_cfg(True, 0, False)
+    tx = oo.tx(bytes(50), cfg)
+    cap = noise[:60_000].copy()
+    cap[: tx.size] += tx.astype(np.complex64)
+    ch = oo.channel(tx, 30.0, 0.02, 1, 5).astype(np.complex64)
+    cap[20_000: 20_000 + ch.size] += ch
+    cap[-700:] += tx[:700].astype(np.complex64)
+    got, ref = eng.sync_search(cap), oo.sync_search(cap)
+    assert [int(x) for x in got["offset"]] == [int(x) for x in ref["offset"]] == [20_008]
+    np.testing.assert_allclose(got["f_delta"], ref["f_delta"], atol=1e-6)
+    # unaligned capture pointer (odd sample offset into a larger buffer) takes the 8-byte load path
+    cap2, truth = _capture_with_frames(oo, rng, 400_001, 50_021, 1001, mod=1)
+    got, ref = eng.sync_search(cap2[1:]), oo.sync_search(cap2[1:])
+    assert [int(x) for x in got["offset"]] == [int(x) for x in ref["offset"]] == [p - 2 for p, _ in truth]
+    eng.close()
