@@ -4,7 +4,7 @@
 // src/signals/mod.rs:186-217: three length-(2M-1) f64 transforms, ~96 GB of scratch at M = 1e9 -- not runnable). Here
 // the capture is scanned once (8 B/sample) with the sliding Schmidl-Cox metric of docs/SPEC.md 4:
 //
-//   sync_scan_kernel   : one CTA per 3920 lags. Coalesced IQ tile -> padded smem rows (one 16-sample row per thread);
+//   sync_scan_kernel   : one CTA per 3928 lags. Coalesced IQ tile -> padded smem rows (one 8-sample row per thread);
 //                        q[n] = conj(a[n]) a[n+80], e[n] = |a[n]|^2; thread-serial + warp-shuffle + block exclusive
 //                        prefix sums; P(d) = Q[d+80]-Q[d], R1(d) = E[d+80]-E[d], R2(d) = E[d+160]-E[d+80]; rising
 //                        edges of |P|^2 > 0.5 R1 R2 are appended to a candidate list.
@@ -17,10 +17,11 @@
 
 namespace ofdm {
 
-constexpr int kScanT = 16;                          // samples per thread = one smem row
-constexpr int kScanRows = 256;                      // rows per CTA (= threads)
-constexpr int kScanEvalRows = kScanRows - 11;       // rows whose lags are evaluated here (row 0 only feeds above(d-1))
-constexpr int kScanD = kScanEvalRows * kScanT;      // 3920 lags per CTA
+constexpr int kScanT = 8;                           // samples per thread = one smem row
+constexpr int kScanRows = 512;                      // rows per CTA (= threads)
+constexpr int kScanR80 = kSym / kScanT;             // rows per 80 samples (10)
+constexpr int kScanEvalRows = kScanRows - 2 * kScanR80 - 1;   // rows whose lags are evaluated here (row 0 only feeds above(d-1))
+constexpr int kScanD = kScanEvalRows * kScanT;      // 3928 lags per CTA
 constexpr int kScanRowStride = kScanT + 1;          // padded row length: conflict-free row-per-thread LDS.64
 constexpr int kSyncCandCap = 8192;                  // candidates the select kernel can sort
 constexpr int kSyncHoldoff = 800;                   // lock + preamble + training: one detection per frame
@@ -43,7 +44,7 @@ struct SyncArgs {
 
 constexpr size_t sync_scan_smem_bytes()
 {
-    return (size_t)kScanRows * kScanRowStride * (sizeof(float2) * 2 + sizeof(float)) + sizeof(float) * 3 * (kScanRows + 8) + sizeof(uint32_t) * (kScanRows + 8);
+    return (size_t)kScanRows * kScanRowStride * (sizeof(float2) * 2 + sizeof(float)) + sizeof(float) * 3 * (kScanRows + 32) + sizeof(uint32_t) * (kScanRows + 8);
 }
 
 __device__ __forceinline__ cpx c_conj_mul(cpx a, cpx b)     // conj(a) * b
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
     unsigned long long *s_q = s_iq + kScanRows * kScanRowStride;                              // thread-local exclusive prefix of q
     float *s_e = reinterpret_cast<float *>(s_q + kScanRows * kScanRowStride);                 // thread-local exclusive prefix of e
     float *s_off = s_e + kScanRows * kScanRowStride;                                          // [3][rows + 8] row offsets (block scan)
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_off + 3 * (kScanRows + 8));
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_off + 3 * (kScanRows + 32));
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const long long n = (long long)a.n;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
             if (s0 >= 0 && s0 < n) v0 = __ldg(reinterpret_cast<const unsigned long long *>(a.iq + s0));
             if (s0 + 1 >= 0 && s0 + 1 < n) v1 = __ldg(reinterpret_cast<const unsigned long long *>(a.iq + s0 + 1));
         }
-        const int row = idx >> 3, col = (idx & 7) * 2;
+        const int row = idx / (kScanT / 2), col = (idx % (kScanT / 2)) * 2;
         s_iq[row * kScanRowStride + col] = v0;
         s_iq[row * kScanRowStride + col + 1] = v1;
     }
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
     float te = 0.0f;
     {
         const unsigned long long *own = s_iq + t * kScanRowStride;
-        const bool has5 = t + 5 < kScanRows;
-        const unsigned long long *nxt = s_iq + (has5 ? t + 5 : t) * kScanRowStride;
+        const bool has5 = t + kScanR80 < kScanRows;
+        const unsigned long long *nxt = s_iq + (has5 ? t + kScanR80 : t) * kScanRowStride;
 #pragma unroll
         for (int j = 0; j < kScanT; j++) {
             cpx x, y;
@@ -116,23 +117,30 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
         float b0 = __shfl_up_sync(0xffffffffu, sr, m), b1 = __shfl_up_sync(0xffffffffu, si, m), b2 = __shfl_up_sync(0xffffffffu, se, m);
         if (lane >= m) { sr += b0; si += b1; se += b2; }
     }
-    float *s_wt = s_off + 3 * kScanRows;                               // 3 x 8 warp totals
-    if (lane == 31) { s_wt[warp] = sr; s_wt[8 + warp] = si; s_wt[16 + warp] = se; }
+    constexpr int NW = kScanRows / 32;
+    float *s_wt = s_off + 3 * kScanRows;                               // 3 x NW warp totals
+    if (lane == 31) { s_wt[warp] = sr; s_wt[NW + warp] = si; s_wt[2 * NW + warp] = se; }
     __syncthreads();
     float or_ = sr - qr, oi = si - qi, oe = se - te;
-    for (int w = 0; w < warp; w++) { or_ += s_wt[w]; oi += s_wt[8 + w]; oe += s_wt[16 + w]; }
+    for (int w = 0; w < warp; w++) { or_ += s_wt[w]; oi += s_wt[NW + w]; oe += s_wt[2 * NW + w]; }
     s_off[t] = or_; s_off[kScanRows + t] = oi; s_off[2 * kScanRows + t] = oe;
     __syncthreads();
 
     // ---- metric per lag: rows 0 .. kScanEvalRows (row 0 only provides above(d_base - 1)) ------------------------------
     uint32_t mask = 0;
     if (t <= kScanEvalRows) {
-        const float dqr = s_off[t + 5] - s_off[t], dqi = s_off[kScanRows + t + 5] - s_off[kScanRows + t];
-        const float de1 = s_off[2 * kScanRows + t + 5] - s_off[2 * kScanRows + t];
-        const float de2 = s_off[2 * kScanRows + t + 10] - s_off[2 * kScanRows + t + 5];
+        constexpr int A = kScanR80, B = 2 * kScanR80;
+        const float dqr = s_off[t + A] - s_off[t], dqi = s_off[kScanRows + t + A] - s_off[kScanRows + t];
+        const float de1 = s_off[2 * kScanRows + t + A] - s_off[2 * kScanRows + t];
+        const float de2 = s_off[2 * kScanRows + t + B] - s_off[2 * kScanRows + t + A];
         const cpx dq = c_make(dqr, dqi);
-        const unsigned long long *q0 = s_q + t * kScanRowStride, *q5 = s_q + (t + 5) * kScanRowStride;
-        const float *e0 = s_e + t * kScanRowStride, *e5 = s_e + (t + 5) * kScanRowStride, *e10 = s_e + (t + 10) * kScanRowStride;
+        const unsigned long long *q0 = s_q + t * kScanRowStride, *q5 = s_q + (t + A) * kScanRowStride;
+        const float *e0 = s_e + t * kScanRowStride, *e5 = s_e + (t + A) * kScanRowStride, *e10 = s_e + (t + B) * kScanRowStride;
+        // lags of this row that exist: 0 <= d <= d_last (hoisted out of the loop as a bit mask)
+        const long long dr = origin + (long long)t * kScanT;
+        uint32_t live = (1u << kScanT) - 1u;
+        if (dr < 0) live = dr <= -kScanT ? 0u : live & ~((1u << (int)(-dr)) - 1u);
+        if (dr + kScanT - 1 > d_last) live = dr > d_last ? 0u : live & ((1u << (int)(d_last - dr + 1)) - 1u);
 #pragma unroll
         for (int j = 0; j < kScanT; j++) {
             cpx a0, a5;
@@ -141,15 +149,15 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
             c_split(c_add(c_sub(a5, a0), dq), pr, pi);
             const float e5j = e5[j];
             const float r1 = (e5j - e0[j]) + de1, r2 = (e10[j] - e5j) + de2;
-            const long long d = origin + (long long)t * kScanT + j;
-            if (d >= 0 && d <= d_last && pr * pr + pi * pi > 0.5f * r1 * r2) mask |= 1u << j;
+            if (pr * pr + pi * pi > 0.5f * r1 * r2) mask |= 1u << j;
         }
+        mask &= live;
     }
     s_mask[t] = mask;
     __syncthreads();
     if (t >= 1 && t <= kScanEvalRows && mask) {
         const uint32_t prev = s_mask[t - 1] >> (kScanT - 1);
-        uint32_t edges = mask & ~((mask << 1) | prev) & 0xFFFFu;       // above(d) && !above(d - 1)
+        uint32_t edges = mask & ~((mask << 1) | prev) & ((1u << kScanT) - 1u);       // above(d) && !above(d - 1)
         while (edges) {
             const int j = __ffs(edges) - 1;
             edges &= edges - 1;
