@@ -121,18 +121,19 @@ static AcquireKernel pick_acquire(const ofdm_cfg &c)
     }
 }
 
-template <int MOD>
+template <int MOD, bool WRITE>
 static TxKernel pick_tx_mod(bool guard, bool fec)
 {
-    if (guard) return fec ? (TxKernel)tx_symbols_kernel<MOD, true, true> : (TxKernel)tx_symbols_kernel<MOD, true, false>;
-    return fec ? (TxKernel)tx_symbols_kernel<MOD, false, true> : (TxKernel)tx_symbols_kernel<MOD, false, false>;
+    if (guard) return fec ? (TxKernel)tx_tile_kernel<MOD, true, true, WRITE> : (TxKernel)tx_tile_kernel<MOD, true, false, WRITE>;
+    return fec ? (TxKernel)tx_tile_kernel<MOD, false, true, WRITE> : (TxKernel)tx_tile_kernel<MOD, false, false, WRITE>;
 }
+template <bool WRITE>
 static TxKernel pick_tx(const ofdm_cfg &c)
 {
     switch (c.modulation) {
-    case 0: return pick_tx_mod<0>(c.guard_bands, c.fec);
-    case 1: return pick_tx_mod<1>(c.guard_bands, c.fec);
-    default: return pick_tx_mod<2>(c.guard_bands, c.fec);
+    case 0: return pick_tx_mod<0, WRITE>(c.guard_bands, c.fec);
+    case 1: return pick_tx_mod<1, WRITE>(c.guard_bands, c.fec);
+    default: return pick_tx_mod<2, WRITE>(c.guard_bands, c.fec);
     }
 }
 
@@ -324,14 +325,12 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     TxArgs a{};
     a.payload = payload; a.payload_len = payload_len; a.payload_stride = payload_stride; a.n_streams = n_streams;
     a.iq = reinterpret_cast<float2 *>(iq); a.iq_stride = iq_stride; a.frame_len = d_flen; a.stream_max = d_max; a.tables = h->d_tables;
-    uint32_t max_syms = iq_stride / 80;
-    uint32_t gx = (max_syms + 31) / 32;
-    if (gx < 1) gx = 1;
-    if (gx > 64) gx = 64;
-    pick_tx(h->cfg)<<<dim3(gx, n_streams), 256, 0, st>>>(a);
-    uint32_t gf = (iq_stride + 256 * 8 - 1) / (256 * 8);
-    if (gf < 1) gf = 1;
-    tx_finalize_kernel<<<dim3(gf, n_streams), 256, 0, st>>>(a, d_flen);
+    a.tile_shift = h->tile_shift;
+    // two passes over the same tiles: maximum for `normalize`, then recompute + store once (8 B/sample written)
+    const long max_syms = (long)iq_stride / 80 - 10;
+    uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + h->tile_shift + kTxTileSyms - 1) / kTxTileSyms) : 1;
+    pick_tx<false>(h->cfg)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
+    pick_tx<true>(h->cfg)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
     h->launches += 2;
     CU(h, cudaGetLastError());
     if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));

@@ -16,54 +16,49 @@ struct TxArgs {
     uint32_t        iq_stride;
     uint32_t       *frame_len;      // optional
     int            *stream_max;     // per stream: max positive component as float bits (atomicMax on int)
+    int32_t         tile_shift;     // Hamming byte alignment of the tile boundaries (same as the decode kernel)
     const RxTables *tables;
 };
 
-// 14-bit Hamming word pair of payload byte b: low nibble codeword | high nibble codeword << 7 (docs/SPEC.md 3)
-__device__ __forceinline__ uint32_t ham74_encode_byte(uint32_t b)
-{
-    return ham74_encode_nibble(b & 15u) | (ham74_encode_nibble(b >> 4) << 7);
-}
-
-// up to 8 bits [q, q+8) of the (optionally Hamming-coded) payload bit stream; zeros past the end
+// byte `B` of the frame byte stream [header 16 B | (Hamming-coded) payload ...] (src/transmitter.rs:37-47, docs/SPEC.md 3)
 template <bool FEC>
-__device__ __forceinline__ uint32_t payload_bits(const uint8_t *__restrict__ pay, uint32_t n, uint64_t q)
+__device__ __forceinline__ uint32_t frame_byte(const uint8_t *__restrict__ pay, uint32_t n, uint64_t coded_len, uint32_t B, const uint8_t *s_enc)
 {
-    if (!FEC) {
-        uint64_t b = q >> 3;
-        uint32_t v = (b < n ? pay[b] : 0u) | ((b + 1 < n ? pay[b + 1] : 0u) << 8);
-        return (v >> (q & 7)) & 255u;
+    if (B < 16) return B < 8 ? (uint32_t)(coded_len >> (8 * B)) & 255u : 0u;     // bincode u128 LE: low 64 bits = length
+    const uint32_t c = B - 16;
+    if (!FEC) return c < n ? pay[c] : 0u;
+    // bits [8c, 8c + 8) of the packed 7-bit codeword stream; codeword m encodes nibble m (byte m >> 1, low nibble first)
+    const uint32_t m0 = (8u * c) / 7u, r = 8u * c - 7u * m0;
+    uint32_t w = 0;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const uint32_t m = m0 + q, b = m >> 1;
+        const uint32_t nib = b < n ? ((uint32_t)pay[b] >> (4 * (m & 1))) & 15u : 0u;
+        w |= (b < n ? (uint32_t)s_enc[nib] : 0u) << (7 * q);
     }
-    uint64_t m = q / 7;                 // codeword index; byte m>>1, nibble m&1
-    uint32_t r = (uint32_t)(q - 7 * m);
-    uint64_t b = m >> 1;
-    uint64_t w = (b < n ? ham74_encode_byte(pay[b]) : 0u) | ((uint64_t)(b + 1 < n ? ham74_encode_byte(pay[b + 1]) : 0u) << 14);
-    return (uint32_t)(w >> (7 * (m & 1) + r)) & 255u;
+    return (w >> r) & 255u;
 }
 
-// `nb` (<= 8) bits of the frame bit stream [header 128 | payload...] starting at bit p (src/transmitter.rs:37-47)
-template <bool FEC>
-__device__ __forceinline__ uint32_t frame_bits(const uint8_t *__restrict__ pay, uint32_t n, uint64_t coded_len, uint64_t p, int nb)
-{
-    uint32_t v;
-    if (p >= kHeaderBits) {
-        v = payload_bits<FEC>(pay, n, p - kHeaderBits);
-    } else {
-        v = p < 64 ? (uint32_t)((coded_len >> p) & 255u) : 0u;      // bincode u128 LE: low 64 bits = length
-        int nh = (int)(kHeaderBits - p);
-        if (nh < nb) v = (v & ((1u << nh) - 1u)) | (payload_bits<FEC>(pay, n, 0) << nh);
-    }
-    return v & ((1u << nb) - 1u);
-}
+constexpr int kTxWarps = 8;
+constexpr int kTxThreads = kTxWarps * 32;
+constexpr int kTxIters = 7;
+constexpr int kTxTileSyms = kTxWarps * 4 * kTxIters;      // 224, same tiling as the decode kernel
 
-// One data OFDM symbol per 8-lane group: bits -> constellation -> IFFT -> CP. Writes un-normalised samples and
-// tracks the per-stream maximum positive component for `normalize` (src/transmitter.rs:183-194).
-template <int MOD, bool GUARD, bool FEC>
-__global__ void __launch_bounds__(256) tx_symbols_kernel(const TxArgs a)
+// One 224-symbol tile of one frame: (Hamming) coded bit stream of the tile -> smem, then per OFDM symbol (8 lanes):
+// 6-bit fields -> constellation LUT -> inverse FFT (packed FFMA2 transform on re/im-swapped data) -> CP.
+// WRITE = false: only the per-stream maximum positive component is produced (`normalize`, src/transmitter.rs:183-194);
+// WRITE = true : the symbols are recomputed and stored once, already normalised, together with the frame head and
+// the zero fill -- 8 B/sample of HBM traffic in total instead of write + read-modify-write.
+template <int MOD, bool GUARD, bool FEC, bool WRITE>
+__global__ void __launch_bounds__(kTxThreads) tx_tile_kernel(const TxArgs a)
 {
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 48 : 64;
-    __shared__ __align__(16) float2 s_tr[8 * kTrWarp];
+    constexpr int BPS = BPC * D;
+    __shared__ __align__(16) float2 s_tr[kTxWarps * kTrWarp];
+    __shared__ __align__(16) uint8_t s_bits[kTxTileSyms * BPS / 8 + 32];
+    __shared__ __align__(8) float2 s_map[64];
+    __shared__ uint8_t s_enc[16];
 
     const uint32_t stream = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
@@ -71,79 +66,136 @@ __global__ void __launch_bounds__(256) tx_symbols_kernel(const TxArgs a)
     const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;
     const uint64_t nbits = kHeaderBits + 8 * coded_len;
     const uint64_t ncar = (nbits + BPC - 1) / BPC;                 // constellation symbols (src/transmitter.rs:108-140)
-    const uint32_t S = (uint32_t)((ncar + D - 1) / D);             // OFDM data symbols (src/transmitter.rs:49-54)
-    const uint32_t frame_len = (kHeadSyms + S) * kSym;
+    const int S = (int)((ncar + D - 1) / D);                       // OFDM data symbols (src/transmitter.rs:49-54)
+    const uint32_t frame_len = (kHeadSyms + (uint32_t)S) * kSym;
     if (a.frame_len && blockIdx.x == 0 && tid == 0) a.frame_len[stream] = frame_len;
-    if (frame_len > a.iq_stride) return;                           // does not fit: host reports the error
-
-    const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+    const bool fits = frame_len <= a.iq_stride;
     float2 *out = a.iq + (size_t)stream * a.iq_stride;
-    float twr[8], twi[8];
-    fft64_lane_twiddles(a.tables->w64, l, twr, twi);
-    float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
 
-    float mx = 0.0f;
-    const uint32_t sym_per_block = 8 * 4;
-    for (uint32_t s = blockIdx.x * sym_per_block + warp * 4 + g; s < ((S + 3) & ~3u) + 0; s += gridDim.x * sym_per_block) {
-        const bool valid = s < S;
-        float xr[8], xi[8];
+    int t0 = (int)blockIdx.x * kTxTileSyms - a.tile_shift, t1 = t0 + kTxTileSyms;
+    if (t0 < 0) t0 = 0;
+    if (t1 > S) t1 = S;
+    float scale = 1.0f / 64.0f;
+    if (WRITE) {
+        const float mx = fmaxf(__int_as_float(a.stream_max[stream]), a.tables->head_max);
+        const float inv = 1.0f / mx;
+        scale *= inv;
+        // frame head (lock | preamble x4 | training x5) and zero fill past the frame
+        if (blockIdx.x == 0)
+            for (uint32_t i = tid; i < (uint32_t)(kHeadSyms * kSym) && i < a.iq_stride; i += kTxThreads) {
+                float2 v = make_float2(0.0f, 0.0f);
+                if (fits) { v = a.tables->head[i]; v.x = v.x / mx; v.y = v.y / mx; }
+                out[i] = v;
+            }
+        if (blockIdx.x == gridDim.x - 1) {
+            const uint32_t z0 = fits ? frame_len : (uint32_t)(kHeadSyms * kSym);
+            for (uint32_t i = z0 + tid; i < a.iq_stride; i += kTxThreads) out[i] = make_float2(0.0f, 0.0f);
+        }
+    }
+    if (!fits || t0 >= t1) return;
+
+    // constellation LUT, stored re/im swapped (the inverse FFT runs as swap . FFT . swap)
+    if (tid < 64) {
+        float re = 0.0f, im = 0.0f;
+        if (MOD == 0) { re = (tid & 1) ? 1.0f : -1.0f; }                              // src/transmitter.rs:112-118
+        else if (MOD == 1) { re = (tid & 1) ? 1.0f : -1.0f; im = (tid & 2) ? 1.0f : -1.0f; }   // src/transmitter.rs:122-132
+        else {
+            const uint32_t ci = tid & 7u, cq = tid >> 3;                               // Gray code -> level (docs/SPEC.md 2)
+            const uint32_t li = ci ^ (ci >> 1) ^ (ci >> 2), lq = cq ^ (cq >> 1) ^ (cq >> 2);
+            re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
+            im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
+        }
+        s_map[tid] = make_float2(im, re);
+    }
+    if (tid < 16) s_enc[tid] = (uint8_t)ham74_encode_nibble(tid);
+    __syncthreads();
+
+    // ---- tile bit stream --------------------------------------------------------------------------------------------
+    const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+    const uint32_t byte0 = (uint32_t)((long)t0 * BPS / 8), nbyte = (uint32_t)((long)(t1 - t0) * BPS / 8);
+    if (FEC) {
+        // header bytes (tile 0), then groups of 4 payload bytes -> 8 codewords -> 7 coded bytes. Tile boundaries fall on group
+        // boundaries (tile_shift: (288 t0 - 128) is a multiple of 56), so every group starts on a coded-byte boundary.
+        const uint32_t hdr = byte0 < 16 ? 16 - byte0 : 0;              // header bytes inside this tile (16 or 0)
+        if (tid < hdr) s_bits[tid] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + tid, s_enc);
+        const uint32_t c0 = byte0 + hdr - 16;                          // first coded byte of the tile: multiple of 7
+        const uint32_t ngrp = (nbyte + 2 - hdr + 6) / 7;
+        for (uint32_t u = tid; u < ngrp; u += kTxThreads) {
+            const uint32_t pb = (c0 / 7 + u) * 4;                      // first payload byte of the group
+            uint64_t w = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = l + 8 * j;                               // encode_block, src/transmitter.rs:144-165
-            float re = 0.0f, im = 0.0f;
-            const int rk = data_rank<GUARD>(k);
-            if (GUARD && is_pilot_bin(k)) { re = 1.0f; }
-            else if (rk >= 0 && valid) {
-                uint64_t c = (uint64_t)s * D + rk;
-                if (c < ncar) {
-                    uint32_t v = frame_bits<FEC>(pay, n, coded_len, c * BPC, BPC);
-                    if (MOD == 0) { re = v ? 1.0f : -1.0f; }
-                    else if (MOD == 1) { re = (v & 1) ? 1.0f : -1.0f; im = (v & 2) ? 1.0f : -1.0f; }
-                    else {
-                        // Gray code -> level index: i = c ^ (c>>1) ^ (c>>2) per axis, amplitude (2i-7)/7
-                        uint32_t ci = v & 7u, cq = v >> 3;
-                        uint32_t li = ci ^ (ci >> 1) ^ (ci >> 2), lq = cq ^ (cq >> 1) ^ (cq >> 2);
-                        re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
-                        im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
-                    }
+            for (int q = 0; q < 4; q++) {
+                const uint32_t v = pb + q < n ? pay[pb + q] : 0u;
+                const uint64_t cw = pb + q < n ? ((uint64_t)s_enc[v & 15u] | ((uint64_t)s_enc[v >> 4] << 7)) : 0ull;
+                w |= cw << (14 * q);
+            }
+            uint8_t *dst = s_bits + hdr + 7 * u;
+#pragma unroll
+            for (int q = 0; q < 7; q++) dst[q] = (uint8_t)(w >> (8 * q));
+        }
+    } else {
+        for (uint32_t b = tid; b < nbyte + 2; b += kTxThreads) s_bits[b] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + b, s_enc);
+    }
+    __syncthreads();
+
+    cpx tw[8];
+#pragma unroll
+    for (int ka = 0; ka < 8; ka++) tw[ka] = c_from(__ldg(a.tables->w64 + ((l * ka) & 63)));
+    int rank[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) rank[j] = data_rank<GUARD>(l + 8 * j);
+    float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
+    const long ncar_local = (long)ncar - (long)t0 * D;            // carriers of the frame that exist from this tile on
+    float mx = 0.0f;
+
+#pragma unroll 1
+    for (int it = 0; it < kTxIters; it++) {
+        const int s = t0 + warp * (4 * kTxIters) + 4 * it + g;
+        const bool valid = s < t1;
+        cpx x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {                              // encode_block, src/transmitter.rs:144-165
+            const int k = l + 8 * j;
+            cpx v = c_make(0.0f, 0.0f);
+            if (GUARD && is_pilot_bin(k)) v = c_make(0.0f, 1.0f);  // pilot 1 + 0j, swapped
+            else if (rank[j] >= 0 && valid) {
+                const long c = (long)(s - t0) * D + rank[j];
+                if (c < ncar_local) {
+                    const uint32_t bit = (uint32_t)c * BPC, bb = bit >> 3;
+                    const uint32_t w = ((uint32_t)s_bits[bb] | ((uint32_t)s_bits[bb + 1] << 8)) >> (bit & 7);
+                    v = c_from(s_map[w & ((1u << BPC) - 1u)]);
                 }
             }
-            xr[j] = re; xi[j] = im;
+            x[j] = v;
         }
-        // inverse FFT = swap(re, im) around the forward transform, scaled 1/64 (src/signals/mod.rs:49-58)
-        fft64_group(xi, xr, twr, twi, tr, l);
-        if (valid) {
-            float2 *sym = out + (size_t)(kHeadSyms + s) * kSym;
+        fft64_group_p(x, tw, tr, l);                               // prefix_block, src/transmitter.rs:168-181 (IFFT part)
+        if (WRITE) {
+            if (valid) {
+                float2 *sym = out + (size_t)(kHeadSyms + s) * kSym;
+#pragma unroll
+                for (int kb = 0; kb < 8; kb++) {
+                    float re, im;
+                    c_split(x[kb], im, re);                        // un-swap
+                    const float2 v = make_float2(re * scale, im * scale);
+                    const int t = l + 8 * kb;                      // time index inside the symbol
+                    sym[kCp + t] = v;
+                    if (kb >= 6) sym[t - (kNfft - kCp)] = v;       // cyclic prefix = last 16 samples
+                }
+            }
+        } else if (valid) {
 #pragma unroll
             for (int kb = 0; kb < 8; kb++) {
-                const int t = l + 8 * kb;                          // time index within the symbol
-                float2 v = make_float2(xr[kb] * (1.0f / 64.0f), xi[kb] * (1.0f / 64.0f));
-                mx = fmaxf(mx, fmaxf(v.x, v.y));
-                sym[kCp + t] = v;                                  // prefix_block, src/transmitter.rs:168-181
-                if (t >= kNfft - kCp) sym[t - (kNfft - kCp)] = v;
+                float re, im;
+                c_split(x[kb], im, re);
+                mx = fmaxf(mx, fmaxf(re, im));
             }
         }
     }
+    if (!WRITE) {
+        mx *= scale;
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-    if (lane == 0 && mx > 0.0f) atomicMax(a.stream_max + stream, __float_as_int(mx));
-}
-
-// normalize (src/transmitter.rs:183-194) + head (lock | preamble | training) + zero fill up to iq_stride
-__global__ void __launch_bounds__(256) tx_finalize_kernel(const TxArgs a, const uint32_t *__restrict__ frame_len)
-{
-    const uint32_t stream = blockIdx.y;
-    const uint32_t flen = frame_len[stream];
-    float2 *out = a.iq + (size_t)stream * a.iq_stride;
-    const bool fits = flen <= a.iq_stride;
-    const float mx = fmaxf(__int_as_float(a.stream_max[stream]), a.tables->head_max);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.iq_stride; i += gridDim.x * blockDim.x) {
-        float2 v = make_float2(0.0f, 0.0f);
-        if (fits && i < flen) {
-            v = i < kHeadSyms * kSym ? a.tables->head[i] : out[i];
-            v.x = v.x / mx; v.y = v.y / mx;
-        }
-        out[i] = v;
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        if (lane == 0 && mx > 0.0f) atomicMax(a.stream_max + stream, __float_as_int(mx));
     }
 }
 
