@@ -169,6 +169,16 @@ int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, of
                      uint32_t *n_peaks, int mem, void *stream);
 
 /*
+ * Streaming receiver: decode every frame ofdm_sync_search found in one long capture -- the loop of
+ * examples/jetson_rx.rs:46-57,83-108 (capture buffer -> decode! -> drop on failure) for all frames of the buffer at once.
+ * Frame i starts at peaks[i].offset and owns the samples up to the next detection (capped by max_frame_samples, 0 = no cap);
+ * out / out_len / status are indexed by frame. peaks may come straight from ofdm_sync_search (same `mem`).
+ */
+int ofdm_rx_decode_capture(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, const ofdm_peak *peaks, uint32_t n_frames,
+                           uint32_t max_frame_samples, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
+                           int mem, void *stream);
+
+/*
  * BER: replaces utils::Analysis::new (src/utils.rs:45-68) for a batch and accumulates into
  * counters[4] = { bit_errs, byte_errs, bits_compared, frames_failed }. A stream whose status != OK or
  * whose length differs from ref_len counts as failed with all its reference bits in error.

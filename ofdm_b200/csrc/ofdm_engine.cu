@@ -52,6 +52,7 @@ struct ofdm_engine {
     DevBuf scratch_f32;                 // channel accumulators
     DevBuf counters;                    // 4 x u64
     DevBuf sync_scratch;                // candidate list + counters of ofdm_sync_search
+    DevBuf cap_base;                    // per-frame base / length of ofdm_rx_decode_capture
     // host-mode staging
     DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
@@ -285,7 +286,7 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     cudaSetDevice(h->device);
     if (h->d_tables) cudaFree(h->d_tables);
     DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
-                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch };
+                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base };
     for (DevBuf *b : bufs) b->release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -370,7 +371,8 @@ extern "C" int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, cons
 // ---- RX ----------------------------------------------------------------------------------------------------------
 static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples, uint32_t n_streams, uint32_t iq_stride,
                      uint32_t max_n_samples, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
-                     const ofdm_rx_diag *diag, cudaStream_t st, size_t state_offset = 0, size_t state_total = 0)
+                     const ofdm_rx_diag *diag, cudaStream_t st, size_t state_offset = 0, size_t state_total = 0,
+                     const uint64_t *stream_base = nullptr)
 {
     if (state_total < n_streams) state_total = n_streams;
     if (state_offset == 0) CU(h, h->state.ensure(sizeof(StreamState) * state_total));
@@ -382,7 +384,8 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
     a.state = h->state.as<StreamState>() + state_offset; a.tables = h->d_tables;
     a.out = out; a.out_stride = out_stride; a.out_len = out_len; a.status = status;
     a.sync_window = h->cfg.sync_window; a.tile_shift = h->tile_shift;
-    a.sync_mode = (int)h->cfg.sync_mode; a.cfo_mode = (int)h->cfg.cfo_mode; a.fec = (int)h->cfg.fec;
+    a.sync_mode = stream_base ? 2 : (int)h->cfg.sync_mode; a.cfo_mode = (int)h->cfg.cfo_mode; a.fec = (int)h->cfg.fec;
+    a.stream_base = stream_base;
     bool points = false;
     if (diag) {
         a.d_offset = diag->offset; a.d_f_delta = diag->f_delta; a.d_h = reinterpret_cast<float2 *>(diag->h_k);
@@ -638,6 +641,50 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
     uint32_t k = 0;
     for (uint32_t i = 0; i < m; i++) if (tmp[i].metric >= 0.0f) peaks[k++] = tmp[i];
     *n_peaks = k;
+    return 0;
+}
+
+// ---- streaming receiver ------------------------------------------------------------------------------------------
+static int capture_decode_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, const ofdm_peak *peaks, uint32_t n_frames,
+                                 uint32_t max_frame, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status, cudaStream_t st)
+{
+    CU(h, h->cap_base.ensure((sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)n_frames));
+    uint64_t *base = h->cap_base.as<uint64_t>();
+    uint32_t *ns = reinterpret_cast<uint32_t *>(base + n_frames);
+    capture_prep_kernel<<<(n_frames + 255) / 256, 256, 0, st>>>(reinterpret_cast<const SyncPeak *>(peaks), n_frames, n, max_frame, base, ns);
+    h->launches += 1;
+    uint64_t cap = max_frame ? max_frame : n;
+    if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+    return rx_device(h, iq, ns, n_frames, (uint32_t)cap, (uint32_t)cap, out, out_stride, out_len, status, nullptr, st, 0, 0, base);
+}
+
+extern "C" int ofdm_rx_decode_capture(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, const ofdm_peak *peaks, uint32_t n_frames,
+                                      uint32_t max_frame_samples, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
+                                      int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!iq || !peaks || !out || !out_len || !status) ENG_FAIL(h, OFDM_E_INVALID, "capture decode: bad arguments");
+    if (n_frames == 0) return 0;
+    if (n_frames > 65535) ENG_FAIL(h, OFDM_E_INVALID, "capture decode: at most 65535 frames per call");
+    CU(h, cudaSetDevice(h->device));
+    if (mem == OFDM_MEM_DEVICE)
+        return capture_decode_device(h, iq, n_samples, peaks, n_frames, max_frame_samples, out, out_stride, out_len, status, (cudaStream_t)stream);
+    cudaStream_t st = h->own_stream;
+    const size_t ob = (size_t)n_frames * out_stride;
+    CU(h, h->s_iq.ensure(n_samples * sizeof(float2) + 16));
+    CU(h, h->s_points.ensure(sizeof(ofdm_peak) * (size_t)n_frames));
+    CU(h, h->s_bytes.ensure(ob));
+    CU(h, h->s_len.ensure(sizeof(uint32_t) * (size_t)n_frames));
+    CU(h, h->s_status.ensure(sizeof(int32_t) * (size_t)n_frames));
+    CU(h, cudaMemcpyAsync(h->s_iq.p, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->s_points.p, peaks, sizeof(ofdm_peak) * (size_t)n_frames, cudaMemcpyHostToDevice, st));
+    int rc = capture_decode_device(h, h->s_iq.as<ofdm_fc32>(), n_samples, h->s_points.as<ofdm_peak>(), n_frames, max_frame_samples,
+                                   h->s_bytes.as<uint8_t>(), out_stride, h->s_len.as<uint32_t>(), h->s_status.as<int32_t>(), st);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(out, h->s_bytes.p, ob, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(out_len, h->s_len.p, sizeof(uint32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -42,6 +42,7 @@ struct RxArgs {
     const uint32_t *n_samples;
     uint32_t        iq_stride;
     uint32_t        n_streams;
+    const uint64_t *stream_base;    // optional: sample index of every stream's capture inside iq (NULL: stream * iq_stride)
     StreamState    *state;
     const RxTables *tables;
     uint8_t        *out;
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
 
     const uint32_t n_samples = a.n_samples[stream];
     const uint32_t offset = (uint32_t)st->offset;
-    const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
+    const float2 *x0 = a.iq + (a.stream_base ? (size_t)a.stream_base[stream] : (size_t)stream * a.iq_stride) + offset;
     const uint32_t n_avail = n_samples - offset;
     const uint64_t fstep = st->fstep;
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     StreamState *st = a.state + stream;
     const long M = (long)a.n_samples[stream];
-    const float2 *x = a.iq + (size_t)stream * a.iq_stride;
+    const float2 *x = a.iq + (a.stream_base ? (size_t)a.stream_base[stream] : (size_t)stream * a.iq_stride);
 
     if (tid < kSym) s_lock[tid] = a.tables->lock[tid].x;
     if (tid == 0) s_d0 = 0x7fffffff;
@@ -619,7 +620,9 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
     int status = ST_OK;
     long offset = 0;
 
-    if (SYNC == 0) {
+    if (SYNC == 2) {
+        offset = 0;                                    // frame start already known (ofdm_rx_decode_capture)
+    } else if (SYNC == 0) {
         offset = (long)ramp_argmax(x, M, -(kSym - 1), W - 1, s_lock, s_val, s_idx) - 1;     // src/receiver.rs:21: lag - 1
     } else {
         // sliding Schmidl-Cox (docs/SPEC.md 4): P(d) = Q[d+80] - Q[d], R1(d) = E[d+80] - E[d], R2(d) = E[d+160] - E[d+80]

@@ -5,8 +5,8 @@
 // the capture is scanned once (8 B/sample) with the sliding Schmidl-Cox metric of docs/SPEC.md 4:
 //
 //   sync_scan_kernel   : one CTA per 3928 lags. Coalesced IQ tile -> padded smem rows (one 8-sample row per thread);
-//                        q[n] = conj(a[n]) a[n+80], e[n] = |a[n]|^2; thread-serial + warp-shuffle + block exclusive
-//                        prefix sums; P(d) = Q[d+80]-Q[d], R1(d) = E[d+80]-E[d], R2(d) = E[d+160]-E[d+80]; rising
+//                        q[n] = conj(a[n]) a[n+80], e[n] = |a[n]|^2; thread-serial prefix sums inside a row plus
+//                        10-row window sums of the row totals; P(d) = Q[d+80]-Q[d], R1(d) = E[d+80]-E[d], R2(d) = E[d+160]-E[d+80]; rising
 //                        edges of |P|^2 > 0.5 R1 R2 are appended to a candidate list.
 //   sync_select_kernel : one CTA: bitonic sort of the candidates, 800-sample hold-off (one detection per frame).
 //   sync_refine_kernel : one CTA per detection: ramp-correlation arg-max around it (lag - 1 rule), CFO estimate.
@@ -44,7 +44,7 @@ struct SyncArgs {
 
 constexpr size_t sync_scan_smem_bytes()
 {
-    return (size_t)kScanRows * kScanRowStride * (sizeof(float2) * 2 + sizeof(float)) + sizeof(float) * 3 * (kScanRows + 32) + sizeof(uint32_t) * (kScanRows + 8);
+    return (size_t)kScanRows * kScanRowStride * (sizeof(float2) * 2 + sizeof(float)) + sizeof(float) * 4 * (kScanRows + 32) + sizeof(uint32_t) * (kScanRows + 8);
 }
 
 __device__ __forceinline__ cpx c_conj_mul(cpx a, cpx b)     // conj(a) * b
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
     unsigned long long *s_q = s_iq + kScanRows * kScanRowStride;                              // thread-local exclusive prefix of q
     float *s_e = reinterpret_cast<float *>(s_q + kScanRows * kScanRowStride);                 // thread-local exclusive prefix of e
     float *s_off = s_e + kScanRows * kScanRowStride;                                          // [3][rows + 8] row offsets (block scan)
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_off + 3 * (kScanRows + 32));
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_off + 4 * (kScanRows + 32));
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const long long n = (long long)a.n;
@@ -108,32 +108,29 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
             te = fmaf(xr, xr, fmaf(xi, xi, te));
         }
     }
-    // ---- block exclusive scan of the row totals: warp shuffle, then across warps -------------------------------------
+    // ---- 80-sample window sums at row granularity: W[t] = sum of the row totals of rows t .. t+9 ---------------------
+    // (summing the ten small row totals directly, instead of differencing a tile-wide prefix sum, keeps fp32 exact enough in
+    // a quiet stretch that follows a loud frame inside the same tile)
     float qr, qi;
     c_split(tq, qr, qi);
-    float sr = qr, si = qi, se = te;
-#pragma unroll
-    for (int m = 1; m < 32; m <<= 1) {
-        float b0 = __shfl_up_sync(0xffffffffu, sr, m), b1 = __shfl_up_sync(0xffffffffu, si, m), b2 = __shfl_up_sync(0xffffffffu, se, m);
-        if (lane >= m) { sr += b0; si += b1; se += b2; }
-    }
-    constexpr int NW = kScanRows / 32;
-    float *s_wt = s_off + 3 * kScanRows;                               // 3 x NW warp totals
-    if (lane == 31) { s_wt[warp] = sr; s_wt[NW + warp] = si; s_wt[2 * NW + warp] = se; }
+    s_off[t] = qr; s_off[kScanRows + t] = qi; s_off[2 * kScanRows + t] = te;
     __syncthreads();
-    float or_ = sr - qr, oi = si - qi, oe = se - te;
-    for (int w = 0; w < warp; w++) { or_ += s_wt[w]; oi += s_wt[NW + w]; oe += s_wt[2 * NW + w]; }
-    s_off[t] = or_; s_off[kScanRows + t] = oi; s_off[2 * kScanRows + t] = oe;
+    float wqr = 0.0f, wqi = 0.0f, we = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kScanR80; k++) {
+        const int r = t + k < kScanRows ? t + k : kScanRows - 1;          // rows past the tile are never used by an evaluated lag
+        wqr += s_off[r]; wqi += s_off[kScanRows + r]; we += s_off[2 * kScanRows + r];
+    }
+    float *s_we = s_off + 3 * kScanRows;                                   // [rows]
+    s_we[t] = we;
     __syncthreads();
 
     // ---- metric per lag: rows 0 .. kScanEvalRows (row 0 only provides above(d_base - 1)) ------------------------------
     uint32_t mask = 0;
     if (t <= kScanEvalRows) {
         constexpr int A = kScanR80, B = 2 * kScanR80;
-        const float dqr = s_off[t + A] - s_off[t], dqi = s_off[kScanRows + t + A] - s_off[kScanRows + t];
-        const float de1 = s_off[2 * kScanRows + t + A] - s_off[2 * kScanRows + t];
-        const float de2 = s_off[2 * kScanRows + t + B] - s_off[2 * kScanRows + t + A];
-        const cpx dq = c_make(dqr, dqi);
+        const float de1 = we, de2 = s_we[t + A];
+        const cpx dq = c_make(wqr, wqi);
         const unsigned long long *q0 = s_q + t * kScanRowStride, *q5 = s_q + (t + A) * kScanRowStride;
         const float *e0 = s_e + t * kScanRowStride, *e5 = s_e + (t + A) * kScanRowStride, *e10 = s_e + (t + B) * kScanRowStride;
         // lags of this row that exist: 0 <= d <= d_last (hoisted out of the loop as a bit mask)
@@ -249,6 +246,24 @@ __global__ void __launch_bounds__(kAcqThreads) sync_refine_kernel(const SyncArgs
         p.metric = ok ? (float)((tt[0] * tt[0] + tt[1] * tt[1]) / (tt[5] * tt[2])) : -1.0f;      // < 0 marks an unusable detection
         a.peaks[i] = p;
     }
+}
+
+// per detected frame: where its capture starts and how many samples belong to it (up to the next frame / max_frame)
+__global__ void capture_prep_kernel(const SyncPeak *__restrict__ peaks, uint32_t n_frames, uint64_t n, uint32_t max_frame,
+                                    uint64_t *__restrict__ base, uint32_t *__restrict__ n_samples)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frames) return;
+    const SyncPeak p = peaks[i];
+    if (p.metric < 0.0f || p.offset >= n) { base[i] = 0; n_samples[i] = 0; return; }      // unusable detection -> TOO_SHORT
+    uint64_t end = n;
+    for (uint32_t k = i + 1; k < n_frames; k++)
+        if (peaks[k].metric >= 0.0f && peaks[k].offset > p.offset) { end = peaks[k].offset; break; }
+    uint64_t len = end - p.offset;
+    if (max_frame && len > max_frame) len = max_frame;
+    if (len > 0xFFFFFFFFull) len = 0xFFFFFFFFull;
+    base[i] = p.offset;
+    n_samples[i] = (uint32_t)len;
 }
 
 }  // namespace ofdm

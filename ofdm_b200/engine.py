@@ -27,7 +27,7 @@ EXPORTS = [
     "ofdm_last_error", "ofdm_get_tables", "ofdm_host_alloc", "ofdm_host_free", "ofdm_coded_len",
     "ofdm_frame_data_syms", "ofdm_frame_len", "ofdm_max_payload", "ofdm_tx_encode_batch", "ofdm_rx_decode_batch",
     "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches", "ofdm_profile_begin", "ofdm_profile_read",
-    "ofdm_sync_search",
+    "ofdm_sync_search", "ofdm_rx_decode_capture",
 ]
 
 
@@ -106,6 +106,8 @@ def load_library(build: bool = False) -> C.CDLL:
     L.ofdm_profile_read.restype = i32
     L.ofdm_sync_search.argtypes = [vp, vp, u64, vp, u32, vp, i32, vp]
     L.ofdm_sync_search.restype = i32
+    L.ofdm_rx_decode_capture.argtypes = [vp, vp, u64, vp, u32, u32, vp, u32, vp, vp, i32, vp]
+    L.ofdm_rx_decode_capture.restype = i32
     L.ofdm_kernel_launches.argtypes = [vp]
     L.ofdm_kernel_launches.restype = u64
     _lib = L
@@ -323,6 +325,21 @@ class Engine:
         self._check(self.lib.ofdm_sync_search(self._h, _ptr(iq), iq.size, _ptr(peaks), max_peaks, C.byref(n), MEM_HOST, None),
                     "ofdm_sync_search")
         return peaks[: n.value].copy()
+
+    def decode_capture(self, iq: np.ndarray, max_frame_samples: int = 0, out_stride: int = 4096, max_peaks: int = 4096):
+        """Streaming receiver (examples/jetson_rx.rs loop): find every frame of one long capture and decode them all.
+        Returns (peaks, list of payload bytes, status array)."""
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        peaks = self.sync_search(iq, max_peaks)
+        n = len(peaks)
+        out = np.zeros((max(n, 1), out_stride), np.uint8)
+        out_len = np.zeros(max(n, 1), np.uint32)
+        status = np.zeros(max(n, 1), np.int32)
+        if n:
+            self._check(self.lib.ofdm_rx_decode_capture(self._h, _ptr(iq), iq.size, _ptr(peaks), n, max_frame_samples, _ptr(out), out_stride,
+                                                        _ptr(out_len), _ptr(status), MEM_HOST, None), "ofdm_rx_decode_capture")
+        data = [bytes(out[i, : out_len[i]]) if status[i] == OK else b"" for i in range(n)]
+        return peaks, data, status[:n]
 
     def sync_search_device(self, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, stream=0):
         self._check(self.lib.ofdm_sync_search(self._h, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, MEM_DEVICE, stream or None),

@@ -107,6 +107,9 @@ extern "C" {
                                mem: c_int, stream: *mut c_void) -> c_int;
     pub fn ofdm_sync_search(h: *mut ofdm_engine, iq: *const ofdm_fc32, n_samples: u64, peaks: *mut ofdm_peak, max_peaks: u32,
                             n_peaks: *mut u32, mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn ofdm_rx_decode_capture(h: *mut ofdm_engine, iq: *const ofdm_fc32, n_samples: u64, peaks: *const ofdm_peak, n_frames: u32,
+                                  max_frame_samples: u32, out: *mut u8, out_stride: u32, out_len: *mut u32, status: *mut i32,
+                                  mem: c_int, stream: *mut c_void) -> c_int;
     pub fn ofdm_profile_begin(h: *mut ofdm_engine, max_calls: u32) -> c_int;
     pub fn ofdm_profile_read(h: *mut ofdm_engine, acquire_ms: *mut f32, decode_ms: *mut f32, n_calls: *mut u32) -> c_int;
     pub fn ofdm_kernel_launches(h: *const ofdm_engine) -> u64;

@@ -330,3 +330,32 @@ def test_capture_sync_search_edges(ob, oo):
     got, ref = eng.sync_search(cap2[1:]), oo.sync_search(cap2[1:])
     assert [int(x) for x in got["offset"]] == [int(x) for x in ref["offset"]] == [p - 2 for p, _ in truth]
     eng.close()
+
+
+def test_streaming_receiver_decodes_every_frame_of_a_capture(ob, oo):
+    """SURVEY 8f rank 3 / examples/jetson_rx.rs: one long capture -> every frame found and decoded in two launches groups.
+    Each decoded payload equals what the oracle decodes from the same frame slice."""
+    cfgk = dict(modulation=2, guard_bands=True, fec=True, cfo_mode=1, phase_mode=1)
+    eng = ob.Engine(ob.Config(**cfgk), 0)
+    ocfg = oo.make_cfg(True, 2, True, oo.SYNC_REFERENCE, 1, 1)
+    rng = np.random.default_rng(77)
+    n = 1_200_000
+    cap = (0.0003 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)     # floor ~49 dB below the frames
+    sent, p = [], 4321
+    while p + 40_000 < n:
+        pay = rng.integers(0, 256, int(rng.integers(1, 9000)), dtype=np.uint8).tobytes()
+        ch = oo.channel(oo.tx(pay, ocfg), 38.0, float(rng.uniform(0, 0.03)), 1, p).astype(np.complex64)
+        cap[p: p + ch.size] += ch
+        sent.append((p, pay))
+        p += ch.size + int(rng.integers(900, 30_000))
+    peaks, data, status = eng.decode_capture(cap, out_stride=9008)
+    assert len(peaks) == len(sent) and (status == 0).all()
+    for (p, pay), pk, got in zip(sent, peaks, data):
+        assert int(pk["offset"]) == p + 8                       # main channel tap at delay 9, lag - 1 rule
+        assert got == pay
+    # against the oracle on one frame slice (known start -> reference sync finds lag 1 -> offset 0)
+    i = 3
+    o = int(peaks[i]["offset"])
+    ref = oo.decode(np.concatenate([[0], cap[o: int(peaks[i + 1]["offset"])]]).astype(np.complex128), ocfg, want_points=False, out_cap=9008)
+    assert ref.status == 0 and ref.data.tobytes() == data[i]
+    eng.close()
