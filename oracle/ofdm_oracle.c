@@ -435,6 +435,22 @@ void oo_training_signals(oo_c64 *out, int len)
 static inline int is_null_bin(int i) { return i >= 59 || i <= 5 || i == 32; }
 static inline int is_pilot_bin(int i) { return i == 6 || i == 25 || i == 39 || i == 58; }
 
+/* layout: N = 64 is the reference's (above); N = 1024 is the wideband variant of docs/SPEC.md section 9 (no reference):
+ * nulls {0..95, 512, 929..1023}, of the remaining 832 bins (ascending) every 13th starting with bin 96 is a pilot
+ * (64 pilots, 1+0j), the other 768 carry data. */
+#define NMAX 1024
+static inline int lay_nfft(const oo_cfg *cfg) { return cfg->nfft == 1024 ? 1024 : 64; }
+static inline int lay_is_null(int nf, int k) { return nf == 64 ? is_null_bin(k) : (k <= 95 || k == 512 || k >= 929); }
+static inline int lay_is_pilot(int nf, int k)
+{
+    if (nf == 64) return is_pilot_bin(k);
+    if (lay_is_null(nf, k)) return 0;
+    int r = k < 512 ? k - 96 : k - 97;
+    return r % 13 == 0;
+}
+static inline int lay_data_carriers(int nf, int guard) { return guard ? (nf == 64 ? 48 : 768) : nf; }
+static inline int lay_pilots(int nf) { return nf == 64 ? 4 : 64; }
+
 /* ------------------------------------------------------------------------------------------------
  * TX -- src/transmitter.rs
  * ---------------------------------------------------------------------------------------------- */
@@ -516,32 +532,36 @@ static size_t n_symbols_for_bytes(size_t n_bytes_with_header, int scheme)
     return (8 * n_bytes_with_header + 5) / 6;
 }
 
-size_t oo_frame_data_syms(size_t n_bytes, int guard_bands, int scheme)
+size_t oo_frame_data_syms_n(size_t n_bytes, int guard_bands, int scheme, int nfft)
 {
-    size_t d = guard_bands ? 48 : 64;
+    size_t d = (size_t)lay_data_carriers(nfft, guard_bands);
     size_t ns = n_symbols_for_bytes(n_bytes + 16, scheme);
     return (ns + d - 1) / d;
 }
-size_t oo_frame_len(size_t n_bytes, int guard_bands, int scheme) { return (10 + oo_frame_data_syms(n_bytes, guard_bands, scheme)) * NSYM; }
+size_t oo_frame_data_syms(size_t n_bytes, int guard_bands, int scheme) { return oo_frame_data_syms_n(n_bytes, guard_bands, scheme, 64); }
+size_t oo_frame_len_n(size_t n_bytes, int guard_bands, int scheme, int nfft) { return (10 + oo_frame_data_syms_n(n_bytes, guard_bands, scheme, nfft)) * (size_t)(nfft + nfft / 4); }
+size_t oo_frame_len(size_t n_bytes, int guard_bands, int scheme) { return oo_frame_len_n(n_bytes, guard_bands, scheme, 64); }
 
-/* src/transmitter.rs:168-181: in-place scaled IFFT then out = x[48..64] ++ x[0..64] */
-static void prefix_block(oo_c64 *freq /* 64, clobbered */, oo_c64 *out /* 80 */)
+/* src/transmitter.rs:168-181: in-place scaled IFFT then out = x[N-CP..N] ++ x[0..N] */
+static void prefix_block(oo_c64 *freq /* nf, clobbered */, oo_c64 *out /* nf + nf/4 */, int nf)
 {
-    oo_fft(freq, NFFT, 1);
-    memcpy(out, freq + (NFFT - NCP), sizeof(oo_c64) * NCP);
-    memcpy(out + NCP, freq, sizeof(oo_c64) * NFFT);
+    int cp = nf / 4;
+    oo_fft(freq, (size_t)nf, 1);
+    memcpy(out, freq + (nf - cp), sizeof(oo_c64) * (size_t)cp);
+    memcpy(out + cp, freq, sizeof(oo_c64) * (size_t)nf);
 }
 
-/* src/transmitter.rs:11-58 */
-size_t oo_encode(const uint8_t *data, size_t n, int guard_bands, int scheme, oo_c64 *out)
+/* src/transmitter.rs:11-58 (nfft = 64); the same construction scaled to nfft = 1024 (docs/SPEC.md section 9) */
+size_t oo_encode_n(const uint8_t *data, size_t n, int guard_bands, int scheme, int nfft, oo_c64 *out)
 {
+    const int NF = nfft == 1024 ? 1024 : 64, LS = NF + NF / 4;
     size_t pos = 0;
-    oo_locking_signal(out + pos, NSYM); pos += NSYM;                        /* :22-24 */
-    for (int i = 0; i < 4; i++) { oo_preamble(out + pos, NSYM); pos += NSYM; }   /* :27-29 */
+    oo_locking_signal(out + pos, LS); pos += LS;                            /* :22-24 */
+    for (int i = 0; i < 4; i++) { oo_preamble(out + pos, LS); pos += LS; }       /* :27-29 */
     for (int i = 0; i < 5; i++) {                                           /* :32-34 */
-        oo_c64 t[NFFT];
-        oo_training_signals(t, NFFT);
-        prefix_block(t, out + pos); pos += NSYM;
+        oo_c64 t[NMAX];
+        oo_training_signals(t, NF);
+        prefix_block(t, out + pos, NF); pos += LS;
     }
     /* :37-47 header (bincode u128 LE, src/packets/mod.rs:20-32) ++ data, modulated as one stream */
     uint8_t *bytes = (uint8_t *)calloc(n + 16, 1);
@@ -555,13 +575,13 @@ size_t oo_encode(const uint8_t *data, size_t n, int guard_bands, int scheme, oo_
     /* :49-54 blocks; encode_block :144-165 */
     size_t k = 0;
     while (k < nsym) {
-        oo_c64 blk[NFFT];
-        for (int i = 0; i < NFFT; i++) {
-            if (guard_bands && is_null_bin(i)) blk[i] = c_make(0.0, 0.0);
-            else if (guard_bands && is_pilot_bin(i)) blk[i] = c_make(1.0, 0.0);
+        oo_c64 blk[NMAX];
+        for (int i = 0; i < NF; i++) {
+            if (guard_bands && lay_is_null(NF, i)) blk[i] = c_make(0.0, 0.0);
+            else if (guard_bands && lay_is_pilot(NF, i)) blk[i] = c_make(1.0, 0.0);
             else blk[i] = (k < nsym) ? syms[k++] : c_make(0.0, 0.0);
         }
-        prefix_block(blk, out + pos); pos += NSYM;
+        prefix_block(blk, out + pos, NF); pos += LS;
     }
     free(syms);
     /* normalize :183-194: max over signed re/im values starting from 0 */
@@ -571,19 +591,21 @@ size_t oo_encode(const uint8_t *data, size_t n, int guard_bands, int scheme, oo_
     return pos;
 }
 
+size_t oo_encode(const uint8_t *data, size_t n, int guard_bands, int scheme, oo_c64 *out) { return oo_encode_n(data, n, guard_bands, scheme, 64, out); }
+
 size_t oo_tx_len(size_t n_payload, const oo_cfg *cfg)
 {
     size_t n = cfg->fec ? oo_hamming74_encoded_len(n_payload) : n_payload;
-    return oo_frame_len(n, cfg->guard_bands, cfg->modulation);
+    return oo_frame_len_n(n, cfg->guard_bands, cfg->modulation, lay_nfft(cfg));
 }
 
 size_t oo_tx(const uint8_t *payload, size_t n, const oo_cfg *cfg, oo_c64 *out)
 {
-    if (!cfg->fec) return oo_encode(payload, n, cfg->guard_bands, cfg->modulation, out);
+    if (!cfg->fec) return oo_encode_n(payload, n, cfg->guard_bands, cfg->modulation, lay_nfft(cfg), out);
     size_t nc = oo_hamming74_encoded_len(n);
     uint8_t *coded = (uint8_t *)malloc(nc + 1);
     oo_hamming74_encode(payload, n, coded);
-    size_t r = oo_encode(coded, nc, cfg->guard_bands, cfg->modulation, out);
+    size_t r = oo_encode_n(coded, nc, cfg->guard_bands, cfg->modulation, lay_nfft(cfg), out);
     free(coded);
     return r;
 }
@@ -647,80 +669,85 @@ static inline oo_c64 sample_or_zero(const oo_c64 *a, size_t n, long i)
     return (i >= 0 && (size_t)i < n) ? a[i] : c_make(0.0, 0.0);
 }
 
-/* c[k] = sum_{n<80} a[n+k] b[n] over k in [k_lo, k_hi]; first strict max of |c|^2 (equivalent direct form of
+/* c[k] = sum_{n<L} a[n+k] b[n] over k in [k_lo, k_hi]; first strict max of |c|^2 (equivalent direct form of
  * src/signals/mod.rs:186-217 restricted to a lag window) */
-static long ramp_argmax(const oo_c64 *a, size_t n, long k_lo, long k_hi, const oo_c64 *lock)
+static long ramp_argmax_n(const oo_c64 *a, size_t n, long k_lo, long k_hi, const oo_c64 *lock, int LS)
 {
     double best = 0.0;
     long kbest = k_lo;
     for (long k = k_lo; k <= k_hi; k++) {
         oo_c64 c = c_make(0.0, 0.0);
-        for (int j = 0; j < NSYM; j++) c = c_add(c, c_mul(sample_or_zero(a, n, k + j), c_conj(lock[j])));
+        for (int j = 0; j < LS; j++) c = c_add(c, c_mul(sample_or_zero(a, n, k + j), c_conj(lock[j])));
         double v = c_norm_sqr(c);
         if (v > best) { best = v; kbest = k; }
     }
     return kbest;
 }
+static long ramp_argmax(const oo_c64 *a, size_t n, long k_lo, long k_hi, const oo_c64 *lock) { return ramp_argmax_n(a, n, k_lo, k_hi, lock, NSYM); }
 
 static int find_offset(const oo_c64 *a, size_t n, const oo_cfg *cfg, long *offset)
 {
-    oo_c64 lock[NSYM];
-    oo_locking_signal(lock, NSYM);
+    const int NF = lay_nfft(cfg), LS = NF + NF / 4;
+    oo_c64 lock[NMAX + NMAX / 4];
+    oo_locking_signal(lock, LS);
     long W = cfg->sync_window > 0 ? (long)cfg->sync_window : (long)n;
     if (W > (long)n) W = (long)n;
     if (cfg->sync_mode == OO_SYNC_REFERENCE) {
         if (cfg->xcorr_fft && cfg->sync_window <= 0) {
             /* src/receiver.rs:20-21 */
             oo_c64 *cross = (oo_c64 *)malloc(sizeof(oo_c64) * (2 * n - 1));
-            size_t idxmax = oo_xcorr_fft(a, n, lock, NSYM, cross);
+            size_t idxmax = oo_xcorr_fft(a, n, lock, (size_t)LS, cross);
             free(cross);
             *offset = (long)idxmax - (long)(((2 * n - 1) - 1) / 2 + 1);
         } else {
-            *offset = ramp_argmax(a, n, -(NSYM - 1), W - 1, lock) - 1;
+            *offset = ramp_argmax_n(a, n, -(LS - 1), W - 1, lock, LS) - 1;
         }
         return OO_OK;
     }
-    /* Schmidl-Cox, docs/SPEC.md section 4 */
+    /* Schmidl-Cox, docs/SPEC.md section 4 (window and lag = one preamble period L) */
     long d0 = -1;
     oo_c64 P = c_make(0.0, 0.0);
     double R1 = 0.0, R2 = 0.0;
-    for (long d = 0; d < W && (size_t)(d + 160) <= n; d++) {
+    for (long d = 0; d < W && (size_t)(d + 2 * LS) <= n; d++) {
         if (d == 0 || (d & 1023) == 0) {           /* exact re-sum periodically: no drift */
             P = c_make(0.0, 0.0); R1 = 0.0; R2 = 0.0;
-            for (int m = 0; m < NSYM; m++) {
-                P = c_add(P, c_mul(c_conj(a[d + m]), a[d + m + NSYM]));
+            for (int m = 0; m < LS; m++) {
+                P = c_add(P, c_mul(c_conj(a[d + m]), a[d + m + LS]));
                 R1 += c_norm_sqr(a[d + m]);
-                R2 += c_norm_sqr(a[d + m + NSYM]);
+                R2 += c_norm_sqr(a[d + m + LS]);
             }
         } else {
-            P = c_sub(P, c_mul(c_conj(a[d - 1]), a[d - 1 + NSYM]));
-            P = c_add(P, c_mul(c_conj(a[d - 1 + NSYM]), a[d - 1 + 2 * NSYM]));
-            R1 += c_norm_sqr(a[d - 1 + NSYM]) - c_norm_sqr(a[d - 1]);
-            R2 += c_norm_sqr(a[d - 1 + 2 * NSYM]) - c_norm_sqr(a[d - 1 + NSYM]);
+            P = c_sub(P, c_mul(c_conj(a[d - 1]), a[d - 1 + LS]));
+            P = c_add(P, c_mul(c_conj(a[d - 1 + LS]), a[d - 1 + 2 * LS]));
+            R1 += c_norm_sqr(a[d - 1 + LS]) - c_norm_sqr(a[d - 1]);
+            R2 += c_norm_sqr(a[d - 1 + 2 * LS]) - c_norm_sqr(a[d - 1 + LS]);
         }
         if (c_norm_sqr(P) > 0.5 * R1 * R2) { d0 = d; break; }
     }
     if (d0 < 0) return OO_NO_SYNC;
-    long k_lo = d0 - 176, k_hi = d0 + 16;
-    if (k_lo < -(NSYM - 1)) k_lo = -(NSYM - 1);
-    *offset = ramp_argmax(a, n, k_lo, k_hi, lock) - 1;
+    long k_lo = d0 - (11 * LS) / 5, k_hi = d0 + LS / 5;            /* 176 / 16 at L = 80 */
+    if (k_lo < -(LS - 1)) k_lo = -(LS - 1);
+    *offset = ramp_argmax_n(a, n, k_lo, k_hi, lock, LS) - 1;
     return OO_OK;
 }
 
 /* src/receiver.rs:99-104 */
-static void unprefix_block(const oo_c64 *row /* 80 */, oo_c64 *out /* 64 */)
+static void unprefix_block(const oo_c64 *row /* L */, oo_c64 *out /* N */, int NF)
 {
-    memcpy(out, row + NCP, sizeof(oo_c64) * NFFT);
-    oo_fft(out, NFFT, 0);
+    memcpy(out, row + NF / 4, sizeof(oo_c64) * (size_t)NF);
+    oo_fft(out, (size_t)NF, 0);
 }
 
 int oo_decode(const oo_c64 *samples, size_t n, const oo_cfg *cfg,
               uint8_t *out, size_t out_cap, size_t *out_len,
               oo_c64 *points, size_t points_cap, oo_diag *diag)
 {
+    const int NF = lay_nfft(cfg), LS = NF + NF / 4;
     oo_diag local;
-    if (!diag) diag = &local;
+    if (!diag) { diag = &local; local.h_full = NULL; }
+    oo_c64 *h_full = diag->h_full;
     memset(diag, 0, sizeof *diag);
+    diag->h_full = h_full;
     *out_len = 0;
 
     long offset = 0;
@@ -728,66 +755,67 @@ int oo_decode(const oo_c64 *samples, size_t n, const oo_cfg *cfg,
     diag->offset = (int32_t)offset;
     if (st != OO_OK) { diag->status = st; return st; }
     if (offset < 0) { diag->status = OO_NEG_OFFSET; return OO_NEG_OFFSET; }  /* :25 panics in the reference */
-    if ((size_t)offset > n || n - (size_t)offset < 800) { diag->status = OO_TOO_SHORT; return OO_TOO_SHORT; } /* :27-29 */
+    if ((size_t)offset > n || n - (size_t)offset < (size_t)(10 * LS)) { diag->status = OO_TOO_SHORT; return OO_TOO_SHORT; } /* :27-29 */
 
     size_t len = n - (size_t)offset;
-    size_t rows = (len + NSYM - 1) / NSYM;                                   /* :36, :192-210 zero-padded tail row */
-    oo_c64 *x = (oo_c64 *)calloc(rows * NSYM, sizeof(oo_c64));
+    size_t rows = (len + LS - 1) / LS;                                   /* :36, :192-210 zero-padded tail row */
+    oo_c64 *x = (oo_c64 *)calloc(rows * LS, sizeof(oo_c64));
     memcpy(x, samples + offset, sizeof(oo_c64) * len);
 
     /* :39, :231-240 */
     double f_delta;
     if (cfg->cfo_mode == OO_CFO_REFERENCE) {
         double acc = 0.0;
-        for (int i = 0; i < NSYM; i++) acc += oo_angle(c_div(x[4 * NSYM + i], x[3 * NSYM + i]));
-        f_delta = fabs((acc / 80.0) / 80.0);
+        for (int i = 0; i < LS; i++) acc += oo_angle(c_div(x[4 * LS + i], x[3 * LS + i]));
+        f_delta = fabs((acc / (double)LS) / (double)LS);
     } else {
         oo_c64 s = c_make(0.0, 0.0);
-        for (int i = 0; i < NSYM; i++) {
-            s = c_add(s, c_mul(c_conj(x[2 * NSYM + i]), x[3 * NSYM + i]));
-            s = c_add(s, c_mul(c_conj(x[3 * NSYM + i]), x[4 * NSYM + i]));
+        for (int i = 0; i < LS; i++) {
+            s = c_add(s, c_mul(c_conj(x[2 * LS + i]), x[3 * LS + i]));
+            s = c_add(s, c_mul(c_conj(x[3 * LS + i]), x[4 * LS + i]));
         }
-        f_delta = oo_angle(s) / 80.0;
+        f_delta = oo_angle(s) / (double)LS;
     }
     diag->f_delta = f_delta;
 
     /* :44-50 */
-    for (size_t i = 0; i < rows * NSYM; i++) x[i] = c_mul(x[i], c_expj(-f_delta * (double)i));
+    for (size_t i = 0; i < rows * LS; i++) x[i] = c_mul(x[i], c_expj(-f_delta * (double)i));
 
     /* :56, :212-229 */
-    oo_c64 hk[NFFT], training[NFFT];
-    oo_training_signals(training, NFFT);
-    for (int i = 0; i < NFFT; i++) hk[i] = c_make(0.0, 0.0);
+    oo_c64 hk[NMAX], training[NMAX];
+    oo_training_signals(training, NF);
+    for (int i = 0; i < NF; i++) hk[i] = c_make(0.0, 0.0);
     for (int b = 5; b < 10; b++) {
-        oo_c64 blk[NFFT];
-        unprefix_block(x + (size_t)b * NSYM, blk);
-        for (int i = 0; i < NFFT; i++) hk[i] = c_add(hk[i], c_div(blk[i], training[i]));
+        oo_c64 blk[NMAX];
+        unprefix_block(x + (size_t)b * LS, blk, NF);
+        for (int i = 0; i < NF; i++) hk[i] = c_add(hk[i], c_div(blk[i], training[i]));
     }
-    for (int i = 0; i < NFFT; i++) { hk[i].re /= 5.0; hk[i].im /= 5.0; }
-    memcpy(diag->h_k, hk, sizeof hk);
+    for (int i = 0; i < NF; i++) { hk[i].re /= 5.0; hk[i].im /= 5.0; }
+    memcpy(diag->h_k, hk, sizeof(oo_c64) * 64);            /* diag carries the first 64 bins */
+    if (diag->h_full) memcpy(diag->h_full, hk, sizeof(oo_c64) * (size_t)NF);
 
     /* :63-74 */
-    size_t S = rows - 10, D = cfg->guard_bands ? 48 : 64;
+    size_t S = rows - 10, D = (size_t)lay_data_carriers(NF, cfg->guard_bands);
     oo_c64 *stream = (oo_c64 *)malloc(sizeof(oo_c64) * (S * D + 8));
     size_t np = 0;
     for (size_t s = 0; s < S; s++) {
-        oo_c64 Y[NFFT];
-        unprefix_block(x + (10 + s) * NSYM, Y);
-        for (int i = 0; i < NFFT; i++) Y[i] = c_div(Y[i], hk[i]);            /* :68-70 */
+        oo_c64 Y[NMAX];
+        unprefix_block(x + (10 + s) * LS, Y, NF);
+        for (int i = 0; i < NF; i++) Y[i] = c_div(Y[i], hk[i]);            /* :68-70 */
         /* decode_block :106-145 */
         double phase = 0.0;
         oo_c64 psum = c_make(0.0, 0.0);
         size_t first = np;
-        for (int i = 0; i < NFFT; i++) {
-            if (cfg->guard_bands && is_null_bin(i)) continue;
-            if (cfg->guard_bands && is_pilot_bin(i)) {
+        for (int i = 0; i < NF; i++) {
+            if (cfg->guard_bands && lay_is_null(NF, i)) continue;
+            if (cfg->guard_bands && lay_is_pilot(NF, i)) {
                 phase += oo_angle(c_div(Y[i], c_make(1.0, 0.0)));            /* :126 */
                 psum = c_add(psum, Y[i]);
                 continue;
             }
             stream[np++] = Y[i];
         }
-        phase /= 4.0;                                                        /* :137 */
+        phase /= (double)lay_pilots(NF);                                     /* :137 (pilot_count = 4.0 at N = 64) */
         if (cfg->guard_bands && cfg->phase_mode == OO_PHASE_ANGLE_OF_SUM) phase = oo_angle(psum);
         oo_c64 rot = c_expj(-phase);                                         /* :140-144 */
         for (size_t i = first; i < np; i++) stream[i] = c_mul(stream[i], rot);
@@ -914,6 +942,7 @@ int oo_decode_batch_fc32(const float *iq, const uint32_t *n_samples, uint32_t n_
         oo_fc32_to_sig(iq + 2 * iq_stride * (size_t)s, n, x);               /* src/utils.rs:239-254 */
         size_t ol = 0;
         oo_diag d;
+        d.h_full = NULL;
         int st = oo_decode(x, n, cfg, out + out_stride * (size_t)s, out_stride, &ol, NULL, 0, &d);
         out_len[s] = (uint32_t)ol;
         status[s] = st;

@@ -43,6 +43,7 @@ typedef struct {
     int32_t phase_mode;
     int32_t sync_window;   /* 0 = whole capture */
     int32_t xcorr_fft;     /* 1: SYNC_REFERENCE uses the FFT cross-correlation like the reference; 0: direct form */
+    int32_t nfft;          /* 0 or 64: the reference's layout; 1024: wideband variant (docs/SPEC.md section 9, CP = 256) */
 } oo_cfg;
 
 typedef struct {
@@ -53,6 +54,7 @@ typedef struct {
     int64_t n_data_syms;     /* data OFDM symbols demodulated */
     int64_t n_points;        /* equalised data points written to `points` */
     uint64_t packet_length;  /* low 64 bits of header */
+    oo_c64  *h_full;         /* optional in: receives all nfft bins of h_k */
 } oo_diag;
 
 /* ---- tables (src/transmitter.rs:60-96) ---- */
@@ -91,6 +93,9 @@ size_t oo_demodulate(const oo_c64 *syms, size_t n, int scheme, uint8_t *out);   
 size_t oo_frame_data_syms(size_t n_bytes, int guard_bands, int scheme);            /* S for n_bytes given to encode */
 size_t oo_frame_len(size_t n_bytes, int guard_bands, int scheme);                  /* (10+S)*80 */
 size_t oo_encode(const uint8_t *data, size_t n, int guard_bands, int scheme, oo_c64 *out);
+size_t oo_encode_n(const uint8_t *data, size_t n, int guard_bands, int scheme, int nfft, oo_c64 *out);
+size_t oo_frame_data_syms_n(size_t n_bytes, int guard_bands, int scheme, int nfft);
+size_t oo_frame_len_n(size_t n_bytes, int guard_bands, int scheme, int nfft);
 /* payload -> (optional Hamming) -> encode; returns frame length in samples */
 size_t oo_tx(const uint8_t *payload, size_t n, const oo_cfg *cfg, oo_c64 *out);
 size_t oo_tx_len(size_t n_payload, const oo_cfg *cfg);

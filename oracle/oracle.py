@@ -32,6 +32,7 @@ class OoCfg(C.Structure):
         ("phase_mode", C.c_int32),
         ("sync_window", C.c_int32),
         ("xcorr_fft", C.c_int32),
+        ("nfft", C.c_int32),
     ]
 
 
@@ -44,6 +45,7 @@ class OoDiag(C.Structure):
         ("n_data_syms", C.c_int64),
         ("n_points", C.c_int64),
         ("packet_length", C.c_uint64),
+        ("h_full", C.c_void_p),
     ]
 
 
@@ -97,6 +99,12 @@ def lib() -> C.CDLL:
     L.oo_frame_len.restype = sz
     L.oo_encode.argtypes = [vp, sz, i32, i32, vp]
     L.oo_encode.restype = sz
+    L.oo_encode_n.argtypes = [vp, sz, i32, i32, i32, vp]
+    L.oo_encode_n.restype = sz
+    L.oo_frame_len_n.argtypes = [sz, i32, i32, i32]
+    L.oo_frame_len_n.restype = sz
+    L.oo_frame_data_syms_n.argtypes = [sz, i32, i32, i32]
+    L.oo_frame_data_syms_n.restype = sz
     L.oo_tx.argtypes = [vp, sz, C.POINTER(OoCfg), vp]
     L.oo_tx.restype = sz
     L.oo_tx_len.argtypes = [sz, C.POINTER(OoCfg)]
@@ -119,9 +127,9 @@ def _p(a: np.ndarray) -> C.c_void_p:
 
 
 def make_cfg(guard_bands=True, modulation=BPSK, fec=False, sync_mode=SYNC_REFERENCE,
-             cfo_mode=CFO_REFERENCE, phase_mode=PHASE_REFERENCE, sync_window=0, xcorr_fft=False) -> OoCfg:
+             cfo_mode=CFO_REFERENCE, phase_mode=PHASE_REFERENCE, sync_window=0, xcorr_fft=False, nfft=64) -> OoCfg:
     return OoCfg(int(guard_bands), int(modulation), int(fec), int(sync_mode), int(cfo_mode),
-                 int(phase_mode), int(sync_window), int(xcorr_fft))
+                 int(phase_mode), int(sync_window), int(xcorr_fft), int(nfft))
 
 
 def _c128(x) -> np.ndarray:
@@ -250,11 +258,11 @@ def demodulate(syms, scheme):
     return o[:n].copy()
 
 
-def encode(data, guard_bands=False, modulation=BPSK):
+def encode(data, guard_bands=False, modulation=BPSK, nfft=64):
     d = _bytes(data)
-    n = lib().oo_frame_len(d.size, int(guard_bands), modulation)
+    n = lib().oo_frame_len_n(d.size, int(guard_bands), modulation, nfft)
     o = np.zeros(n, np.complex128)
-    m = lib().oo_encode(_p(d), d.size, int(guard_bands), modulation, _p(o))
+    m = lib().oo_encode_n(_p(d), d.size, int(guard_bands), modulation, nfft, _p(o))
     assert m == n
     return o
 
@@ -289,17 +297,19 @@ class DecodeResult:
 
 def decode(samples, cfg: OoCfg, want_points=True, out_cap=None) -> DecodeResult:
     s = _c128(samples)
+    nf = 1024 if cfg.nfft == 1024 else 64
     cap = out_cap if out_cap is not None else max(16, s.size)
     out = np.zeros(cap, np.uint8)
-    pts_cap = (s.size // 80 + 2) * 64 if want_points else 0
+    pts_cap = (s.size // (nf + nf // 4) + 2) * nf if want_points else 0
     pts = np.zeros(max(pts_cap, 1), np.complex128)
     ol = C.c_size_t(0)
     diag = OoDiag()
+    hfull = np.zeros(nf, np.complex128)
+    diag.h_full = hfull.ctypes.data
     st = lib().oo_decode(_p(s), s.size, C.byref(cfg), _p(out), cap, C.byref(ol),
                          _p(pts) if want_points else None, pts_cap, C.byref(diag))
-    hk = np.array(diag.h_k[:], dtype=np.float64).view(np.complex128)
     npts = min(int(diag.n_points), pts_cap)
-    return DecodeResult(st, out[: ol.value].copy(), diag.offset, diag.f_delta, hk, pts[:npts].copy(),
+    return DecodeResult(st, out[: ol.value].copy(), diag.offset, diag.f_delta, hfull, pts[:npts].copy(),
                         int(diag.n_data_syms), int(diag.packet_length))
 
 
