@@ -64,8 +64,8 @@ enum {
 
 typedef struct {
     uint32_t struct_size;  /* = sizeof(ofdm_cfg) */
-    uint32_t nfft;         /* 64 (src/receiver.rs:99) */
-    uint32_t cp;           /* 16 */
+    uint32_t nfft;         /* 64 (src/receiver.rs:99), or 1024: wideband variant (docs/SPEC.md 9; no reference) */
+    uint32_t cp;           /* nfft / 4: 16 or 256 */
     uint32_t modulation;   /* decode!/encode! `modulation`, default Bpsk (src/transmitter.rs:17) */
     uint32_t guard_bands;  /* decode!/encode! `guard_bands`, default false (src/transmitter.rs:16) */
     uint32_t fec;          /* 0 none; 1 Hamming(7,4) fused where the reference applies RS (examples/lab3c_image.rs:19-21) */
@@ -74,9 +74,9 @@ typedef struct {
     uint32_t phase_mode;
     uint32_t sync_window;  /* lags searched for the frame start; 0 = whole capture like the reference */
     /* optional table overrides (NULL = the reference's generators, src/transmitter.rs:60-96) */
-    const ofdm_fc32 *locking;   /* 80 */
-    const ofdm_fc32 *preamble;  /* 80 */
-    const ofdm_fc32 *training;  /* 64, frequency domain */
+    const ofdm_fc32 *locking;   /* nfft + cp entries (80) */
+    const ofdm_fc32 *preamble;  /* nfft + cp entries (80) */
+    const ofdm_fc32 *training;  /* nfft entries (64), frequency domain */
 } ofdm_cfg;
 
 /* optional per-stream diagnostics of ofdm_rx_decode_batch; every pointer may be NULL.
@@ -84,7 +84,7 @@ typedef struct {
 typedef struct {
     int32_t   *offset;        /* [n_streams]  src/receiver.rs:21 */
     float     *f_delta;       /* [n_streams]  src/receiver.rs:39 */
-    ofdm_fc32 *h_k;           /* [n_streams][64]  src/receiver.rs:56 */
+    ofdm_fc32 *h_k;           /* [n_streams][nfft]  src/receiver.rs:56 */
     uint32_t  *n_data_syms;   /* [n_streams]  data OFDM symbols demodulated */
     ofdm_fc32 *points;        /* [n_streams][points_stride] equalised + phase-corrected data points (src/receiver.rs:76) */
     uint32_t   points_stride;

@@ -15,6 +15,7 @@
 #include "tables.h"
 #include "sync_kernels.cuh"
 #include "tx_kernels.cuh"
+#include "wide_kernels.cuh"
 
 using namespace ofdm;
 
@@ -46,8 +47,11 @@ struct ofdm_engine {
     std::string err;
     uint64_t launches = 0;
     RxTables *d_tables = nullptr;
-    ofdm_fc32 lock[80], pre[80], train[64];
-    DevBuf state;                       // StreamState[n_streams]
+    wide::WideTables *d_wtables = nullptr;   // nfft = 1024
+    bool wide = false;
+    int nfft = 64, sym_len = 80;
+    std::vector<ofdm_fc32> lock, pre, train;
+    DevBuf state;                       // StreamState[n_streams] (StreamStateW for nfft = 1024)
     DevBuf scratch_u32;                 // frame_len / stream_max
     DevBuf scratch_f32;                 // channel accumulators
     DevBuf counters;                    // 4 x u64
@@ -138,9 +142,66 @@ static TxKernel pick_tx(const ofdm_cfg &c)
     }
 }
 
+// ---- nfft = 1024 dispatch -----------------------------------------------------------------------------------------------
+typedef void (*WDecodeKernel)(const wide::WideRxArgs);
+typedef void (*WTxKernel)(const wide::WideTxArgs);
+template <int MOD, bool GUARD, bool FEC, int PHASE>
+static WDecodeKernel wpick_decode_pts(bool points)
+{
+    return points ? (WDecodeKernel)wide::wide_decode_kernel<MOD, GUARD, FEC, PHASE, true> : (WDecodeKernel)wide::wide_decode_kernel<MOD, GUARD, FEC, PHASE, false>;
+}
+template <int MOD, bool GUARD, bool FEC>
+static WDecodeKernel wpick_decode_phase(int phase, bool points)
+{
+    return phase ? wpick_decode_pts<MOD, GUARD, FEC, 1>(points) : wpick_decode_pts<MOD, GUARD, FEC, 0>(points);
+}
+template <int MOD>
+static WDecodeKernel wpick_decode_mod(bool guard, bool fec, int phase, bool points)
+{
+    if (guard) return fec ? wpick_decode_phase<MOD, true, true>(phase, points) : wpick_decode_phase<MOD, true, false>(phase, points);
+    return fec ? wpick_decode_phase<MOD, false, true>(phase, points) : wpick_decode_phase<MOD, false, false>(phase, points);
+}
+static WDecodeKernel wpick_decode(const ofdm_cfg &c, bool points)
+{
+    switch (c.modulation) {
+    case 0: return wpick_decode_mod<0>(c.guard_bands, c.fec, c.phase_mode, points);
+    case 1: return wpick_decode_mod<1>(c.guard_bands, c.fec, c.phase_mode, points);
+    default: return wpick_decode_mod<2>(c.guard_bands, c.fec, c.phase_mode, points);
+    }
+}
+template <int MOD, bool GUARD>
+static WDecodeKernel wpick_acquire_phase(int phase)
+{
+    return phase ? (WDecodeKernel)wide::wide_acquire_kernel<MOD, GUARD, 1> : (WDecodeKernel)wide::wide_acquire_kernel<MOD, GUARD, 0>;
+}
+static WDecodeKernel wpick_acquire(const ofdm_cfg &c)
+{
+    switch (c.modulation) {
+    case 0: return c.guard_bands ? wpick_acquire_phase<0, true>(c.phase_mode) : wpick_acquire_phase<0, false>(c.phase_mode);
+    case 1: return c.guard_bands ? wpick_acquire_phase<1, true>(c.phase_mode) : wpick_acquire_phase<1, false>(c.phase_mode);
+    default: return c.guard_bands ? wpick_acquire_phase<2, true>(c.phase_mode) : wpick_acquire_phase<2, false>(c.phase_mode);
+    }
+}
+template <int MOD, bool WRITE>
+static WTxKernel wpick_tx_mod(bool guard, bool fec)
+{
+    if (guard) return fec ? (WTxKernel)wide::wide_tx_kernel<MOD, true, true, WRITE> : (WTxKernel)wide::wide_tx_kernel<MOD, true, false, WRITE>;
+    return fec ? (WTxKernel)wide::wide_tx_kernel<MOD, false, true, WRITE> : (WTxKernel)wide::wide_tx_kernel<MOD, false, false, WRITE>;
+}
+template <bool WRITE>
+static WTxKernel wpick_tx(const ofdm_cfg &c)
+{
+    switch (c.modulation) {
+    case 0: return wpick_tx_mod<0, WRITE>(c.guard_bands, c.fec);
+    case 1: return wpick_tx_mod<1, WRITE>(c.guard_bands, c.fec);
+    default: return wpick_tx_mod<2, WRITE>(c.guard_bands, c.fec);
+    }
+}
+
 // ---- sizes -------------------------------------------------------------------------------------------------------
 static int cfg_bpc(const ofdm_cfg *c) { return c->modulation == 0 ? 1 : (c->modulation == 1 ? 2 : 6); }
-static int cfg_dcar(const ofdm_cfg *c) { return c->guard_bands ? 48 : 64; }
+static int cfg_dcar(const ofdm_cfg *c) { return c->nfft == 1024 ? (c->guard_bands ? 768 : 1024) : (c->guard_bands ? 48 : 64); }
+static int cfg_symlen(const ofdm_cfg *c) { return c->nfft == 1024 ? 1280 : 80; }
 
 extern "C" uint32_t ofdm_abi_version(void) { return OFDM_ABI_VERSION; }
 
@@ -177,7 +238,7 @@ extern "C" uint32_t ofdm_frame_data_syms(const ofdm_cfg *cfg, uint32_t payload_l
 }
 extern "C" uint32_t ofdm_frame_len(const ofdm_cfg *cfg, uint32_t payload_len)
 {
-    return (10 + ofdm_frame_data_syms(cfg, payload_len)) * 80;
+    return (10 + ofdm_frame_data_syms(cfg, payload_len)) * (uint32_t)cfg_symlen(cfg);
 }
 extern "C" uint32_t ofdm_max_payload(const ofdm_cfg *cfg, uint32_t n_data_syms)
 {
@@ -191,7 +252,10 @@ extern "C" uint32_t ofdm_max_payload(const ofdm_cfg *cfg, uint32_t n_data_syms)
 static int validate_cfg(const ofdm_cfg *c, std::string &err)
 {
     if (!c || c->struct_size != sizeof(ofdm_cfg)) { err = "ofdm_cfg.struct_size mismatch"; return OFDM_E_INVALID; }
-    if (c->nfft != 64 || c->cp != 16) { err = "only nfft=64, cp=16 (the reference's layout) is implemented"; return OFDM_E_INVALID; }
+    if (!((c->nfft == 64 && c->cp == 16) || (c->nfft == 1024 && c->cp == 256))) {
+        err = "supported layouts: nfft=64/cp=16 (the reference's) and nfft=1024/cp=256 (wideband variant)";
+        return OFDM_E_INVALID;
+    }
     if (c->modulation > 2 || c->guard_bands > 1 || c->fec > 1 || c->sync_mode > 1 || c->cfo_mode > 1 || c->phase_mode > 1) {
         err = "ofdm_cfg field out of range";
         return OFDM_E_INVALID;
@@ -228,41 +292,66 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
         h->tile_shift = (7 - s0) % 7;
     }
 
-    // tables (src/transmitter.rs:60-96) in f64, then fc32
-    std::vector<ofdm_host::cd> lock(80), pre(80), train(64), tsym(64);
-    ofdm_host::locking_signal(lock.data(), 80);
-    ofdm_host::preamble(pre.data(), 80);
-    ofdm_host::training_signals(train.data(), 64);
-    if (cfg->locking) for (int i = 0; i < 80; i++) lock[i] = { cfg->locking[i].re, cfg->locking[i].im };
-    if (cfg->preamble) for (int i = 0; i < 80; i++) pre[i] = { cfg->preamble[i].re, cfg->preamble[i].im };
-    if (cfg->training) for (int i = 0; i < 64; i++) train[i] = { cfg->training[i].re, cfg->training[i].im };
+    // tables (src/transmitter.rs:60-96) in f64, then fc32; nfft = 1024 uses the same generators with LEN = 1280 / 1024
+    h->wide = cfg->nfft == 1024;
+    h->nfft = (int)cfg->nfft;
+    h->sym_len = cfg_symlen(cfg);
+    const int NF = h->nfft, LS = h->sym_len, CPL = NF / 4;
+    std::vector<ofdm_host::cd> lock(LS), pre(LS), train(NF), tsym(NF);
+    ofdm_host::locking_signal(lock.data(), LS);
+    ofdm_host::preamble(pre.data(), LS);
+    ofdm_host::training_signals(train.data(), NF);
+    if (cfg->locking) for (int i = 0; i < LS; i++) lock[i] = { cfg->locking[i].re, cfg->locking[i].im };
+    if (cfg->preamble) for (int i = 0; i < LS; i++) pre[i] = { cfg->preamble[i].re, cfg->preamble[i].im };
+    if (cfg->training) for (int i = 0; i < NF; i++) train[i] = { cfg->training[i].re, cfg->training[i].im };
     h->cfg.locking = h->cfg.preamble = h->cfg.training = nullptr;
-    RxTables *t = new RxTables();
-    for (int i = 0; i < 80; i++) {
+    ofdm_host::idft(train.data(), tsym.data(), NF);
+    h->lock.resize(LS); h->pre.resize(LS); h->train.resize(NF);
+    std::vector<float2> head((size_t)10 * LS), invt(NF), lockf(LS);
+    for (int i = 0; i < LS; i++) {
         h->lock[i] = { (float)lock[i].re, (float)lock[i].im };
         h->pre[i] = { (float)pre[i].re, (float)pre[i].im };
-        t->lock[i] = make_float2((float)lock[i].re, (float)lock[i].im);
-        t->head[i] = t->lock[i];
-        for (int r = 0; r < 4; r++) t->head[80 * (1 + r) + i] = make_float2((float)pre[i].re, (float)pre[i].im);
+        lockf[i] = make_float2((float)lock[i].re, (float)lock[i].im);
+        head[i] = lockf[i];
+        for (int r = 0; r < 4; r++) head[(size_t)LS * (1 + r) + i] = make_float2((float)pre[i].re, (float)pre[i].im);
     }
-    ofdm_host::idft(train.data(), tsym.data(), 64);
-    for (int i = 0; i < 64; i++) {
+    for (int i = 0; i < NF; i++) {
         h->train[i] = { (float)train[i].re, (float)train[i].im };
         double n2 = train[i].re * train[i].re + train[i].im * train[i].im;
-        t->inv_training[i] = make_float2((float)(train[i].re / n2), (float)(-train[i].im / n2));
+        invt[i] = make_float2((float)(train[i].re / n2), (float)(-train[i].im / n2));
     }
     for (int r = 0; r < 5; r++)
-        for (int i = 0; i < 80; i++) {
-            const ofdm_host::cd &v = tsym[i < 16 ? 48 + i : i - 16];        // prefix_block, src/transmitter.rs:168-181
-            t->head[400 + 80 * r + i] = make_float2((float)v.re, (float)v.im);
+        for (int i = 0; i < LS; i++) {
+            const ofdm_host::cd &v = tsym[i < CPL ? NF - CPL + i : i - CPL];        // prefix_block, src/transmitter.rs:168-181
+            head[(size_t)LS * (5 + r) + i] = make_float2((float)v.re, (float)v.im);
         }
     float mx = 0.0f;
-    for (int i = 0; i < 800; i++) { mx = fmaxf(mx, t->head[i].x); mx = fmaxf(mx, t->head[i].y); }
-    t->head_max = mx;
-    for (int i = 0; i < 64; i++) t->w64[i] = h_w64[i];
+    for (size_t i = 0; i < head.size(); i++) { mx = fmaxf(mx, head[i].x); mx = fmaxf(mx, head[i].y); }
+    RxTables *t = new RxTables();
+    wide::WideTables *wt = nullptr;
+    if (!h->wide) {
+        for (int i = 0; i < 80; i++) t->lock[i] = lockf[i];
+        for (int i = 0; i < 64; i++) t->inv_training[i] = invt[i];
+        for (int i = 0; i < 800; i++) t->head[i] = head[i];
+        t->head_max = mx;
+        for (int i = 0; i < 64; i++) t->w64[i] = h_w64[i];
+    } else {
+        wt = new wide::WideTables();
+        for (int i = 0; i < LS; i++) wt->lock[i] = lockf[i];
+        for (int i = 0; i < NF; i++) {
+            wt->inv_training[i] = invt[i];
+            const double ang = -2.0 * 3.14159265358979323846 * (double)i / (double)NF;
+            wt->w1024[i] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+        for (size_t i = 0; i < head.size(); i++) wt->head[i] = head[i];
+        wt->head_max = mx;
+        for (int i = 0; i < 64; i++) t->w64[i] = h_w64[i];
+    }
 
     bool ok = cudaMalloc(&h->d_tables, sizeof(RxTables)) == cudaSuccess &&
               cudaMemcpy(h->d_tables, t, sizeof(RxTables), cudaMemcpyHostToDevice) == cudaSuccess &&
+              (!wt || (cudaMalloc(&h->d_wtables, sizeof(wide::WideTables)) == cudaSuccess &&
+                       cudaMemcpy(h->d_wtables, wt, sizeof(wide::WideTables), cudaMemcpyHostToDevice) == cudaSuccess)) &&
               cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_copied[0], cudaEventDisableTiming) == cudaSuccess &&
@@ -271,6 +360,7 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
               cudaEventCreateWithFlags(&h->ev_done[1], cudaEventDisableTiming) == cudaSuccess &&
               h->counters.ensure(4 * sizeof(uint64_t)) == cudaSuccess;
     delete t;
+    delete wt;
     if (!ok) {
         g_create_error = std::string("engine allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         ofdm_engine_destroy(h);
@@ -285,6 +375,7 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_wtables) cudaFree(h->d_wtables);
     DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
                        &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base };
     for (DevBuf *b : bufs) b->release();
@@ -300,9 +391,9 @@ extern "C" const char *ofdm_last_error(const ofdm_engine *h) { return h ? h->err
 extern "C" int ofdm_get_tables(const ofdm_engine *h, ofdm_fc32 *locking80, ofdm_fc32 *preamble80, ofdm_fc32 *training64)
 {
     if (!h) return OFDM_E_INVALID;
-    if (locking80) memcpy(locking80, h->lock, sizeof h->lock);
-    if (preamble80) memcpy(preamble80, h->pre, sizeof h->pre);
-    if (training64) memcpy(training64, h->train, sizeof h->train);
+    if (locking80) memcpy(locking80, h->lock.data(), sizeof(ofdm_fc32) * h->lock.size());
+    if (preamble80) memcpy(preamble80, h->pre.data(), sizeof(ofdm_fc32) * h->pre.size());
+    if (training64) memcpy(training64, h->train.data(), sizeof(ofdm_fc32) * h->train.size());
     return 0;
 }
 
@@ -323,6 +414,19 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     uint32_t *d_flen = h->scratch_u32.as<uint32_t>();
     int *d_max = reinterpret_cast<int *>(d_flen + n_streams);
     CU(h, cudaMemsetAsync(d_flen, 0, 2 * sizeof(uint32_t) * (size_t)n_streams, st));
+    if (h->wide) {
+        wide::WideTxArgs w{};
+        w.payload = payload; w.payload_len = payload_len; w.payload_stride = payload_stride; w.n_streams = n_streams;
+        w.iq = reinterpret_cast<float2 *>(iq); w.iq_stride = iq_stride; w.frame_len = d_flen; w.stream_max = d_max; w.tables = h->d_wtables;
+        const long max_syms = (long)iq_stride / wide::kL - 10;
+        const uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + 7) / 8) : 1;
+        wpick_tx<false>(h->cfg)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
+        wpick_tx<true>(h->cfg)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
+        h->launches += 2;
+        CU(h, cudaGetLastError());
+        if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     TxArgs a{};
     a.payload = payload; a.payload_len = payload_len; a.payload_stride = payload_stride; a.n_streams = n_streams;
     a.iq = reinterpret_cast<float2 *>(iq); a.iq_stride = iq_stride; a.frame_len = d_flen; a.stream_max = d_max; a.tables = h->d_tables;
@@ -344,7 +448,7 @@ extern "C" int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, cons
                                     int mem, void *stream)
 {
     if (!h) return OFDM_E_INVALID;
-    if (!payload || !payload_len || !iq_out || n_streams == 0 || iq_stride < 880) ENG_FAIL(h, OFDM_E_INVALID, "tx: bad arguments");
+    if (!payload || !payload_len || !iq_out || n_streams == 0 || iq_stride < 11u * (uint32_t)h->sym_len) ENG_FAIL(h, OFDM_E_INVALID, "tx: bad arguments");
     CU(h, cudaSetDevice(h->device));
     if (mem == OFDM_MEM_DEVICE) return tx_device(h, payload, payload_len, payload_stride, n_streams, iq_out, iq_stride, frame_len_out, (cudaStream_t)stream);
 
@@ -375,10 +479,47 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
                      const uint64_t *stream_base = nullptr)
 {
     if (state_total < n_streams) state_total = n_streams;
-    if (state_offset == 0) CU(h, h->state.ensure(sizeof(StreamState) * state_total));
+    const size_t state_sz = h->wide ? sizeof(wide::StreamStateW) : sizeof(StreamState);
+    if (state_offset == 0) CU(h, h->state.ensure(state_sz * state_total));
     const bool prof = h->prof_n < h->prof_cap;
     cudaEvent_t *pe = prof ? &h->prof_ev[3 * (size_t)h->prof_n] : nullptr;
     if (prof) { h->prof_n++; CU(h, cudaEventRecord(pe[0], st)); }
+    if (h->wide) {
+        if (stream_base) ENG_FAIL(h, OFDM_E_INVALID, "capture decode is not implemented for nfft = 1024");
+        wide::WideRxArgs w{};
+        w.iq = reinterpret_cast<const float2 *>(iq); w.n_samples = n_samples; w.iq_stride = iq_stride; w.n_streams = n_streams;
+        w.state = h->state.as<wide::StreamStateW>() + state_offset; w.tables = h->d_wtables;
+        w.out = out; w.out_stride = out_stride; w.out_len = out_len; w.status = status;
+        w.sync_window = h->cfg.sync_window; w.tile_shift = h->tile_shift;
+        w.sync_mode = (int)h->cfg.sync_mode; w.cfo_mode = (int)h->cfg.cfo_mode; w.fec = (int)h->cfg.fec;
+        bool wpoints = false;
+        if (diag) {
+            w.d_offset = diag->offset; w.d_f_delta = diag->f_delta; w.d_h = reinterpret_cast<float2 *>(diag->h_k);
+            w.d_nsyms = diag->n_data_syms; w.d_points = reinterpret_cast<float2 *>(diag->points); w.points_stride = diag->points_stride;
+            wpoints = diag->points != nullptr && diag->points_stride > 0;
+        }
+        WDecodeKernel ka = wpick_acquire(h->cfg);
+        if (h->smem_configured.insert((const void *)ka).second)
+            CU(h, cudaFuncSetAttribute((const void *)ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide::wide_acquire_smem()));
+        ka<<<n_streams, wide::kThreads, wide::wide_acquire_smem(), st>>>(w);
+        if (prof) CU(h, cudaEventRecord(pe[1], st));
+        h->launches += 1;
+        uint32_t mxs = max_n_samples ? max_n_samples : iq_stride;
+        if (mxs > iq_stride) mxs = iq_stride;
+        const long S = ((long)mxs + wide::kL - 1) / wide::kL - 10;
+        if (S > 0) {
+            const uint32_t tiles = (uint32_t)((S + h->tile_shift + wide::kTileSymsW - 1) / wide::kTileSymsW);
+            WDecodeKernel kd = wpick_decode(h->cfg, wpoints);
+            const size_t smem = wide::wide_decode_smem(h->cfg.guard_bands != 0);
+            if (h->smem_configured.insert((const void *)kd).second)
+                CU(h, cudaFuncSetAttribute((const void *)kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kd<<<dim3(tiles, n_streams), wide::kThreads, smem, st>>>(w);
+            h->launches += 1;
+        }
+        if (prof) CU(h, cudaEventRecord(pe[2], st));
+        CU(h, cudaGetLastError());
+        return 0;
+    }
     RxArgs a{};
     a.iq = reinterpret_cast<const float2 *>(iq); a.n_samples = n_samples; a.iq_stride = iq_stride; a.n_streams = n_streams;
     a.state = h->state.as<StreamState>() + state_offset; a.tables = h->d_tables;
@@ -485,7 +626,7 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
     CU(h, h->s_bytes.ensure(ob));
     CU(h, h->s_len.ensure(2 * sizeof(uint32_t) * (size_t)n_streams));
     CU(h, h->s_status.ensure(sizeof(int32_t) * (size_t)n_streams));
-    CU(h, h->state.ensure(sizeof(StreamState) * (size_t)n_streams));
+    CU(h, h->state.ensure((h->wide ? sizeof(wide::StreamStateW) : sizeof(StreamState)) * (size_t)n_streams));
     uint32_t *d_ns = h->s_len.as<uint32_t>(), *d_ol = d_ns + n_streams;
     ofdm_rx_diag dd{};
     if (diag) {
@@ -494,7 +635,7 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
         if (diag->offset) dd.offset = reinterpret_cast<int32_t *>(aux);
         if (diag->f_delta) dd.f_delta = reinterpret_cast<float *>(aux + n_streams);
         if (diag->n_data_syms) dd.n_data_syms = aux + 2 * (size_t)n_streams;
-        if (diag->h_k) { CU(h, h->s_h.ensure(sizeof(float2) * 64 * (size_t)n_streams)); dd.h_k = h->s_h.as<ofdm_fc32>(); }
+        if (diag->h_k) { CU(h, h->s_h.ensure(sizeof(float2) * (size_t)h->nfft * n_streams)); dd.h_k = h->s_h.as<ofdm_fc32>(); }
         if (diag->points && diag->points_stride) {
             CU(h, h->s_points.ensure(sizeof(float2) * (size_t)diag->points_stride * n_streams));
             CU(h, cudaMemsetAsync(h->s_points.p, 0, sizeof(float2) * (size_t)diag->points_stride * n_streams, st));
@@ -515,7 +656,7 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
         if (dc.offset) dc.offset += s0;
         if (dc.f_delta) dc.f_delta += s0;
         if (dc.n_data_syms) dc.n_data_syms += s0;
-        if (dc.h_k) dc.h_k += (size_t)s0 * 64;
+        if (dc.h_k) dc.h_k += (size_t)s0 * h->nfft;
         if (dc.points) dc.points += (size_t)s0 * dc.points_stride;
         int rc = rx_device(h, stage[b]->as<ofdm_fc32>(), d_ns + s0, ns, iq_stride, mx, h->s_bytes.as<uint8_t>() + (size_t)s0 * out_stride,
                            out_stride, d_ol + s0, h->s_status.as<int32_t>() + s0, diag ? &dc : nullptr, st, s0, n_streams);
@@ -529,7 +670,7 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
         if (dd.offset) CU(h, cudaMemcpyAsync(diag->offset, dd.offset, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
         if (dd.f_delta) CU(h, cudaMemcpyAsync(diag->f_delta, dd.f_delta, sizeof(float) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
         if (dd.n_data_syms) CU(h, cudaMemcpyAsync(diag->n_data_syms, dd.n_data_syms, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
-        if (dd.h_k) CU(h, cudaMemcpyAsync(diag->h_k, dd.h_k, sizeof(float2) * 64 * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
+        if (dd.h_k) CU(h, cudaMemcpyAsync(diag->h_k, dd.h_k, sizeof(float2) * (size_t)h->nfft * n_streams, cudaMemcpyDeviceToHost, st));
         if (dd.points) CU(h, cudaMemcpyAsync(diag->points, dd.points, sizeof(float2) * (size_t)diag->points_stride * n_streams, cudaMemcpyDeviceToHost, st));
     }
     CU(h, cudaStreamSynchronize(st));
@@ -622,6 +763,7 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
     if (!h) return OFDM_E_INVALID;
     if (!iq || !peaks || !n_peaks || max_peaks == 0) ENG_FAIL(h, OFDM_E_INVALID, "sync: bad arguments");
     if (n_samples >= 0xFFFFFFFFull) ENG_FAIL(h, OFDM_E_INVALID, "sync: captures are limited to 2^32 - 2 samples per call");
+    if (h->wide) ENG_FAIL(h, OFDM_E_INVALID, "sync search is not implemented for nfft = 1024");
     CU(h, cudaSetDevice(h->device));
     if (mem == OFDM_MEM_DEVICE) return sync_device(h, iq, n_samples, peaks, max_peaks, n_peaks, (cudaStream_t)stream);
     cudaStream_t st = h->own_stream;

@@ -1,0 +1,659 @@
+// wide_kernels.cuh -- the 1024-subcarrier variant (BASELINE.json configs[3]; docs/SPEC.md section 9; no reference
+// implementation exists, the layout is the reference's N=64 construction scaled by 16: CP = 256, L = 1280).
+//
+// First (correct, not yet tuned) implementation: one 256-thread CTA transforms one OFDM symbol at a time with a radix-4
+// Stockham FFT in shared memory (5 stages, 4 points per thread); the stages around it are the same as in the N=64 kernels:
+//   wide_acquire_kernel : sync (ramp correlation / sliding Schmidl-Cox on prefix sums), f64 CFO estimate, channel estimate
+//                         from the 5 training symbols, header symbol decode -> per-stream state.
+//   wide_decode_kernel  : per 28-symbol tile: load (CP stripped) -> derotate -> FFT-1024 -> equalise -> pilot phase (64
+//                         pilots, block reduction) -> demap -> carrier bytes in smem -> Hamming / header strip -> bytes.
+//   wide_tx_kernel      : bits -> constellation -> IFFT-1024 -> CP, two passes (max, then store once) like tx_tile_kernel.
+#pragma once
+
+#include "common.cuh"
+#include "rx_kernels.cuh"
+#include "tx_kernels.cuh"
+
+namespace ofdm {
+namespace wide {
+
+constexpr int kN = 1024, kCpW = 256, kL = kN + kCpW, kHeadW = 10 * kL;
+constexpr int kThreads = 256;
+constexpr int kTileSymsW = 28;                   // symbols per CTA tile (multiple of 7: Hamming byte alignment)
+
+__host__ __device__ __forceinline__ bool w_is_null(int k) { return k <= 95 || k == 512 || k >= 929; }
+__host__ __device__ __forceinline__ int w_rem(int k) { return k < 512 ? k - 96 : k - 97; }          // index among the 832 used bins
+__host__ __device__ __forceinline__ bool w_is_pilot(int k) { return !w_is_null(k) && w_rem(k) % 13 == 0; }
+template <bool GUARD>
+__host__ __device__ __forceinline__ int w_rank(int k)
+{
+    if (!GUARD) return k;
+    if (w_is_null(k)) return -1;
+    const int r = w_rem(k);
+    return r % 13 == 0 ? -1 : r - r / 13 - 1;
+}
+
+struct WideTables {
+    float2 lock[kL];            // locking_signal::<1280>
+    float2 inv_training[kN];    // 1 / training_signals::<1024>
+    float2 w1024[kN];           // W1024^k
+    float2 head[kHeadW];        // un-normalised lock | preamble x4 | (CP + IFFT(training)) x5
+    float  head_max;
+};
+
+struct __align__(16) StreamStateW {
+    int32_t  status;
+    int32_t  offset;
+    uint32_t n_syms;
+    uint32_t out_len;
+    uint64_t fstep;
+    float    f_delta;
+    uint32_t plen;
+    uint32_t n_syms_rx;
+    uint32_t pad[3];
+    float2   g[kN];
+    float2   h[kN];
+};
+
+struct WideRxArgs {
+    const float2   *iq;
+    const uint32_t *n_samples;
+    uint32_t        iq_stride;
+    uint32_t        n_streams;
+    StreamStateW   *state;
+    const WideTables *tables;
+    uint8_t        *out;
+    uint32_t        out_stride;
+    uint32_t       *out_len;
+    int32_t        *status;
+    uint32_t        sync_window;
+    int32_t         tile_shift;
+    int32_t         sync_mode, cfo_mode, fec;
+    int32_t  *d_offset;
+    float    *d_f_delta;
+    float2   *d_h;              // [n_streams][1024]
+    uint32_t *d_nsyms;
+    float2   *d_points;
+    uint32_t  points_stride;
+};
+
+// ---- block FFT: 1024 points, 256 threads, radix-4 Stockham autosort -------------------------------------------------
+// in : v[r] = x[tid + 256 r].  out: natural-order spectrum in `bufA`. `s_w` = W1024 table in smem. 5 barriers.
+__device__ __forceinline__ void radix4(cpx (&v)[4])
+{
+    const cpx a = c_add(v[0], v[2]), b = c_sub(v[0], v[2]), c = c_add(v[1], v[3]), d = c_mul_mj(c_sub(v[1], v[3]));
+    v[0] = c_add(a, c); v[2] = c_sub(a, c); v[1] = c_add(b, d); v[3] = c_sub(b, d);
+}
+__device__ __forceinline__ void fft1024_block(cpx (&v)[4], float2 *bufA, float2 *bufB, const float2 *s_w, int tid)
+{
+    unsigned long long *A = reinterpret_cast<unsigned long long *>(bufA), *B = reinterpret_cast<unsigned long long *>(bufB);
+    // stage 0 (Ns = 1): no twiddles, out[4 j + r]
+    radix4(v);
+#pragma unroll
+    for (int r = 0; r < 4; r++) A[4 * tid + r] = v[r].v;
+    __syncthreads();
+    unsigned long long *in = A, *out = B;
+#pragma unroll
+    for (int st = 1; st < 5; st++) {
+        const int Ns = 1 << (2 * st);
+        const int k = tid & (Ns - 1);
+#pragma unroll
+        for (int r = 0; r < 4; r++) v[r].v = in[tid + 256 * r];
+        const int tstep = k * (256 >> (2 * st));                  // W_{4 Ns}^{r k} = W1024^{r k 256 / Ns}
+#pragma unroll
+        for (int r = 1; r < 4; r++) v[r] = c_mul(v[r], c_from(s_w[(r * tstep) & (kN - 1)]));
+        radix4(v);
+        const int j0 = ((tid - k) << 2) + k;
+#pragma unroll
+        for (int r = 0; r < 4; r++) out[j0 + r * Ns] = v[r].v;
+        __syncthreads();
+        unsigned long long *t = in; in = out; out = t;
+    }
+    // 5 stages: A, B, A, B, A -> result in A
+}
+
+// sum over the block of a packed complex (for the pilot sum) or a float (angles); s_red: 2 * 8 floats
+__device__ __forceinline__ void block_sum2(float &x, float &y, float *s_red, int tid)
+{
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, m); y += __shfl_xor_sync(0xffffffffu, y, m); }
+    if ((tid & 31) == 0) { s_red[tid >> 5] = x; s_red[8 + (tid >> 5)] = y; }
+    __syncthreads();
+    float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { sx += s_red[w]; sy += s_red[8 + w]; }
+    x = sx; y = sy;
+}
+
+// per-thread constants of the symbol pipeline
+struct WideLane {
+    cpx w[4];        // derotation exp(-j f (tid + 256 r))
+    cpx g[4];        // equaliser 1/h at bins tid + 256 r
+    int rank[4];     // data-carrier rank of those bins or -1
+    uint32_t pilot;  // bit r: bin tid + 256 r is a pilot
+};
+
+template <bool GUARD>
+__device__ __forceinline__ void wide_lane_init(WideLane &L, const StreamStateW *st, int tid)
+{
+    L.pilot = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int k = tid + 256 * r;
+        L.w[r] = phasor_from_turns_p(st->fstep * (uint64_t)k);
+        L.g[r] = c_from(st->g[k]);
+        L.rank[r] = w_rank<GUARD>(k);
+        if (GUARD && w_is_pilot(k)) L.pilot |= 1u << r;
+    }
+}
+
+__device__ __forceinline__ void wide_load_symbol(const float2 *__restrict__ x0, uint32_t n_avail, uint32_t sym, bool valid, int tid, cpx (&v)[4])
+{
+    const uint32_t n0 = (10u + sym) * kL + kCpW + tid;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint32_t n = n0 + 256u * r;
+        v[r].v = 0ull;
+        if (valid && n < n_avail) v[r].v = __ldg(reinterpret_cast<const unsigned long long *>(x0 + n));    // zero-padded tail row
+    }
+}
+
+// One OFDM symbol by the whole CTA: derotate, FFT, equalise, pilot phase. On return z[r] = corrected bin tid + 256 r.
+template <bool GUARD, int PHASE>
+__device__ __forceinline__ void wide_symbol(const WideLane &L, cpx base, cpx (&z)[4], float2 *bufA, float2 *bufB, const float2 *s_w,
+                                            float *s_red, int tid)
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++) z[r] = c_mul(z[r], L.w[r]);
+    fft1024_block(z, bufA, bufB, s_w, tid);
+    const unsigned long long *A = reinterpret_cast<const unsigned long long *>(bufA);
+#pragma unroll
+    for (int r = 0; r < 4; r++) { cpx x; x.v = A[tid + 256 * r]; z[r] = c_mul(x, L.g[r]); }
+    cpx rot = base;
+    if (GUARD) {
+        float px = 0.0f, py = 0.0f;
+        if (PHASE == 1) {
+            cpx p = c_make(0.0f, 0.0f);
+#pragma unroll
+            for (int r = 0; r < 4; r++) if (L.pilot & (1u << r)) p = c_add(p, z[r]);
+            c_split(p, px, py);
+            block_sum2(px, py, s_red, tid);
+            const float inv = rsqrtf(fmaxf(px * px + py * py, 1e-30f));
+            rot = c_make(px * inv, -py * inv);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (L.pilot & (1u << r)) { float a, b; c_split(c_mul(z[r], base), a, b); px += atan2f(b, a); }
+            block_sum2(px, py, s_red, tid);
+            float sn, cs;
+            sincosf(-px * (1.0f / 64.0f), &sn, &cs);
+            rot = c_mul(c_make(cs, sn), base);
+        }
+    } else {
+        __syncthreads();                                          // same barrier count on every path (bufA reuse)
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) z[r] = c_mul(z[r], rot);
+}
+
+// ---- tile carrier bytes -> payload bytes (shared with nothing else: same scheme as rx_decode_kernel's second phase) ----
+template <int MOD, bool FEC, int D>
+__device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint8_t *s_ham, int t0, int t1, uint32_t out_len, uint8_t *out,
+                                                int tid)
+{
+    constexpr int BPC = ModTraits<MOD>::kBpc;
+    constexpr int BPS = BPC * D;
+    constexpr int NB = FEC ? 14 : 8;
+    const long bit0 = (long)t0 * BPS, bit1 = (long)t1 * BPS;
+    long j0 = bit0 <= kHeaderBits ? 0 : (bit0 - kHeaderBits + NB - 1) / NB;
+    long j1 = (bit1 - kHeaderBits) / NB;
+    if (j1 > (long)out_len) j1 = (long)out_len;
+    const int pbase = (int)(kHeaderBits + j0 * NB - bit0);
+    const int nbytes = (int)(j1 - j0);
+    for (int u = tid; u < nbytes; u += kThreads) {
+        const int p = pbase + u * NB;
+        const int c = p / BPC, sh = p - c * BPC;
+        constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < NC; i++) v |= (uint32_t)s_car[c + i] << (BPC * i);
+        v >>= sh;
+        uint32_t byte;
+        if (FEC) byte = (uint32_t)s_ham[v & 127u] | ((uint32_t)s_ham[(v >> 7) & 127u] << 4);
+        else byte = v & 255u;
+        out[j0 + u] = (uint8_t)byte;
+    }
+}
+
+constexpr size_t wide_decode_smem(bool guard)
+{
+    return sizeof(float2) * (3 * kN) + (size_t)kTileSymsW * (guard ? 768 : 1024) + 64 + 128 + 64;
+}
+
+template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
+__global__ void __launch_bounds__(kThreads) wide_decode_kernel(const WideRxArgs a)
+{
+    constexpr int D = GUARD ? 768 : 1024;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float2 *bufA = reinterpret_cast<float2 *>(smem_raw), *bufB = bufA + kN, *s_w = bufB + kN;
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_w + kN);
+    uint8_t *s_ham = s_car + kTileSymsW * D + 64;
+    float *s_red = reinterpret_cast<float *>(s_ham + 128);
+
+    const uint32_t stream = blockIdx.y;
+    const StreamStateW *st = a.state + stream;
+    if (st->status != ST_OK) return;
+    const int S = (int)st->n_syms;
+    int t0 = (int)blockIdx.x * kTileSymsW - a.tile_shift, t1 = t0 + kTileSymsW;
+    if (t0 < 0) t0 = 0;
+    if (t1 > S) t1 = S;
+    if (t0 >= t1) return;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kN; i += kThreads) s_w[i] = a.tables->w1024[i];
+    if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
+
+    const uint32_t offset = (uint32_t)st->offset;
+    const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
+    const uint32_t n_avail = a.n_samples[stream] - offset;
+    WideLane L;
+    wide_lane_init<GUARD>(L, st, tid);
+    const uint64_t fstep = st->fstep;
+    cpx base = phasor_from_turns_p(fstep * (uint64_t)((10 + t0) * kL + kCpW));
+    const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)kL);
+    __syncthreads();
+
+    cpx nxt[4];
+    wide_load_symbol(x0, n_avail, (uint32_t)t0, true, tid, nxt);
+#pragma unroll 1
+    for (int s = t0; s < t1; s++) {
+        cpx z[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) z[r] = nxt[r];
+        wide_load_symbol(x0, n_avail, (uint32_t)(s + 1), s + 1 < t1, tid, nxt);            // software prefetch of the next symbol
+        wide_symbol<GUARD, PHASE>(L, base, z, bufA, bufB, s_w, s_red, tid);
+        base = c_mul(base, dbase);
+        uint8_t *row = s_car + (s - t0) * D;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            float zr, zi;
+            c_split(z[r], zr, zi);
+            if (L.rank[r] >= 0) {
+                row[L.rank[r]] = (uint8_t)demap_point<MOD>(zr, zi);
+                if (POINTS) {
+                    size_t p = (size_t)s * D + L.rank[r];
+                    if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    wide_tile_bytes<MOD, FEC, D>(s_car, s_ham, t0, t1, st->out_len, a.out + (size_t)stream * a.out_stride, tid);
+}
+
+// ---- acquisition ---------------------------------------------------------------------------------------------------------
+constexpr int kAcqChunkW = 1024;
+constexpr int kAcqNQ = kAcqChunkW + kL, kAcqNE = kAcqChunkW + 2 * kL;
+constexpr size_t wide_acquire_smem()
+{
+    // lock ramp | union { S&C prefix arrays , FFT buffers + twiddles + header carrier bytes }
+    return sizeof(float) * kL + sizeof(float2) * (kAcqNQ + 1) + sizeof(float) * (kAcqNE + 1) + 256;
+}
+
+__device__ __forceinline__ float ramp_corr_sq_w(const float2 *__restrict__ x, long k, long n_samples, const float *s_lock)
+{
+    float cr = 0.0f, ci = 0.0f;
+    if (k >= 0 && k + kL <= n_samples) {
+#pragma unroll 8
+        for (int n = 0; n < kL; n++) { float2 v = __ldg(x + k + n); cr = fmaf(v.x, s_lock[n], cr); ci = fmaf(v.y, s_lock[n], ci); }
+    } else {
+        for (int n = 0; n < kL; n++) { float2 v = ld_sample(x, k + n, n_samples); cr = fmaf(v.x, s_lock[n], cr); ci = fmaf(v.y, s_lock[n], ci); }
+    }
+    return cr * cr + ci * ci;
+}
+__device__ __forceinline__ long ramp_argmax_w(const float2 *__restrict__ x, long n_samples, long k_lo, long k_hi, const float *s_lock,
+                                              float *s_val, int *s_idx)
+{
+    float best = 0.0f;
+    int bidx = 0x7fffffff;
+    for (long k = k_lo + threadIdx.x; k <= k_hi; k += kThreads) {
+        float v = ramp_corr_sq_w(x, k, n_samples, s_lock);
+        if (v > best) { best = v; bidx = (int)(k - k_lo); }
+    }
+    block_argmax(best, bidx, s_val, s_idx);
+    return best > 0.0f ? k_lo + bidx : k_lo;
+}
+
+template <int MOD, bool GUARD, int PHASE>
+__global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs a)
+{
+    static_assert(kThreads == kAcqThreads, "block_argmax is sized for kAcqThreads");
+    constexpr int BPC = ModTraits<MOD>::kBpc;
+    constexpr int D = GUARD ? 768 : 1024;
+    constexpr int BPS = BPC * D;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *s_lock = reinterpret_cast<float *>(smem_raw);
+    uint8_t *u = reinterpret_cast<uint8_t *>(s_lock + kL);
+    float2 *s_q = reinterpret_cast<float2 *>(u);                       // S&C phase
+    float *s_e = reinterpret_cast<float *>(s_q + kAcqNQ + 1);
+    float2 *bufA = reinterpret_cast<float2 *>(u), *bufB = bufA + kN, *s_w = bufB + kN;      // FFT phase (aliases the S&C arrays)
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_w + kN);            // 1024 carrier bytes
+    __shared__ float s_val[kThreads / 32];
+    __shared__ int s_idx[kThreads / 32];
+    __shared__ int s_d0;
+    __shared__ double s_red[2 * (kThreads / 32)];
+    __shared__ float s_redf[16];
+    __shared__ float s_wtot[3 * (kThreads / 32)];
+
+    const uint32_t stream = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int SYNC = a.sync_mode, CFO = a.cfo_mode;
+    const bool FEC = a.fec != 0;
+    StreamStateW *st = a.state + stream;
+    const long M = (long)a.n_samples[stream];
+    const float2 *x = a.iq + (size_t)stream * a.iq_stride;
+    for (int i = tid; i < kL; i += kThreads) s_lock[i] = a.tables->lock[i].x;
+    if (tid == 0) s_d0 = 0x7fffffff;
+    __syncthreads();
+
+    long W = a.sync_window > 0 ? (long)a.sync_window : M;
+    if (W > M) W = M;
+    int status = ST_OK;
+    long offset = 0;
+    if (SYNC == 0) {
+        offset = ramp_argmax_w(x, M, -(kL - 1), W - 1, s_lock, s_val, s_idx) - 1;
+    } else {
+        long d_end = W;
+        if (d_end > M - 2 * kL + 1) d_end = M - 2 * kL + 1;
+        for (long base = 0; base < d_end; base += kAcqChunkW) {
+            constexpr int RUN = (kAcqNE + kThreads - 1) / kThreads;           // 14 consecutive samples per thread
+            float tqr = 0.0f, tqi = 0.0f, te = 0.0f;
+            float qr[RUN], qi[RUN], ee[RUN];
+#pragma unroll
+            for (int r = 0; r < RUN; r++) {
+                long n = base + (long)tid * RUN + r;
+                float2 v0 = ld_sample(x, n, M), v1 = ld_sample(x, n + kL, M);
+                float pr = v0.x * v1.x + v0.y * v1.y, pi = v0.x * v1.y - v0.y * v1.x;
+                qr[r] = tqr; qi[r] = tqi; ee[r] = te;
+                tqr += pr; tqi += pi; te += v0.x * v0.x + v0.y * v0.y;
+            }
+            float sqr = tqr, sqi = tqi, se = te;
+#pragma unroll
+            for (int m = 1; m < 32; m <<= 1) {
+                float a0 = __shfl_up_sync(0xffffffffu, sqr, m), a1 = __shfl_up_sync(0xffffffffu, sqi, m), a2 = __shfl_up_sync(0xffffffffu, se, m);
+                if (lane >= m) { sqr += a0; sqi += a1; se += a2; }
+            }
+            __syncthreads();
+            if (lane == 31) { s_wtot[warp] = sqr; s_wtot[8 + warp] = sqi; s_wtot[16 + warp] = se; }
+            __syncthreads();
+            float oqr = sqr - tqr, oqi = sqi - tqi, oe = se - te;
+            for (int w2 = 0; w2 < warp; w2++) { oqr += s_wtot[w2]; oqi += s_wtot[8 + w2]; oe += s_wtot[16 + w2]; }
+#pragma unroll
+            for (int r = 0; r < RUN; r++) {
+                int i = tid * RUN + r;
+                if (i <= kAcqNQ) s_q[i] = make_float2(qr[r] + oqr, qi[r] + oqi);
+                if (i <= kAcqNE) s_e[i] = ee[r] + oe;
+            }
+            __syncthreads();
+            int found = 0x7fffffff;
+            for (int i = tid; i < kAcqChunkW && base + i < d_end; i += kThreads) {
+                float2 qa = s_q[i], qb = s_q[i + kL];
+                float pr = qb.x - qa.x, pi = qb.y - qa.y;
+                float r1 = s_e[i + kL] - s_e[i], r2 = s_e[i + 2 * kL] - s_e[i + kL];
+                if (pr * pr + pi * pi > 0.5f * r1 * r2) { found = i; break; }
+            }
+            if (found != 0x7fffffff) atomicMin(&s_d0, (int)(base + found));
+            __syncthreads();
+            if (s_d0 != 0x7fffffff) break;
+        }
+        if (s_d0 == 0x7fffffff) {
+            status = ST_NO_SYNC;
+        } else {
+            long d0 = s_d0, k_lo = d0 - (11 * kL) / 5, k_hi = d0 + kL / 5;
+            if (k_lo < -(kL - 1)) k_lo = -(kL - 1);
+            offset = ramp_argmax_w(x, M, k_lo, k_hi, s_lock, s_val, s_idx) - 1;
+        }
+    }
+    if (status == ST_OK && offset < 0) status = ST_NEG_OFFSET;
+    if (status == ST_OK && (offset > M || M - offset < kHeadW)) status = ST_TOO_SHORT;
+    if (status != ST_OK) {
+        if (tid == 0) {
+            st->status = status; st->offset = (int32_t)offset; st->n_syms = 0; st->out_len = 0; st->f_delta = 0.0f; st->fstep = 0;
+            a.status[stream] = status; a.out_len[stream] = 0;
+            if (a.d_offset) a.d_offset[stream] = (int32_t)offset;
+            if (a.d_f_delta) a.d_f_delta[stream] = 0.0f;
+            if (a.d_nsyms) a.d_nsyms[stream] = 0;
+        }
+        return;
+    }
+    const float2 *x0 = x + offset;
+    const long n_avail = M - offset;
+
+    // ---- CFO estimate (f64) ----------------------------------------------------------------------------------------------
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int i = tid; i < kL; i += kThreads) {
+        float2 r2 = x0[2 * kL + i], r3 = x0[3 * kL + i], r4 = x0[4 * kL + i];
+        if (CFO == 0) {
+            double lr = r3.x, li = r3.y, rr = r4.x, ri = r4.y, nn = lr * lr + li * li;
+            acc0 += atan2((ri * lr - rr * li) / nn, (rr * lr + ri * li) / nn);
+        } else {
+            acc0 += (double)r2.x * r3.x + (double)r2.y * r3.y + (double)r3.x * r4.x + (double)r3.y * r4.y;
+            acc1 += (double)r2.x * r3.y - (double)r2.y * r3.x + (double)r3.x * r4.y - (double)r3.y * r4.x;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, m); acc1 += __shfl_xor_sync(0xffffffffu, acc1, m); }
+    if (lane == 0) { s_red[warp] = acc0; s_red[8 + warp] = acc1; }
+    __syncthreads();
+    double f_delta;
+    {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w2 = 0; w2 < kThreads / 32; w2++) { t0 += s_red[w2]; t1 += s_red[8 + w2]; }
+        if (CFO == 0) f_delta = fabs((t0 / (double)kL) / (double)kL);
+        else f_delta = atan2(t1, t0) / (double)kL;
+    }
+    const uint64_t fstep = (uint64_t)(int64_t)llrint(-f_delta * (0.15915494309189533577 * 18446744073709551616.0));
+    if (tid == 0) { st->fstep = fstep; st->f_delta = (float)f_delta; st->offset = (int32_t)offset; }
+
+    // ---- channel estimate: 5 training symbols ------------------------------------------------------------------------------
+    for (int i = tid; i < kN; i += kThreads) s_w[i] = a.tables->w1024[i];
+    __syncthreads();
+    cpx hsum[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) hsum[r] = c_make(0.0f, 0.0f);
+#pragma unroll 1
+    for (int row = 5; row < 10; row++) {
+        cpx v[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t n = row * kL + kCpW + tid + 256 * r;
+            v[r] = c_mul(c_from(x0[n]), phasor_from_turns_p(fstep * (uint64_t)n));
+        }
+        fft1024_block(v, bufA, bufB, s_w, tid);
+        const unsigned long long *A = reinterpret_cast<const unsigned long long *>(bufA);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            cpx xx; xx.v = A[tid + 256 * r];
+            hsum[r] = c_add(hsum[r], c_mul(xx, c_from(a.tables->inv_training[tid + 256 * r])));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        float hr, hi;
+        c_split(c_scale(hsum[r], 0.2f), hr, hi);
+        const float inv = 1.0f / (hr * hr + hi * hi);
+        const int k = tid + 256 * r;
+        st->h[k] = make_float2(hr, hi);
+        st->g[k] = make_float2(hr * inv, -hi * inv);
+        if (a.d_h) a.d_h[(size_t)stream * kN + k] = make_float2(hr, hi);
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- header symbol (data symbol 0 holds >= 128 bits in every mode) --------------------------------------------------------
+    WideLane L;
+    wide_lane_init<GUARD>(L, st, tid);
+    cpx z[4];
+    wide_load_symbol(x0, (uint32_t)(n_avail > 0xffffffffL ? 0xffffffffL : n_avail), 0u, true, tid, z);
+    const cpx base = phasor_from_turns_p(fstep * (uint64_t)(10 * kL + kCpW));
+    wide_symbol<GUARD, PHASE>(L, base, z, bufA, bufB, s_w, s_redf, tid);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        float zr, zi;
+        c_split(z[r], zr, zi);
+        if (L.rank[r] >= 0) s_car[L.rank[r]] = (uint8_t)demap_point<MOD>(zr, zi);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t lo = 0, hi64 = 0;
+        for (int b = 0; b < 128; b++) {
+            int c = b / BPC, sh = b - c * BPC;
+            uint64_t bit = (s_car[c] >> sh) & 1u;
+            if (b < 64) lo |= bit << b; else hi64 |= bit << (b - 64);
+        }
+        const long rows = (n_avail + kL - 1) / kL;
+        const long s_rx = rows - 10;
+        const long avail_bytes = (s_rx * BPS) / 8 - 16;
+        int stt = ST_OK;
+        uint32_t n_syms = 0, out_len = 0;
+        if (hi64 != 0 || (long)lo > avail_bytes || avail_bytes < 0) {
+            stt = ST_BAD_HEADER;
+        } else {
+            const uint64_t nbits = kHeaderBits + 8 * lo;
+            const uint64_t ncar = (nbits + BPC - 1) / BPC;
+            n_syms = (uint32_t)((ncar + D - 1) / D);
+            out_len = (uint32_t)(FEC ? (8 * lo) / 14 : lo);
+            if (out_len > a.out_stride) { stt = ST_BAD_HEADER; n_syms = 0; out_len = 0; }
+        }
+        st->status = stt; st->n_syms = n_syms; st->out_len = out_len; st->plen = (uint32_t)lo; st->n_syms_rx = (uint32_t)s_rx;
+        a.status[stream] = stt; a.out_len[stream] = out_len;
+        if (a.d_offset) a.d_offset[stream] = (int32_t)offset;
+        if (a.d_f_delta) a.d_f_delta[stream] = (float)f_delta;
+        if (a.d_nsyms) a.d_nsyms[stream] = (uint32_t)s_rx;
+    }
+}
+
+// ---- TX ------------------------------------------------------------------------------------------------------------------
+struct WideTxArgs {
+    const uint8_t  *payload;
+    const uint32_t *payload_len;
+    uint32_t        payload_stride;
+    uint32_t        n_streams;
+    float2         *iq;
+    uint32_t        iq_stride;
+    uint32_t       *frame_len;
+    int            *stream_max;
+    const WideTables *tables;
+};
+
+template <int MOD, bool GUARD, bool FEC, bool WRITE>
+__global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
+{
+    constexpr int BPC = ModTraits<MOD>::kBpc;
+    constexpr int D = GUARD ? 768 : 1024;
+    constexpr int BPS = BPC * D;
+    constexpr int TS = 8;                                            // symbols per CTA
+    __shared__ __align__(16) float2 bufA[kN], bufB[kN], s_w[kN];
+    __shared__ __align__(16) uint8_t s_bits[TS * BPS / 8 + 16];
+    __shared__ __align__(8) float2 s_map[64];
+    __shared__ uint8_t s_enc[16];
+
+    const uint32_t stream = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t n = a.payload_len[stream];
+    const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;
+    const uint64_t nbits = kHeaderBits + 8 * coded_len;
+    const uint64_t ncar = (nbits + BPC - 1) / BPC;
+    const int S = (int)((ncar + D - 1) / D);
+    const uint32_t frame_len = (10u + (uint32_t)S) * kL;
+    if (a.frame_len && blockIdx.x == 0 && tid == 0) a.frame_len[stream] = frame_len;
+    const bool fits = frame_len <= a.iq_stride;
+    float2 *out = a.iq + (size_t)stream * a.iq_stride;
+    int t0 = (int)blockIdx.x * TS, t1 = t0 + TS;
+    if (t1 > S) t1 = S;
+    float scale = 1.0f / (float)kN;
+    if (WRITE) {
+        const float mx = fmaxf(__int_as_float(a.stream_max[stream]), a.tables->head_max);
+        scale *= 1.0f / mx;
+        if (blockIdx.x == 0)
+            for (uint32_t i = tid; i < (uint32_t)kHeadW && i < a.iq_stride; i += kThreads) {
+                float2 v = make_float2(0.0f, 0.0f);
+                if (fits) { v = a.tables->head[i]; v.x = v.x / mx; v.y = v.y / mx; }
+                out[i] = v;
+            }
+        if (blockIdx.x == gridDim.x - 1) {
+            const uint32_t z0 = fits ? frame_len : (uint32_t)kHeadW;
+            for (uint32_t i = z0 + tid; i < a.iq_stride; i += kThreads) out[i] = make_float2(0.0f, 0.0f);
+        }
+    }
+    if (!fits || t0 >= t1) return;
+    if (tid < 64) {
+        float re = 0.0f, im = 0.0f;
+        if (MOD == 0) { re = (tid & 1) ? 1.0f : -1.0f; }
+        else if (MOD == 1) { re = (tid & 1) ? 1.0f : -1.0f; im = (tid & 2) ? 1.0f : -1.0f; }
+        else {
+            const uint32_t ci = tid & 7u, cq = tid >> 3;
+            const uint32_t li = ci ^ (ci >> 1) ^ (ci >> 2), lq = cq ^ (cq >> 1) ^ (cq >> 2);
+            re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
+            im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
+        }
+        s_map[tid] = make_float2(im, re);                            // swapped: the IFFT runs as swap . FFT . swap
+    }
+    if (tid < 16) s_enc[tid] = (uint8_t)ham74_encode_nibble(tid);
+    for (int i = tid; i < kN; i += kThreads) s_w[i] = a.tables->w1024[i];
+    __syncthreads();
+    const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+    const uint32_t byte0 = (uint32_t)((long)t0 * BPS / 8), nbyte = (uint32_t)((long)(t1 - t0) * BPS / 8);
+    for (uint32_t b = tid; b < nbyte + 2; b += kThreads) s_bits[b] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + b, s_enc);
+    __syncthreads();
+
+    const long ncar_local = (long)ncar - (long)t0 * D;
+    float mx = 0.0f;
+#pragma unroll 1
+    for (int s = t0; s < t1; s++) {
+        cpx v[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int k = tid + 256 * r;
+            cpx val = c_make(0.0f, 0.0f);
+            const int rk = w_rank<GUARD>(k);
+            if (GUARD && w_is_pilot(k)) val = c_make(0.0f, 1.0f);
+            else if (rk >= 0) {
+                const long c = (long)(s - t0) * D + rk;
+                if (c < ncar_local) {
+                    const uint32_t bit = (uint32_t)c * BPC, bb = bit >> 3;
+                    const uint32_t w = ((uint32_t)s_bits[bb] | ((uint32_t)s_bits[bb + 1] << 8)) >> (bit & 7);
+                    val = c_from(s_map[w & ((1u << BPC) - 1u)]);
+                }
+            }
+            v[r] = val;
+        }
+        fft1024_block(v, bufA, bufB, s_w, tid);
+        const unsigned long long *A = reinterpret_cast<const unsigned long long *>(bufA);
+        float2 *sym = out + (size_t)(10 + s) * kL;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            cpx x; x.v = A[tid + 256 * r];
+            float re, im;
+            c_split(x, im, re);                                      // un-swap
+            const int t = tid + 256 * r;
+            if (WRITE) {
+                const float2 o = make_float2(re * scale, im * scale);
+                sym[kCpW + t] = o;
+                if (r == 3) sym[t - (kN - kCpW)] = o;                // cyclic prefix = last 256 samples
+            } else {
+                mx = fmaxf(mx, fmaxf(re, im));
+            }
+        }
+        __syncthreads();                                            // bufA is rewritten by the next symbol
+    }
+    if (!WRITE) {
+        mx *= scale;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        if (lane == 0 && mx > 0.0f) atomicMax(a.stream_max + stream, __float_as_int(mx));
+    }
+}
+
+}  // namespace wide
+}  // namespace ofdm

@@ -142,7 +142,13 @@ class Config:
 
     @property
     def data_carriers(self) -> int:
+        if self.nfft == 1024:
+            return 768 if self.guard_bands else 1024
         return 48 if self.guard_bands else 64
+
+    @property
+    def sym_len(self) -> int:
+        return self.nfft + self.cp
 
     def coded_len(self, n: int) -> int:
         return int(load_library().ofdm_coded_len(C.byref(self.to_c()), n))
@@ -237,9 +243,9 @@ class Engine:
         return a[: n.value], d[: n.value]
 
     def tables(self):
-        lock = np.zeros(80, np.complex64)
-        pre = np.zeros(80, np.complex64)
-        tr = np.zeros(64, np.complex64)
+        lock = np.zeros(self.cfg.sym_len, np.complex64)
+        pre = np.zeros(self.cfg.sym_len, np.complex64)
+        tr = np.zeros(self.cfg.nfft, np.complex64)
         self._check(self.lib.ofdm_get_tables(self._h, _ptr(lock), _ptr(pre), _ptr(tr)), "ofdm_get_tables")
         return lock, pre, tr
 
@@ -272,7 +278,7 @@ class Engine:
             n_samples = np.full(n, stride, np.uint32)
         n_samples = np.ascontiguousarray(n_samples, np.uint32)
         if out_stride is None:
-            out_stride = max(16, (stride // 80) * self.cfg.data_carriers * self.cfg.bits_per_carrier // 8)
+            out_stride = max(16, (stride // self.cfg.sym_len) * self.cfg.data_carriers * self.cfg.bits_per_carrier // 8)
         out = np.zeros((n, out_stride), np.uint8)
         out_len = np.zeros(n, np.uint32)
         status = np.zeros(n, np.int32)
@@ -281,11 +287,11 @@ class Engine:
         if diag or points:
             res.offset = np.zeros(n, np.int32)
             res.f_delta = np.zeros(n, np.float32)
-            res.h_k = np.zeros((n, 64), np.complex64)
+            res.h_k = np.zeros((n, self.cfg.nfft), np.complex64)
             res.n_data_syms = np.zeros(n, np.uint32)
             ps = 0
             if points:
-                ps = (stride // 80 + 1) * self.cfg.data_carriers
+                ps = (stride // self.cfg.sym_len + 1) * self.cfg.data_carriers
                 res.points = np.zeros((n, ps), np.complex64)
             d = CRxDiag(_ptr(res.offset), _ptr(res.f_delta), _ptr(res.h_k), _ptr(res.n_data_syms),
                         _ptr(res.points) if points else None, ps)
