@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--workload", default="streams", choices=["streams", "capture"],
                     help="streams: BASELINE configs[1] (the headline line); capture: configs[2], preamble search over one long capture")
     ap.add_argument("--capture-samples", type=float, default=1e9)
+    ap.add_argument("--nfft", type=int, default=64, choices=[64, 1024],
+                    help="64: the reference layout (headline); 1024: wideband variant, BASELINE configs[3] (use --syms 128)")
     return ap.parse_args()
 
 
@@ -64,15 +66,22 @@ SYNC_WINDOW = 2048
 SEED = 0x0FD64
 
 
+NFFT = 64
+
+
+def sync_window():
+    return SYNC_WINDOW if NFFT == 64 else 4096
+
+
 def workload_cfg():
     import ofdm_b200 as ob
     return ob.Config(modulation=ob.MOD_QAM64, guard_bands=True, fec=True, sync_mode=ob.SYNC_SCHMIDL_COX,
-                     cfo_mode=ob.CFO_ANGLE_OF_SUM, phase_mode=ob.PHASE_ANGLE_OF_SUM, sync_window=SYNC_WINDOW)
+                     cfo_mode=ob.CFO_ANGLE_OF_SUM, phase_mode=ob.PHASE_ANGLE_OF_SUM, sync_window=sync_window(), nfft=NFFT, cp=NFFT // 4)
 
 
 def oracle_cfg():
     from oracle import oracle as oo
-    return oo.make_cfg(True, oo.QAM64, True, oo.SYNC_SCHMIDL_COX, oo.CFO_ANGLE_OF_SUM, oo.PHASE_ANGLE_OF_SUM, SYNC_WINDOW)
+    return oo.make_cfg(True, oo.QAM64, True, oo.SYNC_SCHMIDL_COX, oo.CFO_ANGLE_OF_SUM, oo.PHASE_ANGLE_OF_SUM, sync_window(), nfft=NFFT)
 
 
 class ClockSampler:
@@ -172,7 +181,11 @@ def cpu_sample(iq_host: np.ndarray, n_samples: np.ndarray, out_stride: int, targ
 
 
 def main():
+    global NFFT
     args = parse_args()
+    NFFT = args.nfft
+    if NFFT == 1024 and args.snr == 40.0:
+        args.snr = 50.0        # data symbols sit ~12 dB below the frame head at N = 1024 (docs/SPEC.md 9): keep every header decodable
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,10 +209,10 @@ def main():
     n_streams = args.streams
     iq_stride = (frame_len + LEAD_MAX + 63 + 31) // 32 * 32
     out_stride = (payload_len + 15) // 16 * 16
-    workload = f"{n_streams}x64QAM_S{S}"
+    workload = f"{n_streams}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}")
     config = {"workload": workload, "streams_per_gpu": n_streams, "data_syms_per_frame": S, "frame_samples": frame_len,
               "payload_bytes": payload_len, "modulation": "64QAM", "guard_bands": True, "fec": "hamming(7,4)",
-              "sync": "schmidl_cox(window=%d)" % SYNC_WINDOW, "cfo": "angle_of_sum", "snr_db": args.snr,
+              "sync": "schmidl_cox(window=%d)" % sync_window(), "cfo": "angle_of_sum", "snr_db": args.snr, "nfft": NFFT,
               "lead_in": [LEAD_MIN, LEAD_MAX], "l2": "inputs (%.2f GB/GPU) larger than L2" % (n_streams * iq_stride * 8 / 1e9)}
 
     if not torch.cuda.is_available():
@@ -223,7 +236,7 @@ def main():
     eng.tx_encode_device(payload.data_ptr(), plen.data_ptr(), out_stride, n_streams, tx.data_ptr(), frame_len, flen.data_ptr(), stream)
     rx = torch.empty((n_streams, iq_stride, 2), dtype=torch.float32, device=dev)
     rx_len = torch.zeros(n_streams, dtype=torch.int32, device=dev)
-    chan = ob.ChannelParams(snr_db=args.snr, cfo_max=0.9 * np.pi / 80, lead_min=LEAD_MIN, lead_max=LEAD_MAX, multipath=True,
+    chan = ob.ChannelParams(snr_db=args.snr, cfo_max=0.9 * np.pi / (NFFT + NFFT // 4), lead_min=LEAD_MIN, lead_max=LEAD_MAX, multipath=True,
                             noise_mode=1, seed=SEED + 1000 * rank)
     eng.channel_device(tx.data_ptr(), flen.data_ptr(), frame_len, n_streams, chan, rx.data_ptr(), iq_stride, rx_len.data_ptr(), 0, 0, stream)
     torch.cuda.synchronize()
@@ -291,7 +304,7 @@ def main():
     alg_bytes = 8 * total_samples + n_streams * payload_len
     dec_avg_ms = float(np.mean(dec_ms)) if len(dec_ms) else float("nan")
     achieved = alg_bytes / (dec_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "rx_decode_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "rx_decode_kernel" if NFFT == 64 else "wide_decode_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": read_traffic(workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(dec_avg_ms, 4),
                 "acquire_kernel_ms": round(float(np.mean(acq_ms)), 4) if len(acq_ms) else None,
@@ -473,9 +486,9 @@ def reference_arm(args):
     cfg = oracle_cfg()
     S = args.syms
     # largest payload that fits S data symbols (same arithmetic as ofdm_max_payload)
-    coded = (S * 288 - 128) // 8
+    coded = (S * (288 if NFFT == 64 else 4608) - 128) // 8
     payload_len = (8 * coded) // 14
-    frame_len = (10 + S) * 80
+    frame_len = (10 + S) * (NFFT + NFFT // 4)
     iq_stride = (frame_len + LEAD_MAX + 63 + 31) // 32 * 32
     out_stride = (payload_len + 15) // 16 * 16
     k = max(threads, 1) * 2
@@ -489,7 +502,7 @@ def reference_arm(args):
         pays.append(pay)
         tx = oo.tx(pay, cfg)
         assert tx.size == frame_len
-        ch = oo.channel(tx, args.snr, float(rng.uniform(0, 0.9 * np.pi / 80)), 1, SEED + i)
+        ch = oo.channel(tx, args.snr, float(rng.uniform(0, 0.9 * np.pi / (NFFT + NFFT // 4))), 1, SEED + i)
         lead = int(rng.integers(LEAD_MIN, LEAD_MAX + 1))
         sigma = np.sqrt(0.5 * np.mean(np.abs(ch) ** 2) / 10 ** (args.snr / 10))
         noise = sigma * (rng.standard_normal(lead) + 1j * rng.standard_normal(lead))
@@ -507,9 +520,9 @@ def reference_arm(args):
     ok = all(status[i] == 0 and out_len[i] == payload_len and (out[i, :payload_len] == pays[i]).all() for i in range(k))
     v = float(ns.sum()) / dt / 1e6
     gbit = float(out_len[status == 0].sum()) * 8 / dt / 1e9
-    config = {"workload": f"{args.streams}x64QAM_S{S}", "streams_per_gpu": args.streams, "data_syms_per_frame": S,
+    config = {"workload": f"{args.streams}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}"), "nfft": NFFT, "streams_per_gpu": args.streams, "data_syms_per_frame": S,
               "frame_samples": frame_len, "payload_bytes": payload_len, "modulation": "64QAM", "guard_bands": True,
-              "fec": "hamming(7,4)", "sync": "schmidl_cox(window=%d)" % SYNC_WINDOW, "cfo": "angle_of_sum", "snr_db": args.snr,
+              "fec": "hamming(7,4)", "sync": "schmidl_cox(window=%d)" % sync_window(), "cfo": "angle_of_sum", "snr_db": args.snr,
               "lead_in": [LEAD_MIN, LEAD_MAX]}
     cpu = {"value": round(v, 2), "unit": "Msamples/s", "cores": threads, "kind": "port",
            "sample": f"{k} streams of the workload per step (f64 C port of the reference algorithm, {threads} host threads, FFT plans reused)",

@@ -299,25 +299,41 @@ constexpr size_t wide_acquire_smem()
     return sizeof(float) * kL + sizeof(float2) * (kAcqNQ + 1) + sizeof(float) * (kAcqNE + 1) + 256;
 }
 
-__device__ __forceinline__ float ramp_corr_sq_w(const float2 *__restrict__ x, long k, long n_samples, const float *s_lock)
+// ramp correlation |c[k]|^2, c[k] = sum_{n<1280} a[n+k] lock[n], for kRampTile consecutive lags per thread: every loaded
+// sample feeds kRampTile accumulators (register tiling; 1 load per 2*kRampTile FMAs instead of 1 per 2)
+constexpr int kRampTile = 8;
+__device__ __forceinline__ void ramp_corr_tile_w(const float2 *__restrict__ x, long k0, long n_samples, const float *s_lock, float (&out)[kRampTile])
 {
-    float cr = 0.0f, ci = 0.0f;
-    if (k >= 0 && k + kL <= n_samples) {
-#pragma unroll 8
-        for (int n = 0; n < kL; n++) { float2 v = __ldg(x + k + n); cr = fmaf(v.x, s_lock[n], cr); ci = fmaf(v.y, s_lock[n], ci); }
-    } else {
-        for (int n = 0; n < kL; n++) { float2 v = ld_sample(x, k + n, n_samples); cr = fmaf(v.x, s_lock[n], cr); ci = fmaf(v.y, s_lock[n], ci); }
+    float cr[kRampTile], ci[kRampTile];
+#pragma unroll
+    for (int j = 0; j < kRampTile; j++) { cr[j] = 0.0f; ci[j] = 0.0f; }
+    const bool inside = k0 >= 0 && k0 + kL + kRampTile <= n_samples;
+    // sample m (relative to k0) contributes to lag j with tap m - j
+    float tap[kRampTile];                                     // tap[j] = lock[m - j]
+#pragma unroll
+    for (int j = 0; j < kRampTile; j++) tap[j] = 0.0f;
+    for (int m = 0; m < kL + kRampTile - 1; m++) {
+#pragma unroll
+        for (int j = kRampTile - 1; j > 0; j--) tap[j] = tap[j - 1];
+        tap[0] = m < kL ? s_lock[m] : 0.0f;
+        const float2 v = inside ? __ldg(x + k0 + m) : ld_sample(x, k0 + m, n_samples);
+#pragma unroll
+        for (int j = 0; j < kRampTile; j++) { cr[j] = fmaf(v.x, tap[j], cr[j]); ci[j] = fmaf(v.y, tap[j], ci[j]); }
     }
-    return cr * cr + ci * ci;
+#pragma unroll
+    for (int j = 0; j < kRampTile; j++) out[j] = cr[j] * cr[j] + ci[j] * ci[j];
 }
 __device__ __forceinline__ long ramp_argmax_w(const float2 *__restrict__ x, long n_samples, long k_lo, long k_hi, const float *s_lock,
                                               float *s_val, int *s_idx)
 {
     float best = 0.0f;
     int bidx = 0x7fffffff;
-    for (long k = k_lo + threadIdx.x; k <= k_hi; k += kThreads) {
-        float v = ramp_corr_sq_w(x, k, n_samples, s_lock);
-        if (v > best) { best = v; bidx = (int)(k - k_lo); }
+    for (long k = k_lo + (long)threadIdx.x * kRampTile; k <= k_hi; k += (long)kThreads * kRampTile) {
+        float v[kRampTile];
+        ramp_corr_tile_w(x, k, n_samples, s_lock, v);
+#pragma unroll
+        for (int j = 0; j < kRampTile; j++)
+            if (k + j <= k_hi && v[j] > best) { best = v[j]; bidx = (int)(k + j - k_lo); }     // ascending lags: strict > keeps the first
     }
     block_argmax(best, bidx, s_val, s_idx);
     return best > 0.0f ? k_lo + bidx : k_lo;

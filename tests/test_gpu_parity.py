@@ -359,3 +359,42 @@ def test_streaming_receiver_decodes_every_frame_of_a_capture(ob, oo):
     ref = oo.decode(np.concatenate([[0], cap[o: int(peaks[i + 1]["offset"])]]).astype(np.complex128), ocfg, want_points=False, out_cap=9008)
     assert ref.status == 0 and ref.data.tobytes() == data[i]
     eng.close()
+
+
+@pytest.mark.parametrize("mod,guard,fec,modes", [(2, True, True, (1, 1, 1)), (2, True, False, (0, 0, 0)), (1, False, True, (1, 1, 0)),
+                                                 (0, True, True, (0, 1, 1)), (2, False, False, (1, 1, 1)), (1, True, False, (0, 0, 0))])
+def test_wideband_1024_parity(ob, oo, mod, guard, fec, modes):
+    """BASELINE.json configs[3]: 1024-subcarrier variant (docs/SPEC.md 9), TX + RX round trip against the oracle."""
+    sync, cfo, phase = modes
+    win = 0 if sync == 0 else 4096
+    cfg = ob.Config(modulation=mod, guard_bands=guard, fec=fec, sync_mode=sync, cfo_mode=cfo, phase_mode=phase, sync_window=win, nfft=1024, cp=256)
+    eng = ob.Engine(cfg, 0)
+    ocfg = oo.make_cfg(guard, mod, fec, sync, cfo, phase, win, nfft=1024)
+    rng = np.random.default_rng(7 * mod + guard)
+    # lengths around the 28-symbol tile and 7-symbol Hamming boundaries, empty and ragged
+    lens = [cfg.max_payload(60), cfg.max_payload(29) + 1, cfg.max_payload(28), 0, 1, 577]
+    pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    iq, flen = eng.tx_encode(pays)
+    caps = []
+    for i, p in enumerate(pays):
+        ref = oo.tx(p, ocfg)
+        assert ref.size == flen[i]
+        np.testing.assert_allclose(iq[i, : flen[i]], ref, atol=2e-6)
+        lead = int(rng.integers(0, 900))
+        c = oo.channel(ref, 60.0, 0.0012 + 0.0002 * i, 1, 50 + i)
+        caps.append(np.concatenate([1e-4 * (rng.standard_normal(lead) + 1j * rng.standard_normal(lead)), c]))
+    batch, n = _batch(caps)
+    res = eng.rx_decode(batch, n, points=True)
+    for i, p in enumerate(pays):
+        ref = oo.decode(batch[i, : n[i]].astype(np.complex128), ocfg)
+        assert ref.status == res.status[i] == 0 and ref.offset == res.offset[i]
+        assert abs(ref.f_delta - res.f_delta[i]) < ABS_TOL_FDELTA
+        np.testing.assert_allclose(res.h_k[i], ref.h_k, atol=REL_TOL_POINTS * np.abs(ref.h_k).max())
+        npts = cfg.frame_data_syms(len(p)) * cfg.data_carriers
+        assert np.abs(res.points[i, :npts] - ref.points[:npts]).max() <= REL_TOL_POINTS * max(1.0, np.abs(ref.points[:npts]).max())
+        assert res.data[i] == ref.data.tobytes() == p
+    # status paths: too short, nothing there
+    short = eng.rx_decode(batch[:1, :9000], np.array([9000], np.uint32))
+    assert short.status[0] in (ob.TOO_SHORT, ob.NO_SYNC, ob.NEG_OFFSET) and short.out_len[0] == 0
+    assert oo.decode(batch[0, :9000].astype(np.complex128), ocfg).status == short.status[0]
+    eng.close()

@@ -106,3 +106,37 @@ def test_schmidl_cox_matches_reference_sync(oo):
         b = oo.decode(cap, oo.make_cfg(True, oo.QAM64, sync_mode=oo.SYNC_SCHMIDL_COX, sync_window=2048))
         assert a.status == b.status == 0
         assert a.offset == b.offset == lead + 8
+
+
+@pytest.mark.parametrize("mod", [0, 1, 2])
+def test_wideband_1024_oracle_loopback(oo, mod):
+    """docs/SPEC.md 9: nfft = 1024, CP = 256. TX -> lab channel -> RX recovers the payload; frame sizes scale by 16."""
+    import ctypes as C
+    rng = np.random.default_rng(mod)
+    pay = rng.integers(0, 256, 2000, dtype=np.uint8)
+    for guard in (False, True):
+        cfg = oo.make_cfg(guard, mod, True, oo.SYNC_SCHMIDL_COX, 1, 1, 4096, nfft=1024)
+        tx = oo.tx(pay, cfg)
+        D, bpc = (768 if guard else 1024), (1, 2, 6)[mod]
+        coded = (14 * 2000 + 7) // 8
+        S = -(-(-(-(128 + 8 * coded) // bpc)) // D)
+        assert tx.size == (10 + S) * 1280 == oo.lib().oo_tx_len(2000, C.byref(cfg))
+        assert max(tx.real.max(), tx.imag.max()) == pytest.approx(1.0)
+        cap = np.concatenate([np.zeros(333), oo.channel(tx, 60.0, 0.0017, 1, 4)])
+        r = oo.decode(cap, cfg)
+        assert r.status == 0 and r.offset == 333 + 8 and abs(r.f_delta - 0.0017) < 1e-6
+        assert r.data.tobytes() == pay.tobytes()
+        assert r.h_k.size == 1024
+    # carrier map: 192 nulls, 64 pilots, 768 data
+    x = oo.encode(bytes(5000), True, oo.BPSK, nfft=1024)
+    sym = np.fft.fft(x[12800 + 256: 12800 + 1280])
+    mag = np.abs(sym)
+    nulls = [k for k in range(1024) if k <= 95 or k == 512 or k >= 929]
+    assert len(nulls) == 192 and mag[nulls].max() < 1e-9 * mag.max()
+    used = [k for k in range(1024) if k not in set(nulls)]
+    pilots = used[::13]
+    assert len(used) == 832 and len(pilots) == 64 and pilots[0] == 96
+    np.testing.assert_allclose(sym[pilots] / sym[pilots][0], 1.0, atol=1e-9)          # pilots are 1+0j, data is -1 (all-zero bits)
+    data = [k for k in used if k not in set(pilots)]
+    assert len(data) == 768
+    np.testing.assert_allclose(sym[data][16 * 8:] / sym[pilots][0], -1.0, atol=1e-9)
