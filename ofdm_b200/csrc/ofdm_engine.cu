@@ -49,6 +49,7 @@ struct ofdm_engine {
     RxTables *d_tables = nullptr;
     wide::WideTables *d_wtables = nullptr;   // nfft = 1024
     bool wide = false;
+    bool lock_is_ramp = true;           // false when cfg.locking overrides the built-in table
     int nfft = 64, sym_len = 80;
     std::vector<ofdm_fc32> lock, pre, train;
     DevBuf state;                       // StreamState[n_streams] (StreamStateW for nfft = 1024)
@@ -301,7 +302,7 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     ofdm_host::locking_signal(lock.data(), LS);
     ofdm_host::preamble(pre.data(), LS);
     ofdm_host::training_signals(train.data(), NF);
-    if (cfg->locking) for (int i = 0; i < LS; i++) lock[i] = { cfg->locking[i].re, cfg->locking[i].im };
+    if (cfg->locking) { h->lock_is_ramp = false; for (int i = 0; i < LS; i++) lock[i] = { cfg->locking[i].re, cfg->locking[i].im }; }
     if (cfg->preamble) for (int i = 0; i < LS; i++) pre[i] = { cfg->preamble[i].re, cfg->preamble[i].im };
     if (cfg->training) for (int i = 0; i < NF; i++) train[i] = { cfg->training[i].re, cfg->training[i].im };
     h->cfg.locking = h->cfg.preamble = h->cfg.training = nullptr;
@@ -492,6 +493,7 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         w.out = out; w.out_stride = out_stride; w.out_len = out_len; w.status = status;
         w.sync_window = h->cfg.sync_window; w.tile_shift = h->tile_shift;
         w.sync_mode = (int)h->cfg.sync_mode; w.cfo_mode = (int)h->cfg.cfo_mode; w.fec = (int)h->cfg.fec;
+        w.lock_is_ramp = h->lock_is_ramp ? 1 : 0;
         bool wpoints = false;
         if (diag) {
             w.d_offset = diag->offset; w.d_f_delta = diag->f_delta; w.d_h = reinterpret_cast<float2 *>(diag->h_k);

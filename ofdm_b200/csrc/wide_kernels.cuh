@@ -69,6 +69,7 @@ struct WideRxArgs {
     uint32_t        sync_window;
     int32_t         tile_shift;
     int32_t         sync_mode, cfo_mode, fec;
+    int32_t         lock_is_ramp;   // the locking table is the built-in ramp: closed-form ramp correlation
     int32_t  *d_offset;
     float    *d_f_delta;
     float2   *d_h;              // [n_streams][1024]
@@ -84,32 +85,51 @@ __device__ __forceinline__ void radix4(cpx (&v)[4])
     const cpx a = c_add(v[0], v[2]), b = c_sub(v[0], v[2]), c = c_add(v[1], v[3]), d = c_mul_mj(c_sub(v[1], v[3]));
     v[0] = c_add(a, c); v[2] = c_sub(a, c); v[1] = c_add(b, d); v[3] = c_sub(b, d);
 }
-__device__ __forceinline__ void fft1024_block(cpx (&v)[4], float2 *bufA, float2 *bufB, const float2 *s_w, int tid)
+// Padded layouts keep every stage free of bank conflicts (64-bit accesses, 16 lanes per phase): buffer A inserts one
+// element per 16 (stage-0 writes A[4t + r]), buffer B four per 16 (stage-1 writes B[16m + k + 4r], t = 4m + k).
+constexpr int kBufA = kN + kN / 16, kBufB = kN + kN / 4;
+__device__ __forceinline__ int padA(int i) { return i + (i >> 4); }
+__device__ __forceinline__ int padB(int i) { return i + ((i >> 4) << 2); }
+
+// per-thread twiddles of stages 1..4 (W_{4 Ns}^{k}, k = tid mod Ns): constant for the thread, kept in registers; the powers
+// 2 and 3 are formed by two complex multiplies per stage instead of (bank-conflicting) table look-ups
+struct FftTw { cpx w[4]; };
+__device__ __forceinline__ void fft1024_tw_init(FftTw &T, const float2 *__restrict__ w1024, int tid)
+{
+#pragma unroll
+    for (int st = 1; st < 5; st++) {
+        const int Ns = 1 << (2 * st);
+        T.w[st - 1] = c_from(__ldg(w1024 + (tid & (Ns - 1)) * (256 >> (2 * st))));
+    }
+}
+
+__device__ __forceinline__ void fft1024_block(cpx (&v)[4], float2 *bufA, float2 *bufB, const FftTw &T, int tid)
 {
     unsigned long long *A = reinterpret_cast<unsigned long long *>(bufA), *B = reinterpret_cast<unsigned long long *>(bufB);
     // stage 0 (Ns = 1): no twiddles, out[4 j + r]
     radix4(v);
 #pragma unroll
-    for (int r = 0; r < 4; r++) A[4 * tid + r] = v[r].v;
+    for (int r = 0; r < 4; r++) A[padA(4 * tid + r)] = v[r].v;
     __syncthreads();
-    unsigned long long *in = A, *out = B;
 #pragma unroll
     for (int st = 1; st < 5; st++) {
         const int Ns = 1 << (2 * st);
         const int k = tid & (Ns - 1);
+        const bool fromA = (st & 1) != 0;                          // stages 1, 3 read A and write B; 2, 4 read B and write A
 #pragma unroll
-        for (int r = 0; r < 4; r++) v[r].v = in[tid + 256 * r];
-        const int tstep = k * (256 >> (2 * st));                  // W_{4 Ns}^{r k} = W1024^{r k 256 / Ns}
-#pragma unroll
-        for (int r = 1; r < 4; r++) v[r] = c_mul(v[r], c_from(s_w[(r * tstep) & (kN - 1)]));
+        for (int r = 0; r < 4; r++) v[r].v = fromA ? A[padA(tid + 256 * r)] : B[padB(tid + 256 * r)];
+        const cpx w1 = T.w[st - 1], w2 = c_mul(w1, w1), w3 = c_mul(w2, w1);
+        v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3);
         radix4(v);
         const int j0 = ((tid - k) << 2) + k;
 #pragma unroll
-        for (int r = 0; r < 4; r++) out[j0 + r * Ns] = v[r].v;
+        for (int r = 0; r < 4; r++) {
+            if (fromA) B[padB(j0 + r * Ns)] = v[r].v;
+            else A[padA(j0 + r * Ns)] = v[r].v;
+        }
         __syncthreads();
-        unsigned long long *t = in; in = out; out = t;
     }
-    // 5 stages: A, B, A, B, A -> result in A
+    // stage 4 wrote A: natural-order spectrum at A[padA(k)]
 }
 
 // sum over the block of a packed complex (for the pilot sum) or a float (angles); s_red: 2 * 8 floats
@@ -160,15 +180,15 @@ __device__ __forceinline__ void wide_load_symbol(const float2 *__restrict__ x0, 
 
 // One OFDM symbol by the whole CTA: derotate, FFT, equalise, pilot phase. On return z[r] = corrected bin tid + 256 r.
 template <bool GUARD, int PHASE>
-__device__ __forceinline__ void wide_symbol(const WideLane &L, cpx base, cpx (&z)[4], float2 *bufA, float2 *bufB, const float2 *s_w,
+__device__ __forceinline__ void wide_symbol(const WideLane &L, cpx base, cpx (&z)[4], float2 *bufA, float2 *bufB, const FftTw &T,
                                             float *s_red, int tid)
 {
 #pragma unroll
     for (int r = 0; r < 4; r++) z[r] = c_mul(z[r], L.w[r]);
-    fft1024_block(z, bufA, bufB, s_w, tid);
+    fft1024_block(z, bufA, bufB, T, tid);
     const unsigned long long *A = reinterpret_cast<const unsigned long long *>(bufA);
 #pragma unroll
-    for (int r = 0; r < 4; r++) { cpx x; x.v = A[tid + 256 * r]; z[r] = c_mul(x, L.g[r]); }
+    for (int r = 0; r < 4; r++) { cpx x; x.v = A[padA(tid + 256 * r)]; z[r] = c_mul(x, L.g[r]); }
     cpx rot = base;
     if (GUARD) {
         float px = 0.0f, py = 0.0f;
@@ -227,7 +247,7 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
 
 constexpr size_t wide_decode_smem(bool guard)
 {
-    return sizeof(float2) * (3 * kN) + (size_t)kTileSymsW * (guard ? 768 : 1024) + 64 + 128 + 64;
+    return sizeof(float2) * (kBufA + kBufB) + (size_t)kTileSymsW * (guard ? 768 : 1024) + 64 + 128 + 64;
 }
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
@@ -235,8 +255,8 @@ __global__ void __launch_bounds__(kThreads) wide_decode_kernel(const WideRxArgs 
 {
     constexpr int D = GUARD ? 768 : 1024;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float2 *bufA = reinterpret_cast<float2 *>(smem_raw), *bufB = bufA + kN, *s_w = bufB + kN;
-    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_w + kN);
+    float2 *bufA = reinterpret_cast<float2 *>(smem_raw), *bufB = bufA + kBufA;
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(bufB + kBufB);
     uint8_t *s_ham = s_car + kTileSymsW * D + 64;
     float *s_red = reinterpret_cast<float *>(s_ham + 128);
 
@@ -249,7 +269,8 @@ __global__ void __launch_bounds__(kThreads) wide_decode_kernel(const WideRxArgs 
     if (t1 > S) t1 = S;
     if (t0 >= t1) return;
     const int tid = threadIdx.x;
-    for (int i = tid; i < kN; i += kThreads) s_w[i] = a.tables->w1024[i];
+    FftTw T;
+    fft1024_tw_init(T, a.tables->w1024, tid);
     if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
 
     const uint32_t offset = (uint32_t)st->offset;
@@ -270,7 +291,7 @@ __global__ void __launch_bounds__(kThreads) wide_decode_kernel(const WideRxArgs 
 #pragma unroll
         for (int r = 0; r < 4; r++) z[r] = nxt[r];
         wide_load_symbol(x0, n_avail, (uint32_t)(s + 1), s + 1 < t1, tid, nxt);            // software prefetch of the next symbol
-        wide_symbol<GUARD, PHASE>(L, base, z, bufA, bufB, s_w, s_red, tid);
+        wide_symbol<GUARD, PHASE>(L, base, z, bufA, bufB, T, s_red, tid);
         base = c_mul(base, dbase);
         uint8_t *row = s_car + (s - t0) * D;
 #pragma unroll
@@ -339,6 +360,45 @@ __device__ __forceinline__ long ramp_argmax_w(const float2 *__restrict__ x, long
     return best > 0.0f ? k_lo + bidx : k_lo;
 }
 
+// Closed form of the same arg-max for the built-in locking ramp: lock[n] = 3/8 + n/(4L) for n < L/2 and 1/8 + n/(4L) above
+// (locking_signal::<1280>, src/transmitter.rs:60-72 after fft_shift), so
+//   c[k] = 3/8 S0a(k) + 1/8 S0b(k) + S1(k) / (4L),  S0a/S0b = sums of a over the two half windows, S1 = sum n a[k+n],
+// and all three slide in O(1) per lag. Every thread starts its run of lags with one exact f64 summation and slides in f64
+// (a dozen steps): L loads per thread instead of L per lag.
+__device__ __forceinline__ long ramp_argmax_closed_w(const float2 *__restrict__ x, long n_samples, long k_lo, long k_hi, float *s_val, int *s_idx)
+{
+    const long n_lags = k_hi - k_lo + 1;
+    const int run = (int)((n_lags + kThreads - 1) / kThreads);
+    const long k0 = k_lo + (long)threadIdx.x * run;
+    float best = 0.0f;
+    int bidx = 0x7fffffff;
+    if (k0 <= k_hi) {
+        constexpr int H = kL / 2;
+        double ar = 0, ai = 0, br = 0, bi = 0, mr = 0, mi = 0;          // S0a, S0b, S1
+        for (int n = 0; n < kL; n++) {
+            const float2 v = ld_sample(x, k0 + n, n_samples);
+            if (n < H) { ar += v.x; ai += v.y; } else { br += v.x; bi += v.y; }
+            mr += (double)n * v.x; mi += (double)n * v.y;
+        }
+        const double beta = 1.0 / (4.0 * kL);
+        for (int j = 0; j < run && k0 + j <= k_hi; j++) {
+            const double cr = 0.375 * ar + 0.125 * br + beta * mr, ci = 0.375 * ai + 0.125 * bi + beta * mi;
+            const float v = (float)(cr * cr + ci * ci);
+            if (v > best) { best = v; bidx = (int)(k0 + j - k_lo); }
+            // slide the window by one sample
+            const long k = k0 + j;
+            const float2 a0 = ld_sample(x, k, n_samples), ah = ld_sample(x, k + H, n_samples), al = ld_sample(x, k + kL, n_samples);
+            const double s0r = ar + br, s0i = ai + bi;
+            mr = mr + (double)kL * al.x - (s0r - a0.x + al.x);
+            mi = mi + (double)kL * al.y - (s0i - a0.y + al.y);
+            ar += (double)ah.x - a0.x; ai += (double)ah.y - a0.y;
+            br += (double)al.x - ah.x; bi += (double)al.y - ah.y;
+        }
+    }
+    block_argmax(best, bidx, s_val, s_idx);
+    return best > 0.0f ? k_lo + bidx : k_lo;
+}
+
 template <int MOD, bool GUARD, int PHASE>
 __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs a)
 {
@@ -351,8 +411,8 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
     uint8_t *u = reinterpret_cast<uint8_t *>(s_lock + kL);
     float2 *s_q = reinterpret_cast<float2 *>(u);                       // S&C phase
     float *s_e = reinterpret_cast<float *>(s_q + kAcqNQ + 1);
-    float2 *bufA = reinterpret_cast<float2 *>(u), *bufB = bufA + kN, *s_w = bufB + kN;      // FFT phase (aliases the S&C arrays)
-    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_w + kN);            // 1024 carrier bytes
+    float2 *bufA = reinterpret_cast<float2 *>(u), *bufB = bufA + kBufA;                     // FFT phase (aliases the S&C arrays)
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(bufB + kBufB);        // 1024 carrier bytes
     __shared__ float s_val[kThreads / 32];
     __shared__ int s_idx[kThreads / 32];
     __shared__ int s_d0;
@@ -376,7 +436,7 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
     int status = ST_OK;
     long offset = 0;
     if (SYNC == 0) {
-        offset = ramp_argmax_w(x, M, -(kL - 1), W - 1, s_lock, s_val, s_idx) - 1;
+        offset = (a.lock_is_ramp ? ramp_argmax_closed_w(x, M, -(kL - 1), W - 1, s_val, s_idx) : ramp_argmax_w(x, M, -(kL - 1), W - 1, s_lock, s_val, s_idx)) - 1;
     } else {
         long d_end = W;
         if (d_end > M - 2 * kL + 1) d_end = M - 2 * kL + 1;
@@ -426,7 +486,7 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
         } else {
             long d0 = s_d0, k_lo = d0 - (11 * kL) / 5, k_hi = d0 + kL / 5;
             if (k_lo < -(kL - 1)) k_lo = -(kL - 1);
-            offset = ramp_argmax_w(x, M, k_lo, k_hi, s_lock, s_val, s_idx) - 1;
+            offset = (a.lock_is_ramp ? ramp_argmax_closed_w(x, M, k_lo, k_hi, s_val, s_idx) : ramp_argmax_w(x, M, k_lo, k_hi, s_lock, s_val, s_idx)) - 1;
         }
     }
     if (status == ST_OK && offset < 0) status = ST_NEG_OFFSET;
@@ -471,7 +531,8 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
     if (tid == 0) { st->fstep = fstep; st->f_delta = (float)f_delta; st->offset = (int32_t)offset; }
 
     // ---- channel estimate: 5 training symbols ------------------------------------------------------------------------------
-    for (int i = tid; i < kN; i += kThreads) s_w[i] = a.tables->w1024[i];
+    FftTw T;
+    fft1024_tw_init(T, a.tables->w1024, tid);
     __syncthreads();
     cpx hsum[4];
 #pragma unroll
@@ -484,11 +545,11 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
             const uint32_t n = row * kL + kCpW + tid + 256 * r;
             v[r] = c_mul(c_from(x0[n]), phasor_from_turns_p(fstep * (uint64_t)n));
         }
-        fft1024_block(v, bufA, bufB, s_w, tid);
+        fft1024_block(v, bufA, bufB, T, tid);
         const unsigned long long *A = reinterpret_cast<const unsigned long long *>(bufA);
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            cpx xx; xx.v = A[tid + 256 * r];
+            cpx xx; xx.v = A[padA(tid + 256 * r)];
             hsum[r] = c_add(hsum[r], c_mul(xx, c_from(a.tables->inv_training[tid + 256 * r])));
         }
         __syncthreads();
@@ -512,7 +573,7 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
     cpx z[4];
     wide_load_symbol(x0, (uint32_t)(n_avail > 0xffffffffL ? 0xffffffffL : n_avail), 0u, true, tid, z);
     const cpx base = phasor_from_turns_p(fstep * (uint64_t)(10 * kL + kCpW));
-    wide_symbol<GUARD, PHASE>(L, base, z, bufA, bufB, s_w, s_redf, tid);
+    wide_symbol<GUARD, PHASE>(L, base, z, bufA, bufB, T, s_redf, tid);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         float zr, zi;
@@ -569,7 +630,7 @@ __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
     constexpr int D = GUARD ? 768 : 1024;
     constexpr int BPS = BPC * D;
     constexpr int TS = 8;                                            // symbols per CTA
-    __shared__ __align__(16) float2 bufA[kN], bufB[kN], s_w[kN];
+    __shared__ __align__(16) float2 bufA[kBufA], bufB[kBufB];
     __shared__ __align__(16) uint8_t s_bits[TS * BPS / 8 + 16];
     __shared__ __align__(8) float2 s_map[64];
     __shared__ uint8_t s_enc[16];
@@ -616,7 +677,8 @@ __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
         s_map[tid] = make_float2(im, re);                            // swapped: the IFFT runs as swap . FFT . swap
     }
     if (tid < 16) s_enc[tid] = (uint8_t)ham74_encode_nibble(tid);
-    for (int i = tid; i < kN; i += kThreads) s_w[i] = a.tables->w1024[i];
+    FftTw T;
+    fft1024_tw_init(T, a.tables->w1024, tid);
     __syncthreads();
     const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
     const uint32_t byte0 = (uint32_t)((long)t0 * BPS / 8), nbyte = (uint32_t)((long)(t1 - t0) * BPS / 8);
@@ -644,12 +706,12 @@ __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
             }
             v[r] = val;
         }
-        fft1024_block(v, bufA, bufB, s_w, tid);
+        fft1024_block(v, bufA, bufB, T, tid);
         const unsigned long long *A = reinterpret_cast<const unsigned long long *>(bufA);
         float2 *sym = out + (size_t)(10 + s) * kL;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            cpx x; x.v = A[tid + 256 * r];
+            cpx x; x.v = A[padA(tid + 256 * r)];
             float re, im;
             c_split(x, im, re);                                      // un-swap
             const int t = tid + 256 * r;
