@@ -521,6 +521,7 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
 // acquisition kernel
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kAcqThreads = 256;
+constexpr int kAcq64Threads = 128;               // CTA size of the N=64 acquisition kernel (small per-stream work, many barriers)
 constexpr int kAcqChunk = 1024;                  // Schmidl-Cox lags per smem-staged chunk
 
 __device__ __forceinline__ float2 ld_sample(const float2 *__restrict__ x, long n, long n_samples)
@@ -529,6 +530,7 @@ __device__ __forceinline__ float2 ld_sample(const float2 *__restrict__ x, long n
 }
 
 // block-wide arg-max with "first strict maximum" semantics (larger value wins, ties -> smaller index)
+template <int NT>
 __device__ __forceinline__ void block_argmax(float &val, int &idx, float *s_val, int *s_idx)
 {
 #pragma unroll
@@ -542,8 +544,8 @@ __device__ __forceinline__ void block_argmax(float &val, int &idx, float *s_val,
     if (lane == 0) { s_val[warp] = val; s_idx[warp] = idx; }
     __syncthreads();
     if (warp == 0) {
-        float v = lane < (kAcqThreads / 32) ? s_val[lane] : -1.0f;
-        int i = lane < (kAcqThreads / 32) ? s_idx[lane] : 0x7fffffff;
+        float v = lane < (NT / 32) ? s_val[lane] : -1.0f;
+        int i = lane < (NT / 32) ? s_idx[lane] : 0x7fffffff;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) {
             float ov = __shfl_xor_sync(0xffffffffu, v, m);
@@ -571,21 +573,22 @@ __device__ __forceinline__ float ramp_corr_sq(const float2 *__restrict__ x, long
 }
 
 // arg-max of the ramp correlation over lags [k_lo, k_hi]
+template <int NT>
 __device__ __forceinline__ int ramp_argmax(const float2 *__restrict__ x, long n_samples, long k_lo, long k_hi,
                                            const float *s_lock, float *s_val, int *s_idx)
 {
     float best = 0.0f;
     int bidx = 0x7fffffff;
-    for (long k = k_lo + threadIdx.x; k <= k_hi; k += kAcqThreads) {
+    for (long k = k_lo + threadIdx.x; k <= k_hi; k += NT) {
         float v = ramp_corr_sq(x, k, n_samples, s_lock);
         if (v > best) { best = v; bidx = (int)k; }         // per-thread lags ascend: strict > keeps the first
     }
-    block_argmax(best, bidx, s_val, s_idx);
+    block_argmax<NT>(best, bidx, s_val, s_idx);
     return best > 0.0f ? bidx : (int)k_lo;
 }
 
 template <int MOD, bool GUARD, int PHASE>
-__global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
+__global__ void __launch_bounds__(kAcq64Threads) rx_acquire_kernel(const RxArgs a)
 {
     const int SYNC = a.sync_mode, CFO = a.cfo_mode;
     const bool FEC = a.fec != 0;
@@ -593,12 +596,13 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
     constexpr int D = GUARD ? 48 : 64;
     constexpr int BPS = BPC * D;
     constexpr int HDR_SYMS = (kHeaderBits + BPS - 1) / BPS;         // 1..3
+    constexpr int NW = kAcq64Threads / 32;                          // warps per CTA
 
     __shared__ float s_lock[kSym];
-    __shared__ float s_val[kAcqThreads / 32];
-    __shared__ int s_idx[kAcqThreads / 32];
+    __shared__ float s_val[kAcq64Threads / 32];
+    __shared__ int s_idx[kAcq64Threads / 32];
     __shared__ int s_d0;
-    __shared__ double s_red[2 * (kAcqThreads / 32)];
+    __shared__ double s_red[2 * (kAcq64Threads / 32)];
     __shared__ __align__(16) float2 s_tr[kTrWarp];
     __shared__ uint8_t s_car[HDR_SYMS * D + 32];
     // Schmidl-Cox staging: prefix sums of q[n] = conj(a[n]) a[n+80] and e[n] = |a[n]|^2
@@ -623,7 +627,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
     if (SYNC == 2) {
         offset = 0;                                    // frame start already known (ofdm_rx_decode_capture)
     } else if (SYNC == 0) {
-        offset = (long)ramp_argmax(x, M, -(kSym - 1), W - 1, s_lock, s_val, s_idx) - 1;     // src/receiver.rs:21: lag - 1
+        offset = (long)ramp_argmax<kAcq64Threads>(x, M, -(kSym - 1), W - 1, s_lock, s_val, s_idx) - 1;     // src/receiver.rs:21: lag - 1
     } else {
         // sliding Schmidl-Cox (docs/SPEC.md 4): P(d) = Q[d+80] - Q[d], R1(d) = E[d+80] - E[d], R2(d) = E[d+160] - E[d+80]
         long d_end = W;
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
             // exclusive prefix sums over this chunk (+ halo), built from per-thread serial runs + a warp-shuffle scan
             constexpr int NQ = kAcqChunk + kSym;          // q needed for n in [base, base + chunk + 80)
             constexpr int NE = kAcqChunk + 2 * kSym;      // e needed for n in [base, base + chunk + 160)
-            constexpr int RUN = (NE + kAcqThreads - 1) / kAcqThreads;   // consecutive samples per thread
+            constexpr int RUN = (NE + kAcq64Threads - 1) / kAcq64Threads;   // consecutive samples per thread
             float qr[RUN], qi[RUN], ee[RUN];
             float tqr = 0.0f, tqi = 0.0f, te = 0.0f;
 #pragma unroll
@@ -651,12 +655,12 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
                 float a0 = __shfl_up_sync(0xffffffffu, sqr, m), a1 = __shfl_up_sync(0xffffffffu, sqi, m), a2 = __shfl_up_sync(0xffffffffu, se, m);
                 if (lane >= m) { sqr += a0; sqi += a1; se += a2; }
             }
-            __shared__ float s_wtot[3 * (kAcqThreads / 32)];
+            __shared__ float s_wtot[3 * (kAcq64Threads / 32)];
             __syncthreads();
-            if (lane == 31) { s_wtot[warp] = sqr; s_wtot[8 + warp] = sqi; s_wtot[16 + warp] = se; }
+            if (lane == 31) { s_wtot[warp] = sqr; s_wtot[NW + warp] = sqi; s_wtot[2 * NW + warp] = se; }
             __syncthreads();
             float oqr = sqr - tqr, oqi = sqi - tqi, oe = se - te;       // exclusive offset of this thread inside its warp
-            for (int w2 = 0; w2 < warp; w2++) { oqr += s_wtot[w2]; oqi += s_wtot[8 + w2]; oe += s_wtot[16 + w2]; }
+            for (int w2 = 0; w2 < warp; w2++) { oqr += s_wtot[w2]; oqi += s_wtot[NW + w2]; oe += s_wtot[2 * NW + w2]; }
 #pragma unroll
             for (int r = 0; r < RUN; r++) {
                 int i = tid * RUN + r;
@@ -665,7 +669,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
             }
             __syncthreads();
             int found = 0x7fffffff;
-            for (int i = tid; i < kAcqChunk && base + i < d_end; i += kAcqThreads) {
+            for (int i = tid; i < kAcqChunk && base + i < d_end; i += kAcq64Threads) {
                 float2 qa = s_q[i], qb = s_q[i + kSym];
                 float pr = qb.x - qa.x, pi = qb.y - qa.y;
                 float r1 = s_e[i + kSym] - s_e[i], r2 = s_e[i + 2 * kSym] - s_e[i + kSym];
@@ -680,7 +684,7 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
         } else {
             long d0 = s_d0, k_lo = d0 - 176, k_hi = d0 + 16;
             if (k_lo < -(kSym - 1)) k_lo = -(kSym - 1);
-            offset = (long)ramp_argmax(x, M, k_lo, k_hi, s_lock, s_val, s_idx) - 1;
+            offset = (long)ramp_argmax<kAcq64Threads>(x, M, k_lo, k_hi, s_lock, s_val, s_idx) - 1;
         }
     }
     if (status == ST_OK && offset < 0) status = ST_NEG_OFFSET;                       // src/receiver.rs:25
@@ -718,12 +722,12 @@ __global__ void __launch_bounds__(kAcqThreads) rx_acquire_kernel(const RxArgs a)
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, m);
         acc1 += __shfl_xor_sync(0xffffffffu, acc1, m);
     }
-    if (lane == 0) { s_red[warp] = acc0; s_red[8 + warp] = acc1; }
+    if (lane == 0) { s_red[warp] = acc0; s_red[NW + warp] = acc1; }
     __syncthreads();
     double f_delta;
     {
         double t0 = 0.0, t1 = 0.0;
-        for (int w2 = 0; w2 < kAcqThreads / 32; w2++) { t0 += s_red[w2]; t1 += s_red[8 + w2]; }
+        for (int w2 = 0; w2 < kAcq64Threads / 32; w2++) { t0 += s_red[w2]; t1 += s_red[NW + w2]; }
         if (CFO == 0) f_delta = fabs((t0 / 80.0) / 80.0);
         else f_delta = atan2(t1, t0) / 80.0;
     }

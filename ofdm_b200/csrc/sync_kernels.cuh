@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kAcqThreads) sync_refine_kernel(const SyncArgs
     if (k_lo < -(kSym - 1)) k_lo = -(kSym - 1);
     // the ramp correlation works on lags relative to a window origin (exact for captures beyond 2^31 samples)
     const long long org = k_lo < 0 ? 0 : k_lo;
-    const long long offset = org + (long long)ramp_argmax(a.iq + org, n - org, k_lo - org, k_hi - org, s_lock, s_val, s_idx) - 1;
+    const long long offset = org + (long long)ramp_argmax<kAcqThreads>(a.iq + org, n - org, k_lo - org, k_hi - org, s_lock, s_val, s_idx) - 1;
     const bool ok = offset >= 0 && offset + 800 <= n;
     // metric at the detection lag and (if the frame head fits) the CFO estimate: f64 sums of 80 terms
     double acc[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };

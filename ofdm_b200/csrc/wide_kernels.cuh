@@ -356,7 +356,7 @@ __device__ __forceinline__ long ramp_argmax_w(const float2 *__restrict__ x, long
         for (int j = 0; j < kRampTile; j++)
             if (k + j <= k_hi && v[j] > best) { best = v[j]; bidx = (int)(k + j - k_lo); }     // ascending lags: strict > keeps the first
     }
-    block_argmax(best, bidx, s_val, s_idx);
+    block_argmax<kThreads>(best, bidx, s_val, s_idx);
     return best > 0.0f ? k_lo + bidx : k_lo;
 }
 
@@ -395,14 +395,13 @@ __device__ __forceinline__ long ramp_argmax_closed_w(const float2 *__restrict__ 
             br += (double)al.x - ah.x; bi += (double)al.y - ah.y;
         }
     }
-    block_argmax(best, bidx, s_val, s_idx);
+    block_argmax<kThreads>(best, bidx, s_val, s_idx);
     return best > 0.0f ? k_lo + bidx : k_lo;
 }
 
 template <int MOD, bool GUARD, int PHASE>
 __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs a)
 {
-    static_assert(kThreads == kAcqThreads, "block_argmax is sized for kAcqThreads");
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 768 : 1024;
     constexpr int BPS = BPC * D;
