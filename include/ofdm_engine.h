@@ -190,6 +190,26 @@ int ofdm_ber_accumulate(ofdm_engine *h, const uint8_t *ref, const uint32_t *ref_
                         int mem, void *stream);
 
 /*
+ * Reed-Solomon RS(255,223) outer code with the reference's stream framing.
+ * ofdm_rs_encode_batch replaces create_transmission_bytes (src/utils.rs:97-137): 223-byte blocks, each followed by its
+ * 32 parity bytes; the partially filled -- possibly empty -- last block is always emitted, zero filled:
+ * coded_len = 255 * (data_len / 223 + 1). ofdm_rs_decode_batch replaces decipher_transmission_bytes
+ * (src/utils.rs:152-180): 255-byte blocks, the partial -- possibly empty -- tail zero filled and decoded as well:
+ * data_len = 223 * (coded_len / 255 + 1). Code: the `reed-solomon` 0.2.1 crate's (Cargo.toml:35), i.e. GF(2^8) with
+ * polynomial 0x11d, alpha = 2, roots alpha^0..alpha^31, message first, parity last; up to 16 symbol errors per block
+ * are corrected. n_corrected[s] = symbols corrected in stream s; n_failed[s] = blocks beyond repair (the reference
+ * returns None for the whole stream when it is non-zero; their data bytes are passed through uncorrected).
+ * The *_len outputs are always the required lengths; a stream whose output does not fit its stride is not written.
+ */
+size_t ofdm_rs_encoded_len(size_t data_len);
+size_t ofdm_rs_decoded_len(size_t coded_len);
+int ofdm_rs_encode_batch(ofdm_engine *h, const uint8_t *data, const uint32_t *data_len, uint32_t n_streams, uint32_t data_stride,
+                         uint8_t *coded, uint32_t coded_stride, uint32_t *coded_len, int mem, void *stream);
+int ofdm_rs_decode_batch(ofdm_engine *h, const uint8_t *coded, const uint32_t *coded_len, uint32_t n_streams, uint32_t coded_stride,
+                         uint8_t *data, uint32_t data_stride, uint32_t *data_len, uint32_t *n_corrected, uint32_t *n_failed,
+                         int mem, void *stream);
+
+/*
  * Per-kernel device timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE) for the roofline report: after
  * ofdm_profile_begin(h, n) the next n calls record CUDA events on their stream around the acquisition and the
  * decode kernel; ofdm_profile_read waits for them and returns the durations (ms) of each call.

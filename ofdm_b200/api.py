@@ -122,6 +122,18 @@ def decode(samples, guard_bands: Optional[bool] = None, modulation: Optional[Mod
     return data[0]
 
 
+def create_transmission_bytes(data: bytes, device: int = 0) -> bytes:
+    """RS(255,223) outer code with the reference's framing (src/utils.rs:97-137)."""
+    coded, n = _engine(_e.Config(), device).rs_encode([bytes(data)])
+    return coded[0, :int(n[0])].tobytes()
+
+
+def decipher_transmission_bytes(data: bytes, device: int = 0) -> Optional[bytes]:
+    """Inverse of create_transmission_bytes (src/utils.rs:152-180): None when any block is beyond repair."""
+    out, n, _, n_failed = _engine(_e.Config(), device).rs_decode(np.frombuffer(bytes(data), np.uint8))
+    return None if int(n_failed[0]) else out[0, :int(n[0])].tobytes()
+
+
 def sig_to_bytes(sig) -> bytes:
     """src/utils.rs:228-236: interleaved native-endian f32 re, im."""
     return np.asarray(sig).astype(np.complex64).tobytes()

@@ -16,6 +16,7 @@
 #include "sync_kernels.cuh"
 #include "tx_kernels.cuh"
 #include "wide_kernels.cuh"
+#include "rs_kernels.cuh"
 
 using namespace ofdm;
 
@@ -58,6 +59,7 @@ struct ofdm_engine {
     DevBuf counters;                    // 4 x u64
     DevBuf sync_scratch;                // candidate list + counters of ofdm_sync_search
     DevBuf cap_base;                    // per-frame base / length of ofdm_rx_decode_capture
+    DevBuf rs_tables;                   // RsTables, built on first use
     // host-mode staging
     DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
@@ -378,7 +380,7 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_wtables) cudaFree(h->d_wtables);
     DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
-                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base };
+                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base, &h->rs_tables };
     for (DevBuf *b : bufs) b->release();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -830,6 +832,104 @@ extern "C" int ofdm_rx_decode_capture(ofdm_engine *h, const ofdm_fc32 *iq, uint6
     CU(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     return 0;
+}
+
+// ---- Reed-Solomon outer code -------------------------------------------------------------------------------------
+extern "C" size_t ofdm_rs_encoded_len(size_t n) { return (size_t)kRsN * (n / kRsK + 1); }
+extern "C" size_t ofdm_rs_decoded_len(size_t n) { return (size_t)kRsK * (n / kRsN + 1); }
+
+static int rs_tables_ready(ofdm_engine *h)
+{
+    if (h->rs_tables.p) return 0;
+    std::vector<uint8_t> host(sizeof(RsTables));
+    RsTables *t = reinterpret_cast<RsTables *>(host.data());
+    unsigned x = 1;
+    for (int i = 0; i < 255; i++) {
+        t->exp[i] = (uint8_t)x;
+        t->log[x] = (uint8_t)i;
+        x <<= 1;
+        if (x & 0x100) x ^= 0x11d;
+    }
+    for (int i = 255; i < 512; i++) t->exp[i] = t->exp[i - 255];
+    t->log[0] = 0;
+    auto mul = [&](unsigned a, unsigned b) -> uint8_t { return (a && b) ? t->exp[t->log[a] + t->log[b]] : (uint8_t)0; };
+    uint8_t g[kRsT2 + 1] = { 1 };                                   // highest degree first
+    for (int i = 0; i < kRsT2; i++)
+        for (int j = i + 1; j >= 1; j--) g[j] = (uint8_t)(g[j] ^ mul(g[j - 1], t->exp[i]));
+    for (int f = 0; f < 256; f++)
+        for (int j = 0; j < kRsT2; j++) t->lfsr[f][j] = mul((unsigned)f, g[j + 1]);
+    CU(h, h->rs_tables.ensure(sizeof(RsTables)));
+    CU(h, cudaMemcpy(h->rs_tables.p, host.data(), sizeof(RsTables), cudaMemcpyHostToDevice));
+    CU(h, cudaFuncSetAttribute(rs_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes));
+    CU(h, cudaFuncSetAttribute(rs_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes));
+    return 0;
+}
+
+// encode = true: `blk_in` = 223, `blk_out` = 255
+static int rs_run(ofdm_engine *h, bool encode, const uint8_t *in, const uint32_t *in_len, uint32_t n_streams, uint32_t in_stride,
+                  uint8_t *out, uint32_t out_stride, uint32_t *out_len, uint32_t *n_corrected, uint32_t *n_failed, int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!in || !in_len || !out || !out_len || n_streams == 0 || (!encode && (!n_corrected || !n_failed)))
+        ENG_FAIL(h, OFDM_E_INVALID, "rs: bad arguments");
+    CU(h, cudaSetDevice(h->device));
+    if (int r = rs_tables_ready(h)) return r;
+    const uint32_t blk_in = encode ? kRsK : kRsN;
+    const uint32_t max_blocks = in_stride / blk_in + 1;
+    const uint32_t cps = (max_blocks + 31) / 32;
+    const uint64_t tasks = (uint64_t)cps * n_streams;
+    if (tasks > 0x7fffffffull * kRsWarps) ENG_FAIL(h, OFDM_E_INVALID, "rs: batch too large");
+    const dim3 grid((unsigned)((tasks + kRsWarps - 1) / kRsWarps));
+    RsArgs a{};
+    a.in_stride = in_stride; a.out_stride = out_stride; a.tables = h->rs_tables.as<RsTables>();
+    a.n_streams = n_streams; a.chunks_per_stream = cps;
+    if (mem == OFDM_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        a.in = in; a.in_len = in_len; a.out = out; a.out_len = out_len; a.n_corrected = n_corrected; a.n_failed = n_failed;
+        if (!encode) {
+            CU(h, cudaMemsetAsync(n_corrected, 0, sizeof(uint32_t) * (size_t)n_streams, st));
+            CU(h, cudaMemsetAsync(n_failed, 0, sizeof(uint32_t) * (size_t)n_streams, st));
+            rs_decode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+        } else rs_encode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+        h->launches += 1;
+        CU(h, cudaGetLastError());
+        return 0;
+    }
+    cudaStream_t st = h->own_stream;
+    const size_t ib = (size_t)n_streams * in_stride, ob = (size_t)n_streams * out_stride, lb = sizeof(uint32_t) * (size_t)n_streams;
+    CU(h, h->s_bytes.ensure(ib));
+    CU(h, h->s_bytes2.ensure(ob));
+    CU(h, h->s_len2.ensure(4 * lb));
+    uint32_t *d_il = h->s_len2.as<uint32_t>(), *d_ol = d_il + n_streams, *d_nc = d_ol + n_streams, *d_nf = d_nc + n_streams;
+    CU(h, cudaMemcpyAsync(h->s_bytes.p, in, ib, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_il, in_len, lb, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemsetAsync(d_nc, 0, 2 * lb, st));
+    a.in = h->s_bytes.as<uint8_t>(); a.in_len = d_il; a.out = h->s_bytes2.as<uint8_t>(); a.out_len = d_ol; a.n_corrected = d_nc; a.n_failed = d_nf;
+    if (encode) rs_encode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+    else rs_decode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(out, h->s_bytes2.p, ob, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(out_len, d_ol, lb, cudaMemcpyDeviceToHost, st));
+    if (!encode) {
+        CU(h, cudaMemcpyAsync(n_corrected, d_nc, lb, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(n_failed, d_nf, lb, cudaMemcpyDeviceToHost, st));
+    }
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int ofdm_rs_encode_batch(ofdm_engine *h, const uint8_t *data, const uint32_t *data_len, uint32_t n_streams, uint32_t data_stride,
+                                    uint8_t *coded, uint32_t coded_stride, uint32_t *coded_len, int mem, void *stream)
+{
+    return rs_run(h, true, data, data_len, n_streams, data_stride, coded, coded_stride, coded_len, nullptr, nullptr, mem, stream);
+}
+
+extern "C" int ofdm_rs_decode_batch(ofdm_engine *h, const uint8_t *coded, const uint32_t *coded_len, uint32_t n_streams, uint32_t coded_stride,
+                                    uint8_t *data, uint32_t data_stride, uint32_t *data_len, uint32_t *n_corrected, uint32_t *n_failed,
+                                    int mem, void *stream)
+{
+    return rs_run(h, false, coded, coded_len, n_streams, coded_stride, data, data_stride, data_len, n_corrected, n_failed, mem, stream);
 }
 
 // ---- BER ---------------------------------------------------------------------------------------------------------

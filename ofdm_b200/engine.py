@@ -28,6 +28,7 @@ EXPORTS = [
     "ofdm_frame_data_syms", "ofdm_frame_len", "ofdm_max_payload", "ofdm_tx_encode_batch", "ofdm_rx_decode_batch",
     "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches", "ofdm_profile_begin", "ofdm_profile_read",
     "ofdm_sync_search", "ofdm_rx_decode_capture",
+    "ofdm_rs_encoded_len", "ofdm_rs_decoded_len", "ofdm_rs_encode_batch", "ofdm_rs_decode_batch",
 ]
 
 
@@ -108,6 +109,13 @@ def load_library(build: bool = False) -> C.CDLL:
     L.ofdm_sync_search.restype = i32
     L.ofdm_rx_decode_capture.argtypes = [vp, vp, u64, vp, u32, u32, vp, u32, vp, vp, i32, vp]
     L.ofdm_rx_decode_capture.restype = i32
+    for f in (L.ofdm_rs_encoded_len, L.ofdm_rs_decoded_len):
+        f.argtypes = [sz]
+        f.restype = sz
+    L.ofdm_rs_encode_batch.argtypes = [vp, vp, vp, u32, u32, vp, u32, vp, i32, vp]
+    L.ofdm_rs_encode_batch.restype = i32
+    L.ofdm_rs_decode_batch.argtypes = [vp, vp, vp, u32, u32, vp, u32, vp, vp, vp, i32, vp]
+    L.ofdm_rs_decode_batch.restype = i32
     L.ofdm_kernel_launches.argtypes = [vp]
     L.ofdm_kernel_launches.restype = u64
     _lib = L
@@ -363,6 +371,52 @@ class Engine:
                                                  got.shape[1], _ptr(status), ref.shape[0], _ptr(counters), MEM_HOST, None),
                     "ofdm_ber_accumulate")
         return counters
+
+    # ---- Reed-Solomon outer code (src/utils.rs:97-137, 152-180) ---------------------------------------
+    def rs_encode(self, payloads: Sequence[bytes]):
+        """create_transmission_bytes for a batch -> (coded [n, stride] u8, coded_len [n])."""
+        n = len(payloads)
+        lens = np.array([len(p) for p in payloads], np.uint32)
+        in_stride = max(1, int(lens.max()))
+        out_stride = int(self.lib.ofdm_rs_encoded_len(int(lens.max())))
+        data = np.zeros((n, in_stride), np.uint8)
+        for i, p in enumerate(payloads):
+            data[i, :len(p)] = np.frombuffer(bytes(p), np.uint8)
+        coded = np.zeros((n, out_stride), np.uint8)
+        coded_len = np.zeros(n, np.uint32)
+        self._check(self.lib.ofdm_rs_encode_batch(self._h, _ptr(data), _ptr(lens), n, in_stride, _ptr(coded), out_stride,
+                                                  _ptr(coded_len), MEM_HOST, None), "ofdm_rs_encode_batch")
+        return coded, coded_len
+
+    def rs_decode(self, coded: np.ndarray, coded_len=None):
+        """decipher_transmission_bytes for a batch -> (data [n, stride] u8, data_len, n_corrected, n_failed)."""
+        coded = np.ascontiguousarray(coded, np.uint8)
+        if coded.ndim == 1:
+            coded = coded[None, :]
+        n, in_stride = coded.shape
+        lens = np.full(n, in_stride, np.uint32) if coded_len is None else np.ascontiguousarray(coded_len, np.uint32)
+        if in_stride == 0:
+            coded = np.zeros((n, 1), np.uint8)
+            in_stride = 1
+        out_stride = int(self.lib.ofdm_rs_decoded_len(int(lens.max())))
+        data = np.zeros((n, out_stride), np.uint8)
+        data_len = np.zeros(n, np.uint32)
+        n_corr = np.zeros(n, np.uint32)
+        n_fail = np.zeros(n, np.uint32)
+        self._check(self.lib.ofdm_rs_decode_batch(self._h, _ptr(coded), _ptr(lens), n, in_stride, _ptr(data), out_stride,
+                                                  _ptr(data_len), _ptr(n_corr), _ptr(n_fail), MEM_HOST, None),
+                    "ofdm_rs_decode_batch")
+        return data, data_len, n_corr, n_fail
+
+    def rs_encode_device(self, data_ptr, data_len_ptr, n_streams, data_stride, coded_ptr, coded_stride, coded_len_ptr, stream=0):
+        self._check(self.lib.ofdm_rs_encode_batch(self._h, data_ptr, data_len_ptr, n_streams, data_stride, coded_ptr, coded_stride,
+                                                  coded_len_ptr, MEM_DEVICE, stream or None), "ofdm_rs_encode_batch")
+
+    def rs_decode_device(self, coded_ptr, coded_len_ptr, n_streams, coded_stride, data_ptr, data_stride, data_len_ptr,
+                         n_corrected_ptr, n_failed_ptr, stream=0):
+        self._check(self.lib.ofdm_rs_decode_batch(self._h, coded_ptr, coded_len_ptr, n_streams, coded_stride, data_ptr, data_stride,
+                                                  data_len_ptr, n_corrected_ptr, n_failed_ptr, MEM_DEVICE, stream or None),
+                    "ofdm_rs_decode_batch")
 
     # ---- device-pointer API (raw addresses, e.g. torch.Tensor.data_ptr(); `stream` = cudaStream_t handle) ---
     def tx_encode_device(self, payload_ptr, payload_len_ptr, payload_stride, n_streams, iq_ptr, iq_stride,

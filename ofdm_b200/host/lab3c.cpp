@@ -1,7 +1,8 @@
 // lab3c.cpp -- the reference's lab3c example (examples/lab3c.rs:15-74) on the engine: --transmit writes an fc32 file,
 // --receive reads one (optionally sliced with --start/--stop) and decodes it.
 //   lab3c --transmit tx.dat --payload in.bin [--qpsk|--qam] [--guard]
-//   lab3c --receive rx.dat --out out.bin [--start N] [--stop M] [--qpsk|--qam] [--guard]
+//   lab3c --receive rx.dat --out out.bin [--start N] [--stop M] [--qpsk|--qam] [--guard] [--ecc]
+// --ecc wraps the payload in the RS(255,223) outer code like examples/lab3c_image.rs:19-21,33-36.
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -26,7 +27,7 @@ int main(int argc, char **argv)
 {
     std::string transmit, receive, payload, out;
     size_t start = 0, stop = (size_t)-1;
-    bool guard = false;
+    bool guard = false, ecc = false;
     ofdm::ModulationScheme mod = ofdm::ModulationScheme::Bpsk;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -38,6 +39,7 @@ int main(int argc, char **argv)
         else if (a == "--start") start = std::stoull(next());
         else if (a == "--stop") stop = std::stoull(next());
         else if (a == "--guard") guard = true;
+        else if (a == "--ecc") ecc = true;
         else if (a == "--qpsk") mod = ofdm::ModulationScheme::Qpsk;
         else if (a == "--qam") mod = ofdm::ModulationScheme::Qam;
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -49,7 +51,9 @@ int main(int argc, char **argv)
     try {
         ofdm::Modem modem(guard, mod);
         if (!transmit.empty()) {
-            auto samples = modem.encode(read_file(payload));
+            auto bytes = read_file(payload);
+            if (ecc) bytes = ofdm::create_transmission_bytes(modem, bytes);
+            auto samples = modem.encode(bytes);
             write_file(transmit, ofdm::sig_to_bytes(samples));
             std::printf("wrote %zu samples\n", samples.size());
         } else {
@@ -57,6 +61,11 @@ int main(int argc, char **argv)
             if (stop > samples.size()) stop = samples.size();
             ofdm::SignalVec slice(samples.begin() + (std::ptrdiff_t)start, samples.begin() + (std::ptrdiff_t)stop);
             auto data = modem.decode(slice);
+            if (ecc) {
+                auto fixed = ofdm::decipher_transmission_bytes(modem, data);
+                if (!fixed) throw std::runtime_error("Reed-Solomon: block beyond repair");
+                data = *fixed;
+            }
             write_file(out, data);
             std::printf("decoded %zu bytes\n", data.size());
         }

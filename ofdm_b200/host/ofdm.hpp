@@ -8,6 +8,7 @@
 //   ofdm::Header                                                                         src/packets/mod.rs:20-32
 //   ofdm::Analysis                                                                       src/utils.rs:38-69
 //   ofdm::sig_to_bytes / bytes_to_sig                                                    src/utils.rs:228-254
+//   ofdm::create_transmission_bytes / decipher_transmission_bytes (RS(255,223))          src/utils.rs:97-137,152-180
 //   ofdm::Modem::encode_batch / decode_batch : the batched forms a GPU needs
 #pragma once
 
@@ -163,6 +164,33 @@ inline std::vector<uint8_t> decode(const SignalVec &samples, std::optional<bool>
                                    std::optional<ModulationScheme> modulation = std::nullopt)
 {
     return Modem(guard_bands, modulation).decode(samples);
+}
+
+// RS(255,223) outer code with the reference's block framing
+inline std::vector<uint8_t> create_transmission_bytes(Modem &m, const std::vector<uint8_t> &data)      // src/utils.rs:97-137
+{
+    const uint32_t n = (uint32_t)data.size();
+    std::vector<uint8_t> coded(ofdm_rs_encoded_len(n));
+    uint32_t clen = 0;
+    const uint8_t zero = 0;
+    if (ofdm_rs_encode_batch(m.handle(), n ? data.data() : &zero, &n, 1, n ? n : 1, coded.data(), (uint32_t)coded.size(), &clen,
+                             OFDM_MEM_HOST, nullptr) != 0)
+        throw std::runtime_error(ofdm_last_error(m.handle()));
+    coded.resize(clen);
+    return coded;
+}
+inline std::optional<std::vector<uint8_t>> decipher_transmission_bytes(Modem &m, const std::vector<uint8_t> &coded)   // src/utils.rs:152-180
+{
+    const uint32_t n = (uint32_t)coded.size();
+    std::vector<uint8_t> data(ofdm_rs_decoded_len(n));
+    uint32_t dlen = 0, fixed = 0, failed = 0;
+    const uint8_t zero = 0;
+    if (ofdm_rs_decode_batch(m.handle(), n ? coded.data() : &zero, &n, 1, n ? n : 1, data.data(), (uint32_t)data.size(), &dlen, &fixed,
+                             &failed, OFDM_MEM_HOST, nullptr) != 0)
+        throw std::runtime_error(ofdm_last_error(m.handle()));
+    if (failed) return std::nullopt;                                 // `.ok()?`, src/utils.rs:165,172
+    data.resize(dlen);
+    return data;
 }
 
 struct Analysis {                     // src/utils.rs:38-69

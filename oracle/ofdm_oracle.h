@@ -87,6 +87,14 @@ size_t oo_hamming74_decoded_len(size_t n_coded);
 void oo_hamming74_encode(const uint8_t *in, size_t n, uint8_t *out);
 void oo_hamming74_decode(const uint8_t *in, size_t n_coded, uint8_t *out);
 
+/* Reed-Solomon outer code (rs255.c): the reference's `reed-solomon` 0.2.1 call sites, src/utils.rs:97-137,152-180 */
+void oo_rs_encode_block(const uint8_t *msg, int k, int nsym, uint8_t *parity);
+int oo_rs_correct_block(uint8_t *word, int n, int nsym);
+size_t oo_rs_encoded_len(size_t n);
+size_t oo_rs_decoded_len(size_t n);
+void oo_rs_encode(const uint8_t *in, size_t n, uint8_t *out);
+int oo_rs_decode(const uint8_t *in, size_t n, uint8_t *out, uint32_t *n_corrected, uint32_t *n_failed);
+
 /* ---- TX (src/transmitter.rs) ---- */
 size_t oo_modulate(const uint8_t *bytes, size_t n, int scheme, oo_c64 *out);      /* returns #symbols */
 size_t oo_demodulate(const oo_c64 *syms, size_t n, int scheme, uint8_t *out);      /* returns #bytes */

@@ -89,6 +89,17 @@ def lib() -> C.CDLL:
         f.restype = sz
     L.oo_hamming74_encode.argtypes = [vp, sz, vp]
     L.oo_hamming74_decode.argtypes = [vp, sz, vp]
+    for f in (L.oo_rs_encoded_len, L.oo_rs_decoded_len):
+        f.argtypes = [sz]
+        f.restype = sz
+    L.oo_rs_encode_block.argtypes = [vp, i32, i32, vp]
+    L.oo_rs_encode_block.restype = None
+    L.oo_rs_correct_block.argtypes = [vp, i32, i32]
+    L.oo_rs_correct_block.restype = i32
+    L.oo_rs_encode.argtypes = [vp, sz, vp]
+    L.oo_rs_encode.restype = None
+    L.oo_rs_decode.argtypes = [vp, sz, vp, vp, vp]
+    L.oo_rs_decode.restype = i32
     L.oo_modulate.argtypes = [vp, sz, i32, vp]
     L.oo_modulate.restype = sz
     L.oo_demodulate.argtypes = [vp, sz, i32, vp]
@@ -239,6 +250,40 @@ def hamming74_decode(coded):
     o = np.zeros(lib().oo_hamming74_decoded_len(d.size), np.uint8)
     lib().oo_hamming74_decode(_p(d), d.size, _p(o))
     return o
+
+
+def rs_encode_block(msg, nsym=32):
+    """parity bytes of one block (`Encoder::new(nsym).encode`, src/utils.rs:108,118)"""
+    d = _bytes(msg)
+    o = np.zeros(nsym, np.uint8)
+    lib().oo_rs_encode_block(_p(d), d.size, nsym, _p(o))
+    return o
+
+
+def rs_correct_block(word, nsym=32):
+    """(corrected word, n_corrected) or (word, -1): `Decoder::new(nsym).correct`, src/utils.rs:154,165"""
+    w = _bytes(word).copy()
+    r = lib().oo_rs_correct_block(_p(w), w.size, nsym)
+    return w, int(r)
+
+
+def rs_encode(data):
+    """create_transmission_bytes, src/utils.rs:97-137"""
+    d = _bytes(data)
+    o = np.zeros(lib().oo_rs_encoded_len(d.size), np.uint8)
+    lib().oo_rs_encode(_p(d), d.size, _p(o))
+    return o
+
+
+def rs_decode(coded):
+    """decipher_transmission_bytes, src/utils.rs:152-180 -> (bytes, n_corrected, n_failed); the reference returns
+    None when n_failed > 0"""
+    d = _bytes(coded)
+    o = np.zeros(lib().oo_rs_decoded_len(d.size), np.uint8)
+    nc = np.zeros(1, np.uint32)
+    nf = np.zeros(1, np.uint32)
+    lib().oo_rs_decode(_p(d), d.size, _p(o), _p(nc), _p(nf))
+    return o, int(nc[0]), int(nf[0])
 
 
 # ---- TX / channel / RX ---------------------------------------------------------------------

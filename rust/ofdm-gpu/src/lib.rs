@@ -86,6 +86,36 @@ impl Engine {
             .collect())
     }
 
+    /// `create_transmission_bytes` (src/utils.rs:97-137): RS(255,223) blocks, the tail block always emitted.
+    pub fn rs_encode(&mut self, data: &[u8]) -> Result<Vec<u8>> {
+        let n = [data.len() as u32];
+        let cap = unsafe { sys::ofdm_rs_encoded_len(data.len()) };
+        let mut coded = vec![0u8; cap];
+        let mut clen = [0u32];
+        let rc = unsafe {
+            sys::ofdm_rs_encode_batch(self.h, data.as_ptr(), n.as_ptr(), 1, data.len().max(1) as u32, coded.as_mut_ptr(), cap as u32,
+                                      clen.as_mut_ptr(), sys::OFDM_MEM_HOST, ptr::null_mut())
+        };
+        self.check(rc)?;
+        coded.truncate(clen[0] as usize);
+        Ok(coded)
+    }
+
+    /// `decipher_transmission_bytes` (src/utils.rs:152-180): `None` when a block is beyond repair.
+    pub fn rs_decode(&mut self, coded: &[u8]) -> Result<Option<Vec<u8>>> {
+        let n = [coded.len() as u32];
+        let cap = unsafe { sys::ofdm_rs_decoded_len(coded.len()) };
+        let mut data = vec![0u8; cap];
+        let (mut dlen, mut fixed, mut failed) = ([0u32], [0u32], [0u32]);
+        let rc = unsafe {
+            sys::ofdm_rs_decode_batch(self.h, coded.as_ptr(), n.as_ptr(), 1, coded.len().max(1) as u32, data.as_mut_ptr(), cap as u32,
+                                      dlen.as_mut_ptr(), fixed.as_mut_ptr(), failed.as_mut_ptr(), sys::OFDM_MEM_HOST, ptr::null_mut())
+        };
+        self.check(rc)?;
+        data.truncate(dlen[0] as usize);
+        Ok(if failed[0] == 0 { Some(data) } else { None })
+    }
+
     fn check(&self, rc: i32) -> Result<()> {
         if rc == 0 {
             Ok(())

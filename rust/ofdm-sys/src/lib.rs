@@ -110,6 +110,13 @@ extern "C" {
     pub fn ofdm_rx_decode_capture(h: *mut ofdm_engine, iq: *const ofdm_fc32, n_samples: u64, peaks: *const ofdm_peak, n_frames: u32,
                                   max_frame_samples: u32, out: *mut u8, out_stride: u32, out_len: *mut u32, status: *mut i32,
                                   mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn ofdm_rs_encoded_len(data_len: usize) -> usize;
+    pub fn ofdm_rs_decoded_len(coded_len: usize) -> usize;
+    pub fn ofdm_rs_encode_batch(h: *mut ofdm_engine, data: *const u8, data_len: *const u32, n_streams: u32, data_stride: u32,
+                                coded: *mut u8, coded_stride: u32, coded_len: *mut u32, mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn ofdm_rs_decode_batch(h: *mut ofdm_engine, coded: *const u8, coded_len: *const u32, n_streams: u32, coded_stride: u32,
+                                data: *mut u8, data_stride: u32, data_len: *mut u32, n_corrected: *mut u32, n_failed: *mut u32,
+                                mem: c_int, stream: *mut c_void) -> c_int;
     pub fn ofdm_profile_begin(h: *mut ofdm_engine, max_calls: u32) -> c_int;
     pub fn ofdm_profile_read(h: *mut ofdm_engine, acquire_ms: *mut f32, decode_ms: *mut f32, n_calls: *mut u32) -> c_int;
     pub fn ofdm_kernel_launches(h: *const ofdm_engine) -> u64;

@@ -137,3 +137,37 @@ def test_cpp_host_lab3c_file_roundtrip(tmp_path):
     r = subprocess.run([exe, "--receive", str(tmp_path / "rx.dat"), "--out", str(tmp_path / "o2.bin"), "--stop", "500", "--qpsk", "--guard"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "Input not long enough" in r.stderr
+
+
+def test_cpp_host_lab3c_ecc_roundtrip(tmp_path):
+    """lab3c --ecc: RS(255,223) outer code around the modem like examples/lab3c_image.rs:19-21,33-36, at an SNR where BPSK
+    alone leaves byte errors."""
+    import subprocess
+    from ofdm_b200 import _build
+    from oracle import oracle as oo
+    import ofdm_b200 as ob
+    exe = _build.build_host_example()
+    pay = bytes((7 * i + 3) & 255 for i in range(576))
+    (tmp_path / "in.bin").write_bytes(pay)
+    subprocess.run([exe, "--transmit", str(tmp_path / "tx.dat"), "--payload", str(tmp_path / "in.bin"), "--guard", "--ecc"], check=True)
+    tx = ob.bytes_to_sig((tmp_path / "tx.dat").read_bytes())
+    assert tx.size == 11280                                            # 765 coded bytes, BPSK (SURVEY.md 8d config 1)
+    np.testing.assert_allclose(tx, oo.encode(oo.rs_encode(np.frombuffer(pay, np.uint8)).tobytes(), True, oo.BPSK), atol=2e-6)
+    done = 0
+    for seed in range(1, 9):
+        cap = oo.channel(tx, 8.0, 0.01, 0, seed)
+        ref = oo.decode(cap.astype(np.complex64).astype(np.complex128), oo.make_cfg(True, oo.BPSK, False, 0, 0, 0, 0), want_points=False)
+        if ref.status != 0 or len(ref.data) != 765:
+            continue                                                   # the unprotected header took a hit
+        want, _, nf = oo.rs_decode(np.frombuffer(ref.data, np.uint8))
+        (tmp_path / "rx.dat").write_bytes(ob.sig_to_bytes(cap))
+        r = subprocess.run([exe, "--receive", str(tmp_path / "rx.dat"), "--out", str(tmp_path / "out.bin"), "--guard", "--ecc"],
+                           capture_output=True, text=True)
+        if nf:
+            assert r.returncode == 1 and "beyond repair" in r.stderr
+        else:
+            assert r.returncode == 0, r.stderr
+            got = (tmp_path / "out.bin").read_bytes()
+            assert got == want.tobytes() and got[:576] == pay
+            done += 1
+    assert done >= 3

@@ -1,0 +1,193 @@
+"""Reed-Solomon RS(255,223) outer code: oracle pins on CPU, CUDA kernels vs oracle on the GPU.
+
+The reference calls the `reed-solomon` 0.2.1 crate (Cargo.toml:35; call sites src/utils.rs:108-118,154-172), which is not
+under /root/reference and whose only reference test (`ecc_packets`, src/utils.rs:358-367) prints instead of asserting:
+parity is unpinned beyond the published construction (GF(2^8)/0x11d, alpha = 2, roots alpha^0.., message first). The oracle is
+pinned on that construction's published vector and on the defining properties of the code.
+"""
+import numpy as np
+import pytest
+
+
+# ---- CPU: the oracle ------------------------------------------------------------------------------------------------
+def test_rs_oracle_published_vector(oo):
+    # "Reed-Solomon codes for coders" (the construction the crate ports): QR 1-M message, 10 parity symbols
+    msg = bytes.fromhex("40d2754776173206272696c6c69670ec")
+    assert oo.rs_encode_block(msg, 10).tobytes().hex() == "bc2a90136bafeffd4be0"
+
+
+def test_rs_oracle_codeword_roots_and_linearity(oo):
+    rng = np.random.default_rng(7)
+    exp = [1]
+    for _ in range(254):
+        v = exp[-1] << 1
+        exp.append(v ^ 0x11d if v & 0x100 else v)
+    log = {v: i for i, v in enumerate(exp)}
+
+    def mul(a, b):
+        return exp[(log[a] + log[b]) % 255] if a and b else 0
+
+    a = rng.integers(0, 256, 223, dtype=np.uint8)
+    b = rng.integers(0, 256, 223, dtype=np.uint8)
+    pa, pb, pab = oo.rs_encode_block(a), oo.rs_encode_block(b), oo.rs_encode_block(a ^ b)
+    assert (pa ^ pb == pab).all()                                      # linear over GF(2)
+    word = np.concatenate([a, pa])
+    for i in range(32):                                                # alpha^0 .. alpha^31 are roots of every codeword
+        y = 0
+        for c in word:
+            y = mul(y, exp[i]) ^ int(c)
+        assert y == 0
+
+
+def test_rs_oracle_framing_lengths(oo):
+    # src/utils.rs:113-134: the partially filled (possibly empty) last block is always emitted
+    for n, blocks in ((0, 1), (1, 1), (222, 1), (223, 2), (224, 2), (576, 3), (1024, 5)):
+        coded = oo.rs_encode(np.arange(n, dtype=np.uint8))
+        assert coded.size == 255 * blocks
+        dec, nc, nf = oo.rs_decode(coded)
+        assert dec.size == 223 * (blocks + 1) and nc == 0 and nf == 0   # src/utils.rs:160-176: the empty tail decodes too
+        assert (dec[:n] == np.arange(n, dtype=np.uint8)).all() and not dec[n:].any()
+    # 576-byte dancing.bytes -> 765 coded -> 892 decoded
+    assert oo.rs_encode(np.zeros(576, np.uint8)).size == 765
+
+
+def test_rs_oracle_corrects_16_fails_17(oo):
+    rng = np.random.default_rng(11)
+    data = rng.integers(0, 256, 223, dtype=np.uint8)
+    word = np.concatenate([data, oo.rs_encode_block(data)])
+    for ne in (1, 2, 8, 15, 16):
+        for _ in range(20):
+            w = word.copy()
+            pos = rng.choice(255, ne, replace=False)
+            w[pos] ^= rng.integers(1, 256, ne, dtype=np.uint8)
+            fixed, r = oo.rs_correct_block(w)
+            assert r == ne and (fixed == word).all()
+    fails = 0
+    for _ in range(50):
+        w = word.copy()
+        pos = rng.choice(255, 17, replace=False)
+        w[pos] ^= rng.integers(1, 256, 17, dtype=np.uint8)
+        fixed, r = oo.rs_correct_block(w)
+        fails += r < 0
+        assert r < 0 or not (fixed == word).all()                      # never "corrects" back to the sent word
+    assert fails >= 45                                                 # miscorrection probability ~ 1/16! per word
+
+
+def test_rs_exports_present(engine_lib):
+    for name in ("ofdm_rs_encoded_len", "ofdm_rs_decoded_len", "ofdm_rs_encode_batch", "ofdm_rs_decode_batch"):
+        assert hasattr(engine_lib, name)
+    assert engine_lib.ofdm_rs_encoded_len(576) == 765 and engine_lib.ofdm_rs_decoded_len(765) == 892
+
+
+# ---- GPU: kernels vs oracle -------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def eng():
+    from ofdm_b200 import engine
+    e = engine.Engine(engine.Config())
+    yield e
+    e.close()
+
+
+@pytest.mark.gpu
+def test_rs_encode_matches_oracle_ragged_batch(oo, eng):
+    rng = np.random.default_rng(3)
+    lens = [0, 1, 222, 223, 224, 445, 446, 576, 1000, 223 * 128, 223 * 128 + 1, 223 * 300 + 17]
+    payloads = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    coded, coded_len = eng.rs_encode(payloads)
+    for i, p in enumerate(payloads):
+        want = oo.rs_encode(np.frombuffer(p, np.uint8))
+        assert int(coded_len[i]) == want.size
+        assert (coded[i, :want.size] == want).all(), f"stream {i} (len {lens[i]})"
+
+
+@pytest.mark.gpu
+def test_rs_decode_matches_oracle_with_errors(oo, eng):
+    rng = np.random.default_rng(5)
+    lens = [0, 100, 223, 576, 5000, 223 * 130]
+    coded_list = []
+    for n in lens:
+        c = oo.rs_encode(rng.integers(0, 256, n, dtype=np.uint8))
+        nb = c.size // 255
+        for b in range(nb):                                            # 0..18 symbol errors per block, incl. the parity bytes
+            ne = int(rng.integers(0, 19))
+            pos = rng.choice(255, ne, replace=False) + 255 * b
+            c[pos] ^= rng.integers(1, 256, ne, dtype=np.uint8)
+        coded_list.append(c)
+    stride = max(c.size for c in coded_list) + 3                       # odd stride: unaligned stream bases
+    coded = np.zeros((len(lens), stride), np.uint8)
+    clen = np.zeros(len(lens), np.uint32)
+    for i, c in enumerate(coded_list):
+        coded[i, :c.size] = c
+        clen[i] = c.size
+    data, data_len, n_corr, n_fail = eng.rs_decode(coded, clen)
+    saw_fail = saw_fix = False
+    for i, c in enumerate(coded_list):
+        want, wc, wf = oo.rs_decode(c)
+        assert int(data_len[i]) == want.size
+        assert (int(n_corr[i]), int(n_fail[i])) == (wc, wf), f"stream {i}"
+        assert (data[i, :want.size] == want).all(), f"stream {i}"
+        saw_fail |= wf > 0
+        saw_fix |= wc > 0
+    assert saw_fail and saw_fix
+
+
+@pytest.mark.gpu
+def test_rs_truncated_and_ragged_tail(oo, eng):
+    # a stream cut inside a block: the missing bytes read as zeros (src/utils.rs:157,167) and count as errors
+    rng = np.random.default_rng(9)
+    c = oo.rs_encode(rng.integers(1, 256, 500, dtype=np.uint8))
+    for cut in (1, 10, 16, 17, 40, 254, 255, 256):
+        part = c[:c.size - cut]
+        want, wc, wf = oo.rs_decode(part)
+        data, data_len, n_corr, n_fail = eng.rs_decode(part)
+        assert int(data_len[0]) == want.size and (int(n_corr[0]), int(n_fail[0])) == (wc, wf), cut
+        assert (data[0, :want.size] == want).all(), cut
+
+
+@pytest.mark.gpu
+def test_rs_api_mirror_round_trip(eng):
+    from ofdm_b200 import api
+    text = bytes(range(256)) * 3
+    coded = api.create_transmission_bytes(text)
+    assert len(coded) == 255 * (len(text) // 223 + 1)
+    bad = bytearray(coded)
+    for b in range(len(coded) // 255):
+        for k in range(16):
+            bad[255 * b + 7 * k] ^= 0x5A
+    out = api.decipher_transmission_bytes(bytes(bad))
+    assert out is not None and out[:len(text)] == text and not any(out[len(text):])
+    bad[3] ^= 1; bad[100] ^= 7                                         # 18 errors in block 0 -> None, like the reference
+    assert api.decipher_transmission_bytes(bytes(bad)) is None
+
+
+@pytest.mark.gpu
+def test_lab3c_image_chain_bpsk_rs(oo, eng):
+    # what examples/lab3c_image.rs:15-40 runs: RS -> encode(guard_bands) -> channel(30 dB, CFO) -> decode -> RS^-1 -> Analysis
+    from ofdm_b200 import engine
+    rng = np.random.default_rng(21)
+    payload = rng.integers(0, 256, 576, dtype=np.uint8).tobytes()
+    n = 32
+    coded, clen = eng.rs_encode([payload] * n)
+    assert int(clen[0]) == 765
+    cfg = engine.Config(modulation=engine.MOD_BPSK, guard_bands=True)
+    e2 = engine.Engine(cfg)
+    try:
+        tx, tx_len = e2.tx_encode([coded[i, :765].tobytes() for i in range(n)])
+        assert int(tx_len[0]) == 11280
+        rx, rx_len, _, _ = e2.channel(tx, tx_len, engine.ChannelParams(snr_db=7.0, cfo_max=0.02, seed=77))
+        res = e2.rx_decode(rx, rx_len)
+        good = np.flatnonzero((res.status == 0) & (res.out_len == 765))    # the 16-byte header is not protected
+        assert good.size >= n // 2
+        data, data_len, n_corr, n_fail = eng.rs_decode(res.out[:, :765], np.where(res.status == 0, res.out_len, 0))
+        raw_errs = repaired = 0
+        for i in good:
+            want, wc, wf = oo.rs_decode(res.out[i, :765])
+            assert int(data_len[i]) == 892 and (int(n_corr[i]), int(n_fail[i])) == (wc, wf)
+            assert (data[i, :892] == want).all()
+            raw_errs += int((res.out[i, :765] != coded[i, :765]).sum())
+            if wf == 0:
+                assert data[i, :576].tobytes() == payload and not data[i, 576:892].any()
+                repaired += 1
+        assert raw_errs > 0 and repaired >= good.size // 2             # the outer code had work to do and did it
+    finally:
+        e2.close()
