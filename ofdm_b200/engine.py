@@ -359,6 +359,12 @@ class Engine:
         self._check(self.lib.ofdm_sync_search(self._h, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, MEM_DEVICE, stream or None),
                     "ofdm_sync_search")
 
+    def decode_capture_device(self, iq_ptr, n_samples, peaks_ptr, n_frames, max_frame_samples, out_ptr, out_stride, out_len_ptr,
+                              status_ptr, stream=0):
+        self._check(self.lib.ofdm_rx_decode_capture(self._h, iq_ptr, n_samples, peaks_ptr, n_frames, max_frame_samples, out_ptr,
+                                                    out_stride, out_len_ptr, status_ptr, MEM_DEVICE, stream or None),
+                    "ofdm_rx_decode_capture")
+
     def ber(self, ref: np.ndarray, ref_len, got: np.ndarray, got_len, status) -> np.ndarray:
         """Batch utils::Analysis (src/utils.rs:45-68) -> [bit_errs, byte_errs, bits_compared, frames_failed]."""
         ref = np.ascontiguousarray(ref, np.uint8)
