@@ -44,5 +44,5 @@ def test_ecc_packets_round_trip():
     assert text is not None and text.encode() == (raw * 3)[:1024]
     words = decipher_transmision_colorspace(bytes(bad), True)
     assert words is not None and words.size == 223 * (len(bad) // 255 + 1)
-    bad[0] ^= 1; bad[1] ^= 1
+    bad[1] ^= 1; bad[2] ^= 1
     assert decipher_transmission_text(1024, bytes(bad), True) is None    # 17 errors in block 0
