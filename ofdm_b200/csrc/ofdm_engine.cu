@@ -746,7 +746,10 @@ static int sync_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_pea
     CU(h, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), st));
     if (n >= 2 * kSym) {
         const uint64_t lags = n - 2 * kSym + 1;
-        const uint32_t grid = (uint32_t)((lags + kScanD - 1) / kScanD);
+        a.n_tiles = (uint32_t)((lags + kScanD - 1) / kScanD);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const uint32_t grid = a.n_tiles < (uint32_t)(2 * sms) ? a.n_tiles : (uint32_t)(2 * sms);    // persistent: 2 CTAs per SM
         if (h->smem_configured.insert((const void *)sync_scan_kernel).second)
             CU(h, cudaFuncSetAttribute((const void *)sync_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_scan_smem_bytes()));
         sync_scan_kernel<<<grid, kScanRows, sync_scan_smem_bytes(), st>>>(a);

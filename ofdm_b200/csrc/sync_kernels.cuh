@@ -5,8 +5,11 @@
 // the capture is scanned once (8 B/sample) with the sliding Schmidl-Cox metric of docs/SPEC.md 4:
 //
 //   sync_scan_kernel   : one CTA per 3928 lags. Coalesced IQ tile -> padded smem rows (one 8-sample row per thread);
-//                        q[n] = conj(a[n]) a[n+80], e[n] = |a[n]|^2; thread-serial prefix sums inside a row plus
-//                        10-row window sums of the row totals; P(d) = Q[d+80]-Q[d], R1(d) = E[d+80]-E[d], R2(d) = E[d+160]-E[d+80]; rising
+//                        q[n] = conj(a[n]) a[n+80], e[n] = |a[n]|^2; per-row totals, 10-row window sums of the totals, and
+//                        for the 8 lags of a row P(d) = W_q + pre_q(row+10) - pre_q(row), R1, R2 likewise from the
+//                        thread-serial prefix sums inside rows t, t+10, t+20. A row whose bound
+//                        (|W_q| + sum|q_t| + sum|q_t+10|)^2 stays below 0.5 min R1 min R2 cannot hold a lag above the
+//                        threshold and skips the per-lag work (all but the preamble plateaus of a capture). Rising
 //                        edges of |P|^2 > 0.5 R1 R2 are appended to a candidate list.
 //   sync_select_kernel : one CTA: bitonic sort of the candidates, 800-sample hold-off (one detection per frame).
 //   sync_refine_kernel : one CTA per detection: ramp-correlation arg-max around it (lag - 1 rule), CFO estimate.
@@ -40,11 +43,12 @@ struct SyncArgs {
     const RxTables *tables;
     SyncPeak *peaks;
     uint32_t max_peaks;
+    uint32_t n_tiles;        // 3928-lag tiles of the capture; the scan grid is persistent and strides over them
 };
 
 constexpr size_t sync_scan_smem_bytes()
 {
-    return (size_t)kScanRows * kScanRowStride * (sizeof(float2) * 2 + sizeof(float)) + sizeof(float) * 4 * (kScanRows + 32) + sizeof(uint32_t) * (kScanRows + 8);
+    return (size_t)kScanRows * kScanRowStride * sizeof(float2) + sizeof(float) * 5 * (kScanRows + 32) + sizeof(uint32_t) * (kScanRows + 8);
 }
 
 __device__ __forceinline__ cpx c_conj_mul(cpx a, cpx b)     // conj(a) * b
@@ -54,27 +58,17 @@ __device__ __forceinline__ cpx c_conj_mul(cpx a, cpx b)     // conj(a) * b
     return c_fma2(c_make(bi, -br), c_make(ai, ai), c_mul2(b, c_make(ar, ar)));
 }
 
-__global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs a)
+// one tile's samples in flight: 4 x 16 B per thread
+struct ScanTileRegs { unsigned long long v[kScanT]; };
+
+__device__ __forceinline__ void scan_tile_load(const SyncArgs &a, long long tile, int t, ScanTileRegs &r)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    unsigned long long *s_iq = reinterpret_cast<unsigned long long *>(smem_raw);              // [row][17] packed complex
-    unsigned long long *s_q = s_iq + kScanRows * kScanRowStride;                              // thread-local exclusive prefix of q
-    float *s_e = reinterpret_cast<float *>(s_q + kScanRows * kScanRowStride);                 // thread-local exclusive prefix of e
-    float *s_off = s_e + kScanRows * kScanRowStride;                                          // [3][rows + 8] row offsets (block scan)
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_off + 4 * (kScanRows + 32));
-
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const long long n = (long long)a.n;
-    const long long d_base = (long long)blockIdx.x * kScanD;          // first lag evaluated by this CTA (row 1)
-    const long long origin = d_base - kScanT;                         // sample index of row 0, column 0
-    const long long d_last = n - 2 * kSym;                            // largest valid lag
-
-    // ---- coalesced tile load: 2 samples (16 B) per thread per step -> padded rows ---------------------------------
+    const long long origin = tile * kScanD - kScanT;                   // sample index of row 0, column 0
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.iq) & 15) == 0) && ((origin & 1) == 0);
 #pragma unroll
     for (int i = 0; i < kScanT / 2; i++) {
-        const int idx = i * kScanRows + t;                             // float4 index inside the tile
-        const long long s0 = origin + 2 * idx;
+        const long long s0 = origin + 2 * (i * kScanRows + t);         // coalesced: 2 samples (16 B) per thread per step
         unsigned long long v0 = 0, v1 = 0;
         if (aligned && s0 >= 0 && s0 + 1 < n) {
             const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(a.iq + s0));
@@ -83,15 +77,45 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
             if (s0 >= 0 && s0 < n) v0 = __ldg(reinterpret_cast<const unsigned long long *>(a.iq + s0));
             if (s0 + 1 >= 0 && s0 + 1 < n) v1 = __ldg(reinterpret_cast<const unsigned long long *>(a.iq + s0 + 1));
         }
-        const int row = idx / (kScanT / 2), col = (idx % (kScanT / 2)) * 2;
-        s_iq[row * kScanRowStride + col] = v0;
-        s_iq[row * kScanRowStride + col + 1] = v1;
+        r.v[2 * i] = v0; r.v[2 * i + 1] = v1;
     }
+}
+
+__global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    unsigned long long *s_iq = reinterpret_cast<unsigned long long *>(smem_raw);              // [row][9] packed complex
+    float *s_off = reinterpret_cast<float *>(s_iq + kScanRows * kScanRowStride);              // row totals: q.re | q.im | e | sum |q|
+    float *s_we = s_off + 4 * (kScanRows + 32);                                               // 80-sample energy windows at row granularity
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_we + (kScanRows + 32));
+    constexpr int TQR = 0, TQI = kScanRows, TE = 2 * kScanRows, TA = 3 * kScanRows;
+
+    const int t = threadIdx.x;
+    const long long n = (long long)a.n;
+    const long long d_last = n - 2 * kSym;                            // largest valid lag
+
+    // persistent CTA: the next tile's samples are fetched into registers while this tile is processed from shared memory
+    ScanTileRegs pre;
+    if (blockIdx.x < a.n_tiles) scan_tile_load(a, blockIdx.x, t, pre);
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < (long long)a.n_tiles; tile += gridDim.x) {
+    const long long d_base = tile * kScanD;                           // first lag evaluated from this tile (row 1)
+    const long long origin = d_base - kScanT;                         // sample index of row 0, column 0
+#pragma unroll
+    for (int i = 0; i < kScanT / 2; i++) {
+        const int idx = i * kScanRows + t;                             // float4 index inside the tile
+        const int row = idx / (kScanT / 2), col = (idx % (kScanT / 2)) * 2;
+        s_iq[row * kScanRowStride + col] = pre.v[2 * i];
+        s_iq[row * kScanRowStride + col + 1] = pre.v[2 * i + 1];
+    }
+    if (tile + gridDim.x < (long long)a.n_tiles) scan_tile_load(a, tile + gridDim.x, t, pre);
     __syncthreads();
 
-    // ---- q, e and their thread-local exclusive prefix sums (one row per thread) -------------------------------------
+    // ---- row totals of q, e and of |q| (L1 norm, for the bound) -- one row per thread ---------------------------------
+    // The running sums go through exactly the operations the per-lag prefix sums below use, so a total equals the prefix
+    // "after column 7" bit for bit.
     cpx tq = c_make(0.0f, 0.0f);
-    float te = 0.0f;
+    float te = 0.0f, ta = 0.0f;
     {
         const unsigned long long *own = s_iq + t * kScanRowStride;
         const bool has5 = t + kScanR80 < kScanRows;
@@ -100,12 +124,13 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
         for (int j = 0; j < kScanT; j++) {
             cpx x, y;
             x.v = own[j]; y.v = has5 ? nxt[j] : 0ull;
-            s_q[t * kScanRowStride + j] = tq.v;
-            s_e[t * kScanRowStride + j] = te;
-            float xr, xi;
+            float xr, xi, pr, pi;
             c_split(x, xr, xi);
-            tq = c_add(tq, c_conj_mul(x, y));
+            const cpx q = c_conj_mul(x, y);
+            c_split(q, pr, pi);
+            tq = c_add(tq, q);
             te = fmaf(xr, xr, fmaf(xi, xi, te));
+            ta += fabsf(pr) + fabsf(pi);
         }
     }
     // ---- 80-sample window sums at row granularity: W[t] = sum of the row totals of rows t .. t+9 ---------------------
@@ -113,15 +138,14 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
     // a quiet stretch that follows a loud frame inside the same tile)
     float qr, qi;
     c_split(tq, qr, qi);
-    s_off[t] = qr; s_off[kScanRows + t] = qi; s_off[2 * kScanRows + t] = te;
+    s_off[TQR + t] = qr; s_off[TQI + t] = qi; s_off[TE + t] = te; s_off[TA + t] = ta;
     __syncthreads();
     float wqr = 0.0f, wqi = 0.0f, we = 0.0f;
 #pragma unroll
     for (int k = 0; k < kScanR80; k++) {
         const int r = t + k < kScanRows ? t + k : kScanRows - 1;          // rows past the tile are never used by an evaluated lag
-        wqr += s_off[r]; wqi += s_off[kScanRows + r]; we += s_off[2 * kScanRows + r];
+        wqr += s_off[TQR + r]; wqi += s_off[TQI + r]; we += s_off[TE + r];
     }
-    float *s_we = s_off + 3 * kScanRows;                                   // [rows]
     s_we[t] = we;
     __syncthreads();
 
@@ -130,25 +154,41 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
     if (t <= kScanEvalRows) {
         constexpr int A = kScanR80, B = 2 * kScanR80;
         const float de1 = we, de2 = s_we[t + A];
-        const cpx dq = c_make(wqr, wqi);
-        const unsigned long long *q0 = s_q + t * kScanRowStride, *q5 = s_q + (t + A) * kScanRowStride;
-        const float *e0 = s_e + t * kScanRowStride, *e5 = s_e + (t + A) * kScanRowStride, *e10 = s_e + (t + B) * kScanRowStride;
-        // lags of this row that exist: 0 <= d <= d_last (hoisted out of the loop as a bit mask)
-        const long long dr = origin + (long long)t * kScanT;
-        uint32_t live = (1u << kScanT) - 1u;
-        if (dr < 0) live = dr <= -kScanT ? 0u : live & ~((1u << (int)(-dr)) - 1u);
-        if (dr + kScanT - 1 > d_last) live = dr > d_last ? 0u : live & ((1u << (int)(d_last - dr + 1)) - 1u);
+        // Can any of the 8 lags of this row be above the threshold? For lag column j:
+        //   P  = W_q + pre_q(t+A)[j] - pre_q(t)[j]            =>  |P| <= |W_q| + sum|q_t| + sum|q_t+A|
+        //   R1 = W_e(t) + pre_e(t+A)[j] - pre_e(t)[j]         >=  W_e(t) - E_t       (likewise R2 one window later)
+        // with slack for fp32 rounding of either side. Products that underflow compare 0 < 0 = false and take the exact path.
+        const float bp = (fabsf(wqr) + fabsf(wqi) + ta + s_off[TA + t + A]) * 1.0001f;
+        const float r1m = fmaxf(0.0f, (de1 - te) - 8e-6f * de1);
+        const float r2m = fmaxf(0.0f, (de2 - s_off[TE + t + A]) - 8e-6f * de2);
+        if (!(bp * bp < 0.499f * r1m * r2m)) {
+            const cpx dq = c_make(wqr, wqi);
+            const unsigned long long *x0 = s_iq + t * kScanRowStride, *x5 = x0 + A * kScanRowStride, *x10 = x0 + B * kScanRowStride;
+            // lags of this row that exist: 0 <= d <= d_last (hoisted out of the loop as a bit mask)
+            const long long dr = origin + (long long)t * kScanT;
+            uint32_t live = (1u << kScanT) - 1u;
+            if (dr < 0) live = dr <= -kScanT ? 0u : live & ~((1u << (int)(-dr)) - 1u);
+            if (dr + kScanT - 1 > d_last) live = dr > d_last ? 0u : live & ((1u << (int)(d_last - dr + 1)) - 1u);
+            cpx q0 = c_make(0.0f, 0.0f), q5 = q0;                          // exclusive prefix sums inside rows t, t+A (q) and t, t+A, t+B (e)
+            float e0 = 0.0f, e5 = 0.0f, e10 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kScanT; j++) {
-            cpx a0, a5;
-            a0.v = q0[j]; a5.v = q5[j];
-            float pr, pi;
-            c_split(c_add(c_sub(a5, a0), dq), pr, pi);
-            const float e5j = e5[j];
-            const float r1 = (e5j - e0[j]) + de1, r2 = (e10[j] - e5j) + de2;
-            if (pr * pr + pi * pi > 0.5f * r1 * r2) mask |= 1u << j;
+            for (int j = 0; j < kScanT; j++) {
+                float pr, pi;
+                c_split(c_add(c_sub(q5, q0), dq), pr, pi);
+                const float r1 = (e5 - e0) + de1, r2 = (e10 - e5) + de2;
+                if (pr * pr + pi * pi > 0.5f * r1 * r2) mask |= 1u << j;
+                cpx u, v, w;
+                u.v = x0[j]; v.v = x5[j]; w.v = x10[j];
+                float ur, ui, vr, vi, wr, wi;
+                c_split(u, ur, ui); c_split(v, vr, vi); c_split(w, wr, wi);
+                q0 = c_add(q0, c_conj_mul(u, v));
+                q5 = c_add(q5, c_conj_mul(v, w));
+                e0 = fmaf(ur, ur, fmaf(ui, ui, e0));
+                e5 = fmaf(vr, vr, fmaf(vi, vi, e5));
+                e10 = fmaf(wr, wr, fmaf(wi, wi, e10));
+            }
+            mask &= live;
         }
-        mask &= live;
     }
     s_mask[t] = mask;
     __syncthreads();
@@ -161,6 +201,8 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
             const uint32_t slot = atomicAdd(a.counters, 1u);
             if (slot < kSyncCandCap) a.cand[slot] = (uint32_t)(origin + (long long)t * kScanT + j);
         }
+    }
+    __syncthreads();                                                   // s_iq / s_mask are rewritten by the next tile
     }
 }
 
