@@ -361,44 +361,90 @@ __device__ __forceinline__ long ramp_argmax_w(const float2 *__restrict__ x, long
 }
 
 // Closed form of the same arg-max for the built-in locking ramp: lock[n] = 3/8 + n/(4L) for n < L/2 and 1/8 + n/(4L) above
-// (locking_signal::<1280>, src/transmitter.rs:60-72 after fft_shift), so
-//   c[k] = 3/8 S0a(k) + 1/8 S0b(k) + S1(k) / (4L),  S0a/S0b = sums of a over the two half windows, S1 = sum n a[k+n],
-// and all three slide in O(1) per lag. Every thread starts its run of lags with one exact f64 summation and slides in f64
-// (a dozen steps): L loads per thread instead of L per lag.
+// (locking_signal::<1280>, src/transmitter.rs:60-72 after fft_shift), so with i counting samples from lag k_lo
+//   c[q] = 3/8 S0a(q) + 1/8 S0b(q) + (M(q) - q S0(q)) / (4L),
+//   S0a/S0b = sums of a over the two half windows of lag q, S0 = S0a + S0b, M(q) = sum_{i=q}^{q+L-1} i a[i].
+// S0a, S0b and M slide by data-only increments, so the start values of every thread's run of lags come from one block
+// reduction (lag k_lo: L samples over the CTA) plus a block prefix scan of the per-run increments; each thread then slides
+// through its run. All in f64. Samples read per stream: about 7 (L + lags) instead of L per thread.
 __device__ __forceinline__ long ramp_argmax_closed_w(const float2 *__restrict__ x, long n_samples, long k_lo, long k_hi, float *s_val, int *s_idx)
 {
+    __shared__ double s_ramp[2][kThreads / 32][6];
     const long n_lags = k_hi - k_lo + 1;
     const int run = (int)((n_lags + kThreads - 1) / kThreads);
-    const long k0 = k_lo + (long)threadIdx.x * run;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int H = kL / 2;
+    const float2 *xl = x + k_lo;                                       // local index 0 = lag k_lo
+    const long nl = n_samples - k_lo;                                  // local indices [-k_lo, nl) exist
+    auto ld = [&](long i) -> float2 { return (i >= -k_lo && i < nl) ? __ldg(xl + i) : make_float2(0.0f, 0.0f); };
+
+    // (1) partial sums of lag k_lo's window, (2) this thread's increments over its run of lags [q0, q0 + run)
+    double base[6] = { 0, 0, 0, 0, 0, 0 };                             // S0a, S0b, M (re, im each)
+    for (int i = tid; i < kL; i += kThreads) {
+        const float2 v = ld(i);
+        if (i < H) { base[0] += v.x; base[1] += v.y; } else { base[2] += v.x; base[3] += v.y; }
+        base[4] += (double)i * v.x; base[5] += (double)i * v.y;
+    }
+    const long q0 = (long)tid * run;
+    double inc[6] = { 0, 0, 0, 0, 0, 0 };
+    for (int j = 0; j < run; j++) {
+        const long q = q0 + j;
+        const float2 a0 = ld(q), ah = ld(q + H), al = ld(q + kL);
+        inc[0] += (double)ah.x - a0.x; inc[1] += (double)ah.y - a0.y;
+        inc[2] += (double)al.x - ah.x; inc[3] += (double)al.y - ah.y;
+        inc[4] += (double)(q + kL) * al.x - (double)q * a0.x; inc[5] += (double)(q + kL) * al.y - (double)q * a0.y;
+    }
+    // block sum of `base`, block exclusive scan of `inc`
+    double mine[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        mine[c] = inc[c];
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, inc[c], m);
+            if (lane >= m) inc[c] += up;
+            base[c] += __shfl_xor_sync(0xffffffffu, base[c], m);
+        }
+    }
+    __syncthreads();                                                   // s_ramp may still be read by a previous call
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) s_ramp[0][warp][c] = inc[c];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) s_ramp[1][warp][c] = base[c];
+    }
+    __syncthreads();
+    double cur[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        double v = inc[c] - mine[c];                                   // exclusive inside the warp
+        for (int w = 0; w < kThreads / 32; w++) {
+            if (w < warp) v += s_ramp[0][w][c];
+            v += s_ramp[1][w][c];
+        }
+        cur[c] = v;
+    }
+
     float best = 0.0f;
     int bidx = 0x7fffffff;
-    if (k0 <= k_hi) {
-        constexpr int H = kL / 2;
-        double ar = 0, ai = 0, br = 0, bi = 0, mr = 0, mi = 0;          // S0a, S0b, S1
-        for (int n = 0; n < kL; n++) {
-            const float2 v = ld_sample(x, k0 + n, n_samples);
-            if (n < H) { ar += v.x; ai += v.y; } else { br += v.x; bi += v.y; }
-            mr += (double)n * v.x; mi += (double)n * v.y;
-        }
-        const double beta = 1.0 / (4.0 * kL);
-        for (int j = 0; j < run && k0 + j <= k_hi; j++) {
-            const double cr = 0.375 * ar + 0.125 * br + beta * mr, ci = 0.375 * ai + 0.125 * bi + beta * mi;
-            const float v = (float)(cr * cr + ci * ci);
-            if (v > best) { best = v; bidx = (int)(k0 + j - k_lo); }
-            // slide the window by one sample
-            const long k = k0 + j;
-            const float2 a0 = ld_sample(x, k, n_samples), ah = ld_sample(x, k + H, n_samples), al = ld_sample(x, k + kL, n_samples);
-            const double s0r = ar + br, s0i = ai + bi;
-            mr = mr + (double)kL * al.x - (s0r - a0.x + al.x);
-            mi = mi + (double)kL * al.y - (s0i - a0.y + al.y);
-            ar += (double)ah.x - a0.x; ai += (double)ah.y - a0.y;
-            br += (double)al.x - ah.x; bi += (double)al.y - ah.y;
-        }
+    const double beta = 1.0 / (4.0 * kL);
+    for (int j = 0; j < run && q0 + j < n_lags; j++) {
+        const long q = q0 + j;
+        const double s0r = cur[0] + cur[2], s0i = cur[1] + cur[3];
+        const double cr = 0.375 * cur[0] + 0.125 * cur[2] + beta * (cur[4] - (double)q * s0r);
+        const double ci = 0.375 * cur[1] + 0.125 * cur[3] + beta * (cur[5] - (double)q * s0i);
+        const float v = (float)(cr * cr + ci * ci);
+        if (v > best) { best = v; bidx = (int)q; }
+        const float2 a0 = ld(q), ah = ld(q + H), al = ld(q + kL);     // slide the window by one sample
+        cur[0] += (double)ah.x - a0.x; cur[1] += (double)ah.y - a0.y;
+        cur[2] += (double)al.x - ah.x; cur[3] += (double)al.y - ah.y;
+        cur[4] += (double)(q + kL) * al.x - (double)q * a0.x; cur[5] += (double)(q + kL) * al.y - (double)q * a0.y;
     }
     block_argmax<kThreads>(best, bidx, s_val, s_idx);
     return best > 0.0f ? k_lo + bidx : k_lo;
 }
-
 template <int MOD, bool GUARD, int PHASE>
 __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs a)
 {
