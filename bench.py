@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="streams", choices=["streams", "capture", "rs", "ingest"],
+    ap.add_argument("--workload", default="streams", choices=["streams", "capture", "rs", "ingest", "tx"],
                     help="streams: BASELINE configs[1] (the headline line); capture: configs[2], preamble search over one long capture")
     ap.add_argument("--capture-samples", type=float, default=1e9)
     ap.add_argument("--nfft", type=int, default=64, choices=[64, 1024],
@@ -200,6 +200,8 @@ def main():
 
     if args.workload == "rs":
         return rs_bench(args, rank, local_rank, world)
+    if args.workload == "tx":
+        return tx_bench(args, rank, local_rank, world)
     if args.workload == "ingest":
         return ingest_bench(args, rank, local_rank, world)
     if args.workload == "capture":
@@ -475,6 +477,62 @@ def capture_bench(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    return 0
+
+
+def tx_bench(args, rank, local_rank, world):
+    """TX side of the path: payload bytes -> Hamming -> 64QAM -> IFFT -> CP -> head -> normalise, for the
+    headline workload's frames; the round trip against the RX path and the oracle is in tests/. 8 B/sample written once."""
+    import torch
+    import ofdm_b200 as ob
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = workload_cfg()
+    eng = ob.Engine(cfg, local_rank)
+    n, S = args.streams, args.syms
+    plen_b = cfg.max_payload(S)
+    frame_len = cfg.frame_len(plen_b)
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + rank)
+    st = torch.cuda.current_stream().cuda_stream
+    pstride = (plen_b + 15) // 16 * 16
+    payload = torch.randint(0, 256, (n, pstride), dtype=torch.uint8, device=dev, generator=g)
+    plen = torch.full((n,), plen_b, dtype=torch.int32, device=dev)
+    tx = torch.empty((n, frame_len, 2), dtype=torch.float32, device=dev)
+    flen = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def step():
+        eng.tx_encode_device(payload.data_ptr(), plen.data_ptr(), pstride, n, tx.data_ptr(), frame_len, flen.data_ptr(), st)
+
+    steps = max(1, min(args.steps, 50))
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = eng.kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / steps
+    samples = n * frame_len
+    by = 8 * samples + n * plen_b
+    peak, src = read_peaks()
+    mx = float(tx.max().item())
+    print(json.dumps({"metric": "tx_msamples_per_s", "value": round(samples / (ms * 1e-3) / 1e6, 1), "unit": "Msamples/s", "n_gpus": 1,
+                      "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"tx_{n}x64QAM_S{S}", "streams_per_gpu": n, "data_syms_per_frame": S, "frame_samples": frame_len,
+                                 "payload_bytes": plen_b, "l2": "output (%.2f GB) larger than L2" % (8 * samples / 1e9)},
+                      "roofline": {"bound": "hbm", "kernel": "tx_tile_kernel (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
+                                   "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                                   "peak_source": src, "algorithmic_bytes_per_launch": by},
+                      "max_component": round(mx, 6), "frames_ok": bool((flen == frame_len).all().item()),
+                      "gpu_launches": int(eng.kernel_launches - l0), "clocks": clocks}))
     return 0
 
 

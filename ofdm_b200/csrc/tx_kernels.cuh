@@ -50,15 +50,16 @@ constexpr int kTxTileSyms = kTxWarps * 4 * kTxIters;      // 224, same tiling as
 // WRITE = true : the symbols are recomputed and stored once, already normalised, together with the frame head and
 // the zero fill -- 8 B/sample of HBM traffic in total instead of write + read-modify-write.
 template <int MOD, bool GUARD, bool FEC, bool WRITE>
-__global__ void __launch_bounds__(kTxThreads) tx_tile_kernel(const TxArgs a)
+__global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
 {
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 48 : 64;
     constexpr int BPS = BPC * D;
     __shared__ __align__(16) float2 s_tr[kTxWarps * kTrWarp];
     __shared__ __align__(16) uint8_t s_bits[kTxTileSyms * BPS / 8 + 32];
-    __shared__ __align__(8) float2 s_map[64];
+    __shared__ __align__(8) float2 s_map[66];          // constellation | [64] null carrier | [65] pilot
     __shared__ uint8_t s_enc[16];
+    __shared__ uint16_t s_enc14[256];                  // payload byte -> its two 7-bit codewords (low nibble first)
 
     const uint32_t stream = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
@@ -107,7 +108,10 @@ __global__ void __launch_bounds__(kTxThreads) tx_tile_kernel(const TxArgs a)
         }
         s_map[tid] = make_float2(im, re);
     }
+    if (tid == 64) s_map[64] = make_float2(0.0f, 0.0f);
+    if (tid == 65) s_map[65] = make_float2(0.0f, 1.0f);               // pilot 1 + 0j, swapped (src/transmitter.rs:150-161)
     if (tid < 16) s_enc[tid] = (uint8_t)ham74_encode_nibble(tid);
+    if (FEC) s_enc14[tid] = (uint16_t)(ham74_encode_nibble(tid & 15) | (ham74_encode_nibble(tid >> 4) << 7));
     __syncthreads();
 
     // ---- tile bit stream --------------------------------------------------------------------------------------------
@@ -120,15 +124,18 @@ __global__ void __launch_bounds__(kTxThreads) tx_tile_kernel(const TxArgs a)
         if (tid < hdr) s_bits[tid] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + tid, s_enc);
         const uint32_t c0 = byte0 + hdr - 16;                          // first coded byte of the tile: multiple of 7
         const uint32_t ngrp = (nbyte + 2 - hdr + 6) / 7;
+        const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
         for (uint32_t u = tid; u < ngrp; u += kTxThreads) {
             const uint32_t pb = (c0 / 7 + u) * 4;                      // first payload byte of the group
-            uint64_t w = 0;
+            uint32_t v4 = 0;                                           // bytes past the payload encode to zero codewords
+            if (pay_aligned && pb + 4 <= n) v4 = __ldg(reinterpret_cast<const uint32_t *>(pay + pb));
+            else {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t v = pb + q < n ? pay[pb + q] : 0u;
-                const uint64_t cw = pb + q < n ? ((uint64_t)s_enc[v & 15u] | ((uint64_t)s_enc[v >> 4] << 7)) : 0ull;
-                w |= cw << (14 * q);
+                for (int q = 0; q < 4; q++) if (pb + q < n) v4 |= (uint32_t)pay[pb + q] << (8 * q);
             }
+            const uint32_t lo = (uint32_t)s_enc14[v4 & 255u] | ((uint32_t)s_enc14[(v4 >> 8) & 255u] << 14);      // 28 bits
+            const uint32_t hi = (uint32_t)s_enc14[(v4 >> 16) & 255u] | ((uint32_t)s_enc14[v4 >> 24] << 14);
+            const uint64_t w = (uint64_t)lo | ((uint64_t)hi << 28);
             uint8_t *dst = s_bits + hdr + 7 * u;
 #pragma unroll
             for (int q = 0; q < 7; q++) dst[q] = (uint8_t)(w >> (8 * q));
@@ -141,32 +148,62 @@ __global__ void __launch_bounds__(kTxThreads) tx_tile_kernel(const TxArgs a)
     cpx tw[8];
 #pragma unroll
     for (int ka = 0; ka < 8; ka++) tw[ka] = c_from(__ldg(a.tables->w64 + ((l * ka) & 63)));
-    int rank[8];
+    // per lane: where the bits of its 8 bins sit inside an OFDM symbol's SB bytes (bit offset = rank * BPC), or which fixed
+    // constellation entry a null / pilot bin takes. Only bins l, 24 + l, 32 + l, 56 + l can be null or pilot.
+    constexpr int SB = BPS / 8;                                   // bytes of the bit stream per OFDM symbol (6 .. 48)
+    uint32_t boff[8];                                             // byte offset << 3 | bit shift
+    uint32_t fixed = 0;                                           // byte q: entry of bin l + 8 {0,3,4,7}[q] when it is null / pilot, else 0
 #pragma unroll
-    for (int j = 0; j < 8; j++) rank[j] = data_rank<GUARD>(l + 8 * j);
+    for (int j = 0; j < 8; j++) {
+        const int r = data_rank<GUARD>(l + 8 * j);
+        boff[j] = r >= 0 ? (uint32_t)r * BPC : 0u;
+        if (GUARD && r < 0) {
+            const int q = j == 0 ? 0 : j == 3 ? 1 : j == 4 ? 2 : 3;
+            fixed |= (is_pilot_bin(l + 8 * j) ? 65u : 64u) << (8 * q);
+        }
+    }
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
     const long ncar_local = (long)ncar - (long)t0 * D;            // carriers of the frame that exist from this tile on
+    const int n_full = (int)(ncar_local / D < (long)(t1 - t0) ? ncar_local / D : (long)(t1 - t0));   // symbols of the tile with all D carriers
     float mx = 0.0f;
 
 #pragma unroll 1
     for (int it = 0; it < kTxIters; it++) {
-        const int s = t0 + warp * (4 * kTxIters) + 4 * it + g;
+        const int sl = warp * (4 * kTxIters) + 4 * it + g;        // symbol index inside the tile
+        const int s = t0 + sl;
         const bool valid = s < t1;
         cpx x[8];
+        if (__all_sync(0xffffffffu, sl < n_full)) {
+            // every carrier of the warp's 4 symbols exists: byte offsets and shifts are lane constants
+            const uint8_t *sym = s_bits + sl * SB;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {                              // encode_block, src/transmitter.rs:144-165
-            const int k = l + 8 * j;
-            cpx v = c_make(0.0f, 0.0f);
-            if (GUARD && is_pilot_bin(k)) v = c_make(0.0f, 1.0f);  // pilot 1 + 0j, swapped
-            else if (rank[j] >= 0 && valid) {
-                const long c = (long)(s - t0) * D + rank[j];
-                if (c < ncar_local) {
-                    const uint32_t bit = (uint32_t)c * BPC, bb = bit >> 3;
-                    const uint32_t w = ((uint32_t)s_bits[bb] | ((uint32_t)s_bits[bb + 1] << 8)) >> (bit & 7);
-                    v = c_from(s_map[w & ((1u << BPC) - 1u)]);
+            for (int j = 0; j < 8; j++) {                          // encode_block, src/transmitter.rs:144-165
+                const uint8_t *pb = sym + (boff[j] >> 3);
+                uint32_t w = pb[0];
+                if (BPC > 2) w |= (uint32_t)pb[1] << 8;            // 1- and 2-bit fields never straddle a byte
+                uint32_t idx = (w >> (boff[j] & 7u)) & ((1u << BPC) - 1u);
+                if (GUARD && (j == 0 || j == 3 || j == 4 || j == 7)) {
+                    const uint32_t f = (fixed >> (8 * (j == 0 ? 0 : j == 3 ? 1 : j == 4 ? 2 : 3))) & 255u;
+                    if (f) idx = f;
                 }
+                x[j] = c_from(s_map[idx]);
             }
-            x[j] = v;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int k = l + 8 * j;
+                cpx v = c_make(0.0f, 0.0f);
+                if (GUARD && is_pilot_bin(k)) v = c_make(0.0f, 1.0f);
+                else if (data_rank<GUARD>(k) >= 0 && valid) {
+                    const long c = (long)sl * D + data_rank<GUARD>(k);
+                    if (c < ncar_local) {
+                        const uint32_t bit = (uint32_t)c * BPC, bb = bit >> 3;
+                        const uint32_t w = ((uint32_t)s_bits[bb] | ((uint32_t)s_bits[bb + 1] << 8)) >> (bit & 7);
+                        v = c_from(s_map[w & ((1u << BPC) - 1u)]);
+                    }
+                }
+                x[j] = v;
+            }
         }
         fft64_group_p(x, tw, tr, l);                               // prefix_block, src/transmitter.rs:168-181 (IFFT part)
         if (WRITE) {
