@@ -127,23 +127,24 @@ __device__ __forceinline__ uint32_t demap_point(float re, float im)
 }
 
 // 64QAM demap for the hot kernel: 4 FMA-pipe ops + 1 shift-add + 1 smem table look-up.
-//   t = sat((3.5 v + 4) / 8) in [0, 1];  2^23 + floor(8 t) by a round-down FMA -> level index 0..8 in the mantissa;
-//   x = ui + (uq << 4) = 0xFB000000 + ii + 16 iq indexes a 256-byte table holding gray(min(ii,7)) | gray(min(iq,7)) << 3.
-constexpr uint32_t kQamLutBias = 0xFB000000u;
+//   t = sat((3.5 v + 4) / 8) in [0, 1]. A round-down FMA whose result is a DENORMAL has the integer floor(.) as its bit
+//   pattern: bits(fma_rd(tq, 2^-146, 0)) = floor(8 tq) = iq (0..8), and with the addend c = lut + 16 iq taken as the
+//   denormal c 2^-149, bits(fma_rd(ti, 2^-146, c)) = lut + 16 iq + ii -- the shared-memory address of the table entry
+//   gray(min(ii,7)) | gray(min(iq,7)) << 3 (256-byte table, rows of 16). Denormal FMAs run at full rate (no -ftz).
 __device__ __forceinline__ uint8_t qam64_lut_entry(int t)
 {
     int ii = t & 15, iq = t >> 4;
     ii = ii > 7 ? 7 : ii; iq = iq > 7 ? 7 : iq;
     return (uint8_t)((ii ^ (ii >> 1)) | ((iq ^ (iq >> 1)) << 3));
 }
-__device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, uint32_t lut_biased_saddr)
+__device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, uint32_t lut_saddr)
 {
-    float ti = __saturatef(fmaf(re, 0.4375f, 0.5f));
-    float tq = __saturatef(fmaf(im, 0.4375f, 0.5f));
-    uint32_t ui = __float_as_uint(__fmaf_rd(ti, 8.0f, 8388608.0f));
-    uint32_t uq = __float_as_uint(__fmaf_rd(tq, 8.0f, 8388608.0f));
+    const float ti = __saturatef(fmaf(re, 0.4375f, 0.5f));
+    const float tq = __saturatef(fmaf(im, 0.4375f, 0.5f));
+    const uint32_t uq = __float_as_uint(__fmul_rd(tq, 0x1p-146f));
+    const uint32_t addr = __float_as_uint(__fmaf_rd(ti, 0x1p-146f, __uint_as_float(lut_saddr + (uq << 4))));
     uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(lut_biased_saddr + ui + (uq << 4)));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
     const uint32_t n_avail = n_samples - offset;
     const uint64_t fstep = st->fstep;
     float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
-    const uint32_t qam_biased = (uint32_t)__cvta_generic_to_shared(s_qam) - kQamLutBias;
+    const uint32_t qam_biased = (uint32_t)__cvta_generic_to_shared(s_qam);      // shared-memory address of the demap table
 
     // ---- TMA prefetch: one bulk copy per OFDM symbol (its 64 CP-stripped samples, widened to 16-byte alignment) lands in
     // this warp's staging slot one warp-iteration ahead -- also across tile boundaries, so only the very first iteration of
