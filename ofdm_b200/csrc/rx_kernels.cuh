@@ -299,15 +299,15 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
 // ------------------------------------------------------------------------------------------------------------------
 // hot kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDecWarps = 8;
+constexpr int kDecWarps = 7;
 constexpr int kDecThreads = kDecWarps * 32;      // 256
-constexpr int kDecIters = 7;                     // 4 symbols per warp iteration -> 28 symbols per warp
+constexpr int kDecIters = 8;                     // 4 symbols per warp iteration -> 32 symbols per warp
 constexpr int kTileSyms = kDecWarps * 4 * kDecIters;   // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
 constexpr int kStageBytes = 4 * kSym * 8 + 16;       // 4 consecutive OFDM symbols (CPs included) + 1 leading / 1 trailing alignment sample
 constexpr int kStageGroup = (kStageBytes + 15) / 16 * 2 / 4 + 1;   // float2 per warp staging slot / 4
 template <bool GUARD> constexpr size_t rx_decode_smem_bytes()
 {
-    return sizeof(float2) * (kDecWarps * 4 * kStageGroup + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * kDecWarps + 8 * kTrRow * sizeof(float2);
+    return sizeof(float2) * (kDecWarps * 4 * kStageGroup + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * 8 + 8 * kTrRow * sizeof(float2);
 }
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
     uint8_t *s_ham = s_car + (kTileSyms * D + 64);
     uint8_t *s_qam = s_ham + 128;
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_qam + 256);
-    float2 *s_g = reinterpret_cast<float2 *>(s_bar + kDecWarps);                    // [lane l][kTrRow]: 1/h at bins l + 8kb, padded rows
+    float2 *s_g = reinterpret_cast<float2 *>(s_bar + 8);                            // [lane l][kTrRow]: 1/h at bins l + 8kb, padded rows
 
     // A CTA owns `tiles_per_cta` consecutive 224-symbol tiles of one stream. Tile k covers symbols
     // [k*224 - tile_shift, (k+1)*224 - tile_shift) n [0, S): every inner boundary falls on a Hamming byte boundary.
