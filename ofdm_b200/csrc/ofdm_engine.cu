@@ -550,6 +550,7 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         uint32_t tpc = (uint32_t)(((uint64_t)tiles * n_streams) / (16u * 148u * 3u));
         if (tpc < 1) tpc = 1;
         if (tpc > tiles) tpc = tiles;
+        if (tpc > (uint32_t)kDecBaseTiles) tpc = kDecBaseTiles;        // start phasors of a CTA's tiles are tabulated in smem
         a.tiles_per_cta = (int)tpc;
         tiles = (tiles + tpc - 1) / tpc;
         DecodeKernel k = pick_decode(h->cfg, points);

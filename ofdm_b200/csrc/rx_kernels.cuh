@@ -107,6 +107,14 @@ __device__ __forceinline__ void st_shared_u8_if_nonneg(uint8_t *p, uint32_t v, i
                  :: "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v), "r"(cond) : "memory");
 }
 
+// the same with the condition held as one bit of a lane-constant mask (one LOP3 with a predicate result per store)
+template <uint32_t BIT>
+__device__ __forceinline__ void st_shared_u8_if_bit(uint8_t *p, uint32_t v, uint32_t mask)
+{
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\t@q st.shared.u8 [%0], %1;\n\t}"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v), "r"(mask), "n"(BIT) : "memory");
+}
+
 // hard decision of one data point -> BPC bits (src/receiver.rs:155-178; 64QAM docs/SPEC.md 2)
 template <int MOD>
 __device__ __forceinline__ uint32_t demap_point(float re, float im)
@@ -302,12 +310,13 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
 constexpr int kDecWarps = 7;
 constexpr int kDecThreads = kDecWarps * 32;      // 256
 constexpr int kDecIters = 8;                     // 4 symbols per warp iteration -> 32 symbols per warp
+constexpr int kDecBaseTiles = 8;                 // tiles per CTA whose start phasors are tabulated (tiles_per_cta <= 8, kDecBaseTiles * 4 * kDecWarps <= threads)
 constexpr int kTileSyms = kDecWarps * 4 * kDecIters;   // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
 constexpr int kStageBytes = 4 * kSym * 8 + 16;       // 4 consecutive OFDM symbols (CPs included) + 1 leading / 1 trailing alignment sample
 constexpr int kStageGroup = (kStageBytes + 15) / 16 * 2 / 4 + 1;   // float2 per warp staging slot / 4
 template <bool GUARD> constexpr size_t rx_decode_smem_bytes()
 {
-    return sizeof(float2) * (kDecWarps * 4 * kStageGroup + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * 8 + 8 * kTrRow * sizeof(float2);
+    return sizeof(float2) * (kDecWarps * 4 * kStageGroup + kDecWarps * kTrWarp) + (kDecWarps * 4 * kDecIters * (GUARD ? 48 : 64) + 64) + 128 + 256 + 8 * 8 + 8 * kTrRow * sizeof(float2) + sizeof(float2) * kDecBaseTiles * kDecWarps * 4;
 }
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
@@ -389,13 +398,25 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
     }
 
     const int rot = g & 1;                                          // see rx_lane_init_p
+    // derotation phasor at the first symbol of every (tile, warp, group) of this CTA: one exact evaluation per thread here
+    // instead of one per thread and tile in the loop (the 8 lanes of a group need the same value)
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_g + 8 * kTrRow);
+    if (tid < (tile_end - tile_first) * (4 * kDecWarps)) {
+        const int bt = tid / (4 * kDecWarps), wg = tid - bt * (4 * kDecWarps);
+        const int sf = tile_t0(tile_first + bt) + (wg >> 2) * (4 * kDecIters) + (wg & 3);
+        s_base[tid] = phasor_from_turns_p(fstep * (uint64_t)((kHeadSyms + sf) * kSym + kCp)).v;
+    }
     RxLaneP L;
     rx_lane_init_p(L, st, a.tables->w64, l, rot);
     // byte offset of each of this lane's 8 bins inside a symbol's carrier row (null / pilot bins are not stored)
     int off[8];
 #pragma unroll
     for (int kb = 0; kb < 8; kb++) off[kb] = data_rank<GUARD>(l + 8 * kb);
-    const int d3 = 24 - (l >= 2), d4 = 31 - (l >= 1);               // rank(l + 24) - (l - 7), rank(l + 32) - (l - 7)
+    int d3 = 24 - (l >= 2), d4 = 31 - (l >= 1);                     // rank(l + 24) - (l - 7), rank(l + 32) - (l - 7)
+    // bins l, l + 24, l + 32, l + 56 are data carriers on some lanes only: one mask bit each. The mask and the two
+    // lane-dependent offsets are made opaque so that they stay in registers instead of being re-derived from l per iteration.
+    uint32_t dmask = (off[0] >= 0 ? 1u : 0u) | (off[3] >= 0 ? 2u : 0u) | (off[4] >= 0 ? 4u : 0u) | (off[7] >= 0 ? 8u : 0u);
+    asm volatile("" : "+r"(dmask), "+r"(d3), "+r"(d4));
     const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)(4 * kSym));
     uint8_t *out = a.out + (size_t)stream * a.out_stride;
     uint32_t phase = 0;                                             // mbarrier phase parity
@@ -408,7 +429,8 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
         const int s_warp = t0 + warp * (4 * kDecIters);             // first symbol of this warp
         const int s_first = s_warp + g;
         // base phasor of this group's first symbol, then a x4-symbol recurrence (7 steps: negligible drift)
-        cpx base = phasor_from_turns_p(fstep * (uint64_t)((kHeadSyms + s_first) * kSym + kCp));
+        cpx base;
+        base.v = s_base[(tile - tile_first) * (4 * kDecWarps) + 4 * warp + g];
         uint8_t *rowp = s_car + (s_first - t0) * D + (GUARD ? l - 7 : l);       // row of this group's symbol, biased by the lane
 
 #pragma unroll 1
@@ -449,9 +471,10 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
                 if (!GUARD) rowp[8 * kb] = (uint8_t)v;
                 else if (kb == 1 || kb == 2) rowp[8 * kb] = (uint8_t)v;
                 else if (kb == 5 || kb == 6) rowp[8 * kb - 3] = (uint8_t)v;
-                else if (kb == 3) st_shared_u8_if_nonneg(rowp + d3, v, off[3]);
-                else if (kb == 4) st_shared_u8_if_nonneg(rowp + d4, v, off[4]);
-                else st_shared_u8_if_nonneg(rowp + (kb == 0 ? 0 : 53), v, off[kb]);
+                else if (kb == 3) st_shared_u8_if_bit<2>(rowp + d3, v, dmask);
+                else if (kb == 4) st_shared_u8_if_bit<4>(rowp + d4, v, dmask);
+                else if (kb == 0) st_shared_u8_if_bit<1>(rowp, v, dmask);
+                else st_shared_u8_if_bit<8>(rowp + 53, v, dmask);
                 if (POINTS && s < t1 && (!GUARD || off[kb] >= 0)) {
                     size_t p = (size_t)s * D + off[kb];
                     if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
