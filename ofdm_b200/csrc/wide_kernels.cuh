@@ -230,6 +230,38 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
     if (j1 > (long)out_len) j1 = (long)out_len;
     const int pbase = (int)(kHeaderBits + j0 * NB - bit0);
     const int nbytes = (int)(j1 - j0);
+    if (MOD == 2) {
+        // 3 output bytes per thread: 42 (Hamming) or 24 stream bits = 7 or 4 six-bit carriers (+1 for the bit shift)
+        constexpr int NC = (3 * NB + 5) / 6 + 1;
+        uint8_t *o0 = out + j0;
+        for (int u = 3 * tid; u < nbytes; u += 3 * kThreads) {
+            const int p = pbase + u * NB;
+            const int c = p / 6, sh = p - 6 * c;
+            const uint8_t *cp = s_car + c;
+            uint32_t lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
+            uint32_t hi = 0;
+            if (NC > 5) {
+                uint32_t b5 = cp[5];
+                lo |= b5 << 30;
+                hi = (b5 >> 2) | (cp[6] << 4) | (cp[7] << 10);
+            }
+            lo = __funnelshift_r(lo, hi, sh);
+            hi >>= sh;
+            uint32_t w0, w1, w2;
+            if (FEC) {
+                w0 = lo & 0x3FFFu; w1 = (lo >> 14) & 0x3FFFu; w2 = __funnelshift_r(lo, hi, 28) & 0x3FFFu;
+                w0 = s_ham[w0 & 127u] | (s_ham[w0 >> 7] << 4);
+                w1 = s_ham[w1 & 127u] | (s_ham[w1 >> 7] << 4);
+                w2 = s_ham[w2 & 127u] | (s_ham[w2 >> 7] << 4);
+            } else {
+                w0 = lo & 255u; w1 = (lo >> 8) & 255u; w2 = (lo >> 16) & 255u;
+            }
+            uint8_t *o = o0 + u;
+            o[0] = (uint8_t)w0;
+            if (u + 1 < nbytes) o[1] = (uint8_t)w1;
+            if (u + 2 < nbytes) o[2] = (uint8_t)w2;
+        }
+    } else {
     for (int u = tid; u < nbytes; u += kThreads) {
         const int p = pbase + u * NB;
         const int c = p / BPC, sh = p - c * BPC;
@@ -243,22 +275,77 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
         else byte = v & 255u;
         out[j0 + u] = (uint8_t)byte;
     }
+    }
 }
 
+// ---- decode kernel: register-resident 1024-point FFT as 16 x 64 ------------------------------------------------------
+// A 64-thread team owns one OFDM symbol; the CTA runs four teams over the 28 symbols of its tile. With n = n2 + 64 n1 and
+// k = k1 + 16 k2:   X[k1 + 16 k2] = sum_n2 W64^(n2 k2) { W1024^(n2 k1) sum_n1 x[n2 + 64 n1] W16^(n1 k1) }
+//   A. thread n2 loads its 16 samples x[n2 + 64 n1] (coalesced), applies the uniform part of the CFO derotation
+//      exp(-j f 64 n1), does the 16-point DFT in registers and multiplies by the per-thread constants
+//      W1024^(n2 k1) exp(-j f n2) (twiddle and the rest of the derotation in one);
+//   B. one exchange through shared memory, E[k1][n2];
+//   C. every 8-lane group runs the N=64 kernels' register FFT64 (one in-warp 8x8 transpose) for k1 = q and q + 8;
+//   D. equalise, pilot sum (team reduction), phase rotation, demap, carrier bytes -- 16 bins per thread.
+// Two team barriers per symbol (named barriers, 64 threads), no CTA barrier inside the tile.
+constexpr int kTeam = 64, kTeams = kThreads / kTeam;
+constexpr int kERow = 72;                        // E row pitch (complex): 8-lane groups of a half-warp read rows one bank group apart
+constexpr int kTwRow = 17;                       // step-A constants row pitch (complex): thread-private rows, one bank pair apart
+constexpr int kGRow = 18;                        // equaliser row pitch (complex): conflict-free LDS.128 of thread-private rows
 constexpr size_t wide_decode_smem(bool guard)
 {
-    return sizeof(float2) * (kBufA + kBufB) + (size_t)kTileSymsW * (guard ? 768 : 1024) + 64 + 128 + 64;
+    return sizeof(float2) * (kTeams * 16 * kERow + kTeams * 8 * kTrGroup + kTeam * kGRow + kTeam * kTwRow + 16) + sizeof(int16_t) * kTeam * 16 +
+           (size_t)kTileSymsW * (guard ? 768 : 1024) + 64 + 128 + 256 + sizeof(float) * 4 * kTeams;
 }
 
+// 16-point DFT in registers (radix 4 x 4), natural order in and out
+__device__ __forceinline__ void dft16_p(cpx (&v)[16])
+{
+    cpx t[16];
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) {                                   // DFT4 over n_a: elements nb, nb+4, nb+8, nb+12
+        cpx u[4] = { v[nb], v[nb + 4], v[nb + 8], v[nb + 12] };
+        radix4(u);
+#pragma unroll
+        for (int ka = 0; ka < 4; ka++) t[nb + 4 * ka] = u[ka];
+    }
+    // twiddles W16^(nb ka)
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+    t[1 + 4 * 1] = c_mul(t[1 + 4 * 1], c_make(C1, -S1));              // W16^1
+    t[2 + 4 * 1] = c_mul(t[2 + 4 * 1], c_make(R2, -R2));              // W16^2
+    t[3 + 4 * 1] = c_mul(t[3 + 4 * 1], c_make(S1, -C1));              // W16^3
+    t[1 + 4 * 2] = c_mul(t[1 + 4 * 2], c_make(R2, -R2));              // W16^2
+    t[2 + 4 * 2] = c_mul_mj(t[2 + 4 * 2]);                            // W16^4 = -j
+    t[3 + 4 * 2] = c_mul(t[3 + 4 * 2], c_make(-R2, -R2));             // W16^6
+    t[1 + 4 * 3] = c_mul(t[1 + 4 * 3], c_make(S1, -C1));              // W16^3
+    t[2 + 4 * 3] = c_mul(t[2 + 4 * 3], c_make(-R2, -R2));             // W16^6
+    t[3 + 4 * 3] = c_mul(t[3 + 4 * 3], c_make(-C1, S1));              // W16^9
+#pragma unroll
+    for (int ka = 0; ka < 4; ka++) {                                   // DFT4 over n_b -> X[ka + 4 kb]
+        cpx u[4] = { t[4 * ka], t[1 + 4 * ka], t[2 + 4 * ka], t[3 + 4 * ka] };
+        radix4(u);
+#pragma unroll
+        for (int kb = 0; kb < 4; kb++) v[ka + 4 * kb] = u[kb];
+    }
+}
+
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "n"(kTeam) : "memory"); }
+
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
-__global__ void __launch_bounds__(kThreads) wide_decode_kernel(const WideRxArgs a)
+__global__ void __launch_bounds__(kThreads, 2) wide_decode_kernel(const WideRxArgs a)
 {
     constexpr int D = GUARD ? 768 : 1024;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float2 *bufA = reinterpret_cast<float2 *>(smem_raw), *bufB = bufA + kBufA;
-    uint8_t *s_car = reinterpret_cast<uint8_t *>(bufB + kBufB);
+    float2 *s_E = reinterpret_cast<float2 *>(smem_raw);                          // [team][16][kERow]
+    float2 *s_trw = s_E + kTeams * 16 * kERow;                                   // [team][8 groups][kTrGroup] transpose scratch
+    float2 *s_geq = s_trw + kTeams * 8 * kTrGroup;                               // [thread of a team][kGRow]: 1/h of its 16 bins
+    float2 *s_twp = s_geq + kTeam * kGRow;                                       // [thread of a team][kTwRow]: W1024^(n2 k1) exp(-j f n2)
+    float2 *s_step = s_twp + kTeam * kTwRow;                                     // [16]: exp(-j f 64 n1)
+    int16_t *s_rk = reinterpret_cast<int16_t *>(s_step + 16);                    // [16][thread of a team]: carrier rank or -1
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_rk + kTeam * 16);
     uint8_t *s_ham = s_car + kTileSymsW * D + 64;
-    float *s_red = reinterpret_cast<float *>(s_ham + 128);
+    uint8_t *s_qam = s_ham + 128;                                                // 64QAM demap table (see demap_qam64_lut)
+    float *s_pil = reinterpret_cast<float *>(s_qam + 256);                       // [team][2 warps][2]
 
     const uint32_t stream = blockIdx.y;
     const StreamStateW *st = a.state + stream;
@@ -268,40 +355,133 @@ __global__ void __launch_bounds__(kThreads) wide_decode_kernel(const WideRxArgs 
     if (t0 < 0) t0 = 0;
     if (t1 > S) t1 = S;
     if (t0 >= t1) return;
-    const int tid = threadIdx.x;
-    FftTw T;
-    fft1024_tw_init(T, a.tables->w1024, tid);
+    const int tid = threadIdx.x, team = tid >> 6, u = tid & (kTeam - 1), lane = tid & 31;
+    const int q = u >> 3, l = u & 7;                                             // step C / D: 8-lane group and lane inside it
+    const uint64_t fstep = st->fstep;
     if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
+    if (tid < 16) s_step[tid] = c_to(phasor_from_turns_p(fstep * (uint64_t)(64 * tid)));
+    if (MOD == 2) s_qam[tid] = qam64_lut_entry(tid);
+    const uint32_t qam_saddr = (uint32_t)__cvta_generic_to_shared(s_qam);
+    // constants of this thread's 16 output bins k = q + 8h + 16 l + 128 kb (i = 8h + kb); the four teams share one copy
+    uint32_t pilots = 0;                                                         // bit i: bin is a pilot
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int k = q + 8 * (i >> 3) + 16 * l + 128 * (i & 7);
+        if (team == 0) {
+            s_geq[u * kGRow + i] = st->g[k];
+            s_rk[i * kTeam + u] = (int16_t)w_rank<GUARD>(k);
+        }
+        if (GUARD && w_is_pilot(k)) pilots |= 1u << i;
+    }
+    // step A constants of sample column n2 = u: W1024^(n2 k1) exp(-j f n2) (shared by the four teams)
+    if (team == 0) {
+        const cpx w0 = phasor_from_turns_p(fstep * (uint64_t)u);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) s_twp[u * kTwRow + k1] = c_to(c_mul(c_from(__ldg(a.tables->w1024 + ((u * k1) & (kN - 1)))), w0));
+    }
+    const unsigned long long *twp = reinterpret_cast<const unsigned long long *>(s_twp + u * kTwRow);
+    cpx tw64[8];                                                                 // FFT64 lane twiddles W64^(l ka) = W1024^(16 l ka)
+#pragma unroll
+    for (int ka = 0; ka < 8; ka++) tw64[ka] = c_from(__ldg(a.tables->w1024 + ((16 * l * ka) & (kN - 1))));
 
     const uint32_t offset = (uint32_t)st->offset;
     const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
     const uint32_t n_avail = a.n_samples[stream] - offset;
-    WideLane L;
-    wide_lane_init<GUARD>(L, st, tid);
-    const uint64_t fstep = st->fstep;
-    cpx base = phasor_from_turns_p(fstep * (uint64_t)((10 + t0) * kL + kCpW));
-    const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)kL);
+    const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)(kTeams * kL));
+    cpx base = phasor_from_turns_p(fstep * (uint64_t)((10 + t0 + team) * kL + kCpW));
+    unsigned long long *E = reinterpret_cast<unsigned long long *>(s_E + team * 16 * kERow);
+    float2 *tr = s_trw + (team * 8 + q) * kTrGroup;
+    const ulonglong2 *grow = reinterpret_cast<const ulonglong2 *>(s_geq + u * kGRow);
+    const int16_t *rk = s_rk + u;
     __syncthreads();
 
-    cpx nxt[4];
-    wide_load_symbol(x0, n_avail, (uint32_t)t0, true, tid, nxt);
+    // the 16 samples of column n2 = u of symbol sym (zero-padded tail row); fetched one symbol ahead
+    auto load16 = [&](int sym, cpx (&d)[16]) {
+        const uint32_t n0 = (10u + (uint32_t)sym) * kL + kCpW + (uint32_t)u;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            const uint32_t n = n0 + 64u * n1;
+            d[n1].v = (sym < t1 && n < n_avail) ? __ldg(reinterpret_cast<const unsigned long long *>(x0 + n)) : 0ull;
+        }
+    };
+    cpx nxt[16];
+    load16(t0 + team, nxt);
 #pragma unroll 1
-    for (int s = t0; s < t1; s++) {
-        cpx z[4];
+    for (int s = t0 + team; s < t1; s += kTeams) {
+        // ---- A: derotate (uniform part), DFT16, twiddle ------------------------------------------------------------------
+        cpx v[16];
 #pragma unroll
-        for (int r = 0; r < 4; r++) z[r] = nxt[r];
-        wide_load_symbol(x0, n_avail, (uint32_t)(s + 1), s + 1 < t1, tid, nxt);            // software prefetch of the next symbol
-        wide_symbol<GUARD, PHASE>(L, base, z, bufA, bufB, T, s_red, tid);
+        for (int n1 = 0; n1 < 16; n1++) v[n1] = nxt[n1];
+        load16(s + kTeams, nxt);                                                 // this team's next symbol
+#pragma unroll
+        for (int n1 = 1; n1 < 16; n1++) v[n1] = c_mul(v[n1], c_from(s_step[n1]));
+        dft16_p(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) { cpx w; w.v = twp[k1]; v[k1] = c_mul(v[k1], w); }
+        // ---- B: exchange E[k1][n2] -------------------------------------------------------------------------------------
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) E[k1 * kERow + u] = v[k1].v;
+        team_sync(team);
+        // ---- C + D(equalise, pilots): FFT64 over n2 for k1 = q and q + 8 --------------------------------------------------
+        cpx psum = c_make(0.0f, 0.0f);
+        float pang = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            cpx x[8];
+            const unsigned long long *row = E + (q + 8 * h) * kERow + l;
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j].v = row[8 * j];
+            fft64_group_p(x, tw64, tr, l);
+#pragma unroll
+            for (int p2 = 0; p2 < 4; p2++) {
+                const ulonglong2 gg = grow[4 * h + p2];
+                cpx g0, g1;
+                g0.v = gg.x; g1.v = gg.y;
+                x[2 * p2] = c_mul(x[2 * p2], g0); x[2 * p2 + 1] = c_mul(x[2 * p2 + 1], g1);
+            }
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                v[8 * h + kb] = x[kb];
+                if (GUARD && (pilots >> (8 * h + kb) & 1u)) {
+                    if (PHASE == 1) psum = c_add(psum, x[kb]);
+                    else { float pa, pb; c_split(c_mul(x[kb], base), pa, pb); pang += atan2f(pb, pa); }
+                }
+            }
+        }
+        // ---- pilot phase (docs/SPEC.md 9: 64 pilots) -------------------------------------------------------------------
+        cpx rot = base;
+        if (GUARD) {
+            float px, py;
+            if (PHASE == 1) c_split(psum, px, py); else { px = pang; py = 0.0f; }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) { px += __shfl_xor_sync(0xffffffffu, px, m); py += __shfl_xor_sync(0xffffffffu, py, m); }
+            float *sp = s_pil + team * 4;
+            if (lane == 0) { sp[2 * ((u >> 5) & 1)] = px; sp[2 * ((u >> 5) & 1) + 1] = py; }
+            team_sync(team);
+            px = sp[0] + sp[2]; py = sp[1] + sp[3];
+            if (PHASE == 1) {
+                const float inv = rsqrtf(fmaxf(px * px + py * py, 1e-30f));
+                rot = c_make(px * inv, -py * inv);
+            } else {
+                float sn, cs;
+                sincosf(-px * (1.0f / 64.0f), &sn, &cs);
+                rot = c_mul(c_make(cs, sn), base);
+            }
+        } else {
+            team_sync(team);                                                     // E is rewritten by the next symbol
+        }
         base = c_mul(base, dbase);
-        uint8_t *row = s_car + (s - t0) * D;
+        // ---- D: rotate, demap, carrier bytes -----------------------------------------------------------------------------
+        uint8_t *crow = s_car + (s - t0) * D;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 16; i++) {
             float zr, zi;
-            c_split(z[r], zr, zi);
-            if (L.rank[r] >= 0) {
-                row[L.rank[r]] = (uint8_t)demap_point<MOD>(zr, zi);
+            c_split(c_mul(v[i], rot), zr, zi);
+            const int r = rk[i * kTeam];
+            if (r >= 0) {
+                crow[r] = (uint8_t)(MOD == 2 ? demap_qam64_lut(zr, zi, qam_saddr) : demap_point<MOD>(zr, zi));
                 if (POINTS) {
-                    size_t p = (size_t)s * D + L.rank[r];
+                    size_t p = (size_t)s * D + r;
                     if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
                 }
             }
