@@ -84,6 +84,33 @@ def oracle_cfg():
     return oo.make_cfg(True, oo.QAM64, True, oo.SYNC_SCHMIDL_COX, oo.CFO_ANGLE_OF_SUM, oo.PHASE_ANGLE_OF_SUM, sync_window(), nfft=NFFT)
 
 
+def bind_host_to_gpu_node(gpu_index: int):
+    """Run this process on the CPUs NVML reports as local to the GPU, so that the pinned host buffers of the e2e leg are
+    first-touched on the GPU's own NUMA node (with 8 ranks on one host the PCIe copies otherwise cross the socket link).
+    Returns the number of CPUs bound to, or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = gpu_index
+        if vis:
+            try:
+                idx = int(vis.split(",")[gpu_index])
+            except Exception:           # noqa: BLE001
+                idx = gpu_index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:                   # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled through NVML every ~5 ms DURING the timed region (the recipe's clocks line)."""
 
@@ -320,6 +347,8 @@ def main():
     e2e = None
     rx_host = None
     if not args.no_e2e:
+        all_cpus = os.sched_getaffinity(0)
+        local_cpus = bind_host_to_gpu_node(local_rank)
         rx_host = torch.empty((n_streams, iq_stride, 2), dtype=torch.float32, pin_memory=True)
         rx_host.copy_(rx)
         n_host = rx_len.cpu().numpy().astype(np.uint32)
@@ -349,7 +378,8 @@ def main():
                "d2h_bytes_per_step": int(n_streams * out_stride + n_streams * 8), "ms_per_step": round(dt * 1e3, 3),
                "decoded_gbit_per_s": round(world * n_streams * payload_len * 8 / dt / 1e9, 2),
                "h2d_gb_per_s_per_gpu": round(n_streams * iq_stride * 8 / dt / 1e9, 1), "steps": args.e2e_steps,
-               "matches_device_path": same}
+               "matches_device_path": same, "host_cpus_local_to_gpu": local_cpus}
+        os.sched_setaffinity(0, all_cpus)                      # the CPU baseline below uses every core again
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same workload ------------------
     cpu_baseline = None

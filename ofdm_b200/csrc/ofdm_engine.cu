@@ -880,13 +880,12 @@ static int rs_run(ofdm_engine *h, bool encode, const uint8_t *in, const uint32_t
     if (int r = rs_tables_ready(h)) return r;
     const uint32_t blk_in = encode ? kRsK : kRsN;
     const uint32_t max_blocks = in_stride / blk_in + 1;
-    const uint32_t cps = (max_blocks + 31) / 32;
-    const uint64_t tasks = (uint64_t)cps * n_streams;
-    if (tasks > 0x7fffffffull * kRsWarps) ENG_FAIL(h, OFDM_E_INVALID, "rs: batch too large");
-    const dim3 grid((unsigned)((tasks + kRsWarps - 1) / kRsWarps));
+    const uint64_t tasks = (uint64_t)max_blocks * n_streams;                 // one thread per (stream, block)
+    if (tasks > 0x7fffffffull * kRsThreads) ENG_FAIL(h, OFDM_E_INVALID, "rs: batch too large");
+    const dim3 grid((unsigned)((tasks + kRsThreads - 1) / kRsThreads));
     RsArgs a{};
     a.in_stride = in_stride; a.out_stride = out_stride; a.tables = h->rs_tables.as<RsTables>();
-    a.n_streams = n_streams; a.chunks_per_stream = cps;
+    a.n_streams = n_streams; a.blocks_per_stream = max_blocks;
     if (mem == OFDM_MEM_DEVICE) {
         cudaStream_t st = (cudaStream_t)stream;
         a.in = in; a.in_len = in_len; a.out = out; a.out_len = out_len; a.n_corrected = n_corrected; a.n_failed = n_failed;

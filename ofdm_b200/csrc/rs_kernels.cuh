@@ -2,20 +2,20 @@
 // create_transmission_bytes (src/utils.rs:97-137) and decipher_transmission_bytes (src/utils.rs:152-180), which call the
 // `reed-solomon` 0.2.1 crate (GF(2^8), polynomial 0x11d, alpha = 2, g(x) = prod_{i<32} (x - alpha^i), systematic).
 //
-// One thread owns one 255-byte block; a warp owns a chunk of 32 consecutive blocks of one stream (the grid is flat over
-// streams x chunks, so ragged batches fill the CTAs) and keeps their codewords in a
-// private shared-memory image (255-byte pitch, i.e. exactly the coded stream), so after the table load warps never wait for
-// each other. The coded side of the image moves with 16-byte accesses (the image is placed at the same address modulo 16 as
-// the global bytes); the data side (223-byte blocks) is re-blocked through aligned 4-byte global accesses.
-// Every thread runs the byte-serial generator LFSR on its block: the 32-byte parity register lives in 8 registers and one
-// step is a 32-byte row fetch from a 256-row table (feedback byte x generator), an 8-register byte shift and 8 XORs.
-// The table is laid out for conflict-free LDS.128: four copies of every row side by side (128 B per feedback value, copy c
-// in banks 8c..8c+7), lane l uses copy l & 3, and lanes 4..7 of each quarter-warp fetch the two 16-byte halves in the
-// opposite order -- they keep the parity register rotated by four words so that no data movement is needed -- which puts
-// the 8 lanes of a quarter-warp on 8 different 16-byte bank groups whatever their feedback bytes are.
+// One thread owns one 255-byte block and streams it through registers: aligned 32-bit words of its own bytes are fetched
+// straight from global memory (the 8 loads a sector serves hit L1), re-aligned with a funnel shift, clocked through the
+// generator LFSR four bytes at a time and written back -- re-aligned again for the output block -- as aligned words; only
+// the ragged first / last bytes of a block are stored byte-wise. No shared-memory image, so the CTA needs the tables only
+// and the SM runs as many blocks as registers allow. The grid is flat over streams x blocks.
+// LFSR: the 32-byte parity register lives in 8 registers; one step is a 32-byte row fetch from a 256-row table (feedback
+// byte x generator), an 8-register byte shift and 8 XORs. The table is laid out for conflict-free LDS.128: four copies of
+// every row side by side (128 B per feedback value, copy c in banks 8c..8c+7), lane l uses copy l & 3, and lanes 4..7 of each
+// quarter-warp fetch the two 16-byte halves in the opposite order -- they keep the parity register rotated by four words
+// so that no data movement is needed -- which puts the 8 lanes of a quarter-warp on 8 different 16-byte bank groups
+// whatever their feedback bytes are.
 // Decoding re-encodes the 223 received data bytes; parity register XOR received parity = r(x) mod g(x). A zero remainder
-// (the common case) finishes the block; otherwise the thread computes the 32 syndromes from the remainder and runs
-// Berlekamp-Massey, a Chien search and Forney's formula on its own.
+// (the common case) finishes the block; otherwise the thread computes the 32 syndromes from the remainder, runs
+// Berlekamp-Massey, a Chien search and Forney's formula on its own and patches the data bytes it has just written.
 #pragma once
 
 #include <cstdint>
@@ -24,10 +24,8 @@
 namespace ofdm {
 
 constexpr int kRsN = 255, kRsK = 223, kRsT2 = 32;
-constexpr int kRsWarps = 8;
-constexpr int kRsThreads = 32 * kRsWarps;                         // blocks of one stream per CTA
-constexpr int kRsImgWarp = 32 * kRsN + 16;                        // one warp's image + room for the alignment phase
-constexpr size_t kRsSmemBytes = 256 * 128 + kRsWarps * kRsImgWarp + 512 + 256;
+constexpr int kRsThreads = 256;
+constexpr size_t kRsSmemBytes = 256 * 128 + 512 + 256;
 
 struct RsTables {
     uint8_t lfsr[256][32];      // lfsr[f][j] = f * g_{31-j}: what feedback byte f adds to the parity register
@@ -45,101 +43,104 @@ struct RsArgs {
     uint32_t       *n_corrected;    // decode only, per stream (atomic)
     uint32_t       *n_failed;       // decode only, per stream (atomic)
     uint32_t        n_streams;
-    uint32_t        chunks_per_stream;   // 32-block chunks per stream the grid provides (from the input stride)
+    uint32_t        blocks_per_stream;   // blocks per stream the grid provides (from the input stride)
     const RsTables *tables;
 };
 
-// ---- warp-level staging ------------------------------------------------------------------------------------------
-// coded side, global -> image: `have` bytes exist, the image is zero filled up to `total` (scratch_buf.fill(0), src/utils.rs:167)
-__device__ __forceinline__ void rs_warp_copy_in(uint8_t *img, const uint8_t *__restrict__ src, uint32_t have, uint32_t total, int lane)
-{
-    const uint32_t head = min(have, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15));
-    const uint32_t body = (have - head) >> 4;
-    for (uint32_t i = lane; i < head; i += 32) img[i] = src[i];
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
-    uint4 *d4 = reinterpret_cast<uint4 *>(img + head);
-#pragma unroll 8
-    for (uint32_t i = lane; i < body; i += 32) d4[i] = __ldg(s4 + i);
-    for (uint32_t i = head + (body << 4) + lane; i < have; i += 32) img[i] = src[i];
-    for (uint32_t i = have + lane; i < total; i += 32) img[i] = 0;
-}
-
-// coded side, image -> global
-__device__ __forceinline__ void rs_warp_copy_out(uint8_t *__restrict__ dst, const uint8_t *img, uint32_t n, int lane)
-{
-    const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
-    const uint32_t body = (n - head) >> 4;
-    for (uint32_t i = lane; i < head; i += 32) dst[i] = img[i];
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(img + head);
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
-#pragma unroll 4
-    for (uint32_t i = lane; i < body; i += 32) d4[i] = s4[i];
-    for (uint32_t i = head + (body << 4) + lane; i < n; i += 32) dst[i] = img[i];
-}
-
-// data side, global -> image: `total` = 223 x blocks contiguous bytes at `src` (the first `have` exist, the rest read as
-// zero: scratch_buf.fill(0), src/utils.rs:120) go to the first 223 bytes of each 255-byte image row
-__device__ __forceinline__ void rs_warp_scatter_in(uint8_t *img, const uint8_t *__restrict__ src, uint32_t total, uint32_t have, int lane)
-{
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(src - a);        // aligned words; word k holds bytes 4k - a ..
-    const uint32_t nw = (total + a + 3) >> 2;
-    for (uint32_t k0 = 0; k0 < nw; k0 += 32 * 8) {
-        uint32_t v[8];
+// ---- one block's bytes as a stream of 32-bit words ---------------------------------------------------------------------
+// word j = bytes 4j .. 4j+3 of the block that starts at `p` (any alignment); bytes at or beyond `have` read as zero
+// (scratch_buf.fill(0), src/utils.rs:120,167). The bytes come in as aligned 16-byte chunks -- one L2 access per 16 bytes
+// and lane, fetched one chunk ahead of their use -- and are re-aligned in registers (word rotation by selects, byte
+// shift by funnel shifts). Only chunks that hold at least one existing byte are touched.
+struct RsReader {
+    const uint4 *c;         // aligned chunk that holds byte 0
+    uint32_t off;           // p & 15
+    uint32_t have;          // bytes that exist
+    uint4 a, b, n;          // chunks q, q + 1 (in use) and q + 2 (in flight), q = the group fetched next
+    __device__ __forceinline__ uint4 fetch(uint32_t q) const               // chunk q, or 0 when none of its bytes exists
+    {
+        return (16 * q < have + off) ? __ldg(c + q) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __device__ __forceinline__ void init(const uint8_t *p, uint32_t have_)
+    {
+        off = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
+        c = reinterpret_cast<const uint4 *>(p - off);
+        have = have_;
+        a = fetch(0); b = fetch(1); n = fetch(2);
+    }
+    // words 4g .. 4g+3 of the block; call with g = 0, 1, 2, ...
+    __device__ __forceinline__ void next4(uint32_t g, uint32_t (&d)[4])
+    {
+        uint32_t t[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+        const bool r1 = (off & 4) != 0, r2 = (off & 8) != 0;
+        uint32_t u[7];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const uint32_t k = k0 + 32 * u + lane;
-            v[u] = (4 * k + 4 > a && 4 * k < have + a) ? __ldg(w + k) : 0u;     // only words that overlap [0, have)
+        for (int i = 0; i < 7; i++) u[i] = r1 ? t[i + 1] : t[i];            // rotate by one word
+        uint32_t v[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) v[i] = r2 ? u[i + 2] : u[i];            // rotate by two words
+        const uint32_t sh = 8 * (off & 3);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t x = __funnelshift_r(v[i], v[i + 1], sh);
+            const uint32_t j = 4 * g + i;
+            if (4 * j + 4 > have) x = 4 * j >= have ? 0u : x & (0xffffffffu >> (8 * (4 * j + 4 - have)));
+            d[i] = x;
         }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const uint32_t k = k0 + 32 * u + lane;
-            if (k >= nw) continue;
-            const int i = (int)(4 * k) - (int)a;
-            const uint32_t i0 = i < 0 ? 0u : (uint32_t)i;
-            uint32_t b = i0 / kRsK, off = i0 - b * kRsK;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int iq = i + q;
-                if (iq >= 0 && (uint32_t)iq < total) {
-                    img[b * kRsN + off] = (uint32_t)iq < have ? (uint8_t)(v[u] >> (8 * q)) : (uint8_t)0;
-                    if (++off == kRsK) { off = 0; b++; }
-                }
-            }
+        a = b; b = n; n = fetch(g + 3);
+    }
+};
+
+// the block at `p` (any alignment) written as a stream of 32-bit words: the aligned words are gathered four at a time and
+// leave as one 16-byte store when they complete an aligned chunk (a lane's scattered 4-byte stores would cost four times
+// the L1/L2 transactions); the ragged ends of a block go out as single words and bytes
+struct RsWriter {
+    uint8_t *p;
+    uint32_t a;             // p & 3
+    uint32_t prev;          // word j - 1 of the block
+    uint32_t *A0;           // aligned word that holds byte 0 of the block
+    uint32_t c0;            // position of A0 inside its 16-byte chunk (0..3)
+    uint32_t q0, q1, q2, q3, filled;    // the last aligned words, oldest first
+    __device__ __forceinline__ void init(uint8_t *p_)
+    {
+        p = p_; a = (uint32_t)(reinterpret_cast<uintptr_t>(p_) & 3); prev = 0;
+        A0 = reinterpret_cast<uint32_t *>(p_ - a);
+        c0 = (uint32_t)((reinterpret_cast<uintptr_t>(A0) >> 2) & 3);
+        q0 = q1 = q2 = q3 = 0; filled = 0;
+    }
+    __device__ __forceinline__ void drain(uint32_t k)                      // the `filled` words that end at aligned word k, one by one
+    {
+        if (filled >= 3) A0[k - 2] = q1;
+        if (filled >= 2) A0[k - 1] = q2;
+        if (filled >= 1) A0[k] = q3;
+        filled = 0;
+    }
+    __device__ __forceinline__ void emit(uint32_t k, uint32_t v)           // aligned word k (address A0 + k), all four bytes ours
+    {
+        q0 = q1; q1 = q2; q2 = q3; q3 = v; filled++;
+        if (((c0 + k) & 3) == 3) {                                         // last word of its 16-byte chunk
+            if (filled >= 4) { *reinterpret_cast<uint4 *>(A0 + k - 3) = make_uint4(q0, q1, q2, q3); filled = 0; }
+            else drain(k);
         }
     }
-}
-
-// data side, image -> global: the first 223 bytes of each image row, contiguous at `dst`
-__device__ __forceinline__ void rs_warp_gather_out(uint8_t *__restrict__ dst, const uint8_t *img, uint32_t total, int lane)
-{
-    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3);
-    uint32_t *w = reinterpret_cast<uint32_t *>(dst - a);
-    const uint32_t nw = (total + a + 3) >> 2;
-#pragma unroll 2
-    for (uint32_t k = lane; k < nw; k += 32) {
-        const int i = (int)(4 * k) - (int)a;
-        const uint32_t i0 = i < 0 ? 0u : (uint32_t)i;
-        uint32_t b = i0 / kRsK, off = i0 - b * kRsK;
-        uint32_t word = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int iq = i + q;
-            if (iq >= 0 && (uint32_t)iq < total) {
-                word |= (uint32_t)img[b * kRsN + off] << (8 * q);
-                if (++off == kRsK) { off = 0; b++; }
-            }
-        }
-        if (i >= 0 && (uint32_t)i + 4 <= total) w[k] = word;
+    // word j (bytes 4j .. 4j+3 of the block), all four bytes valid; call with j = 0, 1, 2, ...
+    __device__ __forceinline__ void put(uint32_t j, uint32_t v)
+    {
+        if (a == 0) emit(j, v);
         else {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int iq = i + q;
-                if (iq >= 0 && (uint32_t)iq < total) dst[iq] = (uint8_t)(word >> (8 * q));
-            }
+            if (j == 0) { for (uint32_t b = 0; b < 4 - a; b++) p[b] = (uint8_t)(v >> (8 * b)); }
+            else emit(j, __funnelshift_r(prev, v, 8 * (4 - a)));
+            prev = v;
         }
     }
-}
+    // the last word: `nv` (1..4) valid low bytes, then the bytes of the previous word still pending
+    __device__ __forceinline__ void put_last(uint32_t j, uint32_t v, uint32_t nv)
+    {
+        drain(a == 0 ? j - 1 : (j > 0 ? j - 1 : 0));                       // aligned words gathered so far end at word j - 1
+        if (a != 0 && j > 0) for (uint32_t b = 0; b < a; b++) p[4 * j - a + b] = (uint8_t)(prev >> (8 * (4 - a + b)));
+        for (uint32_t b = 0; b < nv; b++) p[4 * j + b] = (uint8_t)(v >> (8 * b));
+    }
+};
 
 // The parity register of one thread: r[0..7]; logical word k (bytes 4k..4k+3 of the register, byte 0 = highest-degree
 // coefficient) sits in r[k] on lanes 0..3 of a quarter-warp and in r[(k + 4) & 7] on lanes 4..7 (`rot`).
@@ -175,13 +176,7 @@ struct RsLfsr {
         r[6] = __funnelshift_r(r[6], r[7], 8) ^ b.z;
         r[7] = __funnelshift_r(r[7], r0 & m7, 8) ^ b.w;
     }
-    // clock the 223 message bytes of a shared-memory block through the register
-    __device__ __forceinline__ void run223(const uint8_t *msg)
-    {
-#pragma unroll 1
-        for (int j = 0; j + 4 <= kRsK; j += 4) { step(msg[j]); step(msg[j + 1]); step(msg[j + 2]); step(msg[j + 3]); }
-        step(msg[kRsK - 3]); step(msg[kRsK - 2]); step(msg[kRsK - 1]);
-    }
+    __device__ __forceinline__ void step4(uint32_t v) { step(v); step(v >> 8); step(v >> 16); step(v >> 24); }
     __device__ __forceinline__ uint32_t word(int k) const { return rot ? r[(k + 4) & 7] : r[k]; }
 };
 
@@ -205,41 +200,46 @@ __global__ void __launch_bounds__(kRsThreads) rs_encode_kernel(const RsArgs a)
 {
     extern __shared__ __align__(128) uint8_t rs_smem[];
     uint4 *s_lfsr = reinterpret_cast<uint4 *>(rs_smem);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     rs_load_tables(a.tables, s_lfsr, nullptr, nullptr, tid, kRsThreads);
     __syncthreads();
-    // warp task = one 32-block chunk of one stream; warps are independent from here on
-    const uint32_t task = blockIdx.x * kRsWarps + warp;
-    const uint32_t stream = task / a.chunks_per_stream, chunk = task - stream * a.chunks_per_stream;
+    const uint64_t task = (uint64_t)blockIdx.x * kRsThreads + tid;         // one block of one stream
+    const uint32_t stream = (uint32_t)(task / a.blocks_per_stream), b = (uint32_t)(task - (uint64_t)stream * a.blocks_per_stream);
     if (stream >= a.n_streams) return;
     const uint32_t n = a.in_len[stream];
     const uint32_t nb = n / kRsK + 1;                                      // src/utils.rs:113-134
     const uint32_t need = nb * kRsN;
-    if (chunk == 0 && lane == 0) a.out_len[stream] = need;
-    const uint32_t b0 = chunk * 32;
-    if (b0 >= nb || need > a.out_stride) return;
-    const uint32_t cnt = min(32u, nb - b0);
-    uint8_t *dst = a.out + (size_t)stream * a.out_stride + (size_t)b0 * kRsN;
-    uint8_t *img = rs_smem + 256 * 128 + warp * kRsImgWarp + (reinterpret_cast<uintptr_t>(dst) & 15);
-    const uint8_t *src = a.in + (size_t)stream * a.in_stride + (size_t)b0 * kRsK;
-    const uint32_t have = n > b0 * kRsK ? min(cnt * kRsK, n - b0 * kRsK) : 0;
-    rs_warp_scatter_in(img, src, cnt * kRsK, have, lane);
-    __syncwarp();
-    if ((uint32_t)lane < cnt) {
-        RsLfsr L;
-        L.init((uint32_t)__cvta_generic_to_shared(s_lfsr), lane);
-        uint8_t *blk = img + lane * kRsN;
-        L.run223(blk);
+    if (b == 0) a.out_len[stream] = need;
+    if (b >= nb || need > a.out_stride) return;
+
+    RsReader rd;
+    rd.init(a.in + (size_t)stream * a.in_stride + (size_t)b * kRsK, n > b * kRsK ? min((uint32_t)kRsK, n - b * kRsK) : 0u);
+    RsWriter wr;
+    wr.init(a.out + (size_t)stream * a.out_stride + (size_t)b * kRsN);
+    RsLfsr L;
+    L.init((uint32_t)__cvta_generic_to_shared(s_lfsr), lane);
+    uint32_t dw[4];
+#pragma unroll 1
+    for (uint32_t g = 0; g < 13; g++) {                                    // data words 0..51
+        rd.next4(g, dw);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t w = L.word(k);
-            blk[kRsK + 4 * k] = (uint8_t)w; blk[kRsK + 4 * k + 1] = (uint8_t)(w >> 8);
-            blk[kRsK + 4 * k + 2] = (uint8_t)(w >> 16); blk[kRsK + 4 * k + 3] = (uint8_t)(w >> 24);
-        }
+        for (int i = 0; i < 4; i++) { L.step4(dw[i]); wr.put(4 * g + i, dw[i]); }
     }
-    __syncwarp();
-    rs_warp_copy_out(dst, img, cnt * kRsN, lane);
+    rd.next4(13, dw);                                                      // words 52..54 and bytes 220..222
+#pragma unroll
+    for (int i = 0; i < 3; i++) { L.step4(dw[i]); wr.put(52 + i, dw[i]); }
+    const uint32_t d = dw[3];
+    L.step(d); L.step(d >> 8); L.step(d >> 16);
+    // codeword words 55..63: [d220 d221 d222 p0] [p1..p4] ... [p29 p30 p31 -]
+    uint32_t pw = L.word(0);
+    wr.put(55, (d & 0x00ffffffu) | (pw << 24));
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+        const uint32_t nx = L.word(k);
+        wr.put(55 + k, __funnelshift_r(pw, nx, 8));
+        pw = nx;
+    }
+    wr.put_last(63, pw >> 8, 3);
 }
 
 // ---- decode ------------------------------------------------------------------------------------------------------
@@ -250,9 +250,10 @@ struct RsGf {
     __device__ __forceinline__ uint32_t div(uint32_t x, uint32_t y) const { return x ? ex[lg[x] + 255u - lg[y]] : 0u; }
 };
 
-// Corrects the 255-byte word in place from its remainder rem[0..32) (rem[0] = coefficient of x^31).
+// Corrects the 223 data bytes at `data` (already written, uncorrected) from the remainder rem[0..32) of the 255-byte word
+// (rem[0] = coefficient of x^31); errors in the parity bytes are counted but need no patch.
 // Returns the number of corrected symbols or -1 (more than 16 symbol errors: `correct` fails, src/utils.rs:165).
-__device__ __noinline__ int rs_correct_from_remainder(uint8_t *word, const uint8_t *rem, const RsGf gf)
+__device__ __noinline__ int rs_correct_from_remainder(uint8_t *data, const uint8_t *rem, const RsGf gf)
 {
     uint8_t S[kRsT2];
     for (uint32_t i = 0; i < kRsT2; i++) {                          // S_i = r(alpha^i) = rem(alpha^i)
@@ -313,7 +314,7 @@ __device__ __noinline__ int rs_correct_from_remainder(uint8_t *word, const uint8
         uint32_t dl = 0;
         for (int i = 1; i <= L; i += 2) dl ^= gf.mul_pow(C[i], (einv * (uint32_t)(i - 1)) % 255u);
         if (dl == 0) return -1;
-        word[p] ^= (uint8_t)gf.mul_pow(gf.div(om, dl), e);
+        if (p < (uint32_t)kRsK) data[p] ^= (uint8_t)gf.mul_pow(gf.div(om, dl), e);
     }
     return nerr;
 }
@@ -322,46 +323,59 @@ __global__ void __launch_bounds__(kRsThreads) rs_decode_kernel(const RsArgs a)
 {
     extern __shared__ __align__(128) uint8_t rs_smem[];
     uint4 *s_lfsr = reinterpret_cast<uint4 *>(rs_smem);
-    uint8_t *s_exp = rs_smem + 256 * 128 + kRsWarps * kRsImgWarp, *s_log = s_exp + 512;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *s_exp = rs_smem + 256 * 128, *s_log = s_exp + 512;
+    const int tid = threadIdx.x, lane = tid & 31;
     rs_load_tables(a.tables, s_lfsr, s_exp, s_log, tid, kRsThreads);
     __syncthreads();
-    const uint32_t task = blockIdx.x * kRsWarps + warp;                    // one 32-block chunk of one stream
-    const uint32_t stream = task / a.chunks_per_stream, chunk = task - stream * a.chunks_per_stream;
+    const uint64_t task = (uint64_t)blockIdx.x * kRsThreads + tid;         // one block of one stream
+    const uint32_t stream = (uint32_t)(task / a.blocks_per_stream), b = (uint32_t)(task - (uint64_t)stream * a.blocks_per_stream);
     if (stream >= a.n_streams) return;
     const uint32_t n = a.in_len[stream];
     const uint32_t nb = n / kRsN + 1;                                      // src/utils.rs:160-176
     const uint32_t need = nb * kRsK;
-    if (chunk == 0 && lane == 0) a.out_len[stream] = need;
-    const uint32_t b0 = chunk * 32;
-    if (b0 >= nb || need > a.out_stride) return;
-    const uint32_t cnt = min(32u, nb - b0);
-    const uint8_t *src = a.in + (size_t)stream * a.in_stride + (size_t)b0 * kRsN;
-    uint8_t *img = rs_smem + 256 * 128 + warp * kRsImgWarp + (reinterpret_cast<uintptr_t>(src) & 15);
-    const uint32_t have = n > b0 * kRsN ? min(cnt * kRsN, n - b0 * kRsN) : 0;
-    rs_warp_copy_in(img, src, have, cnt * kRsN, lane);
-    __syncwarp();
-    if ((uint32_t)lane < cnt) {
-        uint8_t *word = img + lane * kRsN;
-        RsLfsr L;
-        L.init((uint32_t)__cvta_generic_to_shared(s_lfsr), lane);
-        L.run223(word);
-        uint32_t any = 0;
-        uint8_t rem[kRsT2];
+    if (b == 0) a.out_len[stream] = need;
+    if (b >= nb || need > a.out_stride) return;
+
+    RsReader rd;
+    rd.init(a.in + (size_t)stream * a.in_stride + (size_t)b * kRsN, n > b * kRsN ? min((uint32_t)kRsN, n - b * kRsN) : 0u);
+    uint8_t *data = a.out + (size_t)stream * a.out_stride + (size_t)b * kRsK;
+    RsWriter wr;
+    wr.init(data);
+    RsLfsr L;
+    L.init((uint32_t)__cvta_generic_to_shared(s_lfsr), lane);
+    uint32_t dw[4];
+#pragma unroll 1
+    for (uint32_t g = 0; g < 13; g++) {                                    // data words 0..51
+        rd.next4(g, dw);
 #pragma unroll
-        for (int i = 0; i < kRsT2; i++) {
-            rem[i] = (uint8_t)((L.word(i >> 2) >> (8 * (i & 3))) ^ word[kRsK + i]);
-            any |= rem[i];
-        }
-        if (any) {
-            const int r = rs_correct_from_remainder(word, rem, RsGf{ s_exp, s_log });
-            if (r < 0) atomicAdd(a.n_failed + stream, 1u);
-            else atomicAdd(a.n_corrected + stream, (uint32_t)r);
+        for (int i = 0; i < 4; i++) { L.step4(dw[i]); wr.put(4 * g + i, dw[i]); }
+    }
+    rd.next4(13, dw);                                                      // words 52..54, bytes 220..222 | received parity byte 0
+#pragma unroll
+    for (int i = 0; i < 3; i++) { L.step4(dw[i]); wr.put(52 + i, dw[i]); }
+    uint32_t d = dw[3];
+    L.step(d); L.step(d >> 8); L.step(d >> 16);
+    wr.put_last(55, d, 3);
+    // remainder = computed parity ^ received parity (bytes 223..254 = byte 3 of word 55 and words 56..63)
+    uint32_t any = 0, rw[8];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        rd.next4(14 + h, dw);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            rw[4 * h + i] = L.word(4 * h + i) ^ __funnelshift_r(d, dw[i], 24);
+            any |= rw[4 * h + i];
+            d = dw[i];
         }
     }
-    __syncwarp();
-    rs_warp_gather_out(a.out + (size_t)stream * a.out_stride + (size_t)b0 * kRsK, img, cnt * kRsK, lane);
+    if (any) {
+        uint8_t rem[kRsT2];
+#pragma unroll
+        for (int i = 0; i < kRsT2; i++) rem[i] = (uint8_t)(rw[i >> 2] >> (8 * (i & 3)));
+        const int r = rs_correct_from_remainder(data, rem, RsGf{ s_exp, s_log });
+        if (r < 0) atomicAdd(a.n_failed + stream, 1u);
+        else atomicAdd(a.n_corrected + stream, (uint32_t)r);
+    }
 }
 
 }  // namespace ofdm
