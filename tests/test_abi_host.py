@@ -126,3 +126,30 @@ def test_cpp_host_example_builds():
     _build.build_engine()
     exe = _build.build_host_example()
     assert os.access(exe, os.X_OK)
+
+
+def test_header_is_plain_c99_and_links_from_c(tmp_path, engine_lib):
+    """The boundary is a C ABI: include/ofdm_engine.h must compile as C99 (what cgo / bindgen / ctypesgen consume) and a C
+    program must link against libofdm_b200.so and get sane answers from the calls that need no GPU."""
+    import subprocess
+    from ofdm_b200 import _build
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include "ofdm_engine.h"
+#include <stdio.h>
+int main(void) {
+    ofdm_cfg c;
+    ofdm_cfg_default(&c);
+    c.modulation = OFDM_MOD_QAM64; c.guard_bands = 1; c.fec = 1;
+    printf("%u %u %u %u %zu %zu %s\n", ofdm_abi_version(), ofdm_coded_len(&c, 576), ofdm_frame_data_syms(&c, 576), ofdm_frame_len(&c, 576),
+           ofdm_rs_encoded_len(576), ofdm_rs_decoded_len(765), ofdm_status_name(OFDM_BAD_HEADER));
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_build.LIB_PATH)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                    "-L", libdir, "-lofdm_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[1:6] == ["1008", "29", "3120", "765", "892"] and out[6] == "BAD_HEADER"      # SURVEY.md 8d config 1 sizes
