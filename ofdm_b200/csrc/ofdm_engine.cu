@@ -546,11 +546,12 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
     if (S > 0) {
         uint32_t tiles = (uint32_t)((S + h->tile_shift + kTileSyms - 1) / kTileSyms);
         // several consecutive tiles per CTA (lane constants and the prefetch pipeline are reused across them), but keep
-        // >= ~16 waves of CTAs (148 SMs x 3 CTAs) so the tail stays small
-        uint32_t tpc = (uint32_t)(((uint64_t)tiles * n_streams) / (16u * 148u * 3u));
+        // >= ~32 waves of CTAs (148 SMs x 4 CTAs) so the tail stays small, and split a stream's tiles evenly over its CTAs
+        uint32_t tpc = (uint32_t)(((uint64_t)tiles * n_streams) / (32u * 148u * 4u));
         if (tpc < 1) tpc = 1;
         if (tpc > tiles) tpc = tiles;
         if (tpc > (uint32_t)kDecBaseTiles) tpc = kDecBaseTiles;        // start phasors of a CTA's tiles are tabulated in smem
+        tpc = (tiles + (tiles + tpc - 1) / tpc - 1) / ((tiles + tpc - 1) / tpc);      // ceil(tiles / ceil(tiles / tpc)): balanced
         a.tiles_per_cta = (int)tpc;
         tiles = (tiles + tpc - 1) / tpc;
         DecodeKernel k = pick_decode(h->cfg, points);
