@@ -92,12 +92,14 @@ __device__ __forceinline__ cpx c_fma2(cpx a, cpx b, cpx c) { cpx r; asm("fma.rn.
 __device__ __forceinline__ cpx c_scale(cpx a, float k) { return c_mul2(a, c_make(k, k)); }
 __device__ __forceinline__ cpx c_mul_mj(cpx a) { float re, im; c_split(a, re, im); return c_make(im, -re); }    // -j a
 __device__ __forceinline__ cpx c_mul_pj(cpx a) { float re, im; c_split(a, re, im); return c_make(-im, re); }    // +j a
-// a * b = (ar, ai) * br + (ai, ar) * (-bi, bi)
+// a * b = (ar, ai) * (br, br) + (-ai, ar) * (bi, bi): both multiplicands of b are scalar broadcasts and (-ai, ar) is a
+// swapped, half-negated view of a -- ptxas folds all three into FMUL2 / FFMA2 operand modifiers, 2 instructions in total
+// (the equivalent (ai, ar) * (-bi, bi) costs an extra negate and a register move whenever b is not a computed scalar)
 __device__ __forceinline__ cpx c_mul(cpx a, cpx b)
 {
     float ar, ai, br, bi;
     c_split(a, ar, ai); c_split(b, br, bi);
-    return c_fma2(c_make(ai, ar), c_make(-bi, bi), c_mul2(a, c_make(br, br)));
+    return c_fma2(c_make(-ai, ar), c_make(bi, bi), c_mul2(a, c_make(br, br)));
 }
 
 // forward radix-8 DFT on packed complex values (same flow graph as dft8): 28 packed instructions
