@@ -253,7 +253,8 @@ __device__ __forceinline__ void rx_lane_init_p(RxLaneP &L, const StreamState *st
 // One OFDM symbol per 8-lane group, derotated samples in z: FFT, equalise, pilot phase.
 // On return z[kb] is the equalised + phase-corrected value of bin l + 8kb.
 template <bool GUARD, int PHASE>
-__device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *__restrict__ g_row, cpx base, float2 *tr, int l, cpx (&z)[8])
+__device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *__restrict__ g_row, cpx base, float2 *tr, int l, cpx (&z)[8],
+                                            uint32_t pmask /* bit q: this lane holds pilot bin 6, 25, 39, 58 in z[0], z[3], z[4], z[7] */)
 {
     fft64_group_p(z, L.tw, tr, l);                                         // src/receiver.rs:99-104
 #pragma unroll
@@ -268,13 +269,12 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
         // pilots: bins 6, 25, 39, 58 = (lane, kb) (6,0) (1,3) (7,4) (2,7)   src/receiver.rs:125-128
         if (PHASE == 1) {
             // angle of the pilot sum: the per-symbol base phasor cancels, rot = conj(sum)/|sum|
-            cpx p = c_make(0.0f, 0.0f);
-            if (l == 6) p = z[0];
-            if (l == 1) p = z[3];
-            if (l == 7) p = z[4];
-            if (l == 2) p = z[7];
-            float pr, pi;
-            c_split(p, pr, pi);
+            // branch-free pick of this lane's pilot (the compiler turns `if (l == ..) p = z[..]` into divergent branches)
+            float pr = 0.0f, pi = 0.0f, ar, ai;
+            c_split(z[0], ar, ai); pr = (pmask & 1u) ? ar : pr; pi = (pmask & 1u) ? ai : pi;
+            c_split(z[3], ar, ai); pr = (pmask & 2u) ? ar : pr; pi = (pmask & 2u) ? ai : pi;
+            c_split(z[4], ar, ai); pr = (pmask & 4u) ? ar : pr; pi = (pmask & 4u) ? ai : pi;
+            c_split(z[7], ar, ai); pr = (pmask & 8u) ? ar : pr; pi = (pmask & 8u) ? ai : pi;
 #pragma unroll
             for (int m = 1; m < 8; m <<= 1) {
                 pr += __shfl_xor_sync(0xffffffffu, pr, m);
@@ -284,14 +284,14 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
             rot = c_make(pr * inv, -pi * inv);
         } else {
             // reference: mean of the four pilot angles (after the full derotation), src/receiver.rs:126,137
-            cpx p = c_make(0.0f, 0.0f);
-            if (l == 6) p = z[0];
-            if (l == 1) p = z[3];
-            if (l == 7) p = z[4];
-            if (l == 2) p = z[7];
+            float qr = 0.0f, qi = 0.0f, ar, ai;
+            c_split(z[0], ar, ai); qr = (pmask & 1u) ? ar : qr; qi = (pmask & 1u) ? ai : qi;
+            c_split(z[3], ar, ai); qr = (pmask & 2u) ? ar : qr; qi = (pmask & 2u) ? ai : qi;
+            c_split(z[4], ar, ai); qr = (pmask & 4u) ? ar : qr; qi = (pmask & 4u) ? ai : qi;
+            c_split(z[7], ar, ai); qr = (pmask & 8u) ? ar : qr; qi = (pmask & 8u) ? ai : qi;
             float pr, pi;
-            c_split(c_mul(p, base), pr, pi);
-            const bool pilot_lane = (l == 6) | (l == 1) | (l == 7) | (l == 2);
+            c_split(c_mul(c_make(qr, qi), base), pr, pi);
+            const bool pilot_lane = pmask != 0;
             float ang = pilot_lane ? atan2f(pi, pr) : 0.0f;
 #pragma unroll
             for (int m = 1; m < 8; m <<= 1) ang += __shfl_xor_sync(0xffffffffu, ang, m);
@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
     // bins l, l + 24, l + 32, l + 56 are data carriers on some lanes only: one mask bit each. The mask and the two
     // lane-dependent offsets are made opaque so that they stay in registers instead of being re-derived from l per iteration.
     uint32_t dmask = (off[0] >= 0 ? 1u : 0u) | (off[3] >= 0 ? 2u : 0u) | (off[4] >= 0 ? 4u : 0u) | (off[7] >= 0 ? 8u : 0u);
-    asm volatile("" : "+r"(dmask), "+r"(d3), "+r"(d4));
+    uint32_t pmask = (l == 6 ? 1u : 0u) | (l == 1 ? 2u : 0u) | (l == 7 ? 4u : 0u) | (l == 2 ? 8u : 0u);     // pilot bins 6, 25, 39, 58
+    asm volatile("" : "+r"(dmask), "+r"(d3), "+r"(d4), "+r"(pmask));
     const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)(4 * kSym));
     uint8_t *out = a.out + (size_t)stream * a.out_stride;
     uint32_t phase = 0;                                             // mbarrier phase parity
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
                 const int n1 = tile_t1(tile + 1);
                 issue(t1 + warp * (4 * kDecIters), s_fast < n1 ? s_fast : n1);
             }
-            rx_symbol_p<GUARD, PHASE>(L, g_row, base, tr, l, z);
+            rx_symbol_p<GUARD, PHASE>(L, g_row, base, tr, l, z, pmask);
             base = c_mul(base, dbase);
             // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
 #pragma unroll
