@@ -478,12 +478,13 @@ __global__ void __launch_bounds__(kThreads, 2) wide_decode_kernel(const WideRxAr
             float zr, zi;
             c_split(c_mul(v[i], rot), zr, zi);
             const int r = rk[i * kTeam];
-            if (r >= 0) {
-                crow[r] = (uint8_t)(MOD == 2 ? demap_qam64_lut(zr, zi, qam_saddr) : demap_point<MOD>(zr, zi));
-                if (POINTS) {
-                    size_t p = (size_t)s * D + r;
-                    if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
-                }
+            // branch-free: null / pilot bins are demapped like data bins and simply not stored (a branch per point would
+            // serialise the 16 demap chains of a thread)
+            const uint32_t sym6 = MOD == 2 ? demap_qam64_lut(zr, zi, qam_saddr) : demap_point<MOD>(zr, zi);
+            st_shared_u8_if_nonneg(crow + r, sym6, r);
+            if (POINTS && r >= 0) {
+                size_t p = (size_t)s * D + r;
+                if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
             }
         }
     }
