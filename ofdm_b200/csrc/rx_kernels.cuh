@@ -379,15 +379,19 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
     const unsigned long long *stage_rd7 = stage_rd + ((g & 1) ? -8 : 56);                       // chunk (7 + rot) & 7
     auto tile_t0 = [&](int tile) { int t = tile * kTileSyms - a.tile_shift; return t < 0 ? 0 : t; };
     auto tile_t1 = [&](int tile) { int t = (tile + 1) * kTileSyms - a.tile_shift; return t > S ? S : t; };
-    // one copy for the 4 symbols sb .. sb+3 of a warp iteration when all of them are below lim; lane 0 only
+    // one copy for the 4 symbols sb .. sb+3 of a warp iteration when all of them are below lim; lane 0 only. The shared
+    // addresses of the slot and its barrier are kept in registers (opaque) instead of being re-derived from tid per issue.
+    uint32_t stage_sa = smem_addr(stage_w), bar_sa = smem_addr(bar);
+    asm volatile("" : "+r"(stage_sa), "+r"(bar_sa));
     auto issue = [&](int sb, int lim) {
         if (lane == 0) {
             const bool full = sb + 4 <= lim;
             if (full) {
                 const uintptr_t src = (xaddr - kCp * 8 + (uintptr_t)sb * (kSym * 8)) & ~(uintptr_t)15;
-                tma_bulk_g2s(stage_w, reinterpret_cast<const void *>(src), kStageBytes, bar);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(stage_sa), "l"(src), "r"((uint32_t)kStageBytes), "r"(bar_sa) : "memory");
             }
-            mbar_arrive_expect_tx(bar, full ? kStageBytes : 0);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_sa), "r"(full ? (uint32_t)kStageBytes : 0u) : "memory");
         }
     };
     if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
