@@ -221,7 +221,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(400);        // back off: a spinning warp steals issue slots
+    while (!mbar_try_wait(bar, parity)) { }                      // try_wait itself suspends the thread (time hint); an extra
+                                                                 // nanosleep back-off measured 0.4 % slower
 }
 // global -> shared bulk copy through the TMA engine; dst/src 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
