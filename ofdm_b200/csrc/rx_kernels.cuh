@@ -107,6 +107,12 @@ __device__ __forceinline__ void st_shared_u8_if_nonneg(uint8_t *p, uint32_t v, i
                  :: "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v), "r"(cond) : "memory");
 }
 
+// predicated byte store to global memory (keeps the look-ups that produce the byte out of a branch)
+__device__ __forceinline__ void st_global_u8_if(uint8_t *p, uint32_t v, bool cond)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u8 [%0], %1;\n\t}" :: "l"(p), "r"(v), "r"((uint32_t)cond) : "memory");
+}
+
 // the same with the condition held as one bit of a lane-constant mask (one LOP3 with a predicate result per store)
 template <uint32_t BIT>
 __device__ __forceinline__ void st_shared_u8_if_bit(uint8_t *p, uint32_t v, uint32_t mask)
@@ -524,8 +530,8 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
                 }
                 uint8_t *o = out + j0 + u;
                 o[0] = (uint8_t)w0;
-                if (u + 1 < nbytes) o[1] = (uint8_t)w1;
-                if (u + 2 < nbytes) o[2] = (uint8_t)w2;
+                st_global_u8_if(o + 1, w1, u + 1 < nbytes);
+                st_global_u8_if(o + 2, w2, u + 2 < nbytes);
             }
         } else {
             for (int u = tid; u < nbytes; u += kDecThreads) {

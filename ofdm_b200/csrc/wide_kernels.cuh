@@ -258,8 +258,8 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
             }
             uint8_t *o = o0 + u;
             o[0] = (uint8_t)w0;
-            if (u + 1 < nbytes) o[1] = (uint8_t)w1;
-            if (u + 2 < nbytes) o[2] = (uint8_t)w2;
+            st_global_u8_if(o + 1, w1, u + 1 < nbytes);
+            st_global_u8_if(o + 2, w2, u + 2 < nbytes);
         }
     } else {
     for (int u = tid; u < nbytes; u += kThreads) {
