@@ -197,6 +197,10 @@ __device__ __forceinline__ void fft64_group_p(cpx (&x)[8], const cpx (&tw)[8], f
     dft8_p(x);
 }
 
+// 1/sqrt(x) for x known to be a normal number: one MUFU.RSQ, without the denormal pre/post-scaling rsqrtf() adds when
+// flush-to-zero is off (the results are identical on normal inputs)
+__device__ __forceinline__ float rsqrt_normal(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)

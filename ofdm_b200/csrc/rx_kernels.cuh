@@ -205,7 +205,7 @@ __device__ __forceinline__ void rx_symbol(const RxLane &L, float br, float bi, f
                 pr += __shfl_xor_sync(0xffffffffu, pr, m);
                 pi += __shfl_xor_sync(0xffffffffu, pi, m);
             }
-            float inv = rsqrtf(fmaxf(pr * pr + pi * pi, 1e-30f));
+            float inv = rsqrt_normal(fmaxf(pr * pr + pi * pi, 1e-30f));
             rr = pr * inv; ri = -pi * inv;
         } else {
             // reference: mean of the four pilot angles (after the full derotation), src/receiver.rs:126,137
@@ -286,7 +286,7 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
                 pr += __shfl_xor_sync(0xffffffffu, pr, m);
                 pi += __shfl_xor_sync(0xffffffffu, pi, m);
             }
-            float inv = rsqrtf(fmaxf(pr * pr + pi * pi, 1e-30f));
+            float inv = rsqrt_normal(fmaxf(pr * pr + pi * pi, 1e-30f));
             rot = c_make(pr * inv, -pi * inv);
         } else {
             // reference: mean of the four pilot angles (after the full derotation), src/receiver.rs:126,137

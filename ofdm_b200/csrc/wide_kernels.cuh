@@ -198,7 +198,7 @@ __device__ __forceinline__ void wide_symbol(const WideLane &L, cpx base, cpx (&z
             for (int r = 0; r < 4; r++) if (L.pilot & (1u << r)) p = c_add(p, z[r]);
             c_split(p, px, py);
             block_sum2(px, py, s_red, tid);
-            const float inv = rsqrtf(fmaxf(px * px + py * py, 1e-30f));
+            const float inv = rsqrt_normal(fmaxf(px * px + py * py, 1e-30f));
             rot = c_make(px * inv, -py * inv);
         } else {
 #pragma unroll
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 2) wide_decode_kernel(const WideRxAr
             team_sync(team);
             px = sp[0] + sp[2]; py = sp[1] + sp[3];
             if (PHASE == 1) {
-                const float inv = rsqrtf(fmaxf(px * px + py * py, 1e-30f));
+                const float inv = rsqrt_normal(fmaxf(px * px + py * py, 1e-30f));
                 rot = c_make(px * inv, -py * inv);
             } else {
                 float sn, cs;
