@@ -151,10 +151,10 @@ __device__ __forceinline__ uint8_t qam64_lut_entry(int t)
     ii = ii > 7 ? 7 : ii; iq = iq > 7 ? 7 : iq;
     return (uint8_t)((ii ^ (ii >> 1)) | ((iq ^ (iq >> 1)) << 3));
 }
-__device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, uint32_t lut_saddr)
+__device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, uint32_t lut_saddr, float k = 0.4375f)
 {
-    const float ti = __saturatef(fmaf(re, 0.4375f, 0.5f));
-    const float tq = __saturatef(fmaf(im, 0.4375f, 0.5f));
+    const float ti = __saturatef(fmaf(re, k, 0.5f));                // k = 3.5 / 8 x (1 / scale of the point)
+    const float tq = __saturatef(fmaf(im, k, 0.5f));
     const uint32_t uq = __float_as_uint(__fmul_rd(tq, 0x1p-146f));
     const uint32_t addr = __float_as_uint(__fmaf_rd(ti, 0x1p-146f, __uint_as_float(lut_saddr + (uq << 4))));
     uint32_t v;
@@ -260,7 +260,8 @@ __device__ __forceinline__ void rx_lane_init_p(RxLaneP &L, const StreamState *st
 // On return z[kb] is the equalised + phase-corrected value of bin l + 8kb.
 template <bool GUARD, int PHASE>
 __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *__restrict__ g_row, cpx base, float2 *tr, int l, cpx (&z)[8],
-                                            uint32_t pmask /* bit q: this lane holds pilot bin 6, 25, 39, 58 in z[0], z[3], z[4], z[7] */)
+                                            uint32_t pmask /* bit q: this lane holds pilot bin 6, 25, 39, 58 in z[0], z[3], z[4], z[7] */,
+                                            float &pscale /* out: multiply the returned points by this to normalise them */)
 {
     fft64_group_p(z, L.tw, tr, l);                                         // src/receiver.rs:99-104
 #pragma unroll
@@ -271,6 +272,7 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
         z[2 * q] = c_mul(z[2 * q], g0); z[2 * q + 1] = c_mul(z[2 * q + 1], g1);
     }
     cpx rot = base;                                                        // common rotation of the data bins
+    pscale = 1.0f;
     if (GUARD) {
         // pilots: bins 6, 25, 39, 58 = (lane, kb) (6,0) (1,3) (7,4) (2,7)   src/receiver.rs:125-128
         if (PHASE == 1) {
@@ -286,8 +288,10 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
                 pr += __shfl_xor_sync(0xffffffffu, pr, m);
                 pi += __shfl_xor_sync(0xffffffffu, pi, m);
             }
-            float inv = rsqrt_normal(fmaxf(pr * pr + pi * pi, 1e-30f));
-            rot = c_make(pr * inv, -pi * inv);
+            // rotate by conj(sum) right away; 1/|sum| (MUFU latency) leaves the dependency chain and is applied by the
+            // consumer: as the scale of the demap threshold FMA and of the stored points
+            pscale = rsqrt_normal(fmaxf(pr * pr + pi * pi, 1e-30f));
+            rot = c_make(pr, -pi);
         } else {
             // reference: mean of the four pilot angles (after the full derotation), src/receiver.rs:126,137
             float qr = 0.0f, qi = 0.0f, ar, ai;
@@ -469,14 +473,16 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
                 const int n1 = tile_t1(tile + 1);
                 issue(t1 + warp * (4 * kDecIters), s_fast < n1 ? s_fast : n1);
             }
-            rx_symbol_p<GUARD, PHASE>(L, g_row, base, tr, l, z, pmask);
+            float pscale;
+            rx_symbol_p<GUARD, PHASE>(L, g_row, base, tr, l, z, pmask, pscale);
+            const float dk = 0.4375f * pscale;
             base = c_mul(base, dbase);
             // rows of symbols past t1 exist in s_car but are never read: no `valid` predicate needed on the stores
 #pragma unroll
             for (int kb = 0; kb < 8; kb++) {
                 float zr, zi;
                 c_split(z[kb], zr, zi);
-                uint32_t v = MOD == 2 ? demap_qam64_lut(zr, zi, qam_biased) : demap_point<MOD>(zr, zi);
+                uint32_t v = MOD == 2 ? demap_qam64_lut(zr, zi, qam_biased, dk) : demap_point<MOD>(zr, zi);
                 // carrier rank of bin l + 8kb is affine in kb except at the pilot / DC crossings (kb = 3, 4): immediate
                 // offsets from one row pointer; kb in {1, 2, 5, 6} are data carriers on every lane
                 if (!GUARD) rowp[8 * kb] = (uint8_t)v;
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
                 else st_shared_u8_if_bit<8>(rowp + 53, v, dmask);
                 if (POINTS && s < t1 && (!GUARD || off[kb] >= 0)) {
                     size_t p = (size_t)s * D + off[kb];
-                    if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
+                    if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr * pscale, zi * pscale);
                 }
             }
             rowp += 4 * D;
