@@ -537,7 +537,10 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         a.d_nsyms = diag->n_data_syms; a.d_points = reinterpret_cast<float2 *>(diag->points); a.points_stride = diag->points_stride;
         points = diag->points != nullptr && diag->points_stride > 0;
     }
-    pick_acquire(h->cfg)<<<n_streams, kAcq64Threads, 0, st>>>(a);
+    AcquireKernel kacq = pick_acquire(h->cfg);
+    if (h->smem_configured.insert((const void *)kacq).second)       // kAcq64Ctas CTAs x ~19 kB static smem must fit the carve-out
+        CU(h, cudaFuncSetAttribute((const void *)kacq, cudaFuncAttributePreferredSharedMemoryCarveout, 80));
+    kacq<<<n_streams, kAcq64Threads, 0, st>>>(a);
     if (prof) CU(h, cudaEventRecord(pe[1], st));
     uint32_t mx = max_n_samples ? max_n_samples : iq_stride;
     if (mx > iq_stride) mx = iq_stride;

@@ -564,6 +564,8 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
 constexpr int kAcqThreads = 256;
 constexpr int kAcq64Threads = 128;               // CTA size of the N=64 acquisition kernel (small per-stream work, many barriers)
 constexpr int kAcqChunk = 1024;                  // Schmidl-Cox lags per smem-staged chunk
+constexpr int kAcq64Ctas = 8;                    // CTAs per SM the N=64 acquisition kernel is compiled for (64 registers; it is
+                                                 // latency / barrier bound, so resident warps are what buys time)
 
 __device__ __forceinline__ float2 ld_sample(const float2 *__restrict__ x, long n, long n_samples)
 {
@@ -629,7 +631,7 @@ __device__ __forceinline__ int ramp_argmax(const float2 *__restrict__ x, long n_
 }
 
 template <int MOD, bool GUARD, int PHASE>
-__global__ void __launch_bounds__(kAcq64Threads) rx_acquire_kernel(const RxArgs a)
+__global__ void __launch_bounds__(kAcq64Threads, kAcq64Ctas) rx_acquire_kernel(const RxArgs a)
 {
     const int SYNC = a.sync_mode, CFO = a.cfo_mode;
     const bool FEC = a.fec != 0;
@@ -765,6 +767,7 @@ __global__ void __launch_bounds__(kAcq64Threads) rx_acquire_kernel(const RxArgs 
     }
     if (lane == 0) { s_red[warp] = acc0; s_red[NW + warp] = acc1; }
     __syncthreads();
+    if (warp != 0) return;                             // the rest (f64 atan2, channel estimate, header) is one warp's work
     double f_delta;
     {
         double t0 = 0.0, t1 = 0.0;
@@ -774,10 +777,9 @@ __global__ void __launch_bounds__(kAcq64Threads) rx_acquire_kernel(const RxArgs 
     }
     const uint64_t fstep = (uint64_t)(int64_t)llrint(-f_delta * (0.15915494309189533577 * 18446744073709551616.0));
     if (tid == 0) { st->fstep = fstep; st->f_delta = (float)f_delta; st->offset = (int32_t)offset; }
-    __syncthreads();
 
     // ---- channel estimate (src/receiver.rs:212-229) and header symbols: warp 0 -----------------------------------
-    if (warp == 0) {
+    {
         const int g = lane >> 3, l = lane & 7;
         float2 *tr = s_tr + g * kTrGroup;
         float twr[8], twi[8];
@@ -841,13 +843,15 @@ __global__ void __launch_bounds__(kAcq64Threads) rx_acquire_kernel(const RxArgs 
             }
         }
         __syncwarp();
+        // the 128 header bits (u128 little-endian length, src/packets/mod.rs:20-32): lane b of ballot j holds bit 32j + b
+        uint32_t hw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int b = 32 * j + lane, c = b / BPC, sh = b - c * BPC;
+            hw[j] = __ballot_sync(0xffffffffu, (s_car[c] >> sh) & 1u);
+        }
         if (lane == 0) {
-            uint64_t lo = 0, hi64 = 0;
-            for (int b = 0; b < 128; b++) {
-                int c = b / BPC, sh = b - c * BPC;
-                uint64_t bit = (s_car[c] >> sh) & 1u;
-                if (b < 64) lo |= bit << b; else hi64 |= bit << (b - 64);
-            }
+            const uint64_t lo = (uint64_t)hw[0] | ((uint64_t)hw[1] << 32), hi64 = (uint64_t)hw[2] | ((uint64_t)hw[3] << 32);
             const long rows = (n_avail + kSym - 1) / kSym;                // src/receiver.rs:192-203
             const long s_rx = rows - kHeadSyms;
             const long avail_bytes = (s_rx * BPS) / 8 - 16;

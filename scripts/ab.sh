@@ -10,6 +10,6 @@ for i in $(seq $N); do
     python bench.py --steps 50 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$L', d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['ber']['bit_errs'], d['clocks']['sm_mhz'])"
+print('$L', d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['roofline']['acquire_kernel_ms'], d['ms_per_step'], d['ber']['bit_errs'], d['clocks']['sm_mhz'])"
   done
 done
