@@ -511,11 +511,12 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
         const int nbytes = (int)(j1 - j0);
         if (MOD == 2) {
             // 3 output bytes per thread: 42 (Hamming) or 24 stream bits = 7 or 4 six-bit carriers (+1 for the bit shift)
+            // 3 NB = 42 or 24 bits is a whole number of carriers, so the sub-carrier bit shift is the same for every thread
             constexpr int NC = (3 * NB + 5) / 6 + 1;
-            for (int u = 3 * tid; u < nbytes; u += 3 * kDecThreads) {
-                const int p = pbase + u * NB;
-                const int c = p / 6, sh = p - 6 * c;
-                const uint8_t *cp = s_car + c;
+            static_assert((3 * NB) % 6 == 0, "3 output bytes must span whole carriers");
+            const int c0 = pbase / 6, sh = pbase - 6 * c0;
+            const uint8_t *cp = s_car + c0 + (NB / 2) * tid;
+            for (int u = 3 * tid; u < nbytes; u += 3 * kDecThreads, cp += (NB / 2) * kDecThreads) {
                 uint32_t lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
                 uint32_t hi = 0;
                 if (NC > 5) {
