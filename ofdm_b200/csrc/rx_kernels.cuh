@@ -151,6 +151,12 @@ __device__ __forceinline__ uint8_t qam64_lut_entry(int t)
     ii = ii > 7 ? 7 : ii; iq = iq > 7 ? 7 : iq;
     return (uint8_t)((ii ^ (ii >> 1)) | ((iq ^ (iq >> 1)) << 3));
 }
+// four carrier bytes (6 valid bits each) -> 24 contiguous bits
+__device__ __forceinline__ uint32_t pack4x6(uint32_t x)
+{
+    const uint32_t t = (x & 0x003F003Fu) | ((x >> 2) & 0x0FC00FC0u);
+    return (t & 0xFFFu) | ((t >> 4) & 0xFFF000u);
+}
 __device__ __forceinline__ uint32_t demap_qam64_lut(float re, float im, uint32_t lut_saddr, float k = 0.4375f)
 {
     const float ti = __saturatef(fmaf(re, k, 0.5f));                // k = 3.5 / 8 x (1 / scale of the point)
@@ -516,13 +522,23 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
             static_assert((3 * NB) % 6 == 0, "3 output bytes must span whole carriers");
             const int c0 = pbase / 6, sh = pbase - 6 * c0;
             const uint8_t *cp = s_car + c0 + (NB / 2) * tid;
-            for (int u = 3 * tid; u < nbytes; u += 3 * kDecThreads, cp += (NB / 2) * kDecThreads) {
-                uint32_t lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
-                uint32_t hi = 0;
+            // FEC: the 8 carrier bytes come from 3 aligned words + 2 byte permutes (the per-iteration stride is a multiple
+            // of 4, so a thread's byte alignment -- the permute selector -- never changes) instead of 8 byte loads
+            const uint32_t cp_s = (uint32_t)__cvta_generic_to_shared(cp);
+            uint32_t wa = cp_s & ~3u;
+            const uint32_t sel = 0x3210u + 0x1111u * (cp_s & 3u);
+            static_assert(((NB / 2) * kDecThreads) % 4 == 0, "carrier stride per iteration must keep the word alignment");
+            for (int u = 3 * tid; u < nbytes; u += 3 * kDecThreads, cp += (NB / 2) * kDecThreads, wa += (NB / 2) * kDecThreads) {
+                uint32_t lo, hi = 0;
                 if (NC > 5) {
-                    uint32_t b5 = cp[5];
-                    lo |= b5 << 30;
-                    hi = (b5 >> 2) | (cp[6] << 4) | (cp[7] << 10);
+                    uint32_t w0, w1, w2;
+                    asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                                 : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(wa));
+                    const uint32_t p0 = pack4x6(__byte_perm(w0, w1, sel)), p1 = pack4x6(__byte_perm(w1, w2, sel));
+                    lo = p0 | (p1 << 24);
+                    hi = p1 >> 8;
+                } else {
+                    lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
                 }
                 lo = __funnelshift_r(lo, hi, sh);
                 hi >>= sh;
