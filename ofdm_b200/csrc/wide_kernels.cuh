@@ -234,16 +234,25 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
         // 3 output bytes per thread: 42 (Hamming) or 24 stream bits = 7 or 4 six-bit carriers (+1 for the bit shift)
         constexpr int NC = (3 * NB + 5) / 6 + 1;
         uint8_t *o0 = out + j0;
-        for (int u = 3 * tid; u < nbytes; u += 3 * kThreads) {
-            const int p = pbase + u * NB;
-            const int c = p / 6, sh = p - 6 * c;
-            const uint8_t *cp = s_car + c;
-            uint32_t lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
-            uint32_t hi = 0;
+        // as in rx_decode_kernel: 3 NB bits = whole carriers -> one bit shift per tile; with FEC the 8 carrier bytes come
+        // from 3 aligned shared words + 2 byte permutes (a thread's byte alignment never changes: stride % 4 == 0)
+        static_assert((3 * NB) % 6 == 0 && ((NB / 2) * kThreads) % 4 == 0, "whole carriers per 3 bytes, word-aligned stride");
+        const int c0 = pbase / 6, sh = pbase - 6 * c0;
+        const uint8_t *cp = s_car + c0 + (NB / 2) * tid;
+        const uint32_t cp_s = (uint32_t)__cvta_generic_to_shared(cp);
+        uint32_t wa = cp_s & ~3u;
+        const uint32_t sel = 0x3210u + 0x1111u * (cp_s & 3u);
+        for (int u = 3 * tid; u < nbytes; u += 3 * kThreads, cp += (NB / 2) * kThreads, wa += (NB / 2) * kThreads) {
+            uint32_t lo, hi = 0;
             if (NC > 5) {
-                uint32_t b5 = cp[5];
-                lo |= b5 << 30;
-                hi = (b5 >> 2) | (cp[6] << 4) | (cp[7] << 10);
+                uint32_t x0, x1, x2;
+                asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                             : "=r"(x0), "=r"(x1), "=r"(x2) : "r"(wa));
+                const uint32_t p0 = pack4x6(__byte_perm(x0, x1, sel)), p1 = pack4x6(__byte_perm(x1, x2, sel));
+                lo = p0 | (p1 << 24);
+                hi = p1 >> 8;
+            } else {
+                lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
             }
             lo = __funnelshift_r(lo, hi, sh);
             hi >>= sh;
