@@ -11,14 +11,18 @@ LIB_PATH = os.path.join(_HERE, "libofdm_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
+    "-Xcompiler", "-fPIC", "-diag-suppress", "177",
 ]
+# one translation unit per kernel family (csrc/kernels.h) + the C ABI; compiled in parallel, linked into one library
+UNITS = ["rx64_m2", "wide_rx_m2", "rx64_m0", "rx64_m1", "wide_rx_m0", "wide_rx_m1", "wide_tx", "tx64", "rx64", "wide_rx",
+         "rs", "sync", "ofdm_engine"]
+OBJ_DIR = os.path.join(_HERE, "build")
 
 
 def _sources():
     out = [os.path.join(ROOT, "include", "ofdm_engine.h")]
     for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".cu", ".cuh", ".h")):
+        if f.endswith((".cu", ".cuh", ".h", ".inc")):
             out.append(os.path.join(CSRC, f))
     return out
 
@@ -30,19 +34,45 @@ def engine_is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build_engine(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> ofdm_b200/libofdm_b200.so (cross-compiles without a GPU)."""
+def _unit_deps(unit: str):
+    """Headers a unit really includes (every unit sees kernels.h, which pulls in all .cuh files)."""
+    deps = [os.path.join(CSRC, unit + ".cu"), os.path.join(ROOT, "include", "ofdm_engine.h")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
+    return deps
+
+
+def build_engine(force: bool = False, verbose: bool = False, units=None) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> ofdm_b200/libofdm_b200.so (cross-compiles without a GPU).
+
+    Every unit of UNITS is compiled to ofdm_b200/build/<unit>.o by its own nvcc process (in parallel), then linked."""
     if not force and not engine_is_stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-o", LIB_PATH, os.path.join(CSRC, "ofdm_engine.cu")]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_unit(unit):
+        obj = os.path.join(OBJ_DIR, unit + ".o")
+        if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(d) for d in _unit_deps(unit)):
+            return unit, 0, ""
+        cmd = [nvcc, *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-c", "-o", obj, os.path.join(CSRC, unit + ".cu")]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return unit, r.returncode, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(UNITS), os.cpu_count() or 1))) as ex:
+        results = list(ex.map(compile_unit, units or UNITS))
+    for unit, rc, log in results:
+        if rc != 0:
+            raise RuntimeError(f"nvcc failed on {unit}.cu:\n{log}")
+        if verbose and log:
+            print(f"==== {unit}.cu\n{log}")
+    objs = [os.path.join(OBJ_DIR, u + ".o") for u in UNITS]
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB_PATH, *objs],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 

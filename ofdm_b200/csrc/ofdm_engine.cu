@@ -10,13 +10,8 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
-#include "rx_kernels.cuh"
+#include "kernels.h"
 #include "tables.h"
-#include "sync_kernels.cuh"
-#include "tx_kernels.cuh"
-#include "wide_kernels.cuh"
-#include "rs_kernels.cuh"
 
 using namespace ofdm;
 
@@ -84,122 +79,6 @@ struct ofdm_engine {
         cudaError_t _e = (call);                                                                 \
         if (_e != cudaSuccess) ENG_FAIL(h, OFDM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
     } while (0)
-
-// ---- kernel dispatch ---------------------------------------------------------------------------------------------
-typedef void (*DecodeKernel)(const RxArgs);
-typedef void (*AcquireKernel)(const RxArgs);
-typedef void (*TxKernel)(const TxArgs);
-
-template <int MOD, bool GUARD, bool FEC, int PHASE>
-static DecodeKernel pick_decode_pts(bool points)
-{
-    return points ? (DecodeKernel)rx_decode_kernel<MOD, GUARD, FEC, PHASE, true> : (DecodeKernel)rx_decode_kernel<MOD, GUARD, FEC, PHASE, false>;
-}
-template <int MOD, bool GUARD, bool FEC>
-static DecodeKernel pick_decode_phase(int phase, bool points)
-{
-    return phase ? pick_decode_pts<MOD, GUARD, FEC, 1>(points) : pick_decode_pts<MOD, GUARD, FEC, 0>(points);
-}
-template <int MOD>
-static DecodeKernel pick_decode_mod(bool guard, bool fec, int phase, bool points)
-{
-    if (guard) return fec ? pick_decode_phase<MOD, true, true>(phase, points) : pick_decode_phase<MOD, true, false>(phase, points);
-    return fec ? pick_decode_phase<MOD, false, true>(phase, points) : pick_decode_phase<MOD, false, false>(phase, points);
-}
-static DecodeKernel pick_decode(const ofdm_cfg &c, bool points)
-{
-    switch (c.modulation) {
-    case 0: return pick_decode_mod<0>(c.guard_bands, c.fec, c.phase_mode, points);
-    case 1: return pick_decode_mod<1>(c.guard_bands, c.fec, c.phase_mode, points);
-    default: return pick_decode_mod<2>(c.guard_bands, c.fec, c.phase_mode, points);
-    }
-}
-
-template <int MOD, bool GUARD>
-static AcquireKernel pick_acquire_phase(int phase)
-{
-    return phase ? (AcquireKernel)rx_acquire_kernel<MOD, GUARD, 1> : (AcquireKernel)rx_acquire_kernel<MOD, GUARD, 0>;
-}
-static AcquireKernel pick_acquire(const ofdm_cfg &c)
-{
-    switch (c.modulation) {
-    case 0: return c.guard_bands ? pick_acquire_phase<0, true>(c.phase_mode) : pick_acquire_phase<0, false>(c.phase_mode);
-    case 1: return c.guard_bands ? pick_acquire_phase<1, true>(c.phase_mode) : pick_acquire_phase<1, false>(c.phase_mode);
-    default: return c.guard_bands ? pick_acquire_phase<2, true>(c.phase_mode) : pick_acquire_phase<2, false>(c.phase_mode);
-    }
-}
-
-template <int MOD, bool WRITE>
-static TxKernel pick_tx_mod(bool guard, bool fec)
-{
-    if (guard) return fec ? (TxKernel)tx_tile_kernel<MOD, true, true, WRITE> : (TxKernel)tx_tile_kernel<MOD, true, false, WRITE>;
-    return fec ? (TxKernel)tx_tile_kernel<MOD, false, true, WRITE> : (TxKernel)tx_tile_kernel<MOD, false, false, WRITE>;
-}
-template <bool WRITE>
-static TxKernel pick_tx(const ofdm_cfg &c)
-{
-    switch (c.modulation) {
-    case 0: return pick_tx_mod<0, WRITE>(c.guard_bands, c.fec);
-    case 1: return pick_tx_mod<1, WRITE>(c.guard_bands, c.fec);
-    default: return pick_tx_mod<2, WRITE>(c.guard_bands, c.fec);
-    }
-}
-
-// ---- nfft = 1024 dispatch -----------------------------------------------------------------------------------------------
-typedef void (*WDecodeKernel)(const wide::WideRxArgs);
-typedef void (*WTxKernel)(const wide::WideTxArgs);
-template <int MOD, bool GUARD, bool FEC, int PHASE>
-static WDecodeKernel wpick_decode_pts(bool points)
-{
-    return points ? (WDecodeKernel)wide::wide_decode_kernel<MOD, GUARD, FEC, PHASE, true> : (WDecodeKernel)wide::wide_decode_kernel<MOD, GUARD, FEC, PHASE, false>;
-}
-template <int MOD, bool GUARD, bool FEC>
-static WDecodeKernel wpick_decode_phase(int phase, bool points)
-{
-    return phase ? wpick_decode_pts<MOD, GUARD, FEC, 1>(points) : wpick_decode_pts<MOD, GUARD, FEC, 0>(points);
-}
-template <int MOD>
-static WDecodeKernel wpick_decode_mod(bool guard, bool fec, int phase, bool points)
-{
-    if (guard) return fec ? wpick_decode_phase<MOD, true, true>(phase, points) : wpick_decode_phase<MOD, true, false>(phase, points);
-    return fec ? wpick_decode_phase<MOD, false, true>(phase, points) : wpick_decode_phase<MOD, false, false>(phase, points);
-}
-static WDecodeKernel wpick_decode(const ofdm_cfg &c, bool points)
-{
-    switch (c.modulation) {
-    case 0: return wpick_decode_mod<0>(c.guard_bands, c.fec, c.phase_mode, points);
-    case 1: return wpick_decode_mod<1>(c.guard_bands, c.fec, c.phase_mode, points);
-    default: return wpick_decode_mod<2>(c.guard_bands, c.fec, c.phase_mode, points);
-    }
-}
-template <int MOD, bool GUARD>
-static WDecodeKernel wpick_acquire_phase(int phase)
-{
-    return phase ? (WDecodeKernel)wide::wide_acquire_kernel<MOD, GUARD, 1> : (WDecodeKernel)wide::wide_acquire_kernel<MOD, GUARD, 0>;
-}
-static WDecodeKernel wpick_acquire(const ofdm_cfg &c)
-{
-    switch (c.modulation) {
-    case 0: return c.guard_bands ? wpick_acquire_phase<0, true>(c.phase_mode) : wpick_acquire_phase<0, false>(c.phase_mode);
-    case 1: return c.guard_bands ? wpick_acquire_phase<1, true>(c.phase_mode) : wpick_acquire_phase<1, false>(c.phase_mode);
-    default: return c.guard_bands ? wpick_acquire_phase<2, true>(c.phase_mode) : wpick_acquire_phase<2, false>(c.phase_mode);
-    }
-}
-template <int MOD, bool WRITE>
-static WTxKernel wpick_tx_mod(bool guard, bool fec)
-{
-    if (guard) return fec ? (WTxKernel)wide::wide_tx_kernel<MOD, true, true, WRITE> : (WTxKernel)wide::wide_tx_kernel<MOD, true, false, WRITE>;
-    return fec ? (WTxKernel)wide::wide_tx_kernel<MOD, false, true, WRITE> : (WTxKernel)wide::wide_tx_kernel<MOD, false, false, WRITE>;
-}
-template <bool WRITE>
-static WTxKernel wpick_tx(const ofdm_cfg &c)
-{
-    switch (c.modulation) {
-    case 0: return wpick_tx_mod<0, WRITE>(c.guard_bands, c.fec);
-    case 1: return wpick_tx_mod<1, WRITE>(c.guard_bands, c.fec);
-    default: return wpick_tx_mod<2, WRITE>(c.guard_bands, c.fec);
-    }
-}
 
 // ---- sizes -------------------------------------------------------------------------------------------------------
 static int cfg_bpc(const ofdm_cfg *c) { return c->modulation == 0 ? 1 : (c->modulation == 1 ? 2 : 6); }
@@ -423,8 +302,8 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         w.iq = reinterpret_cast<float2 *>(iq); w.iq_stride = iq_stride; w.frame_len = d_flen; w.stream_max = d_max; w.tables = h->d_wtables;
         const long max_syms = (long)iq_stride / wide::kL - 10;
         const uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + 7) / 8) : 1;
-        wpick_tx<false>(h->cfg)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
-        wpick_tx<true>(h->cfg)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
+        wpick_tx(h->cfg, false)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
+        wpick_tx(h->cfg, true)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
         h->launches += 2;
         CU(h, cudaGetLastError());
         if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
@@ -437,8 +316,8 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     // two passes over the same tiles: maximum for `normalize`, then recompute + store once (8 B/sample written)
     const long max_syms = (long)iq_stride / 80 - 10;
     uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + h->tile_shift + kTxTileSyms - 1) / kTxTileSyms) : 1;
-    pick_tx<false>(h->cfg)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
-    pick_tx<true>(h->cfg)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
+    pick_tx(h->cfg, false)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
+    pick_tx(h->cfg, true)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
     h->launches += 2;
     CU(h, cudaGetLastError());
     if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
@@ -702,8 +581,8 @@ static int channel_device(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t *t
     a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
     uint32_t gx = (rx_stride + 256 * 8 - 1) / (256 * 8);
     if (gx < 1) gx = 1;
-    channel_conv_kernel<<<dim3(gx, n_streams), 256, 0, st>>>(a);
-    channel_noise_kernel<<<dim3(gx, n_streams), 256, 0, st>>>(a);
+    channel_conv_fn()<<<dim3(gx, n_streams), 256, 0, st>>>(a);
+    channel_noise_fn()<<<dim3(gx, n_streams), 256, 0, st>>>(a);
     h->launches += 2;
     CU(h, cudaGetLastError());
     return 0;
@@ -755,12 +634,12 @@ static int sync_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_pea
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const uint32_t grid = a.n_tiles < (uint32_t)(2 * sms) ? a.n_tiles : (uint32_t)(2 * sms);    // persistent: 2 CTAs per SM
-        if (h->smem_configured.insert((const void *)sync_scan_kernel).second)
-            CU(h, cudaFuncSetAttribute((const void *)sync_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_scan_smem_bytes()));
-        sync_scan_kernel<<<grid, kScanRows, sync_scan_smem_bytes(), st>>>(a);
-        sync_select_kernel<<<1, 1024, 0, st>>>(a);
+        if (h->smem_configured.insert((const void *)sync_scan_fn()).second)
+            CU(h, cudaFuncSetAttribute((const void *)sync_scan_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_scan_smem_bytes()));
+        sync_scan_fn()<<<grid, kScanRows, sync_scan_smem_bytes(), st>>>(a);
+        sync_select_fn()<<<1, 1024, 0, st>>>(a);
         const uint32_t rg = max_peaks < (uint32_t)kSyncCandCap ? max_peaks : (uint32_t)kSyncCandCap;
-        if (rg) sync_refine_kernel<<<rg, kAcqThreads, 0, st>>>(a);
+        if (rg) sync_refine_fn()<<<rg, kAcqThreads, 0, st>>>(a);
         h->launches += 3;
     }
     CU(h, cudaGetLastError());
@@ -805,7 +684,7 @@ static int capture_decode_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n
     CU(h, h->cap_base.ensure((sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)n_frames));
     uint64_t *base = h->cap_base.as<uint64_t>();
     uint32_t *ns = reinterpret_cast<uint32_t *>(base + n_frames);
-    capture_prep_kernel<<<(n_frames + 255) / 256, 256, 0, st>>>(reinterpret_cast<const SyncPeak *>(peaks), n_frames, n, max_frame, base, ns);
+    capture_prep_fn()<<<(n_frames + 255) / 256, 256, 0, st>>>(reinterpret_cast<const SyncPeak *>(peaks), n_frames, n, max_frame, base, ns);
     h->launches += 1;
     uint64_t cap = max_frame ? max_frame : n;
     if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
@@ -868,8 +747,8 @@ static int rs_tables_ready(ofdm_engine *h)
         for (int j = 0; j < kRsT2; j++) t->lfsr[f][j] = mul((unsigned)f, g[j + 1]);
     CU(h, h->rs_tables.ensure(sizeof(RsTables)));
     CU(h, cudaMemcpy(h->rs_tables.p, host.data(), sizeof(RsTables), cudaMemcpyHostToDevice));
-    CU(h, cudaFuncSetAttribute(rs_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes));
-    CU(h, cudaFuncSetAttribute(rs_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes));
+    CU(h, cudaFuncSetAttribute((const void *)rs_encode_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes));
+    CU(h, cudaFuncSetAttribute((const void *)rs_decode_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes));
     return 0;
 }
 
@@ -896,8 +775,8 @@ static int rs_run(ofdm_engine *h, bool encode, const uint8_t *in, const uint32_t
         if (!encode) {
             CU(h, cudaMemsetAsync(n_corrected, 0, sizeof(uint32_t) * (size_t)n_streams, st));
             CU(h, cudaMemsetAsync(n_failed, 0, sizeof(uint32_t) * (size_t)n_streams, st));
-            rs_decode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
-        } else rs_encode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+            rs_decode_fn()<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+        } else rs_encode_fn()<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
         h->launches += 1;
         CU(h, cudaGetLastError());
         return 0;
@@ -912,8 +791,8 @@ static int rs_run(ofdm_engine *h, bool encode, const uint8_t *in, const uint32_t
     CU(h, cudaMemcpyAsync(d_il, in_len, lb, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemsetAsync(d_nc, 0, 2 * lb, st));
     a.in = h->s_bytes.as<uint8_t>(); a.in_len = d_il; a.out = h->s_bytes2.as<uint8_t>(); a.out_len = d_ol; a.n_corrected = d_nc; a.n_failed = d_nf;
-    if (encode) rs_encode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
-    else rs_decode_kernel<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+    if (encode) rs_encode_fn()<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
+    else rs_decode_fn()<<<grid, kRsThreads, kRsSmemBytes, st>>>(a);
     h->launches += 1;
     CU(h, cudaGetLastError());
     CU(h, cudaMemcpyAsync(out, h->s_bytes2.p, ob, cudaMemcpyDeviceToHost, st));
@@ -953,7 +832,7 @@ extern "C" int ofdm_ber_accumulate(ofdm_engine *h, const uint8_t *ref, const uin
     if (mem == OFDM_MEM_DEVICE) {
         a.ref = ref; a.ref_len = ref_len; a.got = got; a.got_len = got_len; a.status = status;
         a.counters = reinterpret_cast<unsigned long long *>(counters);
-        ber_kernel<<<n_streams, 256, 0, (cudaStream_t)stream>>>(a);
+        ber_fn()<<<n_streams, 256, 0, (cudaStream_t)stream>>>(a);
         h->launches += 1;
         CU(h, cudaGetLastError());
         return 0;
@@ -973,7 +852,7 @@ extern "C" int ofdm_ber_accumulate(ofdm_engine *h, const uint8_t *ref, const uin
     CU(h, cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(uint64_t), st));
     a.ref = h->s_bytes.as<uint8_t>(); a.ref_len = d_rl; a.got = h->s_bytes2.as<uint8_t>(); a.got_len = d_gl; a.status = d_st;
     a.counters = h->counters.as<unsigned long long>();
-    ber_kernel<<<n_streams, 256, 0, st>>>(a);
+    ber_fn()<<<n_streams, 256, 0, st>>>(a);
     h->launches += 1;
     CU(h, cudaGetLastError());
     uint64_t tmp[4];

@@ -196,6 +196,7 @@ __device__ __forceinline__ void rs_load_tables(const RsTables *t, uint4 *s_lfsr,
 }
 
 // ---- encode: data bytes -> [223 data | 32 parity] blocks; the partial (possibly empty) tail block is always emitted -------
+template <int = 0>
 __global__ void __launch_bounds__(kRsThreads) rs_encode_kernel(const RsArgs a)
 {
     extern __shared__ __align__(128) uint8_t rs_smem[];
@@ -253,7 +254,7 @@ struct RsGf {
 // Corrects the 223 data bytes at `data` (already written, uncorrected) from the remainder rem[0..32) of the 255-byte word
 // (rem[0] = coefficient of x^31); errors in the parity bytes are counted but need no patch.
 // Returns the number of corrected symbols or -1 (more than 16 symbol errors: `correct` fails, src/utils.rs:165).
-__device__ __noinline__ int rs_correct_from_remainder(uint8_t *data, const uint8_t *rem, const RsGf gf)
+static __device__ __noinline__ int rs_correct_from_remainder(uint8_t *data, const uint8_t *rem, const RsGf gf)
 {
     uint8_t S[kRsT2];
     for (uint32_t i = 0; i < kRsT2; i++) {                          // S_i = r(alpha^i) = rem(alpha^i)
@@ -319,6 +320,7 @@ __device__ __noinline__ int rs_correct_from_remainder(uint8_t *data, const uint8
     return nerr;
 }
 
+template <int = 0>
 __global__ void __launch_bounds__(kRsThreads) rs_decode_kernel(const RsArgs a)
 {
     extern __shared__ __align__(128) uint8_t rs_smem[];

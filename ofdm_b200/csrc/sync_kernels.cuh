@@ -81,6 +81,7 @@ __device__ __forceinline__ void scan_tile_load(const SyncArgs &a, long long tile
     }
 }
 
+template <int = 0>
 __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(kScanRows, 2) sync_scan_kernel(const SyncArgs 
 }
 
 // sort candidates (bitonic, one CTA), then keep the first of every frame (hold-off)
+template <int = 0>
 __global__ void __launch_bounds__(1024) sync_select_kernel(const SyncArgs a)
 {
     __shared__ uint32_t s_key[kSyncCandCap];
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(1024) sync_select_kernel(const SyncArgs a)
 }
 
 // one CTA per accepted detection: refinement + CFO (docs/SPEC.md 4, 5)
+template <int = 0>
 __global__ void __launch_bounds__(kAcqThreads) sync_refine_kernel(const SyncArgs a)
 {
     __shared__ float s_lock[kSym];
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(kAcqThreads) sync_refine_kernel(const SyncArgs
 }
 
 // per detected frame: where its capture starts and how many samples belong to it (up to the next frame / max_frame)
+template <int = 0>
 __global__ void capture_prep_kernel(const SyncPeak *__restrict__ peaks, uint32_t n_frames, uint64_t n, uint32_t max_frame,
                                     uint64_t *__restrict__ base, uint32_t *__restrict__ n_samples)
 {

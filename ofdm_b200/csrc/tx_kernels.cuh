@@ -267,9 +267,10 @@ __device__ __forceinline__ void chan_stream_draws(const ChanArgs &a, uint32_t st
     cfo = a.cfo_max >= 0.0f ? u01_from_u32(c[1]) * a.cfo_max : -1.0f;
 }
 
-__constant__ float kChanTaps[12] = { -0.0f, -0.1912f, 0.9316f, 0.2821f, -0.1990f, 0.1630f, -0.1017f, 0.0544f, -0.0261f, 0.0090f, 0.0f, -0.0034f };
+static __constant__ float kChanTaps[12] = { -0.0f, -0.1912f, 0.9316f, 0.2821f, -0.1990f, 0.1630f, -0.1017f, 0.0544f, -0.0261f, 0.0090f, 0.0f, -0.0034f };
 
 // multipath (src/channel.rs:26-31,45) + CFO (src/channel.rs:54-62) + lead-in; accumulates the signal statistics
+template <int = 0>
 __global__ void __launch_bounds__(256) channel_conv_kernel(const ChanArgs a)
 {
     const uint32_t stream = blockIdx.y;
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(256) channel_conv_kernel(const ChanArgs a)
 
 // noise (src/channel.rs:66-71): mode 0 = reference-faithful (complex "variance", uniform draws); mode 1 = Gaussian AWGN.
 // The lead-in carries noise too (a receiver never sees an exactly silent channel).
+template <int = 0>
 __global__ void __launch_bounds__(256) channel_noise_kernel(const ChanArgs a)
 {
     const uint32_t stream = blockIdx.y;
@@ -377,6 +379,7 @@ struct BerArgs {
     unsigned long long *counters;   // bit_errs, byte_errs, bits_compared, frames_failed
 };
 
+template <int = 0>
 __global__ void __launch_bounds__(256) ber_kernel(const BerArgs a)
 {
     const uint32_t stream = blockIdx.x;
