@@ -22,6 +22,10 @@
  *    src/receiver.rs:25,27-29,87-89).
  *  - There is no CPU fallback: without a CUDA device ofdm_engine_create fails.
  *  - A handle is not thread-safe; use one handle per GPU / host thread. No global state.
+ *  - A handle owns ONE set of device scratch (per-stream state, staging, candidate lists): it supports one call in flight
+ *    at a time. OFDM_MEM_DEVICE calls issued on different CUDA streams with the same handle must be ordered by the caller
+ *    (events) -- or use one handle per stream. Scratch grows on demand with cudaFree + cudaMalloc, which synchronises the
+ *    device; ofdm_engine_reserve sizes it once so that steady-state calls only enqueue work.
  */
 #ifndef OFDM_ENGINE_H
 #define OFDM_ENGINE_H
@@ -109,6 +113,9 @@ const char *ofdm_status_name(int32_t status);
 int  ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine **out);
 void ofdm_engine_destroy(ofdm_engine *h);
 const char *ofdm_last_error(const ofdm_engine *h);        /* h may be NULL: error of the last failed create */
+/* Pre-size the handle's device scratch for batches of up to max_streams streams / frames and captures of up to
+ * max_capture_samples samples (0 = leave as is), so that later OFDM_MEM_DEVICE calls never allocate. */
+int  ofdm_engine_reserve(ofdm_engine *h, uint32_t max_streams, uint64_t max_capture_samples);
 int  ofdm_get_tables(const ofdm_engine *h, ofdm_fc32 *locking80, ofdm_fc32 *preamble80, ofdm_fc32 *training64);
 
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
@@ -158,7 +165,11 @@ int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t
  * 8 B/sample pass of the sliding Schmidl-Cox metric (docs/SPEC.md 4): every frame start is reported once as
  * (offset by the lag-1 rule, CFO estimate, metric). n_samples < 2^32. peaks[0 .. *n_peaks) is in ascending offset order;
  * with OFDM_MEM_DEVICE entries whose metric < 0 are unusable detections (frame head cut by the capture end) and
- * *n_peaks counts them too; with OFDM_MEM_HOST they are removed. More than max_peaks detections are truncated.
+ * *n_peaks counts them too; with OFDM_MEM_HOST they are removed. More than max_peaks detections are truncated:
+ * *n_peaks = min(detections, max_peaks) in both modes, so it can be handed to ofdm_rx_decode_capture as it is.
+ * ofdm_sync_counts (waits for `stream`) tells a device-mode caller whether that happened: counts[0] = threshold crossings the
+ * scan recorded, counts[1] = frames detected after the hold-off, counts[2] = entries written to peaks[];
+ * counts[1] > counts[2] means peaks[] was too small.
  */
 typedef struct {
     uint64_t offset;
@@ -167,6 +178,7 @@ typedef struct {
 } ofdm_peak;
 int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, ofdm_peak *peaks, uint32_t max_peaks,
                      uint32_t *n_peaks, int mem, void *stream);
+int ofdm_sync_counts(ofdm_engine *h, uint32_t counts[3], void *stream);
 
 /*
  * Streaming receiver: decode every frame ofdm_sync_search found in one long capture -- the loop of

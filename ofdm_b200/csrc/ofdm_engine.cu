@@ -50,7 +50,7 @@ struct ofdm_engine {
     std::vector<ofdm_fc32> lock, pre, train;
     DevBuf state;                       // StreamState[n_streams] (StreamStateW for nfft = 1024)
     DevBuf scratch_u32;                 // frame_len / stream_max
-    DevBuf scratch_f32;                 // channel accumulators
+    DevBuf scratch_f32;                 // channel accumulators (5 x f64 per stream)
     DevBuf counters;                    // 4 x u64
     DevBuf sync_scratch;                // candidate list + counters of ofdm_sync_search
     DevBuf cap_base;                    // per-frame base / length of ofdm_rx_decode_capture
@@ -79,6 +79,18 @@ struct ofdm_engine {
         cudaError_t _e = (call);                                                                 \
         if (_e != cudaSuccess) ENG_FAIL(h, OFDM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
     } while (0)
+
+// gridDim.y carries the stream index (<= 65535): larger batches are launched in chunks, the kernels add a.stream0
+template <class K, class A>
+static void launch_streams(K k, A a, uint32_t grid_x, uint32_t n_streams, unsigned threads, size_t smem, cudaStream_t st, uint64_t &launches)
+{
+    for (uint32_t s0 = 0; s0 < n_streams; s0 += 65535u) {
+        a.stream0 = s0;
+        const uint32_t ns = n_streams - s0 < 65535u ? n_streams - s0 : 65535u;
+        k<<<dim3(grid_x, ns), threads, smem, st>>>(a);
+        launches++;
+    }
+}
 
 // ---- sizes -------------------------------------------------------------------------------------------------------
 static int cfg_bpc(const ofdm_cfg *c) { return c->modulation == 0 ? 1 : (c->modulation == 1 ? 2 : 6); }
@@ -138,6 +150,9 @@ static int validate_cfg(const ofdm_cfg *c, std::string &err)
         err = "supported layouts: nfft=64/cp=16 (the reference's) and nfft=1024/cp=256 (wideband variant)";
         return OFDM_E_INVALID;
     }
+    if (c->locking)                 // every sync kernel correlates with the real part only (the reference's table is a real ramp)
+        for (uint32_t i = 0; i < c->nfft + c->cp; i++)
+            if (c->locking[i].im != 0.0f) { err = "ofdm_cfg.locking must be real (imaginary parts are not supported by the sync kernels)"; return OFDM_E_INVALID; }
     if (c->modulation > 2 || c->guard_bands > 1 || c->fec > 1 || c->sync_mode > 1 || c->cfo_mode > 1 || c->phase_mode > 1) {
         err = "ofdm_cfg field out of range";
         return OFDM_E_INVALID;
@@ -270,6 +285,20 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
 
 extern "C" const char *ofdm_last_error(const ofdm_engine *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+extern "C" int ofdm_engine_reserve(ofdm_engine *h, uint32_t max_streams, uint64_t max_capture_samples)
+{
+    if (!h) return OFDM_E_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    if (max_streams) {
+        CU(h, h->state.ensure((h->wide ? sizeof(wide::StreamStateW) : sizeof(StreamState)) * (size_t)max_streams));
+        CU(h, h->scratch_u32.ensure(2 * sizeof(uint32_t) * (size_t)max_streams));
+        CU(h, h->scratch_f32.ensure(5 * sizeof(double) * (size_t)max_streams));
+        CU(h, h->cap_base.ensure((sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)max_streams));
+    }
+    if (max_capture_samples) CU(h, h->sync_scratch.ensure(sizeof(uint32_t) * (kSyncCandCap + 8)));
+    return 0;
+}
+
 extern "C" int ofdm_get_tables(const ofdm_engine *h, ofdm_fc32 *locking80, ofdm_fc32 *preamble80, ofdm_fc32 *training64)
 {
     if (!h) return OFDM_E_INVALID;
@@ -302,9 +331,8 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         w.iq = reinterpret_cast<float2 *>(iq); w.iq_stride = iq_stride; w.frame_len = d_flen; w.stream_max = d_max; w.tables = h->d_wtables;
         const long max_syms = (long)iq_stride / wide::kL - 10;
         const uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + 7) / 8) : 1;
-        wpick_tx(h->cfg, false)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
-        wpick_tx(h->cfg, true)<<<dim3(tiles, n_streams), wide::kThreads, 0, st>>>(w);
-        h->launches += 2;
+        launch_streams(wpick_tx(h->cfg, false), w, tiles, n_streams, wide::kThreads, 0, st, h->launches);
+        launch_streams(wpick_tx(h->cfg, true), w, tiles, n_streams, wide::kThreads, 0, st, h->launches);
         CU(h, cudaGetLastError());
         if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
         return 0;
@@ -316,9 +344,8 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     // two passes over the same tiles: maximum for `normalize`, then recompute + store once (8 B/sample written)
     const long max_syms = (long)iq_stride / 80 - 10;
     uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + h->tile_shift + kTxTileSyms - 1) / kTxTileSyms) : 1;
-    pick_tx(h->cfg, false)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
-    pick_tx(h->cfg, true)<<<dim3(tiles, n_streams), kTxThreads, 0, st>>>(a);
-    h->launches += 2;
+    launch_streams(pick_tx(h->cfg, false), a, tiles, n_streams, kTxThreads, 0, st, h->launches);
+    launch_streams(pick_tx(h->cfg, true), a, tiles, n_streams, kTxThreads, 0, st, h->launches);
     CU(h, cudaGetLastError());
     if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -396,8 +423,7 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
             const size_t smem = wide::wide_decode_smem(h->cfg.guard_bands != 0);
             if (h->smem_configured.insert((const void *)kd).second)
                 CU(h, cudaFuncSetAttribute((const void *)kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kd<<<dim3(tiles, n_streams), wide::kThreads, smem, st>>>(w);
-            h->launches += 1;
+            launch_streams(kd, w, tiles, n_streams, wide::kThreads, smem, st, h->launches);
         }
         if (prof) CU(h, cudaEventRecord(pe[2], st));
         CU(h, cudaGetLastError());
@@ -440,8 +466,7 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         const size_t smem = h->cfg.guard_bands ? rx_decode_smem_bytes<true>() : rx_decode_smem_bytes<false>();
         if (h->smem_configured.insert((const void *)k).second)
             CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<dim3(tiles, n_streams), kDecThreads, smem, st>>>(a);
-        h->launches += 1;
+        launch_streams(k, a, tiles, n_streams, kDecThreads, smem, st, h->launches);
     }
     if (prof) CU(h, cudaEventRecord(pe[2], st));
     CU(h, cudaGetLastError());
@@ -490,7 +515,6 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
     if (!h) return OFDM_E_INVALID;
     if (!iq || !n_samples || !out || !out_len || !status || n_streams == 0 || iq_stride == 0)
         ENG_FAIL(h, OFDM_E_INVALID, "rx: bad arguments");
-    if (n_streams > 65535) ENG_FAIL(h, OFDM_E_INVALID, "rx: at most 65535 streams per call");
     CU(h, cudaSetDevice(h->device));
     if (mem == OFDM_MEM_DEVICE)
         return rx_device(h, iq, n_samples, n_streams, iq_stride, max_n_samples, out, out_stride, out_len, status, diag, (cudaStream_t)stream);
@@ -570,20 +594,19 @@ static int channel_device(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t *t
                           const ofdm_channel_params *p, ofdm_fc32 *rx, uint32_t rx_stride, uint32_t *rx_len,
                           uint32_t *lead_out, float *cfo_out, cudaStream_t st)
 {
-    CU(h, h->scratch_f32.ensure(5 * sizeof(float) * (size_t)n_streams));
-    CU(h, cudaMemsetAsync(h->scratch_f32.p, 0, 5 * sizeof(float) * (size_t)n_streams, st));
+    CU(h, h->scratch_f32.ensure(5 * sizeof(double) * (size_t)n_streams));
+    CU(h, cudaMemsetAsync(h->scratch_f32.p, 0, 5 * sizeof(double) * (size_t)n_streams, st));
     ChanArgs a{};
     a.tx = reinterpret_cast<const float2 *>(tx); a.tx_len = tx_len; a.tx_stride = tx_stride; a.n_streams = n_streams;
     a.rx = reinterpret_cast<float2 *>(rx); a.rx_stride = rx_stride; a.rx_len = rx_len; a.lead_out = lead_out; a.cfo_out = cfo_out;
-    a.accum = h->scratch_f32.as<float>();
+    a.accum = h->scratch_f32.as<double>();
     a.snr_lin = powf(10.0f, p->snr_db / 10.0f);
     a.cfo_max = p->cfo_max; a.lead_min = p->lead_min; a.lead_max = p->lead_max; a.multipath = p->multipath; a.noise_mode = p->noise_mode;
     a.seed_lo = (uint32_t)p->seed; a.seed_hi = (uint32_t)(p->seed >> 32);
     uint32_t gx = (rx_stride + 256 * 8 - 1) / (256 * 8);
     if (gx < 1) gx = 1;
-    channel_conv_fn()<<<dim3(gx, n_streams), 256, 0, st>>>(a);
-    channel_noise_fn()<<<dim3(gx, n_streams), 256, 0, st>>>(a);
-    h->launches += 2;
+    launch_streams(channel_conv_fn(), a, gx, n_streams, 256, 0, st, h->launches);
+    launch_streams(channel_noise_fn(), a, gx, n_streams, 256, 0, st, h->launches);
     CU(h, cudaGetLastError());
     return 0;
 }
@@ -595,7 +618,6 @@ extern "C" int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, con
 {
     if (!h) return OFDM_E_INVALID;
     if (!tx || !tx_len || !p || !rx || !rx_len || n_streams == 0) ENG_FAIL(h, OFDM_E_INVALID, "channel: bad arguments");
-    if (n_streams > 65535) ENG_FAIL(h, OFDM_E_INVALID, "channel: at most 65535 streams per call");
     CU(h, cudaSetDevice(h->device));
     if (mem == OFDM_MEM_DEVICE)
         return channel_device(h, tx, tx_len, tx_stride, n_streams, p, rx, rx_stride, rx_len, lead_out, cfo_out, (cudaStream_t)stream);
@@ -643,7 +665,7 @@ static int sync_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_pea
         h->launches += 3;
     }
     CU(h, cudaGetLastError());
-    // *n_peaks = min(accepted, max_peaks); a candidate overflow is reported through ofdm_sync_candidates()
+    // *n_peaks = min(detections, max_peaks) (clamped on the device); ofdm_sync_counts() reports truncation / overflow
     CU(h, cudaMemcpyAsync(n_peaks, a.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -677,6 +699,18 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
     return 0;
 }
 
+extern "C" int ofdm_sync_counts(ofdm_engine *h, uint32_t counts[3], void *stream)
+{
+    if (!h || !counts) return OFDM_E_INVALID;
+    if (!h->sync_scratch.p) ENG_FAIL(h, OFDM_E_INVALID, "sync counts: no ofdm_sync_search has run on this handle");
+    CU(h, cudaSetDevice(h->device));
+    uint32_t c[3] = { 0, 0, 0 };
+    CU(h, cudaMemcpyAsync(c, h->sync_scratch.as<uint32_t>() + kSyncCandCap, sizeof c, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(h, cudaStreamSynchronize((cudaStream_t)stream));
+    counts[0] = c[0]; counts[1] = c[2]; counts[2] = c[1];
+    return 0;
+}
+
 // ---- streaming receiver ------------------------------------------------------------------------------------------
 static int capture_decode_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, const ofdm_peak *peaks, uint32_t n_frames,
                                  uint32_t max_frame, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status, cudaStream_t st)
@@ -698,7 +732,6 @@ extern "C" int ofdm_rx_decode_capture(ofdm_engine *h, const ofdm_fc32 *iq, uint6
     if (!h) return OFDM_E_INVALID;
     if (!iq || !peaks || !out || !out_len || !status) ENG_FAIL(h, OFDM_E_INVALID, "capture decode: bad arguments");
     if (n_frames == 0) return 0;
-    if (n_frames > 65535) ENG_FAIL(h, OFDM_E_INVALID, "capture decode: at most 65535 frames per call");
     CU(h, cudaSetDevice(h->device));
     if (mem == OFDM_MEM_DEVICE)
         return capture_decode_device(h, iq, n_samples, peaks, n_frames, max_frame_samples, out, out_stride, out_len, status, (cudaStream_t)stream);
@@ -781,6 +814,8 @@ static int rs_run(ofdm_engine *h, bool encode, const uint8_t *in, const uint32_t
         CU(h, cudaGetLastError());
         return 0;
     }
+    for (uint32_t s = 0; s < n_streams; s++)
+        if (in_len[s] > in_stride) ENG_FAIL(h, OFDM_E_INVALID, "rs: in_len[%u] exceeds the input stride", s);
     cudaStream_t st = h->own_stream;
     const size_t ib = (size_t)n_streams * in_stride, ob = (size_t)n_streams * out_stride, lb = sizeof(uint32_t) * (size_t)n_streams;
     CU(h, h->s_bytes.ensure(ib));

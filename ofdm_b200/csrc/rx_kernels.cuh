@@ -53,6 +53,7 @@ struct RxArgs {
     int32_t         tile_shift;     // symbols by which tile boundaries are shifted so they fall on Hamming byte boundaries
     int32_t         sync_mode, cfo_mode, fec;   // run-time switches of the (cold) acquisition kernel
     int32_t         tiles_per_cta;  // consecutive tiles of one stream handled by one CTA of the decode kernel
+    uint32_t        stream0;        // decode kernel: first stream of this launch (gridDim.y <= 65535 streams per launch)
     // diag (optional)
     int32_t  *d_offset;
     float    *d_f_delta;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
 
     // A CTA owns `tiles_per_cta` consecutive 224-symbol tiles of one stream. Tile k covers symbols
     // [k*224 - tile_shift, (k+1)*224 - tile_shift) n [0, S): every inner boundary falls on a Hamming byte boundary.
-    const uint32_t stream = blockIdx.y;
+    const uint32_t stream = blockIdx.y + a.stream0;
     const StreamState *st = a.state + stream;
     if (st->status != ST_OK) return;
     const int S = (int)st->n_syms;
@@ -874,13 +875,13 @@ __global__ void __launch_bounds__(kAcq64Threads, kAcq64Ctas) rx_acquire_kernel(c
             const long avail_bytes = (s_rx * BPS) / 8 - 16;
             int stt = ST_OK;
             uint32_t n_syms = 0, out_len = 0;
-            if (hi64 != 0 || (long)lo > avail_bytes || avail_bytes < 0) {
+            if (hi64 != 0 || avail_bytes < 0 || lo > (uint64_t)avail_bytes) {        // unsigned compare: bit 63 of a corrupt length must not pass
                 stt = ST_BAD_HEADER;
             } else {
                 const uint64_t plen = lo;
                 const uint64_t nbits = kHeaderBits + 8 * plen;
                 const uint64_t ncar = (nbits + BPC - 1) / BPC;
-                n_syms = (uint32_t)((ncar + D - 1) / D);
+                n_syms = (uint32_t)((ncar + D - 1) / D);                             // <= s_rx because plen <= avail_bytes
                 out_len = (uint32_t)(FEC ? (8 * plen) / 14 : plen);
                 if (out_len > a.out_stride) { stt = ST_BAD_HEADER; n_syms = 0; out_len = 0; }
             }

@@ -39,7 +39,7 @@ struct SyncArgs {
     const float2 *iq;
     uint64_t n;
     uint32_t *cand;          // [kSyncCandCap] detection lags (unsorted), then sorted + filtered in place
-    uint32_t *counters;      // [0] candidates found, [1] detections accepted (= entries of peaks[])
+    uint32_t *counters;      // [0] threshold crossings found, [1] entries of peaks[] = min(detections, max_peaks), [2] detections
     const RxTables *tables;
     SyncPeak *peaks;
     uint32_t max_peaks;
@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(1024) sync_select_kernel(const SyncArgs a)
             const long long d = s_key[i];
             if (d >= last + kSyncHoldoff) { a.cand[m++] = (uint32_t)d; last = d; }
         }
-        a.counters[1] = m;
+        a.counters[2] = m;                                             // detections before truncation to max_peaks
+        a.counters[1] = m < a.max_peaks ? m : a.max_peaks;             // entries of peaks[] (what *n_peaks reports)
     }
     __syncthreads();
 }

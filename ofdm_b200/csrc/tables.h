@@ -5,8 +5,11 @@
 //   training_signals::<64> src/transmitter.rs:88-96   StdRng(seed 50),  U(-1,1) + jU(-1,1), frequency domain
 //
 // StdRng of rand 0.8 = ChaCha12 (rand_chacha 0.3) keyed by rand_core 0.6's PCG32 expansion of the u64 seed. The
-// crates are not vendored in the reference and nothing in it pins the table values, so this restatement cannot be
-// verified offline; the engine therefore also accepts the three tables as configuration (ofdm_cfg).
+// crates are not vendored in the reference and nothing in it pins the table values. Pinned by known answers
+// (tests/test_abi_host.py::test_tables_stdrng_known_answers): the ChaCha12 block function (published zero-key vector) and
+// StdRng::from_seed -> next_u64 (the two values of rand 0.8's own `test_stdrng_construction`). Not pinned offline: the
+// PCG32 expansion of seed_from_u64 and the u64 -> f64 range conversion; the engine therefore also accepts the three
+// tables as configuration (ofdm_cfg).
 #pragma once
 
 #include <cmath>
@@ -26,6 +29,14 @@ public:
             uint32_t rot = (uint32_t)(seed >> 59);
             key_[i] = rot ? ((xs >> rot) | (xs << (32 - rot))) : xs;
         }
+    }
+    // StdRng::from_seed: the 32 seed bytes are the ChaCha key (little-endian words); used by the known-answer test
+    static StdRng from_seed(const uint8_t seed[32])
+    {
+        StdRng g(0);
+        for (int i = 0; i < 8; i++)
+            g.key_[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+        return g;
     }
     uint64_t next_u64()
     {

@@ -18,6 +18,7 @@ struct TxArgs {
     int            *stream_max;     // per stream: max positive component as float bits (atomicMax on int)
     int32_t         tile_shift;     // Hamming byte alignment of the tile boundaries (same as the decode kernel)
     const RxTables *tables;
+    uint32_t        stream0;        // first stream of this launch (gridDim.y <= 65535 streams per launch)
 };
 
 // byte `B` of the frame byte stream [header 16 B | (Hamming-coded) payload ...] (src/transmitter.rs:37-47, docs/SPEC.md 3)
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
     __shared__ uint8_t s_enc[16];
     __shared__ uint16_t s_enc14[256];                  // payload byte -> its two 7-bit codewords (low nibble first)
 
-    const uint32_t stream = blockIdx.y;
+    const uint32_t stream = blockIdx.y + a.stream0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     const uint32_t n = a.payload_len[stream];
     const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;
@@ -249,13 +250,14 @@ struct ChanArgs {
     uint32_t       *rx_len;
     uint32_t       *lead_out;
     float          *cfo_out;
-    float          *accum;          // per stream: sum re, sum im, sum (y^2).re, sum (y^2).im, sum |y|^2
+    double         *accum;          // per stream (f64): sum re, sum im, sum (y^2).re, sum (y^2).im, sum |y|^2
     float           snr_lin;
     float           cfo_max;
     uint32_t        lead_min, lead_max;
     uint32_t        multipath;
     uint32_t        noise_mode;
     uint32_t        seed_lo, seed_hi;
+    uint32_t        stream0;        // first stream of this launch
 };
 
 __device__ __forceinline__ void chan_stream_draws(const ChanArgs &a, uint32_t stream, uint32_t &lead, float &cfo)
@@ -273,7 +275,7 @@ static __constant__ float kChanTaps[12] = { -0.0f, -0.1912f, 0.9316f, 0.2821f, -
 template <int = 0>
 __global__ void __launch_bounds__(256) channel_conv_kernel(const ChanArgs a)
 {
-    const uint32_t stream = blockIdx.y;
+    const uint32_t stream = blockIdx.y + a.stream0;
     uint32_t lead; float cfo;
     chan_stream_draws(a, stream, lead, cfo);
     const uint32_t n_tx = a.tx_len[stream];
@@ -310,15 +312,18 @@ __global__ void __launch_bounds__(256) channel_conv_kernel(const ChanArgs a)
         }
         rx[n] = make_float2(yr, yi);
     }
+    // a thread's few samples are summed in fp32, everything above in f64: the statistics of a 1.6e5-sample frame keep
+    // 12+ digits, so sum (mean - y)^2 = sum y^2 - n mean^2 can be formed without cancellation trouble in the noise kernel
+    double d0 = s0, d1 = s1, d2 = s2, d3 = s3, d4 = s4;
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, m); s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, m); s3 += __shfl_xor_sync(0xffffffffu, s3, m);
-        s4 += __shfl_xor_sync(0xffffffffu, s4, m);
+        d0 += __shfl_xor_sync(0xffffffffu, d0, m); d1 += __shfl_xor_sync(0xffffffffu, d1, m);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, m); d3 += __shfl_xor_sync(0xffffffffu, d3, m);
+        d4 += __shfl_xor_sync(0xffffffffu, d4, m);
     }
     if ((threadIdx.x & 31) == 0) {
-        float *acc = a.accum + 5 * (size_t)stream;
-        atomicAdd(acc + 0, s0); atomicAdd(acc + 1, s1); atomicAdd(acc + 2, s2); atomicAdd(acc + 3, s3); atomicAdd(acc + 4, s4);
+        double *acc = a.accum + 5 * (size_t)stream;
+        atomicAdd(acc + 0, d0); atomicAdd(acc + 1, d1); atomicAdd(acc + 2, d2); atomicAdd(acc + 3, d3); atomicAdd(acc + 4, d4);
     }
 }
 
@@ -327,23 +332,24 @@ __global__ void __launch_bounds__(256) channel_conv_kernel(const ChanArgs a)
 template <int = 0>
 __global__ void __launch_bounds__(256) channel_noise_kernel(const ChanArgs a)
 {
-    const uint32_t stream = blockIdx.y;
+    const uint32_t stream = blockIdx.y + a.stream0;
     const uint32_t n_rx = a.rx_len[stream];
     if (n_rx == 0) return;
     uint32_t lead; float cfo;
     chan_stream_draws(a, stream, lead, cfo);
-    const float *acc = a.accum + 5 * (size_t)stream;
-    const float cnt = (float)(n_rx - lead);
+    const double *acc = a.accum + 5 * (size_t)stream;
+    const double cnt = (double)(n_rx - lead);
     float ar, ai;                                         // complex noise amplitude
     if (a.noise_mode == 0) {
-        // var = E[y^2] - mean^2 (no conjugate, src/signals/mod.rs:239-249); amp = sqrt(0.5 var / snr) (complex sqrt)
-        float mr = acc[0] / cnt, mi = acc[1] / cnt;
-        float vr = acc[2] / cnt - (mr * mr - mi * mi), vi = acc[3] / cnt - 2.0f * mr * mi;
-        vr = 0.5f * vr / a.snr_lin; vi = 0.5f * vi / a.snr_lin;
-        float r = sqrtf(sqrtf(vr * vr + vi * vi)), th = 0.5f * atan2f(vi, vr);
-        ar = r * cosf(th); ai = r * sinf(th);
+        // var = sum (mean - y)^2 / len with NO conjugate -> complex (src/signals/mod.rs:239-249), formed in f64 as
+        // sum y^2 / len - mean^2; amp = sqrt(0.5 var / snr), the principal complex square root (src/channel.rs:66-71)
+        const double mr = acc[0] / cnt, mi = acc[1] / cnt;
+        double vr = acc[2] / cnt - (mr * mr - mi * mi), vi = acc[3] / cnt - 2.0 * mr * mi;
+        vr = 0.5 * vr / (double)a.snr_lin; vi = 0.5 * vi / (double)a.snr_lin;
+        const double r = sqrt(sqrt(vr * vr + vi * vi)), th = 0.5 * atan2(vi, vr);
+        ar = (float)(r * cos(th)); ai = (float)(r * sin(th));
     } else {
-        ar = sqrtf(0.5f * (acc[4] / cnt) / a.snr_lin); ai = 0.0f;
+        ar = (float)sqrt(0.5 * (acc[4] / cnt) / (double)a.snr_lin); ai = 0.0f;
     }
     float2 *rx = a.rx + (size_t)stream * a.rx_stride;
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < n_rx; n += gridDim.x * blockDim.x) {

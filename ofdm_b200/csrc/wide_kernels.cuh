@@ -76,6 +76,7 @@ struct WideRxArgs {
     uint32_t *d_nsyms;
     float2   *d_points;
     uint32_t  points_stride;
+    uint32_t  stream0;          // decode kernel: first stream of this launch (gridDim.y <= 65535)
 };
 
 // ---- block FFT: 1024 points, 256 threads, radix-4 Stockham autosort -------------------------------------------------
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 2) wide_decode_kernel(const WideRxAr
     uint8_t *s_qam = s_ham + 128;                                                // 64QAM demap table (see demap_qam64_lut)
     float *s_pil = reinterpret_cast<float *>(s_qam + 256);                       // [team][2 warps][2]
 
-    const uint32_t stream = blockIdx.y;
+    const uint32_t stream = blockIdx.y + a.stream0;
     const StreamStateW *st = a.state + stream;
     if (st->status != ST_OK) return;
     const int S = (int)st->n_syms;
@@ -828,7 +829,7 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
         const long avail_bytes = (s_rx * BPS) / 8 - 16;
         int stt = ST_OK;
         uint32_t n_syms = 0, out_len = 0;
-        if (hi64 != 0 || (long)lo > avail_bytes || avail_bytes < 0) {
+        if (hi64 != 0 || avail_bytes < 0 || lo > (uint64_t)avail_bytes) {            // unsigned compare (see rx_acquire_kernel)
             stt = ST_BAD_HEADER;
         } else {
             const uint64_t nbits = kHeaderBits + 8 * lo;
@@ -856,6 +857,7 @@ struct WideTxArgs {
     uint32_t       *frame_len;
     int            *stream_max;
     const WideTables *tables;
+    uint32_t        stream0;        // first stream of this launch
 };
 
 template <int MOD, bool GUARD, bool FEC, bool WRITE>
@@ -870,7 +872,7 @@ __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
     __shared__ __align__(8) float2 s_map[64];
     __shared__ uint8_t s_enc[16];
 
-    const uint32_t stream = blockIdx.y;
+    const uint32_t stream = blockIdx.y + a.stream0;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = a.payload_len[stream];
     const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;

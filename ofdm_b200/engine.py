@@ -27,7 +27,7 @@ EXPORTS = [
     "ofdm_last_error", "ofdm_get_tables", "ofdm_host_alloc", "ofdm_host_free", "ofdm_coded_len",
     "ofdm_frame_data_syms", "ofdm_frame_len", "ofdm_max_payload", "ofdm_tx_encode_batch", "ofdm_rx_decode_batch",
     "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches", "ofdm_profile_begin", "ofdm_profile_read",
-    "ofdm_sync_search", "ofdm_rx_decode_capture",
+    "ofdm_sync_search", "ofdm_sync_counts", "ofdm_engine_reserve", "ofdm_rx_decode_capture",
     "ofdm_rs_encoded_len", "ofdm_rs_decoded_len", "ofdm_rs_encode_batch", "ofdm_rs_decode_batch",
 ]
 
@@ -107,6 +107,10 @@ def load_library(build: bool = False) -> C.CDLL:
     L.ofdm_profile_read.restype = i32
     L.ofdm_sync_search.argtypes = [vp, vp, u64, vp, u32, vp, i32, vp]
     L.ofdm_sync_search.restype = i32
+    L.ofdm_sync_counts.argtypes = [vp, vp, vp]
+    L.ofdm_sync_counts.restype = i32
+    L.ofdm_engine_reserve.argtypes = [vp, u32, u64]
+    L.ofdm_engine_reserve.restype = i32
     L.ofdm_rx_decode_capture.argtypes = [vp, vp, u64, vp, u32, u32, vp, u32, vp, vp, i32, vp]
     L.ofdm_rx_decode_capture.restype = i32
     for f in (L.ofdm_rs_encoded_len, L.ofdm_rs_decoded_len):
@@ -358,6 +362,15 @@ class Engine:
     def sync_search_device(self, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, stream=0):
         self._check(self.lib.ofdm_sync_search(self._h, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, MEM_DEVICE, stream or None),
                     "ofdm_sync_search")
+
+    def sync_counts(self, stream=0):
+        """(threshold crossings, frames detected, entries written to peaks[]) of the last sync search; waits for `stream`."""
+        c = (C.c_uint32 * 3)()
+        self._check(self.lib.ofdm_sync_counts(self._h, c, stream or None), "ofdm_sync_counts")
+        return int(c[0]), int(c[1]), int(c[2])
+
+    def reserve(self, max_streams: int, max_capture_samples: int = 0):
+        self._check(self.lib.ofdm_engine_reserve(self._h, max_streams, max_capture_samples), "ofdm_engine_reserve")
 
     def decode_capture_device(self, iq_ptr, n_samples, peaks_ptr, n_frames, max_frame_samples, out_ptr, out_stride, out_len_ptr,
                               status_ptr, stream=0):

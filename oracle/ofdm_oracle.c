@@ -133,6 +133,27 @@ static double stdrng_range_pm1(stdrng *g)
     }
 }
 
+/* known-answer hooks: the ChaCha12 block of a given key / block counter, and StdRng::from_seed(seed).next_u64() x n
+ * (pinned on the published zero-key vector and on rand 0.8's own `test_stdrng_construction`, tests/test_oracle_kats.py) */
+void oo_chacha12_block(const uint32_t key[8], uint64_t counter, uint32_t out[16])
+{
+    stdrng g;
+    for (int i = 0; i < 8; i++) g.key[i] = key[i];
+    g.counter = counter;
+    chacha12_block(&g);
+    for (int i = 0; i < 16; i++) out[i] = g.buf[i];
+}
+
+void oo_stdrng_from_seed_u64(const uint8_t seed[32], uint64_t *out, int n)
+{
+    stdrng g;
+    for (int i = 0; i < 8; i++)
+        g.key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+    g.counter = 0;
+    g.idx = 16;
+    for (int i = 0; i < n; i++) out[i] = stdrng_next_u64(&g);
+}
+
 void oo_stdrng_uniform_pm1(uint64_t seed, double *out, int n)
 {
     stdrng g;

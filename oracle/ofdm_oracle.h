@@ -63,6 +63,8 @@ void oo_preamble(oo_c64 *out, int len);
 void oo_training_signals(oo_c64 *out, int len);
 /* rand 0.8 StdRng::seed_from_u64 + gen_range(-1.0..1.0) stream, for tests */
 void oo_stdrng_uniform_pm1(uint64_t seed, double *out, int n);
+void oo_chacha12_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]);        /* KAT hook */
+void oo_stdrng_from_seed_u64(const uint8_t seed[32], uint64_t *out, int n);                   /* KAT hook: StdRng::from_seed */
 
 /* ---- signal primitives (src/signals/mod.rs) ---- */
 void oo_fft(oo_c64 *x, size_t n, int inverse_scaled);            /* any n (pow2 fast path, else Bluestein) */

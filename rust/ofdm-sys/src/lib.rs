@@ -87,6 +87,7 @@ extern "C" {
     pub fn ofdm_engine_create(cfg: *const ofdm_cfg, device: c_int, out: *mut *mut ofdm_engine) -> c_int;
     pub fn ofdm_engine_destroy(h: *mut ofdm_engine);
     pub fn ofdm_last_error(h: *const ofdm_engine) -> *const c_char;
+    pub fn ofdm_engine_reserve(h: *mut ofdm_engine, max_streams: u32, max_capture_samples: u64) -> c_int;
     pub fn ofdm_get_tables(h: *const ofdm_engine, locking80: *mut ofdm_fc32, preamble80: *mut ofdm_fc32, training64: *mut ofdm_fc32) -> c_int;
     pub fn ofdm_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn ofdm_host_free(p: *mut c_void);
@@ -107,6 +108,7 @@ extern "C" {
                                mem: c_int, stream: *mut c_void) -> c_int;
     pub fn ofdm_sync_search(h: *mut ofdm_engine, iq: *const ofdm_fc32, n_samples: u64, peaks: *mut ofdm_peak, max_peaks: u32,
                             n_peaks: *mut u32, mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn ofdm_sync_counts(h: *mut ofdm_engine, counts: *mut u32, stream: *mut c_void) -> c_int;
     pub fn ofdm_rx_decode_capture(h: *mut ofdm_engine, iq: *const ofdm_fc32, n_samples: u64, peaks: *const ofdm_peak, n_frames: u32,
                                   max_frame_samples: u32, out: *mut u8, out_stride: u32, out_len: *mut u32, status: *mut i32,
                                   mem: c_int, stream: *mut c_void) -> c_int;

@@ -153,3 +153,34 @@ int main(void) {
                     "-L", libdir, "-lofdm_b200", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert out[1:6] == ["1008", "29", "3120", "765", "892"] and out[6] == "BAD_HEADER"      # SURVEY.md 8d config 1 sizes
+
+
+def test_tables_stdrng_known_answers(tmp_path):
+    """The product's own StdRng restatement (ofdm_b200/csrc/tables.h, host C++) on the same known answers as the oracle's:
+    the published ChaCha12 zero-key vector and rand 0.8's `test_stdrng_construction` values; and the two restatements give
+    identical preamble / training tables (checked on the engine in tests/test_gpu_parity.py)."""
+    import subprocess
+    src = tmp_path / "kat.cpp"
+    src.write_text(r'''
+#include "tables.h"
+#include <cstdio>
+int main() {
+    uint8_t zero[32] = {0};
+    ofdm_host::StdRng z = ofdm_host::StdRng::from_seed(zero);
+    for (int i = 0; i < 4; i++) { uint64_t v = z.next_u64(); for (int b = 0; b < 8; b++) printf("%02x", (unsigned)((v >> (8 * b)) & 255)); }
+    printf("\n");
+    uint8_t seed[32] = {1,0,0,0, 23,0,0,0, 200,1,0,0, 210,30,0,0};
+    ofdm_host::StdRng g = ofdm_host::StdRng::from_seed(seed);
+    printf("%llu\n", (unsigned long long)g.next_u64());
+    uint8_t seed1[32];
+    for (int i = 0; i < 4; i++) { uint64_t v = g.next_u64(); for (int b = 0; b < 8; b++) seed1[8 * i + b] = (uint8_t)(v >> (8 * b)); }
+    ofdm_host::StdRng g1 = ofdm_host::StdRng::from_seed(seed1);
+    printf("%llu\n", (unsigned long long)g1.next_u64());
+    return 0;
+}
+''')
+    exe = tmp_path / "kat"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "ofdm_b200", "csrc"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+    assert out[1:] == ["10719222850664546238", "14064965282130556830"]

@@ -184,3 +184,39 @@ def test_qam64_mapping_is_gray(oo):
         code_of[int(round(p.real * 7))] = b
     lv = sorted(code_of)
     assert all(bin(code_of[a] ^ code_of[b]).count("1") == 1 for a, b in zip(lv, lv[1:]))
+
+
+CHACHA12_ZERO_KEY_32 = "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+# rand 0.8 src/rngs/std.rs `test_stdrng_construction`: StdRng::from_seed(seed).next_u64(), then StdRng::from_rng(rng0).next_u64()
+STDRNG_SEED = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
+STDRNG_TARGET = [10719222850664546238, 14064965282130556830]
+
+
+def test_chacha12_block_published_vector(oo):
+    """StdRng (rand 0.8.3, src/transmitter.rs:76,89) = ChaCha12: the oracle's block function on the published 12-round
+    zero-key / zero-counter vector (first 32 bytes of the key stream)."""
+    import ctypes as C
+    key = (C.c_uint32 * 8)()
+    out = (C.c_uint32 * 16)()
+    oo.lib().oo_chacha12_block(key, C.c_uint64(0), out)
+    assert np.array(out[:8], np.uint32).astype("<u4").tobytes().hex() == CHACHA12_ZERO_KEY_32
+    # the 64-bit block counter sits in words 12/13: block 1 differs from block 0 and is reproducible
+    out1 = (C.c_uint32 * 16)()
+    oo.lib().oo_chacha12_block(key, C.c_uint64(1), out1)
+    assert list(out1) != list(out)
+
+
+def test_stdrng_from_seed_known_answers(oo):
+    """rand 0.8's own value-stability test of StdRng: pins key = seed (LE words), counter 0, stream 0, sequential u32
+    consumption and next_u64 = lo | hi << 32. NOT pinned by any offline vector: seed_from_u64's PCG32 expansion and
+    gen_range's u64 -> f64 conversion (restated from the published rand_core 0.6 / rand 0.8 sources)."""
+    import ctypes as C
+    seed = (C.c_uint8 * 32)(*STDRNG_SEED)
+    out = (C.c_uint64 * 5)()
+    oo.lib().oo_stdrng_from_seed_u64(seed, out, 5)
+    assert out[0] == STDRNG_TARGET[0]
+    # from_rng(rng0): the next 32 bytes of rng0 (u64 draws 1..4, little-endian) seed the second generator
+    seed1 = np.array(out[1:5], np.uint64).astype("<u8").tobytes()
+    out1 = (C.c_uint64 * 1)()
+    oo.lib().oo_stdrng_from_seed_u64((C.c_uint8 * 32)(*seed1), out1, 1)
+    assert out1[0] == STDRNG_TARGET[1]
