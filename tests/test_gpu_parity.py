@@ -365,15 +365,45 @@ def test_config1_sweep(ob, oo, golden, mod, fec, modes):
             continue
         n_ok += 1
         assert abs(ref.f_delta - res.f_delta[i]) < ABS_TOL_FDELTA, what
-        npts = min(ref.points.size, res.points.shape[1])
+        # the engine demodulates the symbols the header asks for, the oracle every symbol of the capture (channel tail included)
+        bpc, dcar = (1, 2, 6)[mod], 48
+        nsy = -(-(-(-(128 + 8 * ref.packet_length) // bpc)) // dcar)
+        npts = min(nsy * dcar, ref.points.size, res.points.shape[1])
         scale = max(1.0, np.abs(ref.points[:npts]).max())
         assert np.abs(res.points[i, :npts] - ref.points[:npts]).max() <= REL_TOL_POINTS * scale, what
-        n_boundary += _assert_bytes_equal_away_from_boundaries(res.data[i], ref.data, ref.points, mod, fec, REL_TOL_POINTS * scale, what)
+        n_boundary += _assert_bytes_equal_away_from_boundaries(res.data[i], ref.data, ref.points[:npts], mod, fec, REL_TOL_POINTS * scale, what)
         if ref.data.tobytes() == sent:
             assert res.data[i] == sent, what                                         # the pass criterion of SURVEY.md 8(d)
             n_clean += 1
     assert n_ok >= 400 and n_clean >= (100 if mod == 2 else 300), (n_ok, n_clean, n_boundary)
     eng.close()
+
+
+def test_repeated_runs_are_bit_identical(ob, oo):
+    """Race evidence without a sanitizer (compute-sanitizer is closed on this GPU pool, profiles/r2_sanitizer.txt): the RX
+    kernels order their shared-memory exchanges with __syncwarp, named barriers and mbarriers (TMA staging); a missing
+    ordering shows up as run-to-run differences. The same batch -- frames spanning several tiles, every output the kernels
+    write (payload, points, h_k, offsets) -- is decoded 12 times, for nfft 64 and 1024, and must be bit-identical each time."""
+    for nfft in (64, 1024):
+        kw = dict(nfft=1024, cp=256, sync_window=4096) if nfft == 1024 else dict(sync_window=2048)
+        cfg = ob.Config(modulation=2, guard_bands=True, fec=True, sync_mode=1, cfo_mode=1, phase_mode=1, **kw)
+        eng = ob.Engine(cfg, 0)
+        rng = np.random.default_rng(1234 + nfft)
+        lens = [cfg.max_payload(700 if nfft == 64 else 60)] * 6 + [577, 1, 0, cfg.max_payload(225 if nfft == 64 else 29)]
+        pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+        iq, flen = eng.tx_encode(pays)
+        rx, rl, _, _ = eng.channel(iq, flen, ob.ChannelParams(snr_db=50.0 if nfft == 1024 else 38.0, cfo_max=0.9 * np.pi / (nfft * 5 // 4),
+                                                              lead_min=8, lead_max=900, noise_mode=1, seed=5))
+        first = None
+        for rep in range(12):
+            res = eng.rx_decode(rx, rl, out_stride=max(lens) + 16, points=True)
+            blob = (tuple(res.data), res.points.tobytes(), res.h_k.tobytes(), tuple(res.offset), tuple(res.status), tuple(res.f_delta))
+            if first is None:
+                first = blob
+                assert all(d == p for d, p in zip(res.data, pays))
+            else:
+                assert blob == first, f"nfft {nfft}: run {rep} differs from run 0"
+        eng.close()
 
 
 def test_host_and_device_paths_agree(ob, oo):
