@@ -418,12 +418,21 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         if (mxs > iq_stride) mxs = iq_stride;
         const long S = ((long)mxs + wide::kL - 1) / wide::kL - 10;
         if (S > 0) {
-            const uint32_t tiles = (uint32_t)((S + h->tile_shift + wide::kTileSymsW - 1) / wide::kTileSymsW);
+            uint32_t tiles = (uint32_t)((S + h->tile_shift + wide::kTileSymsW - 1) / wide::kTileSymsW);
+            // several consecutive tiles per CTA (per-stream tables and the prefetch pipeline are reused), but keep >= ~8 waves
+            // of CTAs (148 SMs x 2 CTAs) and split a stream's tiles evenly over its CTAs
+            uint32_t tpc = (uint32_t)(((uint64_t)tiles * n_streams) / (8u * 148u * 2u));
+            if (tpc < 1) tpc = 1;
+            if (tpc > tiles) tpc = tiles;
+            if (const char *e = getenv("OFDM_WIDE_TPC")) { tpc = (uint32_t)atoi(e); if (tpc < 1) tpc = 1; if (tpc > tiles) tpc = tiles; }   // TEMP tuning knob
+            tpc = (tiles + (tiles + tpc - 1) / tpc - 1) / ((tiles + tpc - 1) / tpc);
+            w.tiles_per_cta = (int)tpc;
+            tiles = (tiles + tpc - 1) / tpc;
             WDecodeKernel kd = wpick_decode(h->cfg, wpoints);
             const size_t smem = wide::wide_decode_smem(h->cfg.guard_bands != 0);
             if (h->smem_configured.insert((const void *)kd).second)
                 CU(h, cudaFuncSetAttribute((const void *)kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            launch_streams(kd, w, tiles, n_streams, wide::kThreads, smem, st, h->launches);
+            launch_streams(kd, w, tiles, n_streams, wide::kWDecThreads, smem, st, h->launches);
         }
         if (prof) CU(h, cudaEventRecord(pe[2], st));
         CU(h, cudaGetLastError());

@@ -19,7 +19,7 @@ namespace wide {
 
 constexpr int kN = 1024, kCpW = 256, kL = kN + kCpW, kHeadW = 10 * kL;
 constexpr int kThreads = 256;
-constexpr int kTileSymsW = 28;                   // symbols per CTA tile (multiple of 7: Hamming byte alignment)
+constexpr int kTileSymsW = 14;                   // symbols per CTA tile (multiple of 7: Hamming byte alignment)
 
 __host__ __device__ __forceinline__ bool w_is_null(int k) { return k <= 95 || k == 512 || k >= 929; }
 __host__ __device__ __forceinline__ int w_rem(int k) { return k < 512 ? k - 96 : k - 97; }          // index among the 832 used bins
@@ -70,6 +70,7 @@ struct WideRxArgs {
     int32_t         tile_shift;
     int32_t         sync_mode, cfo_mode, fec;
     int32_t         lock_is_ramp;   // the locking table is the built-in ramp: closed-form ramp correlation
+    int32_t         tiles_per_cta;  // consecutive tiles of one stream handled by one CTA of the decode kernel
     int32_t  *d_offset;
     float    *d_f_delta;
     float2   *d_h;              // [n_streams][1024]
@@ -218,7 +219,7 @@ __device__ __forceinline__ void wide_symbol(const WideLane &L, cpx base, cpx (&z
 }
 
 // ---- tile carrier bytes -> payload bytes (shared with nothing else: same scheme as rx_decode_kernel's second phase) ----
-template <int MOD, bool FEC, int D>
+template <int MOD, bool FEC, int D, int NT>
 __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint8_t *s_ham, int t0, int t1, uint32_t out_len, uint8_t *out,
                                                 int tid)
 {
@@ -237,13 +238,13 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
         uint8_t *o0 = out + j0;
         // as in rx_decode_kernel: 3 NB bits = whole carriers -> one bit shift per tile; with FEC the 8 carrier bytes come
         // from 3 aligned shared words + 2 byte permutes (a thread's byte alignment never changes: stride % 4 == 0)
-        static_assert((3 * NB) % 6 == 0 && ((NB / 2) * kThreads) % 4 == 0, "whole carriers per 3 bytes, word-aligned stride");
+        static_assert((3 * NB) % 6 == 0 && ((NB / 2) * NT) % 4 == 0, "whole carriers per 3 bytes, word-aligned stride");
         const int c0 = pbase / 6, sh = pbase - 6 * c0;
         const uint8_t *cp = s_car + c0 + (NB / 2) * tid;
         const uint32_t cp_s = (uint32_t)__cvta_generic_to_shared(cp);
         uint32_t wa = cp_s & ~3u;
         const uint32_t sel = 0x3210u + 0x1111u * (cp_s & 3u);
-        for (int u = 3 * tid; u < nbytes; u += 3 * kThreads, cp += (NB / 2) * kThreads, wa += (NB / 2) * kThreads) {
+        for (int u = 3 * tid; u < nbytes; u += 3 * NT, cp += (NB / 2) * NT, wa += (NB / 2) * NT) {
             uint32_t lo, hi = 0;
             if (NC > 5) {
                 uint32_t x0, x1, x2;
@@ -272,7 +273,7 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
             st_global_u8_if(o + 2, w2, u + 2 < nbytes);
         }
     } else {
-    for (int u = tid; u < nbytes; u += kThreads) {
+    for (int u = tid; u < nbytes; u += NT) {
         const int p = pbase + u * NB;
         const int c = p / BPC, sh = p - c * BPC;
         constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
@@ -288,218 +289,313 @@ __device__ __forceinline__ void wide_tile_bytes(const uint8_t *s_car, const uint
     }
 }
 
-// ---- decode kernel: register-resident 1024-point FFT as 16 x 64 ------------------------------------------------------
-// A 64-thread team owns one OFDM symbol; the CTA runs four teams over the 28 symbols of its tile. With n = n2 + 64 n1 and
-// k = k1 + 16 k2:   X[k1 + 16 k2] = sum_n2 W64^(n2 k2) { W1024^(n2 k1) sum_n1 x[n2 + 64 n1] W16^(n1 k1) }
-//   A. thread n2 loads its 16 samples x[n2 + 64 n1] (coalesced), applies the uniform part of the CFO derotation
-//      exp(-j f 64 n1), does the 16-point DFT in registers and multiplies by the per-thread constants
-//      W1024^(n2 k1) exp(-j f n2) (twiddle and the rest of the derotation in one);
-//   B. one exchange through shared memory, E[k1][n2];
-//   C. every 8-lane group runs the N=64 kernels' register FFT64 (one in-warp 8x8 transpose) for k1 = q and q + 8;
-//   D. equalise, pilot sum (team reduction), phase rotation, demap, carrier bytes -- 16 bins per thread.
-// Two team barriers per symbol (named barriers, 64 threads), no CTA barrier inside the tile.
-constexpr int kTeam = 64, kTeams = kThreads / kTeam;
-constexpr int kERow = 72;                        // E row pitch (complex): 8-lane groups of a half-warp read rows one bank group apart
-constexpr int kTwRow = 17;                       // step-A constants row pitch (complex): thread-private rows, one bank pair apart
-constexpr int kGRow = 18;                        // equaliser row pitch (complex): conflict-free LDS.128 of thread-private rows
+// ---- decode kernel: register-resident 1024-point FFT as 32 x 32, one OFDM symbol per WARP ---------------------------------
+// With n = l + 32 j (l = lane, j = register) and k = k1 + 32 k2:
+//     X[k1 + 32 k2] = sum_l W32^(l k2) { W1024^(l k1) sum_j x[l + 32 j] W32^(j k1) }
+//   A. lane l reads its 32 samples x[l + 32 j] from the warp's staging buffer (the CP-stripped symbol, copied there by ONE TMA
+//      bulk copy, cp.async.bulk + mbarrier, issued while the previous symbol was still being processed), applies the part of the
+//      CFO derotation that is uniform over the lanes, exp(-j f 32 j), runs a 32-point DFT in registers and multiplies by
+//      W1024^(l k1) exp(-j f l) (inter-stage twiddle and the rest of the derotation in one per-stream table);
+//   B. 32 x 32 exchange through the same buffer (rows of 34 complex: STS.64 by column and LDS.128 by row are conflict-free);
+//      as soon as the rows are back in registers the buffer is handed to the TMA engine for the warp's next symbol;
+//   C. second 32-point DFT in registers: lane k1 holds X[k1 + 32 k2], k2 = 0..31;
+//   D. equalise (1/h rows in the same 34-pitch layout), pilot sum (predicated adds + 5 xor-shuffles), rotate, LUT demap,
+//      carrier bytes of the tile (double-buffered).
+//   E. warp 7 does nothing but turn the carrier bytes of finished tiles into payload bytes (Hamming / header strip) while
+//      the seven compute warps are already on the next tile: full[2] / empty[2] mbarriers, producer / consumer.
+// No CTA or named barrier after the table set-up: a compute warp only needs __syncwarp and never waits for its siblings.
+// 7 warps x 2 symbols = one 14-symbol tile; a CTA owns `tiles_per_cta` consecutive tiles of one stream (tables and the
+// prefetch pipeline are reused across them).
+constexpr int kWDecWarps = 7;                                   // compute warps; one more warp turns carrier bytes into payload bytes
+constexpr int kWDecThreads = (kWDecWarps + 1) * 32;
+constexpr int kWSymsPerWarp = kTileSymsW / kWDecWarps;          // 2
+constexpr int kWPitch = 34;                                     // complex per row of the 32 x 32 layouts
+constexpr int kWBuf = 32 * kWPitch;                             // complex per warp buffer: 8704 B >= staged symbol + alignment sample
+constexpr int kWStageBytes = kN * 8 + 16;
+constexpr int kWPw = 36;                                        // floats per row of the pilot weight table (conflict-free LDS.128 by row)
+static_assert(kWBuf * 8 >= kWStageBytes && kTileSymsW % kWDecWarps == 0, "wide decode layout");
 constexpr size_t wide_decode_smem(bool guard)
 {
-    return sizeof(float2) * (kTeams * 16 * kERow + kTeams * 8 * kTrGroup + kTeam * kGRow + kTeam * kTwRow + 16) + sizeof(int16_t) * kTeam * 16 +
-           (size_t)kTileSymsW * (guard ? 768 : 1024) + 64 + 128 + 256 + sizeof(float) * 4 * kTeams;
+    return sizeof(float2) * (kWDecWarps * kWBuf + 2 * kWBuf + 32 + 32) + sizeof(float) * 32 * kWPw + sizeof(int16_t) * kN +
+           2 * ((size_t)kTileSymsW * (guard ? 768 : 1024) + 64) + 128 + 256 + 8 * 16;
 }
 
-// 16-point DFT in registers (radix 4 x 4), natural order in and out
-__device__ __forceinline__ void dft16_p(cpx (&v)[16])
+// W32^m = exp(-2 pi j m / 32), m = 0 .. 21 (the inter-stage twiddles of the 8 x 4 split below)
+__device__ constexpr float kW32r[22] = { 1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f, 0.55557023301960229f,
+    0.38268343236508984f, 0.19509032201612833f, 0.0f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f,
+    -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f, -1.0f, -0.98078528040323043f, -0.92387953251128685f, -0.83146961230254546f,
+    -0.70710678118654768f, -0.55557023301960218f };
+__device__ constexpr float kW32i[22] = { -0.0f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f, -0.70710678118654746f, -0.83146961230254524f,
+    -0.92387953251128674f, -0.98078528040323043f, -1.0f, -0.98078528040323043f, -0.92387953251128674f, -0.83146961230254546f, -0.70710678118654757f,
+    -0.55557023301960218f, -0.38268343236508989f, -0.19509032201612861f, 0.0f, 0.19509032201612836f, 0.38268343236508967f, 0.55557023301960196f,
+    0.70710678118654746f, 0.83146961230254524f };
+
+// 32-point forward DFT in registers, natural order in and out: n = n2 + 4 n1, k = k1 + 8 k2 -> four DFT8 over n1, twiddles
+// W32^(n2 k1), eight DFT4 over n2. Everything is unrolled, so the index maps are register renaming.
+__device__ __forceinline__ void dft32_p(cpx (&x)[32])
 {
-    cpx t[16];
+    cpx y[4][8];
 #pragma unroll
-    for (int nb = 0; nb < 4; nb++) {                                   // DFT4 over n_a: elements nb, nb+4, nb+8, nb+12
-        cpx u[4] = { v[nb], v[nb + 4], v[nb + 8], v[nb + 12] };
-        radix4(u);
+    for (int n2 = 0; n2 < 4; n2++) {
+        cpx u[8];
 #pragma unroll
-        for (int ka = 0; ka < 4; ka++) t[nb + 4 * ka] = u[ka];
+        for (int n1 = 0; n1 < 8; n1++) u[n1] = x[n2 + 4 * n1];
+        dft8_p(u);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) {
+            const int m = n2 * k1;
+            if (m == 0) y[n2][k1] = u[k1];
+            else if (m == 8) y[n2][k1] = c_mul_mj(u[k1]);                          // W32^8 = -j
+            else y[n2][k1] = c_mul(u[k1], c_make(kW32r[m], kW32i[m]));
+        }
     }
-    // twiddles W16^(nb ka)
-    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
-    t[1 + 4 * 1] = c_mul(t[1 + 4 * 1], c_make(C1, -S1));              // W16^1
-    t[2 + 4 * 1] = c_mul(t[2 + 4 * 1], c_make(R2, -R2));              // W16^2
-    t[3 + 4 * 1] = c_mul(t[3 + 4 * 1], c_make(S1, -C1));              // W16^3
-    t[1 + 4 * 2] = c_mul(t[1 + 4 * 2], c_make(R2, -R2));              // W16^2
-    t[2 + 4 * 2] = c_mul_mj(t[2 + 4 * 2]);                            // W16^4 = -j
-    t[3 + 4 * 2] = c_mul(t[3 + 4 * 2], c_make(-R2, -R2));             // W16^6
-    t[1 + 4 * 3] = c_mul(t[1 + 4 * 3], c_make(S1, -C1));              // W16^3
-    t[2 + 4 * 3] = c_mul(t[2 + 4 * 3], c_make(-R2, -R2));             // W16^6
-    t[3 + 4 * 3] = c_mul(t[3 + 4 * 3], c_make(-C1, S1));              // W16^9
 #pragma unroll
-    for (int ka = 0; ka < 4; ka++) {                                   // DFT4 over n_b -> X[ka + 4 kb]
-        cpx u[4] = { t[4 * ka], t[1 + 4 * ka], t[2 + 4 * ka], t[3 + 4 * ka] };
+    for (int k1 = 0; k1 < 8; k1++) {
+        cpx u[4] = { y[0][k1], y[1][k1], y[2][k1], y[3][k1] };
         radix4(u);
 #pragma unroll
-        for (int kb = 0; kb < 4; kb++) v[ka + 4 * kb] = u[kb];
+        for (int k2 = 0; k2 < 4; k2++) x[k1 + 8 * k2] = u[k2];
     }
 }
 
-__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "n"(kTeam) : "memory"); }
+// With guard bands the bins k1 + 32 k2 with k2 in {0, 1, 2, 30, 31} are null carriers on every lane (k <= 95 or k >= 960):
+// stage D skips them at compile time, and the unrolled second DFT drops whatever only feeds them.
+template <bool GUARD> __device__ __forceinline__ constexpr bool w_row_used(int k2) { return !GUARD || (k2 >= 3 && k2 <= 29); }
 
 template <int MOD, bool GUARD, bool FEC, int PHASE, bool POINTS>
-__global__ void __launch_bounds__(kThreads, 2) wide_decode_kernel(const WideRxArgs a)
+__global__ void __launch_bounds__(kWDecThreads, 2) wide_decode_kernel(const WideRxArgs a)
 {
     constexpr int D = GUARD ? 768 : 1024;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float2 *s_E = reinterpret_cast<float2 *>(smem_raw);                          // [team][16][kERow]
-    float2 *s_trw = s_E + kTeams * 16 * kERow;                                   // [team][8 groups][kTrGroup] transpose scratch
-    float2 *s_geq = s_trw + kTeams * 8 * kTrGroup;                               // [thread of a team][kGRow]: 1/h of its 16 bins
-    float2 *s_twp = s_geq + kTeam * kGRow;                                       // [thread of a team][kTwRow]: W1024^(n2 k1) exp(-j f n2)
-    float2 *s_step = s_twp + kTeam * kTwRow;                                     // [16]: exp(-j f 64 n1)
-    int16_t *s_rk = reinterpret_cast<int16_t *>(s_step + 16);                    // [16][thread of a team]: carrier rank or -1
-    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_rk + kTeam * 16);
-    uint8_t *s_ham = s_car + kTileSymsW * D + 64;
+    float2 *s_buf = reinterpret_cast<float2 *>(smem_raw);                        // [warp][kWBuf]: staged symbol, then the 32 x 32 exchange
+    float2 *s_tw = s_buf + kWDecWarps * kWBuf;                                   // [l][kWPitch]: W1024^(l k1) exp(-j f l)
+    float2 *s_g = s_tw + kWBuf;                                                  // [k1][kWPitch]: 1/h at bin k1 + 32 k2
+    float2 *s_step = s_g + kWBuf;                                                // [32]: exp(-j f 32 j)
+    float2 *s_lanew = s_step + 32;                                               // [32]: exp(-j f l) (table set-up only)
+    float *s_pw = reinterpret_cast<float *>(s_lanew + 32);                       // [k1][kWPw]: 1 where bin k1 + 32 k2 is a pilot, else 0
+    int16_t *s_rk = reinterpret_cast<int16_t *>(s_pw + 32 * kWPw);               // [k2][k1]: data-carrier rank of bin k1 + 32 k2, or -1
+    constexpr int kCarBuf = kTileSymsW * D + 64;
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_rk + kN);                     // [2][kCarBuf]: carrier bytes of the tile in flight / being converted
+    uint8_t *s_ham = s_car + 2 * kCarBuf;
     uint8_t *s_qam = s_ham + 128;                                                // 64QAM demap table (see demap_qam64_lut)
-    float *s_pil = reinterpret_cast<float *>(s_qam + 256);                       // [team][2 warps][2]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_qam + 256);                 // [0..6] staging, [8..9] tile full, [10..11] tile empty
 
     const uint32_t stream = blockIdx.y + a.stream0;
     const StreamStateW *st = a.state + stream;
     if (st->status != ST_OK) return;
     const int S = (int)st->n_syms;
-    int t0 = (int)blockIdx.x * kTileSymsW - a.tile_shift, t1 = t0 + kTileSymsW;
-    if (t0 < 0) t0 = 0;
-    if (t1 > S) t1 = S;
-    if (t0 >= t1) return;
-    const int tid = threadIdx.x, team = tid >> 6, u = tid & (kTeam - 1), lane = tid & 31;
-    const int q = u >> 3, l = u & 7;                                             // step C / D: 8-lane group and lane inside it
+    const int tile_first = (int)blockIdx.x * a.tiles_per_cta;
+    int tile_end = tile_first + a.tiles_per_cta;
+    {
+        const int n_tiles = (S + a.tile_shift + kTileSymsW - 1) / kTileSymsW;
+        if (tile_end > n_tiles) tile_end = n_tiles;
+    }
+    if (tile_first >= tile_end) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t fstep = st->fstep;
-    if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
-    if (tid < 16) s_step[tid] = c_to(phasor_from_turns_p(fstep * (uint64_t)(64 * tid)));
-    if (MOD == 2) s_qam[tid] = qam64_lut_entry(tid);
-    const uint32_t qam_saddr = (uint32_t)__cvta_generic_to_shared(s_qam);
-    // constants of this thread's 16 output bins k = q + 8h + 16 l + 128 kb (i = 8h + kb); the four teams share one copy
-    uint32_t pilots = 0;                                                         // bit i: bin is a pilot
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int k = q + 8 * (i >> 3) + 16 * l + 128 * (i & 7);
-        if (team == 0) {
-            s_geq[u * kGRow + i] = st->g[k];
-            s_rk[i * kTeam + u] = (int16_t)w_rank<GUARD>(k);
-        }
-        if (GUARD && w_is_pilot(k)) pilots |= 1u << i;
-    }
-    // step A constants of sample column n2 = u: W1024^(n2 k1) exp(-j f n2) (shared by the four teams)
-    if (team == 0) {
-        const cpx w0 = phasor_from_turns_p(fstep * (uint64_t)u);
-#pragma unroll
-        for (int k1 = 0; k1 < 16; k1++) s_twp[u * kTwRow + k1] = c_to(c_mul(c_from(__ldg(a.tables->w1024 + ((u * k1) & (kN - 1)))), w0));
-    }
-    const unsigned long long *twp = reinterpret_cast<const unsigned long long *>(s_twp + u * kTwRow);
-    cpx tw64[8];                                                                 // FFT64 lane twiddles W64^(l ka) = W1024^(16 l ka)
-#pragma unroll
-    for (int ka = 0; ka < 8; ka++) tw64[ka] = c_from(__ldg(a.tables->w1024 + ((16 * l * ka) & (kN - 1))));
-
     const uint32_t offset = (uint32_t)st->offset;
     const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
     const uint32_t n_avail = a.n_samples[stream] - offset;
-    const cpx dbase = phasor_from_turns_p(fstep * (uint64_t)(kTeams * kL));
-    cpx base = phasor_from_turns_p(fstep * (uint64_t)((10 + t0 + team) * kL + kCpW));
-    unsigned long long *E = reinterpret_cast<unsigned long long *>(s_E + team * 16 * kERow);
-    float2 *tr = s_trw + (team * 8 + q) * kTrGroup;
-    const ulonglong2 *grow = reinterpret_cast<const ulonglong2 *>(s_geq + u * kGRow);
-    const int16_t *rk = s_rk + u;
-    __syncthreads();
+    auto tile_t0 = [&](int tile) { int t = tile * kTileSymsW - a.tile_shift; return t < 0 ? 0 : t; };
+    auto tile_t1 = [&](int tile) { int t = (tile + 1) * kTileSymsW - a.tile_shift; return t > S ? S : t; };
 
-    // the 16 samples of column n2 = u of symbol sym (zero-padded tail row); fetched one symbol ahead
-    auto load16 = [&](int sym, cpx (&d)[16]) {
-        const uint32_t n0 = (10u + (uint32_t)sym) * kL + kCpW + (uint32_t)u;
-#pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) {
-            const uint32_t n = n0 + 64u * n1;
-            d[n1].v = (sym < t1 && n < n_avail) ? __ldg(reinterpret_cast<const unsigned long long *>(x0 + n)) : 0ull;
+    // ---- TMA prefetch pipeline: started before the tables are built, so the first symbol's DRAM latency hides behind them ----
+    // Symbols below s_fast lie, with the two alignment samples of their 16-byte aligned superset, inside the capture; the
+    // (rare) others take the bounds-checked direct-load path.
+    const uintptr_t xaddr = reinterpret_cast<uintptr_t>(x0 + (10 * kL + kCpW));  // sample 0 of data symbol 0 (CP skipped)
+    const int shift = (int)((xaddr >> 3) & 1);                                   // symbol pitch 10 240 B keeps the 16-byte phase
+    int s_fast = n_avail >= (uint32_t)(10 * kL + kCpW + kN + 2) ? (int)((n_avail - (10 * kL + kCpW + kN + 2)) / kL) + 1 : 0;
+    if (s_fast > S) s_fast = S;
+    float2 *buf = s_buf + warp * kWBuf;
+    uint64_t *bar = s_bar + warp;
+    uint32_t buf_sa = smem_addr(buf), bar_sa = smem_addr(bar);
+    asm volatile("" : "+r"(buf_sa), "+r"(bar_sa));
+    auto issue = [&](int sym, int lim) {
+        if (lane == 0) {
+            const bool full = sym < lim;
+            if (full) {
+                const uintptr_t src = (xaddr + (uintptr_t)sym * (kL * 8)) & ~(uintptr_t)15;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(buf_sa), "l"(src), "r"((uint32_t)kWStageBytes), "r"(bar_sa) : "memory");
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_sa), "r"(full ? (uint32_t)kWStageBytes : 0u) : "memory");
         }
     };
-    cpx nxt[16];
-    load16(t0 + team, nxt);
+    const bool is_out_warp = warp == kWDecWarps;
+    uint64_t *bar_full = s_bar + 8, *bar_empty = s_bar + 10;
+    if (tid == 0) { mbar_init(bar_full, kWDecWarps); mbar_init(bar_full + 1, kWDecWarps); mbar_init(bar_empty, 1); mbar_init(bar_empty + 1, 1); }
+    if (lane == 0 && !is_out_warp) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    if (!is_out_warp) {
+        const int t1 = tile_t1(tile_first);
+        issue(tile_t0(tile_first) + warp * kWSymsPerWarp, s_fast < t1 ? s_fast : t1);
+    }
+
+    // ---- per-stream tables ------------------------------------------------------------------------------------------------
+    if (FEC && tid < 128) s_ham[tid] = (uint8_t)ham74_decode_word(tid);
+    if (MOD == 2) for (int i = tid; i < 256; i += kWDecThreads) s_qam[i] = qam64_lut_entry(i);
+    if (tid < 32) s_step[tid] = c_to(phasor_from_turns_p(fstep * (uint64_t)(32 * tid)));
+    else if (tid < 64) s_lanew[tid - 32] = c_to(phasor_from_turns_p(fstep * (uint64_t)(tid - 32)));
+    for (int e = tid; e < kN; e += kWDecThreads) {
+        const int r = e >> 5, c = e & 31;
+        s_g[c * kWPitch + r] = st->g[e];                                         // bin e = k1 + 32 k2 with k1 = c, k2 = r
+        const int rank = w_rank<GUARD>(e);
+        s_rk[e] = (int16_t)rank;
+        s_pw[c * kWPw + r] = (GUARD && rank < 0 && !w_is_null(e)) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    for (int e = tid; e < kN; e += kWDecThreads) {
+        const int r = e >> 5, c = e & 31;
+        s_tw[r * kWPitch + c] = c_to(c_mul(c_from(__ldg(a.tables->w1024 + ((r * c) & (kN - 1)))), c_from(s_lanew[r])));
+    }
+    if (tid == 0) mbar_fence_init();
+    const uint32_t qam_saddr = (uint32_t)__cvta_generic_to_shared(s_qam);
+    const unsigned long long *rd = reinterpret_cast<const unsigned long long *>(buf + shift + lane);
+    unsigned long long *wr = reinterpret_cast<unsigned long long *>(buf + lane);
+    const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(buf + lane * kWPitch);
+    const ulonglong2 *tw_row = reinterpret_cast<const ulonglong2 *>(s_tw + lane * kWPitch);
+    const ulonglong2 *g_row = reinterpret_cast<const ulonglong2 *>(s_g + lane * kWPitch);
+    const float4 *pw_row = reinterpret_cast<const float4 *>(s_pw + lane * kWPw);
+    const unsigned long long *step64 = reinterpret_cast<const unsigned long long *>(s_step);
+    const int16_t *rk = s_rk + lane;
+    uint8_t *out = a.out + (size_t)stream * a.out_stride;
+    uint32_t phase = 0;
+    __syncthreads();
+
+    if (is_out_warp) {
+        // ---- E: consumer warp: carrier bytes of every finished tile -> payload bytes ----------------------------------------
 #pragma unroll 1
-    for (int s = t0 + team; s < t1; s += kTeams) {
-        // ---- A: derotate (uniform part), DFT16, twiddle ------------------------------------------------------------------
-        cpx v[16];
+        for (int tile = tile_first; tile < tile_end; tile++) {
+            const int u = tile - tile_first, p = u & 1;
+            mbar_wait(bar_full + p, (uint32_t)(u >> 1) & 1u);
+            wide_tile_bytes<MOD, FEC, D, 32>(s_car + p * kCarBuf, s_ham, tile_t0(tile), tile_t1(tile), st->out_len, out, lane);
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar_empty + p)) : "memory");
+        }
+        return;
+    }
+
+#pragma unroll 1
+    for (int tile = tile_first; tile < tile_end; tile++) {
+        const int t0 = tile_t0(tile), t1 = tile_t1(tile);
+        const int lim = s_fast < t1 ? s_fast : t1;
+        const int u = tile - tile_first, p = u & 1;
+        if (u >= 2) mbar_wait(bar_empty + p, (uint32_t)((u >> 1) - 1) & 1u);      // the consumer is done with this buffer (tile u - 2)
+        uint8_t *car = s_car + p * kCarBuf;
+#pragma unroll 1
+        for (int i = 0; i < kWSymsPerWarp; i++) {
+            const int s = t0 + warp * kWSymsPerWarp + i;
+            cpx x[32];
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            auto issue_next = [&]() {                                            // prefetch this warp's next symbol (possibly of the next tile)
+                if (i + 1 < kWSymsPerWarp) {
+                    issue(s + 1, lim);
+                } else if (tile + 1 < tile_end) {
+                    const int n1 = tile_t1(tile + 1);
+                    issue(t1 + warp * kWSymsPerWarp, s_fast < n1 ? s_fast : n1);
+                }
+            };
+            if (s >= t1) { __syncwarp(); issue_next(); continue; }               // past the frame's last symbol (every lane is past the wait before the barrier is re-armed)
+            // ---- A: samples, uniform derotation, DFT32, twiddle ------------------------------------------------------------
+            if (s < lim) {
 #pragma unroll
-        for (int n1 = 0; n1 < 16; n1++) v[n1] = nxt[n1];
-        load16(s + kTeams, nxt);                                                 // this team's next symbol
+                for (int j = 0; j < 32; j++) x[j].v = rd[32 * j];
+            } else {
+                const uint32_t n0 = (10u + (uint32_t)s) * kL + kCpW + (uint32_t)lane;
 #pragma unroll
-        for (int n1 = 1; n1 < 16; n1++) v[n1] = c_mul(v[n1], c_from(s_step[n1]));
-        dft16_p(v);
-#pragma unroll
-        for (int k1 = 0; k1 < 16; k1++) { cpx w; w.v = twp[k1]; v[k1] = c_mul(v[k1], w); }
-        // ---- B: exchange E[k1][n2] -------------------------------------------------------------------------------------
-#pragma unroll
-        for (int k1 = 0; k1 < 16; k1++) E[k1 * kERow + u] = v[k1].v;
-        team_sync(team);
-        // ---- C + D(equalise, pilots): FFT64 over n2 for k1 = q and q + 8 --------------------------------------------------
-        cpx psum = c_make(0.0f, 0.0f);
-        float pang = 0.0f;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            cpx x[8];
-            const unsigned long long *row = E + (q + 8 * h) * kERow + l;
-#pragma unroll
-            for (int j = 0; j < 8; j++) x[j].v = row[8 * j];
-            fft64_group_p(x, tw64, tr, l);
-#pragma unroll
-            for (int p2 = 0; p2 < 4; p2++) {
-                const ulonglong2 gg = grow[4 * h + p2];
-                cpx g0, g1;
-                g0.v = gg.x; g1.v = gg.y;
-                x[2 * p2] = c_mul(x[2 * p2], g0); x[2 * p2 + 1] = c_mul(x[2 * p2 + 1], g1);
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t n = n0 + 32u * j;
+                    x[j].v = (s < t1 && n < n_avail) ? __ldg(reinterpret_cast<const unsigned long long *>(x0 + n)) : 0ull;   // zero-padded tail row
+                }
             }
 #pragma unroll
-            for (int kb = 0; kb < 8; kb++) {
-                v[8 * h + kb] = x[kb];
-                if (GUARD && (pilots >> (8 * h + kb) & 1u)) {
-                    if (PHASE == 1) psum = c_add(psum, x[kb]);
-                    else { float pa, pb; c_split(c_mul(x[kb], base), pa, pb); pang += atan2f(pb, pa); }
+            for (int j = 1; j < 32; j++) { cpx w; w.v = step64[j]; x[j] = c_mul(x[j], w); }
+            dft32_p(x);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const ulonglong2 ww = tw_row[q];
+                cpx w0, w1;
+                w0.v = ww.x; w1.v = ww.y;
+                x[2 * q] = c_mul(x[2 * q], w0); x[2 * q + 1] = c_mul(x[2 * q + 1], w1);
+            }
+            __syncwarp();                                                        // every lane has read its staged samples
+            // ---- B: 32 x 32 exchange --------------------------------------------------------------------------------------
+#pragma unroll
+            for (int k1 = 0; k1 < 32; k1++) wr[k1 * kWPitch] = x[k1].v;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 16; q++) { const ulonglong2 v = row[q]; x[2 * q].v = v.x; x[2 * q + 1].v = v.y; }
+            __syncwarp();                                                        // buffer free: prefetch this warp's next symbol
+            issue_next();
+            // ---- C: second DFT32 -> lane k1 holds X[k1 + 32 k2] --------------------------------------------------------------
+            dft32_p(x);
+            // ---- D: equalise, pilot phase, demap ----------------------------------------------------------------------------
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                if (!w_row_used<GUARD>(2 * q) && !w_row_used<GUARD>(2 * q + 1)) continue;
+                const ulonglong2 gg = g_row[q];
+                cpx g0, g1;
+                g0.v = gg.x; g1.v = gg.y;
+                if (w_row_used<GUARD>(2 * q)) x[2 * q] = c_mul(x[2 * q], g0);
+                if (w_row_used<GUARD>(2 * q + 1)) x[2 * q + 1] = c_mul(x[2 * q + 1], g1);
+            }
+            cpx base = c_make(1.0f, 0.0f);
+            if (!GUARD || PHASE == 0) base = phasor_from_turns_p(fstep * (uint64_t)((10 + s) * kL + kCpW));
+            cpx rot = base;
+            if (GUARD) {
+                float px, py;
+                if (PHASE == 1) {
+                    // pilot sum as a multiply-accumulate with the 0 / 1 weights of this lane's bins: 8 LDS.128 + 27 FFMA2
+                    cpx psum = c_make(0.0f, 0.0f);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 w4 = pw_row[q];
+                        if (w_row_used<GUARD>(4 * q)) psum = c_fma2(x[4 * q], c_make(w4.x, w4.x), psum);
+                        if (w_row_used<GUARD>(4 * q + 1)) psum = c_fma2(x[4 * q + 1], c_make(w4.y, w4.y), psum);
+                        if (w_row_used<GUARD>(4 * q + 2)) psum = c_fma2(x[4 * q + 2], c_make(w4.z, w4.z), psum);
+                        if (w_row_used<GUARD>(4 * q + 3)) psum = c_fma2(x[4 * q + 3], c_make(w4.w, w4.w), psum);
+                    }
+                    c_split(psum, px, py);
+                } else {
+                    // reference: mean of the 64 pilot angles (src/receiver.rs:126,137 scaled to 64 pilots, docs/SPEC.md 9)
+                    px = 0.0f; py = 0.0f;
+#pragma unroll
+                    for (int k2 = 0; k2 < 32; k2++) {
+                        if (!w_row_used<GUARD>(k2)) continue;
+                        if (s_pw[lane * kWPw + k2] != 0.0f) { float pa, pb; c_split(c_mul(x[k2], base), pa, pb); px += atan2f(pb, pa); }
+                    }
+                }
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) { px += __shfl_xor_sync(0xffffffffu, px, m); py += __shfl_xor_sync(0xffffffffu, py, m); }
+                if (PHASE == 1) {
+                    const float inv = rsqrt_normal(fmaxf(px * px + py * py, 1e-30f));
+                    rot = c_make(px * inv, -py * inv);
+                } else {
+                    float sn, cs;
+                    sincosf(-px * (1.0f / 64.0f), &sn, &cs);
+                    rot = c_mul(c_make(cs, sn), base);
+                }
+            }
+            uint8_t *crow = car + (s - t0) * D;                                  // rows of symbols past t1 exist but are never read
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) {
+                if (!w_row_used<GUARD>(k2)) continue;
+                float zr, zi;
+                c_split(c_mul(x[k2], rot), zr, zi);
+                const int r = rk[32 * k2];
+                // branch-free: null / pilot bins are demapped like data bins and simply not stored
+                const uint32_t sym6 = MOD == 2 ? demap_qam64_lut(zr, zi, qam_saddr) : demap_point<MOD>(zr, zi);
+                st_shared_u8_if_nonneg(crow + r, sym6, r);
+                if (POINTS && r >= 0 && s < t1) {
+                    size_t p = (size_t)s * D + r;
+                    if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
                 }
             }
         }
-        // ---- pilot phase (docs/SPEC.md 9: 64 pilots) -------------------------------------------------------------------
-        cpx rot = base;
-        if (GUARD) {
-            float px, py;
-            if (PHASE == 1) c_split(psum, px, py); else { px = pang; py = 0.0f; }
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) { px += __shfl_xor_sync(0xffffffffu, px, m); py += __shfl_xor_sync(0xffffffffu, py, m); }
-            float *sp = s_pil + team * 4;
-            if (lane == 0) { sp[2 * ((u >> 5) & 1)] = px; sp[2 * ((u >> 5) & 1) + 1] = py; }
-            team_sync(team);
-            px = sp[0] + sp[2]; py = sp[1] + sp[3];
-            if (PHASE == 1) {
-                const float inv = rsqrt_normal(fmaxf(px * px + py * py, 1e-30f));
-                rot = c_make(px * inv, -py * inv);
-            } else {
-                float sn, cs;
-                sincosf(-px * (1.0f / 64.0f), &sn, &cs);
-                rot = c_mul(c_make(cs, sn), base);
-            }
-        } else {
-            team_sync(team);                                                     // E is rewritten by the next symbol
-        }
-        base = c_mul(base, dbase);
-        // ---- D: rotate, demap, carrier bytes -----------------------------------------------------------------------------
-        uint8_t *crow = s_car + (s - t0) * D;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            float zr, zi;
-            c_split(c_mul(v[i], rot), zr, zi);
-            const int r = rk[i * kTeam];
-            // branch-free: null / pilot bins are demapped like data bins and simply not stored (a branch per point would
-            // serialise the 16 demap chains of a thread)
-            const uint32_t sym6 = MOD == 2 ? demap_qam64_lut(zr, zi, qam_saddr) : demap_point<MOD>(zr, zi);
-            st_shared_u8_if_nonneg(crow + r, sym6, r);
-            if (POINTS && r >= 0) {
-                size_t p = (size_t)s * D + r;
-                if (p < a.points_stride) a.d_points[(size_t)stream * a.points_stride + p] = make_float2(zr, zi);
-            }
-        }
+        __syncwarp();                                                            // this warp's carrier bytes of the tile are written
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar_full + p)) : "memory");
     }
-    __syncthreads();
-    wide_tile_bytes<MOD, FEC, D>(s_car, s_ham, t0, t1, st->out_len, a.out + (size_t)stream * a.out_stride, tid);
 }
 
 // ---- acquisition ---------------------------------------------------------------------------------------------------------

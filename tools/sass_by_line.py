@@ -18,9 +18,15 @@ for r in rows:
         cur_sec["data"].append(r)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-start = next(i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l)
+dis, start = None, None
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):     # one cubin per translation unit: find the kernel's
+    if kern not in subprocess.run(["cuobjdump", "-elf", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout:
+        continue
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    start = next((i for i, l in enumerate(dis) if l.startswith(".text.") and kern in l), None)
+    if start is not None:
+        break
+assert start is not None, f"kernel {kern} not found in {lib}"
 lines = []          # (file:line stack, sass text)
 cur = "?"
 for l in dis[start + 1:]:
