@@ -344,8 +344,22 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     // two passes over the same tiles: maximum for `normalize`, then recompute + store once (8 B/sample written)
     const long max_syms = (long)iq_stride / 80 - 10;
     uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + h->tile_shift + kTxTileSyms - 1) / kTxTileSyms) : 1;
-    launch_streams(pick_tx(h->cfg, false), a, tiles, n_streams, kTxThreads, 0, st, h->launches);
-    launch_streams(pick_tx(h->cfg, true), a, tiles, n_streams, kTxThreads, 0, st, h->launches);
+    // several consecutive tiles per CTA (tables are built once per CTA), but keep >= ~16 waves of CTAs (148 SMs x 4 CTAs)
+    {
+        uint32_t tpc = (uint32_t)(((uint64_t)tiles * n_streams) / (16u * 148u * 4u));
+        if (tpc < 1) tpc = 1;
+        if (tpc > tiles) tpc = tiles;
+        tpc = (tiles + (tiles + tpc - 1) / tpc - 1) / ((tiles + tpc - 1) / tpc);
+        a.tiles_per_cta = (int)tpc;
+        tiles = (tiles + tpc - 1) / tpc;
+    }
+    const size_t tx_smem = sizeof(float2) * kTxWarps * kTrWarp + (size_t)kTxTileSyms * h->dcar + 64 + sizeof(float2) * 16 * ((1u << h->bpc) + 2) + 16 + 512;
+    for (int pass = 0; pass < 2; pass++) {
+        TxKernel k = pick_tx(h->cfg, pass == 1);
+        if (h->smem_configured.insert((const void *)k).second)
+            CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tx_smem));
+        launch_streams(k, a, tiles, n_streams, kTxThreads, tx_smem, st, h->launches);
+    }
     CU(h, cudaGetLastError());
     if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
     return 0;

@@ -17,6 +17,7 @@ struct TxArgs {
     uint32_t       *frame_len;      // optional
     int            *stream_max;     // per stream: max positive component as float bits (atomicMax on int)
     int32_t         tile_shift;     // Hamming byte alignment of the tile boundaries (same as the decode kernel)
+    int32_t         tiles_per_cta;  // consecutive tiles of one frame handled by one CTA
     const RxTables *tables;
     uint32_t        stream0;        // first stream of this launch (gridDim.y <= 65535 streams per launch)
 };
@@ -45,8 +46,19 @@ constexpr int kTxThreads = kTxWarps * 32;
 constexpr int kTxIters = 7;
 constexpr int kTxTileSyms = kTxWarps * 4 * kTxIters;      // 224, same tiling as the decode kernel
 
-// One 224-symbol tile of one frame: (Hamming) coded bit stream of the tile -> smem, then per OFDM symbol (8 lanes):
-// 6-bit fields -> constellation LUT -> inverse FFT (packed FFMA2 transform on re/im-swapped data) -> CP.
+// dynamic shared memory of tx_tile_kernel: transpose scratch (the tile's packed bit stream lives in it until it has been
+// unpacked) | one byte per data carrier | per-lane constellation table | Hamming encode tables
+template <int MOD, bool GUARD> constexpr size_t tx_smem_bytes()
+{
+    return sizeof(float2) * kTxWarps * kTrWarp + (size_t)kTxTileSyms * (GUARD ? 48 : 64) + 64 +
+           sizeof(float2) * 16 * ((1 << ModTraits<MOD>::kBpc) + 2) + 16 + 512;
+}
+
+// One 224-symbol tile of one frame: (Hamming) coded bit stream of the tile -> one byte per data carrier in smem, then per OFDM
+// symbol (8 lanes): carrier byte -> constellation point -> inverse FFT (packed FFMA2 transform on re/im-swapped data) -> CP.
+// The constellation table holds every entry once per lane of a half-warp ([entry][lane & 15], LDS.64 at bank 2 (lane & 15):
+// conflict-free whatever the lanes look up); null and pilot bins are two more entries. A CTA owns `tiles_per_cta` consecutive
+// tiles of one frame (tables are built once).
 // WRITE = false: only the per-stream maximum positive component is produced (`normalize`, src/transmitter.rs:183-194);
 // WRITE = true : the symbols are recomputed and stored once, already normalised, together with the frame head and
 // the zero fill -- 8 B/sample of HBM traffic in total instead of write + read-modify-write.
@@ -56,11 +68,15 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 48 : 64;
     constexpr int BPS = BPC * D;
-    __shared__ __align__(16) float2 s_tr[kTxWarps * kTrWarp];
-    __shared__ __align__(16) uint8_t s_bits[kTxTileSyms * BPS / 8 + 32];
-    __shared__ __align__(8) float2 s_map[66];          // constellation | [64] null carrier | [65] pilot
-    __shared__ uint8_t s_enc[16];
-    __shared__ uint16_t s_enc14[256];                  // payload byte -> its two 7-bit codewords (low nibble first)
+    constexpr int NE = 1 << BPC;                        // constellation entries; NE = null carrier, NE + 1 = pilot
+    extern __shared__ __align__(128) uint8_t tx_smem[];
+    float2 *s_tr = reinterpret_cast<float2 *>(tx_smem);
+    uint8_t *s_bits = tx_smem;                                                   // aliases s_tr: consumed before the first transform
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_tr + kTxWarps * kTrWarp);    // one byte (BPC valid bits) per data carrier of the tile
+    float2 *s_lut = reinterpret_cast<float2 *>(s_car + kTxTileSyms * D + 64);   // [NE + 2][16 lanes], stored re/im swapped
+    uint8_t *s_enc = reinterpret_cast<uint8_t *>(s_lut + 16 * (NE + 2));
+    uint16_t *s_enc14 = reinterpret_cast<uint16_t *>(s_enc + 16);               // payload byte -> its two 7-bit codewords (low nibble first)
+    static_assert(kTxTileSyms * BPS / 8 + 32 <= (int)sizeof(float2) * kTxWarps * kTrWarp, "the packed bit stream must fit the transpose scratch");
 
     const uint32_t stream = blockIdx.y + a.stream0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
@@ -74,9 +90,10 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
     const bool fits = frame_len <= a.iq_stride;
     float2 *out = a.iq + (size_t)stream * a.iq_stride;
 
-    int t0 = (int)blockIdx.x * kTxTileSyms - a.tile_shift, t1 = t0 + kTxTileSyms;
-    if (t0 < 0) t0 = 0;
-    if (t1 > S) t1 = S;
+    const int n_tiles = (S + a.tile_shift + kTxTileSyms - 1) / kTxTileSyms;
+    const int tile_first = (int)blockIdx.x * a.tiles_per_cta;
+    int tile_end = tile_first + a.tiles_per_cta;
+    if (tile_end > n_tiles) tile_end = n_tiles;
     float scale = 1.0f / 64.0f;
     if (WRITE) {
         const float mx = fmaxf(__int_as_float(a.stream_max[stream]), a.tables->head_max);
@@ -94,118 +111,137 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
             for (uint32_t i = z0 + tid; i < a.iq_stride; i += kTxThreads) out[i] = make_float2(0.0f, 0.0f);
         }
     }
-    if (!fits || t0 >= t1) return;
+    if (!fits || tile_first >= tile_end) return;
 
-    // constellation LUT, stored re/im swapped (the inverse FFT runs as swap . FFT . swap)
-    if (tid < 64) {
+    // constellation table, stored re/im swapped (the inverse FFT runs as swap . FFT . swap), one copy per lane of a half-warp
+    for (int e = tid; e < 16 * (NE + 2); e += kTxThreads) {
+        const int idx = e >> 4;
         float re = 0.0f, im = 0.0f;
-        if (MOD == 0) { re = (tid & 1) ? 1.0f : -1.0f; }                              // src/transmitter.rs:112-118
-        else if (MOD == 1) { re = (tid & 1) ? 1.0f : -1.0f; im = (tid & 2) ? 1.0f : -1.0f; }   // src/transmitter.rs:122-132
+        if (idx == NE + 1) re = 1.0f;                                                 // pilot 1 + 0j (src/transmitter.rs:150-161)
+        else if (idx == NE) { }                                                       // null carrier / padding
+        else if (MOD == 0) { re = (idx & 1) ? 1.0f : -1.0f; }                         // src/transmitter.rs:112-118
+        else if (MOD == 1) { re = (idx & 1) ? 1.0f : -1.0f; im = (idx & 2) ? 1.0f : -1.0f; }   // src/transmitter.rs:122-132
         else {
-            const uint32_t ci = tid & 7u, cq = tid >> 3;                               // Gray code -> level (docs/SPEC.md 2)
+            const uint32_t ci = idx & 7u, cq = (uint32_t)idx >> 3;                     // Gray code -> level (docs/SPEC.md 2)
             const uint32_t li = ci ^ (ci >> 1) ^ (ci >> 2), lq = cq ^ (cq >> 1) ^ (cq >> 2);
             re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
             im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
         }
-        s_map[tid] = make_float2(im, re);
+        s_lut[e] = make_float2(im, re);
     }
-    if (tid == 64) s_map[64] = make_float2(0.0f, 0.0f);
-    if (tid == 65) s_map[65] = make_float2(0.0f, 1.0f);               // pilot 1 + 0j, swapped (src/transmitter.rs:150-161)
     if (tid < 16) s_enc[tid] = (uint8_t)ham74_encode_nibble(tid);
     if (FEC) s_enc14[tid] = (uint16_t)(ham74_encode_nibble(tid & 15) | (ham74_encode_nibble(tid >> 4) << 7));
-    __syncthreads();
+
+    cpx tw[8];
+#pragma unroll
+    for (int ka = 0; ka < 8; ka++) tw[ka] = c_from(__ldg(a.tables->w64 + ((l * ka) & 63)));
+    // bins l, l + 24, l + 32, l + 56 are null / pilot carriers on some lanes: their table entry replaces the looked-up byte.
+    // Carrier rank of bin l + 8 j is affine in j except at the pilot / DC crossings (j = 3, 4), as in the decode kernel.
+    int d3 = 24 - (l >= 2), d4 = 31 - (l >= 1);                     // rank(l + 24) - (l - 7), rank(l + 32) - (l - 7)
+    uint32_t fix0 = 0xFFu, fix3 = 0xFFu, fix4 = 0xFFu, fix7 = 0xFFu;      // 0xFF: data carrier, else the fixed table entry
+    if (GUARD) {
+        if (data_rank<GUARD>(l) < 0) fix0 = is_pilot_bin(l) ? NE + 1 : NE;
+        if (data_rank<GUARD>(l + 24) < 0) fix3 = is_pilot_bin(l + 24) ? NE + 1 : NE;
+        if (data_rank<GUARD>(l + 32) < 0) fix4 = is_pilot_bin(l + 32) ? NE + 1 : NE;
+        if (data_rank<GUARD>(l + 56) < 0) fix7 = is_pilot_bin(l + 56) ? NE + 1 : NE;
+    }
+    asm volatile("" : "+r"(d3), "+r"(d4), "+r"(fix0), "+r"(fix3), "+r"(fix4), "+r"(fix7));
+    float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
+    const unsigned long long *lut = reinterpret_cast<const unsigned long long *>(s_lut) + (lane & 15);
+    const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+    float mx = 0.0f;
+
+#pragma unroll 1
+    for (int tile = tile_first; tile < tile_end; tile++) {
+    int t0 = tile * kTxTileSyms - a.tile_shift, t1 = t0 + kTxTileSyms;
+    if (t0 < 0) t0 = 0;
+    if (t1 > S) t1 = S;
+    __syncthreads();                                               // tables ready / the previous tile's transforms are done with s_tr
 
     // ---- tile bit stream --------------------------------------------------------------------------------------------
-    const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
     const uint32_t byte0 = (uint32_t)((long)t0 * BPS / 8), nbyte = (uint32_t)((long)(t1 - t0) * BPS / 8);
     if (FEC) {
-        // header bytes (tile 0), then groups of 4 payload bytes -> 8 codewords -> 7 coded bytes. Tile boundaries fall on group
-        // boundaries (tile_shift: (288 t0 - 128) is a multiple of 56), so every group starts on a coded-byte boundary.
+        // header bytes (tile 0), then groups of 16 payload bytes -> 32 codewords -> 28 coded bytes = 7 aligned words. Tile
+        // boundaries fall on 4-byte group boundaries (tile_shift: (288 t0 - 128) is a multiple of 56), so every group of
+        // four starts on a coded-byte boundary that is a multiple of 4 inside the tile.
         const uint32_t hdr = byte0 < 16 ? 16 - byte0 : 0;              // header bytes inside this tile (16 or 0)
         if (tid < hdr) s_bits[tid] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + tid, s_enc);
         const uint32_t c0 = byte0 + hdr - 16;                          // first coded byte of the tile: multiple of 7
-        const uint32_t ngrp = (nbyte + 2 - hdr + 6) / 7;
+        const uint32_t ngrp = ((nbyte + 2 - hdr + 6) / 7 + 3) / 4;     // groups of 16 payload bytes
         const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
         for (uint32_t u = tid; u < ngrp; u += kTxThreads) {
-            const uint32_t pb = (c0 / 7 + u) * 4;                      // first payload byte of the group
-            uint32_t v4 = 0;                                           // bytes past the payload encode to zero codewords
-            if (pay_aligned && pb + 4 <= n) v4 = __ldg(reinterpret_cast<const uint32_t *>(pay + pb));
-            else {
+            const uint32_t pb = (c0 / 7) * 4 + 16 * u;                 // first payload byte of the group
+            uint32_t v[4] = { 0, 0, 0, 0 };                            // bytes past the payload encode to zero codewords
+            if (pay_aligned && pb + 16 <= n) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) if (pb + q < n) v4 |= (uint32_t)pay[pb + q] << (8 * q);
+                for (int q = 0; q < 4; q++) v[q] = __ldg(reinterpret_cast<const uint32_t *>(pay + pb) + q);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; q++) if (pb + q < n) v[q >> 2] |= (uint32_t)pay[pb + q] << (8 * (q & 3));
             }
-            const uint32_t lo = (uint32_t)s_enc14[v4 & 255u] | ((uint32_t)s_enc14[(v4 >> 8) & 255u] << 14);      // 28 bits
-            const uint32_t hi = (uint32_t)s_enc14[(v4 >> 16) & 255u] | ((uint32_t)s_enc14[v4 >> 24] << 14);
-            const uint64_t w = (uint64_t)lo | ((uint64_t)hi << 28);
-            uint8_t *dst = s_bits + hdr + 7 * u;
+            uint64_t w[4];                                             // 4 x 56 coded bits
 #pragma unroll
-            for (int q = 0; q < 7; q++) dst[q] = (uint8_t)(w >> (8 * q));
+            for (int q = 0; q < 4; q++) {
+                const uint32_t lo = (uint32_t)s_enc14[v[q] & 255u] | ((uint32_t)s_enc14[(v[q] >> 8) & 255u] << 14);      // 28 bits
+                const uint32_t hi = (uint32_t)s_enc14[(v[q] >> 16) & 255u] | ((uint32_t)s_enc14[v[q] >> 24] << 14);
+                w[q] = (uint64_t)lo | ((uint64_t)hi << 28);
+            }
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_bits + hdr + 28 * u);
+            dst[0] = (uint32_t)w[0];
+            dst[1] = (uint32_t)(w[0] >> 32) | ((uint32_t)w[1] << 24);
+            dst[2] = (uint32_t)(w[1] >> 8);
+            dst[3] = (uint32_t)(w[1] >> 40) | ((uint32_t)w[2] << 16);
+            dst[4] = (uint32_t)(w[2] >> 16);
+            dst[5] = (uint32_t)(w[2] >> 48) | ((uint32_t)w[3] << 8);
+            dst[6] = (uint32_t)(w[3] >> 24);
         }
     } else {
         for (uint32_t b = tid; b < nbyte + 2; b += kTxThreads) s_bits[b] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + b, s_enc);
     }
     __syncthreads();
 
-    cpx tw[8];
+    // ---- bit stream -> one byte per data carrier (modulate, src/transmitter.rs:108-140); carriers past the frame's last
+    // constellation symbol are padding (encode_block's exhausted iterator, src/transmitter.rs:144-165) and get the null entry
+    {
+        const long ncar_local = (long)ncar - (long)t0 * D;            // carriers of the frame that exist from this tile on
+        long have = (long)(t1 - t0) * D;                              // ... and inside this tile; rows past t1 are all padding
+        if (ncar_local < have) have = ncar_local;
+        const int ncar_have = (int)have;
+        const uint32_t *bits32 = reinterpret_cast<const uint32_t *>(s_bits);
+        for (int c4 = 4 * tid; c4 < kTxTileSyms * D; c4 += 4 * kTxThreads) {  // 4 carriers = 4 BPC bits from bit 4 BPC (c4 / 4)
+            const uint32_t bit = (uint32_t)c4 * BPC, wi = bit >> 5, sh = bit & 31;
+            const uint32_t v = __funnelshift_r(bits32[wi], bits32[wi + 1], sh);
+            constexpr uint32_t M = (uint32_t)(NE - 1);
+            uint32_t packed = (v & M) | (((v >> BPC) & M) << 8) | (((v >> (2 * BPC)) & M) << 16) | (((v >> (3 * BPC)) & M) << 24);
+            if (c4 + 4 > ncar_have) {                                  // the frame's last carriers / padding rows (rare)
 #pragma unroll
-    for (int ka = 0; ka < 8; ka++) tw[ka] = c_from(__ldg(a.tables->w64 + ((l * ka) & 63)));
-    // per lane: where the bits of its 8 bins sit inside an OFDM symbol's SB bytes (bit offset = rank * BPC), or which fixed
-    // constellation entry a null / pilot bin takes. Only bins l, 24 + l, 32 + l, 56 + l can be null or pilot.
-    constexpr int SB = BPS / 8;                                   // bytes of the bit stream per OFDM symbol (6 .. 48)
-    uint32_t boff[8];                                             // byte offset << 3 | bit shift
-    uint32_t fixed = 0;                                           // byte q: entry of bin l + 8 {0,3,4,7}[q] when it is null / pilot, else 0
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int r = data_rank<GUARD>(l + 8 * j);
-        boff[j] = r >= 0 ? (uint32_t)r * BPC : 0u;
-        if (GUARD && r < 0) {
-            const int q = j == 0 ? 0 : j == 3 ? 1 : j == 4 ? 2 : 3;
-            fixed |= (is_pilot_bin(l + 8 * j) ? 65u : 64u) << (8 * q);
+                for (int q = 0; q < 4; q++) if (c4 + q >= ncar_have) packed = (packed & ~(0xFFu << (8 * q))) | ((uint32_t)NE << (8 * q));
+            }
+            *reinterpret_cast<uint32_t *>(s_car + c4) = packed;
         }
     }
-    float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
-    const long ncar_local = (long)ncar - (long)t0 * D;            // carriers of the frame that exist from this tile on
-    const int n_full = (int)(ncar_local / D < (long)(t1 - t0) ? ncar_local / D : (long)(t1 - t0));   // symbols of the tile with all D carriers
-    float mx = 0.0f;
+    __syncthreads();                                               // s_bits (= s_tr) is free for the transforms from here on
 
+    const uint8_t *rowp = s_car + (warp * (4 * kTxIters) + g) * D + (GUARD ? l - 7 : l);      // this group's first symbol, biased by the lane
 #pragma unroll 1
     for (int it = 0; it < kTxIters; it++) {
         const int sl = warp * (4 * kTxIters) + 4 * it + g;        // symbol index inside the tile
         const int s = t0 + sl;
         const bool valid = s < t1;
         cpx x[8];
-        if (__all_sync(0xffffffffu, sl < n_full)) {
-            // every carrier of the warp's 4 symbols exists: byte offsets and shifts are lane constants
-            const uint8_t *sym = s_bits + sl * SB;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {                          // encode_block, src/transmitter.rs:144-165
-                const uint8_t *pb = sym + (boff[j] >> 3);
-                uint32_t w = pb[0];
-                if (BPC > 2) w |= (uint32_t)pb[1] << 8;            // 1- and 2-bit fields never straddle a byte
-                uint32_t idx = (w >> (boff[j] & 7u)) & ((1u << BPC) - 1u);
-                if (GUARD && (j == 0 || j == 3 || j == 4 || j == 7)) {
-                    const uint32_t f = (fixed >> (8 * (j == 0 ? 0 : j == 3 ? 1 : j == 4 ? 2 : 3))) & 255u;
-                    if (f) idx = f;
-                }
-                x[j] = c_from(s_map[idx]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int k = l + 8 * j;
-                cpx v = c_make(0.0f, 0.0f);
-                if (GUARD && is_pilot_bin(k)) v = c_make(0.0f, 1.0f);
-                else if (data_rank<GUARD>(k) >= 0 && valid) {
-                    const long c = (long)sl * D + data_rank<GUARD>(k);
-                    if (c < ncar_local) {
-                        const uint32_t bit = (uint32_t)c * BPC, bb = bit >> 3;
-                        const uint32_t w = ((uint32_t)s_bits[bb] | ((uint32_t)s_bits[bb + 1] << 8)) >> (bit & 7);
-                        v = c_from(s_map[w & ((1u << BPC) - 1u)]);
-                    }
-                }
-                x[j] = v;
-            }
+        for (int j = 0; j < 8; j++) {                              // encode_block, src/transmitter.rs:144-165
+            uint32_t idx;
+            if (!GUARD) idx = rowp[8 * j];
+            else if (j == 1 || j == 2) idx = rowp[8 * j];
+            else if (j == 5 || j == 6) idx = rowp[8 * j - 3];
+            else if (j == 3) idx = fix3 != 0xFFu ? fix3 : rowp[d3];
+            else if (j == 4) idx = fix4 != 0xFFu ? fix4 : rowp[d4];
+            else if (j == 0) idx = fix0 != 0xFFu ? fix0 : rowp[0];
+            else idx = fix7 != 0xFFu ? fix7 : rowp[53];
+            x[j].v = lut[idx * 16];
         }
+        rowp += 4 * D;
         fft64_group_p(x, tw, tr, l);                               // prefix_block, src/transmitter.rs:168-181 (IFFT part)
         if (WRITE) {
             if (valid) {
@@ -228,6 +264,7 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
                 mx = fmaxf(mx, fmaxf(re, im));
             }
         }
+    }
     }
     if (!WRITE) {
         mx *= scale;

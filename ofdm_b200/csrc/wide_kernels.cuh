@@ -733,7 +733,7 @@ __device__ __forceinline__ long ramp_argmax_closed_w(const float2 *__restrict__ 
     return best > 0.0f ? k_lo + bidx : k_lo;
 }
 template <int MOD, bool GUARD, int PHASE>
-__global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs a)
+__global__ void __launch_bounds__(kThreads, 3) wide_acquire_kernel(const WideRxArgs a)
 {
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 768 : 1024;
@@ -866,16 +866,21 @@ __global__ void __launch_bounds__(kThreads) wide_acquire_kernel(const WideRxArgs
     FftTw T;
     fft1024_tw_init(T, a.tables->w1024, tid);
     __syncthreads();
-    cpx hsum[4];
+    cpx hsum[4], wt[4];
 #pragma unroll
-    for (int r = 0; r < 4; r++) hsum[r] = c_make(0.0f, 0.0f);
+    for (int r = 0; r < 4; r++) {
+        hsum[r] = c_make(0.0f, 0.0f);
+        wt[r] = phasor_from_turns_p(fstep * (uint64_t)(5 * kL + kCpW + tid + 256 * r));      // derotation at this thread's samples of row 5
+    }
+    const cpx row_step = phasor_from_turns_p(fstep * (uint64_t)kL);                         // ... advanced by one symbol per row (4 steps: no drift)
 #pragma unroll 1
     for (int row = 5; row < 10; row++) {
         cpx v[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const uint32_t n = row * kL + kCpW + tid + 256 * r;
-            v[r] = c_mul(c_from(x0[n]), phasor_from_turns_p(fstep * (uint64_t)n));
+            v[r] = c_mul(c_from(x0[n]), wt[r]);
+            wt[r] = c_mul(wt[r], row_step);
         }
         fft1024_block(v, bufA, bufB, T, tid);
         const unsigned long long *A = reinterpret_cast<const unsigned long long *>(bufA);
