@@ -163,13 +163,15 @@ int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t
  * Preamble search over ONE long capture: replaces `samples.xcorr_fft(locking_signal)` on a whole radio buffer
  * (src/receiver.rs:20-21, src/signals/mod.rs:186-217; examples/jetson_rx.rs:46-57,84 is the 2 M-sample case) with a single
  * 8 B/sample pass of the sliding Schmidl-Cox metric (docs/SPEC.md 4): every frame start is reported once as
- * (offset by the lag-1 rule, CFO estimate, metric). n_samples < 2^32. peaks[0 .. *n_peaks) is in ascending offset order;
+ * (offset by the lag-1 rule, CFO estimate, metric). Captures of any length that fits the device (64-bit offsets; with
+ * OFDM_MEM_HOST the capture is copied in chunks that overlap the scan). peaks[0 .. *n_peaks) is in ascending offset order;
  * with OFDM_MEM_DEVICE entries whose metric < 0 are unusable detections (frame head cut by the capture end) and
  * *n_peaks counts them too; with OFDM_MEM_HOST they are removed. More than max_peaks detections are truncated:
  * *n_peaks = min(detections, max_peaks) in both modes, so it can be handed to ofdm_rx_decode_capture as it is.
  * ofdm_sync_counts (waits for `stream`) tells a device-mode caller whether that happened: counts[0] = threshold crossings the
- * scan recorded, counts[1] = frames detected after the hold-off, counts[2] = entries written to peaks[];
- * counts[1] > counts[2] means peaks[] was too small.
+ * scan recorded, counts[1] = frames detected after the hold-off, counts[2] = entries written to peaks[], counts[3] = 3928-lag
+ * tiles that held more than 12 threshold crossings (their surplus is dropped; a capture made of frames never does that --
+ * OFDM_MEM_HOST turns it into an error). counts[1] > counts[2] means peaks[] was too small.
  */
 typedef struct {
     uint64_t offset;
@@ -178,7 +180,7 @@ typedef struct {
 } ofdm_peak;
 int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, ofdm_peak *peaks, uint32_t max_peaks,
                      uint32_t *n_peaks, int mem, void *stream);
-int ofdm_sync_counts(ofdm_engine *h, uint32_t counts[3], void *stream);
+int ofdm_sync_counts(ofdm_engine *h, uint32_t counts[4], void *stream);
 
 /*
  * Streaming receiver: decode every frame ofdm_sync_search found in one long capture -- the loop of

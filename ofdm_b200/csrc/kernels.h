@@ -21,6 +21,7 @@ typedef void (*TxKernel)(const TxArgs);
 typedef void (*ChanKernel)(const ChanArgs);
 typedef void (*BerKernel)(const BerArgs);
 typedef void (*SyncKernel)(const SyncArgs);
+typedef void (*SyncScanKernel)(const SyncArgs, const ScanTensorMap);
 typedef void (*CapturePrepKernel)(const SyncPeak *, uint32_t, uint64_t, uint32_t, uint64_t *, uint32_t *);
 typedef void (*RsKernel)(const RsArgs);
 typedef void (*WDecodeKernel)(const wide::WideRxArgs);
@@ -39,7 +40,7 @@ ChanKernel channel_conv_fn();
 ChanKernel channel_noise_fn();
 BerKernel ber_fn();
 // sync.cu
-SyncKernel sync_scan_fn();
+SyncScanKernel sync_scan_fn(bool tma);
 SyncKernel sync_select_fn();
 SyncKernel sync_refine_fn();
 CapturePrepKernel capture_prep_fn();

@@ -1,6 +1,7 @@
 // ofdm_engine.cu -- C ABI (include/ofdm_engine.h) over the sm_100a kernels. No torch types, no CPU fallback.
 #include "../../include/ofdm_engine.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -295,7 +296,10 @@ extern "C" int ofdm_engine_reserve(ofdm_engine *h, uint32_t max_streams, uint64_
         CU(h, h->scratch_f32.ensure(5 * sizeof(double) * (size_t)max_streams));
         CU(h, h->cap_base.ensure((sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)max_streams));
     }
-    if (max_capture_samples) CU(h, h->sync_scratch.ensure(sizeof(uint32_t) * (kSyncCandCap + 8)));
+    if (max_capture_samples >= 2 * (uint64_t)kSym) {                       // same layout as sync_plan
+        const uint64_t T = (max_capture_samples - 2 * kSym + 1 + kScanD - 1) / kScanD;
+        CU(h, h->sync_scratch.ensure(((32 + 4 * T + 7) & ~(size_t)7) + (size_t)T * kTileCand * 19 + 16));
+    }
     return 0;
 }
 
@@ -664,33 +668,105 @@ extern "C" int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, con
 }
 
 // ---- capture search ----------------------------------------------------------------------------------------------
-static int sync_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak *peaks, uint32_t max_peaks, uint32_t *n_peaks, cudaStream_t st)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+struct SyncPlan {
+    SyncArgs a;
+    ScanTensorMap tmap;
+    bool tma;
+    uint32_t grid;
+};
+
+// scratch + arguments of one capture search; the per-tile slots mean there is no candidate capacity to overflow globally
+static int sync_plan(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak *peaks, uint32_t max_peaks, cudaStream_t st, SyncPlan &p)
 {
     static_assert(sizeof(SyncPeak) == sizeof(ofdm_peak), "peak layout");
-    CU(h, h->sync_scratch.ensure(sizeof(uint32_t) * (kSyncCandCap + 8)));
-    SyncArgs a{};
+    static_assert(sizeof(ScanTensorMap) == sizeof(CUtensorMap), "tensor map size");
+    memset(&p, 0, sizeof p);
+    SyncArgs &a = p.a;
     a.iq = reinterpret_cast<const float2 *>(iq); a.n = n;
-    a.cand = h->sync_scratch.as<uint32_t>(); a.counters = a.cand + kSyncCandCap;
     a.tables = h->d_tables; a.peaks = reinterpret_cast<SyncPeak *>(peaks); a.max_peaks = max_peaks;
-    CU(h, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), st));
-    if (n >= 2 * kSym) {
-        const uint64_t lags = n - 2 * kSym + 1;
-        a.n_tiles = (uint32_t)((lags + kScanD - 1) / kScanD);
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        const uint32_t grid = a.n_tiles < (uint32_t)(2 * sms) ? a.n_tiles : (uint32_t)(2 * sms);    // persistent: 2 CTAs per SM
-        if (h->smem_configured.insert((const void *)sync_scan_fn()).second)
-            CU(h, cudaFuncSetAttribute((const void *)sync_scan_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_scan_smem_bytes()));
-        sync_scan_fn()<<<grid, kScanRows, sync_scan_smem_bytes(), st>>>(a);
-        sync_select_fn()<<<1, 1024, 0, st>>>(a);
-        const uint32_t rg = max_peaks < (uint32_t)kSyncCandCap ? max_peaks : (uint32_t)kSyncCandCap;
-        if (rg) sync_refine_fn()<<<rg, kAcqThreads, 0, st>>>(a);
-        h->launches += 3;
+    const uint64_t lags = n >= 2 * (uint64_t)kSym ? n - 2 * kSym + 1 : 0;
+    const uint64_t T = (lags + kScanD - 1) / kScanD;
+    if (T > 0xFFFFFFFFull) ENG_FAIL(h, OFDM_E_INVALID, "sync: capture too long");
+    a.n_tiles = (uint32_t)T;
+    const size_t C = (size_t)T * kTileCand;
+    const size_t off_cnt = 32, off_ord = (off_cnt + 4 * T + 7) & ~(size_t)7, off_sel = off_ord + 8 * C, off_cand = off_sel + 8 * C, off_keep = off_cand + 2 * C;
+    CU(h, h->sync_scratch.ensure(off_keep + C + 16));
+    uint8_t *base = h->sync_scratch.as<uint8_t>();
+    a.counters = reinterpret_cast<uint32_t *>(base);
+    a.tile_cnt = reinterpret_cast<uint32_t *>(base + off_cnt);
+    a.ordered = reinterpret_cast<uint64_t *>(base + off_ord);
+    a.sel = reinterpret_cast<uint64_t *>(base + off_sel);
+    a.tile_cand = reinterpret_cast<uint16_t *>(base + off_cand);
+    a.keep = base + off_keep;
+    CU(h, cudaMemsetAsync(base, 0, off_cnt + 4 * T, st));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    p.grid = (uint32_t)(2 * sms);                                          // persistent: 2 CTAs per SM
+    // TMA staging needs a 16-byte aligned capture and at least one full 8-sample row
+    p.tma = false;
+    if ((reinterpret_cast<uintptr_t>(iq) & 15) == 0 && n / kScanT >= 1 && n / kScanT < 0x7FFFFF00ull && encode_tiled_fn()) {
+        const cuuint64_t dims[2] = { 16, (cuuint64_t)(n / kScanT) };        // [rows][16 floats = 8 fc32 samples]
+        const cuuint64_t strides[1] = { 64 };
+        const cuuint32_t box[2] = { 16, 256 }, estr[2] = { 1, 1 };
+        const CUresult r = encode_tiled_fn()(reinterpret_cast<CUtensorMap *>(&p.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<ofdm_fc32 *>(iq),
+                                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        p.tma = r == CUDA_SUCCESS;
+    }
+    SyncScanKernel k = sync_scan_fn(p.tma);
+    if (h->smem_configured.insert((const void *)k).second)
+        CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_scan_smem_bytes(p.tma)));
+    return 0;
+}
+
+// scan tiles [tile_first, tile_first + tile_count)
+static int sync_scan_range(ofdm_engine *h, SyncPlan &p, uint32_t tile_first, uint32_t tile_count, cudaStream_t st)
+{
+    if (tile_count == 0) return 0;
+    p.a.tile_first = tile_first; p.a.tile_count = tile_count;
+    const uint32_t grid = tile_count < p.grid ? tile_count : p.grid;
+    sync_scan_fn(p.tma)<<<grid, kScanRows, sync_scan_smem_bytes(p.tma), st>>>(p.a, p.tmap);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+// hold-off + refinement of everything the scan launches recorded; *n_peaks = min(detections, max_peaks), on the device
+static int sync_finish(ofdm_engine *h, SyncPlan &p, uint32_t *n_peaks, cudaStream_t st)
+{
+    if (p.a.n_tiles) {
+        sync_select_fn()<<<1, kSelThreads, 0, st>>>(p.a);
+        // one CTA per detection; the launch is sized by max_peaks (in chunks), CTAs beyond the detection count exit at once
+        const uint32_t worst = p.a.n_tiles > 0xFFFFFFFFu / kTileCand ? 0xFFFFFFFFu : p.a.n_tiles * kTileCand;
+        const uint32_t rg = p.a.max_peaks < worst ? p.a.max_peaks : worst;
+        if (rg) sync_refine_fn()<<<rg, kAcqThreads, 0, st>>>(p.a);
+        h->launches += 2;
     }
     CU(h, cudaGetLastError());
-    // *n_peaks = min(detections, max_peaks) (clamped on the device); ofdm_sync_counts() reports truncation / overflow
-    CU(h, cudaMemcpyAsync(n_peaks, a.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaMemcpyAsync(n_peaks, p.a.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+static int sync_device(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak *peaks, uint32_t max_peaks, uint32_t *n_peaks, cudaStream_t st)
+{
+    SyncPlan p;
+    if (int rc = sync_plan(h, iq, n, peaks, max_peaks, st, p)) return rc;
+    if (int rc = sync_scan_range(h, p, 0, p.a.n_tiles, st)) return rc;
+    return sync_finish(h, p, n_peaks, st);
 }
 
 extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_samples, ofdm_peak *peaks, uint32_t max_peaks,
@@ -698,22 +774,42 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
 {
     if (!h) return OFDM_E_INVALID;
     if (!iq || !peaks || !n_peaks || max_peaks == 0) ENG_FAIL(h, OFDM_E_INVALID, "sync: bad arguments");
-    if (n_samples >= 0xFFFFFFFFull) ENG_FAIL(h, OFDM_E_INVALID, "sync: captures are limited to 2^32 - 2 samples per call");
     if (h->wide) ENG_FAIL(h, OFDM_E_INVALID, "sync search is not implemented for nfft = 1024");
     CU(h, cudaSetDevice(h->device));
     if (mem == OFDM_MEM_DEVICE) return sync_device(h, iq, n_samples, peaks, max_peaks, n_peaks, (cudaStream_t)stream);
-    cudaStream_t st = h->own_stream;
+
+    // Host capture: copied in chunks on the copy stream; the scan of the tiles a chunk completes runs while the next chunk
+    // is on the PCIe link. Hold-off, refinement and the peak list come once at the end.
+    cudaStream_t st = h->own_stream, cs = h->copy_stream;
     CU(h, h->s_iq.ensure(n_samples * sizeof(float2) + 16));
     CU(h, h->s_points.ensure(sizeof(ofdm_peak) * (size_t)max_peaks + 16));
     CU(h, h->s_len.ensure(16));
-    CU(h, cudaMemcpyAsync(h->s_iq.p, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, st));
-    int rc = sync_device(h, h->s_iq.as<ofdm_fc32>(), n_samples, h->s_points.as<ofdm_peak>(), max_peaks, h->s_len.as<uint32_t>(), st);
-    if (rc) return rc;
-    uint32_t cnt[2] = { 0, 0 };
-    CU(h, cudaMemcpyAsync(cnt, h->sync_scratch.as<uint32_t>() + kSyncCandCap, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    SyncPlan p;
+    if (int rc = sync_plan(h, h->s_iq.as<ofdm_fc32>(), n_samples, h->s_points.as<ofdm_peak>(), max_peaks, st, p)) return rc;
+    const uint64_t chunk = 8ull << 20;                                     // samples per copy (64 MB)
+    uint32_t tiles_done = 0;
+    int ev = 0;
+    for (uint64_t s0 = 0; s0 < n_samples || s0 == 0; s0 += chunk) {
+        const uint64_t s1 = s0 + chunk < n_samples ? s0 + chunk : n_samples;
+        if (s1 > s0) CU(h, cudaMemcpyAsync(h->s_iq.as<ofdm_fc32>() + s0, iq + s0, (s1 - s0) * sizeof(float2), cudaMemcpyHostToDevice, cs));
+        CU(h, cudaEventRecord(h->ev_copied[ev], cs));
+        CU(h, cudaStreamWaitEvent(st, h->ev_copied[ev], 0));
+        ev ^= 1;
+        // tile k reads samples [3928 k - 8, 3928 k - 8 + 4096): complete once s1 covers them (or the capture ends)
+        uint64_t ready = s1 >= n_samples ? p.a.n_tiles : (s1 + kScanT >= (uint64_t)kScanRows * kScanT ? (s1 + kScanT - (uint64_t)kScanRows * kScanT) / kScanD + 1 : 0);
+        if (ready > p.a.n_tiles) ready = p.a.n_tiles;
+        if (ready > tiles_done) {
+            if (int rc = sync_scan_range(h, p, tiles_done, (uint32_t)ready - tiles_done, st)) return rc;
+            tiles_done = (uint32_t)ready;
+        }
+        if (s1 >= n_samples) break;
+    }
+    if (int rc = sync_finish(h, p, h->s_len.as<uint32_t>(), st)) return rc;
+    uint32_t cnt[4] = { 0, 0, 0, 0 };
+    CU(h, cudaMemcpyAsync(cnt, p.a.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
-    if (cnt[0] > (uint32_t)kSyncCandCap) ENG_FAIL(h, OFDM_E_INVALID, "sync: %u threshold crossings exceed the candidate capacity %d; split the capture", cnt[0], kSyncCandCap);
-    uint32_t m = cnt[1] < max_peaks ? cnt[1] : max_peaks;
+    if (cnt[3]) ENG_FAIL(h, OFDM_E_INVALID, "sync: %u tile(s) of %d lags hold more than %d threshold crossings (the capture is not a sequence of frames)", cnt[3], kScanD, kTileCand);
+    const uint32_t m = cnt[1];
     std::vector<ofdm_peak> tmp(m);
     if (m) CU(h, cudaMemcpy(tmp.data(), h->s_points.p, sizeof(ofdm_peak) * m, cudaMemcpyDeviceToHost));
     uint32_t k = 0;
@@ -722,15 +818,15 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
     return 0;
 }
 
-extern "C" int ofdm_sync_counts(ofdm_engine *h, uint32_t counts[3], void *stream)
+extern "C" int ofdm_sync_counts(ofdm_engine *h, uint32_t counts[4], void *stream)
 {
     if (!h || !counts) return OFDM_E_INVALID;
     if (!h->sync_scratch.p) ENG_FAIL(h, OFDM_E_INVALID, "sync counts: no ofdm_sync_search has run on this handle");
     CU(h, cudaSetDevice(h->device));
-    uint32_t c[3] = { 0, 0, 0 };
-    CU(h, cudaMemcpyAsync(c, h->sync_scratch.as<uint32_t>() + kSyncCandCap, sizeof c, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    uint32_t c[4] = { 0, 0, 0, 0 };
+    CU(h, cudaMemcpyAsync(c, h->sync_scratch.p, sizeof c, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(h, cudaStreamSynchronize((cudaStream_t)stream));
-    counts[0] = c[0]; counts[1] = c[2]; counts[2] = c[1];
+    counts[0] = c[0]; counts[1] = c[2]; counts[2] = c[1]; counts[3] = c[3];
     return 0;
 }
 

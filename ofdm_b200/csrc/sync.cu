@@ -3,7 +3,7 @@
 
 namespace ofdm {
 
-SyncKernel sync_scan_fn() { return sync_scan_kernel<>; }
+SyncScanKernel sync_scan_fn(bool tma) { return tma ? (SyncScanKernel)sync_scan_kernel<true> : (SyncScanKernel)sync_scan_kernel<false>; }
 SyncKernel sync_select_fn() { return sync_select_kernel<>; }
 SyncKernel sync_refine_fn() { return sync_refine_kernel<>; }
 CapturePrepKernel capture_prep_fn() { return capture_prep_kernel<>; }

@@ -364,10 +364,11 @@ class Engine:
                     "ofdm_sync_search")
 
     def sync_counts(self, stream=0):
-        """(threshold crossings, frames detected, entries written to peaks[]) of the last sync search; waits for `stream`."""
-        c = (C.c_uint32 * 3)()
+        """(threshold crossings, frames detected, entries written to peaks[], overflowed tiles) of the last sync search;
+        waits for `stream`."""
+        c = (C.c_uint32 * 4)()
         self._check(self.lib.ofdm_sync_counts(self._h, c, stream or None), "ofdm_sync_counts")
-        return int(c[0]), int(c[1]), int(c[2])
+        return int(c[0]), int(c[1]), int(c[2]), int(c[3])
 
     def reserve(self, max_streams: int, max_capture_samples: int = 0):
         self._check(self.lib.ofdm_engine_reserve(self._h, max_streams, max_capture_samples), "ofdm_engine_reserve")

@@ -503,7 +503,8 @@ def test_device_mode_sync_search_truncates_to_max_peaks(ob, oo):
         peaks = torch.zeros((max_peaks, 2), dtype=torch.int64, device="cuda")
         n_peaks = torch.full((1,), 12345, dtype=torch.int32, device="cuda")
         eng.sync_search_device(d_cap.data_ptr(), cap.size, peaks.data_ptr(), max_peaks, n_peaks.data_ptr())
-        crossings, detections, written = eng.sync_counts()
+        crossings, detections, written, overflowed = eng.sync_counts()
+        assert overflowed == 0
         k = int(n_peaks.item())
         assert k == written == min(len(truth), max_peaks) and detections == len(truth) and crossings >= detections
         rec = peaks[:k].cpu().numpy().view(ob.engine.PEAK_DTYPE).reshape(-1)
@@ -550,6 +551,69 @@ def test_more_than_65535_streams_per_call(ob, oo):
         cap = rx[i, : int(rl[i])].cpu().numpy().view(np.complex64).reshape(-1).astype(np.complex128)
         ref = oo.decode(cap, ocfg, want_points=False)
         assert ref.status == 0 and ref.data.tobytes() == bytes(out[i, :plen_b].cpu().numpy())
+    eng.close()
+
+
+def test_capture_search_dense_short_frames(ob, oo):
+    """More than 50 000 back-to-back short frames in one capture (the old design capped a search at 8 192 candidates): every
+    frame start is found, in order, and the list equals the oracle's."""
+    eng = ob.Engine(ob.Config(modulation=0, guard_bands=True), 0)
+    cfg = oo.make_cfg(True, 0, False)
+    tx = oo.tx(b"", cfg).astype(np.complex64)                                       # 13 symbols = 1040 samples
+    assert tx.size == 1040
+    rng = np.random.default_rng(51)
+    n_frames = 50_500
+    gaps = rng.integers(0, 200, n_frames)
+    starts = 700 + np.cumsum(tx.size + gaps) - (tx.size + gaps[0])
+    n = int(starts[-1]) + tx.size + 500
+    cap = (0.004 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    cfos = rng.uniform(-0.03, 0.03, n_frames)
+    t = np.arange(tx.size)
+    for p, f in zip(starts, cfos):
+        cap[p: p + tx.size] += tx * np.exp(1j * f * t).astype(np.complex64)
+    got = eng.sync_search(cap, max_peaks=60_000)
+    crossings, detections, written, overflowed = eng.sync_counts()
+    assert overflowed == 0 and detections == written == len(got) and crossings >= detections
+    ref = oo.sync_search(cap, max_peaks=60_000)
+    assert len(got) == len(ref) >= n_frames
+    assert (got["offset"] == ref["offset"]).all()
+    np.testing.assert_allclose(got["f_delta"], ref["f_delta"], atol=1e-6)
+    found = set(int(x) for x in got["offset"])
+    # lag - 1 rule, no channel; a frame that follows its predecessor within a few samples can be detected a little off
+    assert sum((int(p) - 1) in found for p in starts) >= 0.99 * n_frames
+    assert (np.diff(got["offset"].astype(np.int64)) > 0).all()
+    eng.close()
+
+
+def test_capture_search_beyond_2_pow_32_samples(ob, oo):
+    """64-bit offsets: frames on both sides of sample 2^32 of a 4.4e9-sample device capture (35 GB of HBM)."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 45 << 30:
+        pytest.skip("needs 45 GB of free device memory")
+    eng = ob.Engine(ob.Config(modulation=1, guard_bands=True, fec=True, cfo_mode=1, phase_mode=1), 0)
+    cfg = oo.make_cfg(True, 1, True)
+    pay = bytes(range(200))
+    tx = torch.from_numpy(oo.tx(pay, cfg).astype(np.complex64).view(np.float32).reshape(-1, 2)).cuda()
+    n = 4_400_000_123
+    cap = torch.zeros((n, 2), dtype=torch.float32, device="cuda")                   # an all-zero floor never crosses the threshold (0 > 0)
+    starts = [5_000, (1 << 32) - 1_000, (1 << 32) + 77_777, n - tx.shape[0] - 3]
+    for p in starts:
+        cap[p: p + tx.shape[0]] += tx
+    peaks = torch.zeros((16, 2), dtype=torch.int64, device="cuda")
+    n_peaks = torch.zeros(1, dtype=torch.int32, device="cuda")
+    eng.sync_search_device(cap.data_ptr(), n, peaks.data_ptr(), 16, n_peaks.data_ptr())
+    k = int(n_peaks.item())
+    rec = peaks[:k].cpu().numpy().view(ob.engine.PEAK_DTYPE).reshape(-1)
+    assert [int(x) for x in rec["offset"]] == [p - 1 for p in starts]
+    out = torch.zeros((k, 256), dtype=torch.uint8, device="cuda")
+    out_len = torch.zeros(k, dtype=torch.int32, device="cuda")
+    status = torch.full((k,), -1, dtype=torch.int32, device="cuda")
+    eng.decode_capture_device(cap.data_ptr(), n, peaks.data_ptr(), k, 1 << 16, out.data_ptr(), 256, out_len.data_ptr(), status.data_ptr())
+    torch.cuda.synchronize()
+    # the lag - 1 rule puts the frame start one sample early; the decoder then finds lag 1 itself
+    assert (status == 0).all().item() and all(bytes(out[i, :200].cpu().numpy()) == pay for i in range(k))
+    del cap
     eng.close()
 
 
