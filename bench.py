@@ -541,9 +541,13 @@ def wide_leg(args, steps, barrier, local_rank):
 def capture_bench(args, rank, local_rank, world, steps=None):
     """BASELINE.json configs[2]: Schmidl-Cox preamble search + CFO estimation over one long capture (8 B/sample, one pass).
     A noise floor (sigma 0.01) with one 64QAM frame (S=2038) every 1 000 003 samples (prime stride), each with its own CFO.
-    Under torchrun every rank searches its own capture (weak scaling)."""
+    Under torchrun ONE capture of --capture-samples x N samples is split over the N ranks (SURVEY.md 8e partition 2:
+    contiguous ranges, 2 L + frame_len overlap, duplicates removed by ownership of the offset, peak counts gathered); every rank
+    synthesises just the samples it reads. Only CPU baseline this config has: the reference's own method on a 2 M-sample
+    window (examples/jetson_rx.rs:16), timed on the host in the same run (cpu_baseline)."""
     import torch
     import ofdm_b200 as ob
+    from ofdm_b200 import dist as od
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -551,15 +555,19 @@ def capture_bench(args, rank, local_rank, world, steps=None):
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload_cfg()
     eng = ob.Engine(cfg, local_rank)
-    n = int(args.capture_samples)
+    n_total = int(args.capture_samples) * world
     stride, S = 1_000_003, args.syms
     payload_len = cfg.max_payload(S)
     frame_len = cfg.frame_len(payload_len)
+    shard = od.capture_shards(n_total, world, frame_len)[rank]
+    n = shard.read_hi - shard.read_lo                                          # samples this rank reads
     g = torch.Generator(device=dev)
     g.manual_seed(0x0FD3 + rank)
     st = torch.cuda.current_stream().cuda_stream
-    # one transmitted frame, reused with a different CFO at every position
-    pay = torch.randint(0, 256, (1, payload_len), dtype=torch.uint8, device=dev, generator=g)
+    # one transmitted frame (same on every rank), reused with a different CFO at every position
+    gp = torch.Generator(device=dev)
+    gp.manual_seed(0x0FD3)
+    pay = torch.randint(0, 256, (1, payload_len), dtype=torch.uint8, device=dev, generator=gp)
     pl = torch.full((1,), payload_len, dtype=torch.int32, device=dev)
     tx = torch.empty((1, frame_len, 2), dtype=torch.float32, device=dev)
     fl = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -569,14 +577,19 @@ def capture_bench(args, rank, local_rank, world, steps=None):
     cap = torch.empty((n, 2), dtype=torch.float32, device=dev)
     cap.normal_(0.0, 0.01, generator=g)
     capc = torch.view_as_complex(cap)
-    positions = list(range(5000 + 7 * rank, n - frame_len - 200, stride))
-    cfos = (torch.rand(len(positions), generator=g, device=dev) * 2 - 1) * (0.9 * np.pi / 80)
+    positions = np.arange(5000, n_total - frame_len - 200, stride, dtype=np.int64)              # global frame starts
+    cfo_all = ((positions * 2654435761 % (1 << 32)) / float(1 << 32) * 2 - 1) * (0.9 * np.pi / 80)       # per frame, the same on every rank
     t = torch.arange(frame_len, device=dev, dtype=torch.float32)
-    for p, f in zip(positions, cfos):
-        capc[p: p + frame_len] += frame * torch.polar(torch.ones_like(t), f * t)
-    max_peaks = 8192
+    touching = np.flatnonzero((positions + frame_len > shard.read_lo) & (positions < shard.read_hi))
+    for i in touching:                                                         # frames cut by the range's ends are added in part
+        p, f = int(positions[i]), float(cfo_all[i])
+        lo, hi = max(p, shard.read_lo), min(p + frame_len, shard.read_hi)
+        rot = torch.polar(torch.ones(hi - lo, device=dev), f * t[lo - p: hi - p])
+        capc[lo - shard.read_lo: hi - shard.read_lo] += frame[lo - p: hi - p] * rot
+    max_peaks = 16384
     peaks = torch.zeros((max_peaks, 2), dtype=torch.int64, device=dev)          # 16-byte ofdm_peak records
     n_peaks = torch.zeros(1, dtype=torch.int32, device=dev)
+    eng.reserve(0, n)
     torch.cuda.synchronize()
 
     def step():
@@ -596,6 +609,7 @@ def capture_bench(args, rank, local_rank, world, steps=None):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     ev0.record()
     for _ in range(steps):
         step()
@@ -603,37 +617,72 @@ def capture_bench(args, rank, local_rank, world, steps=None):
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1) / steps
-    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms = float(tt.item())
     k = int(n_peaks.item())
     rec = peaks[:k].cpu().numpy().view(ob.engine.PEAK_DTYPE).reshape(-1)
-    found = rec["offset"].astype(np.int64)
-    want = np.array(positions, np.int64) - 1                                   # lag - 1 rule, no channel delay
-    exact = bool(k == len(positions) and (found == want).all())
-    cfo_err = float(np.abs(rec["f_delta"] - cfos.cpu().numpy()).max()) if exact else None
+    rec = rec[rec["metric"] >= 0]                                              # frame heads cut by the range's end
+    found, mine = od.owned_peaks(rec["offset"].astype(np.int64), shard)        # de-duplication: keep what this rank owns
+    own = (positions - 1 >= shard.own_lo) & (positions - 1 < shard.own_hi)     # lag - 1 rule, no channel delay
+    want = positions[own] - 1
+    exact = bool(int(mine.sum()) == len(want) and (found[mine] == want).all())
+    cfo_err = float(np.abs(rec["f_delta"][mine] - cfo_all[own]).max()) if exact and len(want) else (0.0 if exact else float("nan"))
+    red = torch.tensor([ms, 0.0 if exact else 1.0, cfo_err if exact else 1e9], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([int(mine.sum()), k], dtype=torch.int64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)                              # the gather of the (owned) peak counts
+    ms, exact_all, cfo_err = float(red[0].item()), float(red[1].item()) == 0.0, float(red[2].item())
+    frames_once, detections_raw = int(cnt[0].item()), int(cnt[1].item())
     peak, src = read_peaks()
-    achieved = 8.0 * n / (ms * 1e-3) / 1e9
+    achieved = 8.0 * n / (ms * 1e-3) / 1e9                                     # per-GPU kernel rate on the samples a rank reads
     line = None
     if rank == 0:
-        line = ({"metric": "sync_search_msamples_per_s", "value": round(world * n / (ms * 1e-3) / 1e6, 1), "unit": "Msamples/s",
-                          "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4),
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": f"capture_{n}", "samples": n, "frames": len(positions), "frame_stride": stride,
-                                     "frame_samples": frame_len, "noise_sigma": 0.01, "l2": "input (%.1f GB) larger than L2" % (8 * n / 1e9)},
-                          "roofline": {"bound": "hbm", "kernel": "sync_scan_kernel (+select, refine)", "achieved": round(achieved, 1), "peak": peak,
-                                       "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": src,
-                                       "algorithmic_bytes_per_launch": 8 * n},
-                          "all_offsets_exact": exact, "max_cfo_abs_err": cfo_err, "peaks_found": k,
-                          "gpu_launches": int(eng.kernel_launches - l0), "clocks": clocks})
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = capture_cpu_baseline(cap, args)
+        line = ({"metric": "sync_search_msamples_per_s", "value": round(n_total / (ms * 1e-3) / 1e6, 1), "unit": "Msamples/s",
+                 "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4),
+                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                 "config": {"workload": f"capture_{n_total}", "samples": n_total, "samples_read_per_gpu": n, "frames": int(len(positions)),
+                            "frame_stride": stride, "frame_samples": frame_len, "noise_sigma": 0.01,
+                            "sharding": "one capture, contiguous ranges, overlap 2L + frame_len, de-duplicated by offset ownership" if world > 1 else "none",
+                            "l2": "input (%.1f GB/GPU) larger than L2" % (8 * n / 1e9)},
+                 "roofline": {"bound": "hbm", "kernel": "sync_scan_kernel (+select, refine)", "achieved": round(achieved, 1), "peak": peak,
+                              "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": src,
+                              "algorithmic_bytes_per_launch": 8 * n, "kernel_ms": round(ms, 4)},
+                 "all_offsets_exact": exact_all, "max_cfo_abs_err": cfo_err, "peaks_found": frames_once,
+                 "each_frame_found_once": bool(exact_all and frames_once == len(positions)), "detections_before_dedup": detections_raw,
+                 "cpu_baseline": cpu, "gpu_launches": int(eng.kernel_launches - l0), "clocks": clocks})
     eng.close()
     del cap, capc
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
     return line
+
+
+def capture_cpu_baseline(cap, args):
+    """The reference's own method for this config (src/signals/mod.rs:186-217 via src/receiver.rs:20-21): one whole-buffer
+    cross-correlation against the locking ramp + arg-max, on the radio example's 2 000 000-sample buffer
+    (examples/jetson_rx.rs:16) -- three length-(2M - 1) complex f64 transforms. Timed with the oracle's FFT-based restatement
+    on one host thread (the reference is single-threaded), windows taken from the start of this run's capture."""
+    from oracle import oracle as oo
+    M = 2_000_000
+    lock = oo.locking_signal(80)
+    win = cap[:M].cpu().numpy().view(np.complex64).reshape(-1).astype(np.complex128)
+    oo.xcorr_fft(win[:4096], lock)                                             # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        idx, _ = oo.xcorr_fft(win, lock)                                         # correlation + first strict arg-max of |c|^2
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min(args.cpu_seconds, 6.0):
+            break
+    return {"value": round(M * reps / dt / 1e6, 3), "unit": "Msamples/s", "cores": 1, "kind": "port",
+            "sample": f"{reps} x one 2 000 000-sample window ({dt:.1f} s): xcorr_fft against the locking ramp + arg-max, f64, three power-of-two "
+                      "transforms (the reference's are of length 2M - 1: this is an upper bound on its speed); the reference's whole-buffer "
+                      "search yields ONE frame per buffer, the engine every frame",
+            "argmax_index": idx}
 
 
 def tx_bench(args, rank, local_rank, world, steps=None):

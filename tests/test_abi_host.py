@@ -104,8 +104,9 @@ def test_shard_helpers():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     sh = dist.capture_shards(10_000_000, 8, 163840)
-    assert sh[0][0] == 0 and sh[-1][1] == 10_000_000
-    assert all(a[1] - b[0] == 2 * 80 + 163840 for a, b in zip(sh, sh[1:]))
+    assert sh[0].read_lo == 0 and sh[-1].read_hi == 10_000_000
+    assert sh[0].own_lo == 0 and sh[-1].own_hi == 10_000_000 and all(a.own_hi == b.own_lo for a, b in zip(sh, sh[1:]))    # owned ranges partition
+    assert all(a.read_hi - b.own_lo == 2 * 80 + 163840 and b.own_lo - b.read_lo == dist.CAPTURE_GUARD for a, b in zip(sh, sh[1:]))
     assert dist.err_rate([3, 2, 300, 0]) == 0.01
 
 
