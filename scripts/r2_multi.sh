@@ -18,4 +18,4 @@ for k in ("weak", "strong", "capture"):
     except Exception as e:
         print(k, "failed", e)
 EOF
-tail -3 $O/multi_weak.err $O/multi_strong.err $O/multi_cap.err
+tail -n 3 $O/multi_weak.err $O/multi_strong.err $O/multi_cap.err
