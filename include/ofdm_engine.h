@@ -193,6 +193,28 @@ int ofdm_rx_decode_capture(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_sampl
                            int mem, void *stream);
 
 /*
+ * fc32 capture FILE -> every frame decoded: `decode!(bytes_to_sig(read(path))[start..stop])` of examples/lab3c.rs:57-74
+ * (src/utils.rs:238-254 is the file format: interleaved native-endian f32 pairs, what `rx_samples_to_file --type float` writes,
+ * data/receive.sh:1) for captures of any length holding any number of frames -- the radio loop of examples/jetson_rx.rs:46-57
+ * decodes one frame per buffer. The file is read in chunks of chunk_samples (0 = 32 Mi samples) straight into two pinned
+ * buffers, one chunk ahead of the GPU; a chunk is one PCIe copy + ofdm_sync_search + ofdm_rx_decode_capture on the device;
+ * chunks overlap by max_frame_samples (the longest frame the link carries, head included), so every frame is decoded exactly
+ * once from a chunk that holds all of it. start / stop are sample indices into the file (stop = 0: end of file); frame
+ * offsets are relative to start. Frame i's payload is at out[i * out_stride .. + frames[i].out_len).
+ * Fails (OFDM_E_INVALID) when the file holds more than max_frames frames or a chunk more than 16 384.
+ */
+typedef struct {
+    uint64_t offset;     /* frame start, samples from `start` (lag - 1 rule, src/receiver.rs:21) */
+    float    f_delta;    /* CFO estimate, rad/sample */
+    float    metric;     /* Schmidl-Cox metric at the detection */
+    int32_t  status;     /* OFDM_OK ... */
+    uint32_t out_len;    /* decoded payload bytes */
+} ofdm_frame_info;
+int ofdm_rx_decode_file(ofdm_engine *h, const char *path, uint64_t start, uint64_t stop, uint32_t chunk_samples,
+                        uint32_t max_frame_samples, uint8_t *out, uint32_t out_stride, ofdm_frame_info *frames,
+                        uint32_t max_frames, uint32_t *n_frames);
+
+/*
  * BER: replaces utils::Analysis::new (src/utils.rs:45-68) for a batch and accumulates into
  * counters[4] = { bit_errs, byte_errs, bits_compared, frames_failed }. A stream whose status != OK or
  * whose length differs from ref_len counts as failed with all its reference bits in error.
@@ -202,6 +224,15 @@ int ofdm_ber_accumulate(ofdm_engine *h, const uint8_t *ref, const uint32_t *ref_
                         const uint8_t *got, const uint32_t *got_len, uint32_t got_stride,
                         const int32_t *status, uint32_t n_streams, uint64_t *counters,
                         int mem, void *stream);
+
+/*
+ * The path's only collective: sum-reduce counters[4] over the ranks of an NCCL communicator (one process per GPU; the
+ * fields of utils::Analysis, src/utils.rs:39-43, plus the failure count). nccl_comm is the caller's ncclComm_t. The library
+ * has no link-time NCCL dependency: ncclAllReduce is resolved at the first call from the NCCL already loaded in the
+ * process (else libnccl.so.2). OFDM_MEM_DEVICE: in place on `stream`; OFDM_MEM_HOST: copied to the device, reduced, copied
+ * back, synchronous. Callers without NCCL sum the four integers themselves -- that is all this does.
+ */
+int ofdm_stats_allreduce(ofdm_engine *h, uint64_t *counters, void *nccl_comm, int mem, void *stream);
 
 /*
  * Reed-Solomon RS(255,223) outer code with the reference's stream framing.

@@ -69,7 +69,7 @@ def build_engine(force: bool = False, verbose: bool = False, units=None) -> str:
         if verbose and log:
             print(f"==== {unit}.cu\n{log}")
     objs = [os.path.join(OBJ_DIR, u + ".o") for u in UNITS]
-    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB_PATH, *objs],
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB_PATH, *objs, "-ldl", "-lpthread"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -4,7 +4,15 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cstdio>
+#include <future>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <set>
@@ -65,6 +73,8 @@ struct ofdm_engine {
     std::vector<cudaEvent_t> prof_ev;
     uint32_t prof_cap = 0, prof_n = 0;
     std::set<const void *> smem_configured;   // kernels whose dynamic shared memory limit has been raised
+    void *pin[2] = { nullptr, nullptr };      // pinned chunk buffers of ofdm_rx_decode_file
+    size_t pin_bytes = 0;
 };
 
 #define ENG_FAIL(h, code, ...)                                   \
@@ -277,6 +287,7 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
                        &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base, &h->rs_tables };
     for (DevBuf *b : bufs) b->release();
+    for (void *p : h->pin) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
@@ -869,6 +880,174 @@ extern "C" int ofdm_rx_decode_capture(ofdm_engine *h, const ofdm_fc32 *iq, uint6
     CU(h, cudaMemcpyAsync(out, h->s_bytes.p, ob, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(out_len, h->s_len.p, sizeof(uint32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int32_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- fc32 file ingest ------------------------------------------------------------------------------------------------
+// pread `bytes` at `off` into dst, split over `pieces` threads (page-cache / NVMe reads scale with the queue depth)
+static bool pread_parallel(int fd, uint64_t off, uint8_t *dst, size_t bytes, int pieces)
+{
+    std::vector<std::thread> th;
+    std::vector<int> ok((size_t)pieces, 1);
+    const size_t step = (bytes + pieces - 1) / pieces;
+    for (int i = 0; i < pieces; i++) {
+        const size_t a = (size_t)i * step;
+        if (a >= bytes) break;
+        const size_t b = std::min(bytes, a + step);
+        th.emplace_back([=, &ok] {
+            size_t done = a;
+            while (done < b) {
+                const ssize_t got = pread(fd, dst + done, b - done, (off_t)(off + done));
+                if (got <= 0) { ok[(size_t)i] = 0; return; }
+                done += (size_t)got;
+            }
+        });
+    }
+    for (auto &t : th) t.join();
+    return std::all_of(ok.begin(), ok.end(), [](int v) { return v != 0; });
+}
+
+extern "C" int ofdm_rx_decode_file(ofdm_engine *h, const char *path, uint64_t start, uint64_t stop, uint32_t chunk_samples,
+                                   uint32_t max_frame_samples, uint8_t *out, uint32_t out_stride, ofdm_frame_info *frames,
+                                   uint32_t max_frames, uint32_t *n_frames)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!path || !out || !frames || !n_frames || max_frames == 0 || out_stride == 0 || max_frame_samples == 0)
+        ENG_FAIL(h, OFDM_E_INVALID, "decode file: bad arguments");
+    if (h->wide) ENG_FAIL(h, OFDM_E_INVALID, "decode file is not implemented for nfft = 1024");
+    *n_frames = 0;
+    const uint64_t chunk = chunk_samples ? chunk_samples : (1u << 25);
+    const uint64_t overlap = max_frame_samples;
+    if (chunk <= overlap) ENG_FAIL(h, OFDM_E_INVALID, "decode file: chunk_samples must exceed max_frame_samples");
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) ENG_FAIL(h, OFDM_E_INVALID, "decode file: cannot open %s", path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); ENG_FAIL(h, OFDM_E_INVALID, "decode file: cannot stat %s", path); }
+    const uint64_t n_file = (uint64_t)sb.st_size / 8;                      // bytes_to_sig: 8 bytes per sample (src/utils.rs:238-254)
+    if (stop == 0 || stop > n_file) stop = n_file;
+    if (start > stop) start = stop;
+    const uint64_t n = stop - start;
+    struct Closer { int fd; ~Closer() { close(fd); } } closer{ fd };
+    if (n == 0) return 0;
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t buf_samples = std::min(chunk, n);
+    if (h->pin_bytes < buf_samples * 8) {
+        for (void *&p : h->pin) { if (p) cudaFreeHost(p); p = nullptr; }
+        h->pin_bytes = 0;
+        for (void *&p : h->pin) CU(h, cudaHostAlloc(&p, buf_samples * 8, cudaHostAllocDefault));
+        h->pin_bytes = buf_samples * 8;
+    }
+    const uint32_t max_peaks = std::min<uint32_t>(max_frames, 16384u);     // detections one chunk may hold
+    cudaStream_t st = h->own_stream;
+    CU(h, h->s_iq.ensure(buf_samples * 8 + 16));
+    CU(h, h->s_points.ensure(sizeof(ofdm_peak) * (size_t)max_peaks + 16));
+    CU(h, h->s_bytes.ensure((size_t)max_peaks * out_stride));
+    CU(h, h->s_len.ensure(sizeof(uint32_t) * (size_t)max_peaks + 16));
+    CU(h, h->s_status.ensure(sizeof(int32_t) * (size_t)max_peaks));
+    CU(h, h->s_aux.ensure(16));
+    uint32_t *d_npk = h->s_aux.as<uint32_t>();
+
+    // chunk plan: chunks advance by chunk - overlap; a chunk owns the frames that start before its last `overlap` samples
+    std::vector<std::pair<uint64_t, uint64_t>> plan;
+    for (uint64_t a = 0;;) {
+        const uint64_t b = std::min(n, a + chunk);
+        plan.emplace_back(a, b);
+        if (b >= n) break;
+        a = b - overlap;
+    }
+    auto load = [&](size_t i) { return pread_parallel(fd, 8 * (start + plan[i].first), (uint8_t *)h->pin[i & 1], 8 * (plan[i].second - plan[i].first), 8); };
+    std::future<bool> ahead = std::async(std::launch::async, load, (size_t)0);
+    std::vector<ofdm_peak> pk(max_peaks);
+    std::vector<uint32_t> lens(max_peaks);
+    std::vector<int32_t> stat(max_peaks);
+    std::vector<uint8_t> rows;
+    uint32_t count = 0;
+    bool have_last = false;
+    uint64_t last = 0;
+    for (size_t i = 0; i < plan.size(); i++) {
+        if (!ahead.get()) ENG_FAIL(h, OFDM_E_INVALID, "decode file: short read from %s", path);
+        if (i + 1 < plan.size()) ahead = std::async(std::launch::async, load, i + 1);       // overlaps this chunk's PCIe copy and kernels
+        const uint64_t cn = plan[i].second - plan[i].first;
+        const bool final = i + 1 == plan.size();
+        auto drain = [&]() { if (ahead.valid()) ahead.wait(); };                            // never leave a reader running on an error path
+        if (cn < (uint64_t)kHeadSyms * kSym) continue;
+#define FCU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { drain(); ENG_FAIL(h, OFDM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
+        FCU(cudaMemcpyAsync(h->s_iq.p, h->pin[i & 1], cn * 8, cudaMemcpyHostToDevice, st));
+        if (int rc = sync_device(h, h->s_iq.as<ofdm_fc32>(), cn, h->s_points.as<ofdm_peak>(), max_peaks, d_npk, st)) { drain(); return rc; }
+        uint32_t cnt[4] = { 0, 0, 0, 0 };
+        FCU(cudaMemcpyAsync(cnt, h->sync_scratch.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        if (cnt[3] || cnt[2] > cnt[1]) { drain(); ENG_FAIL(h, OFDM_E_INVALID, "decode file: a chunk holds more than %u detections; use a smaller chunk_samples", max_peaks); }
+        const uint32_t k = cnt[1];
+        if (k == 0) continue;
+        if (int rc = capture_decode_device(h, h->s_iq.as<ofdm_fc32>(), cn, h->s_points.as<ofdm_peak>(), k, (uint32_t)overlap, h->s_bytes.as<uint8_t>(),
+                                           out_stride, h->s_len.as<uint32_t>(), h->s_status.as<int32_t>(), st)) { drain(); return rc; }
+        FCU(cudaMemcpyAsync(pk.data(), h->s_points.p, sizeof(ofdm_peak) * k, cudaMemcpyDeviceToHost, st));
+        FCU(cudaMemcpyAsync(lens.data(), h->s_len.p, sizeof(uint32_t) * k, cudaMemcpyDeviceToHost, st));
+        FCU(cudaMemcpyAsync(stat.data(), h->s_status.p, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        uint32_t width = 0;
+        for (uint32_t j = 0; j < k; j++) if (stat[j] == OFDM_OK && lens[j] > width) width = lens[j];
+        if (width) {                                                        // one strided device -> host copy of the payload rows
+            rows.resize((size_t)k * width);
+            FCU(cudaMemcpy2DAsync(rows.data(), width, h->s_bytes.p, out_stride, width, k, cudaMemcpyDeviceToHost, st));
+            FCU(cudaStreamSynchronize(st));
+        }
+#undef FCU
+        for (uint32_t j = 0; j < k; j++) {
+            if (pk[j].metric < 0.0f) continue;                             // frame head cut by the chunk end
+            if (!final && pk[j].offset >= cn - overlap) continue;          // owned by the next chunk
+            const uint64_t absolute = plan[i].first + pk[j].offset;
+            if (have_last && absolute < last + (uint64_t)kSyncHoldoff) continue;           // already reported from the previous chunk's body
+            have_last = true; last = absolute;
+            if (count >= max_frames) { drain(); ENG_FAIL(h, OFDM_E_INVALID, "decode file: more than max_frames = %u frames", max_frames); }
+            ofdm_frame_info &f = frames[count];
+            f.offset = absolute; f.f_delta = pk[j].f_delta; f.metric = pk[j].metric; f.status = stat[j];
+            f.out_len = stat[j] == OFDM_OK ? lens[j] : 0;
+            if (f.out_len) memcpy(out + (size_t)count * out_stride, rows.data() + (size_t)j * width, f.out_len);
+            count++;
+        }
+    }
+    *n_frames = count;
+    return 0;
+}
+
+// ---- statistics reduction (the path's only collective) ---------------------------------------------------------------------
+typedef int (*NcclAllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+static NcclAllReduceFn nccl_allreduce_fn()
+{
+    static NcclAllReduceFn fn = [] {
+        void *sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");                  // an NCCL the process already exposes globally
+        if (!sym) {
+            void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the NCCL already loaded (e.g. by the caller's framework)
+            if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+            if (lib) sym = dlsym(lib, "ncclAllReduce");
+        }
+        return (NcclAllReduceFn)sym;
+    }();
+    return fn;
+}
+
+extern "C" int ofdm_stats_allreduce(ofdm_engine *h, uint64_t *counters, void *nccl_comm, int mem, void *stream)
+{
+    if (!h) return OFDM_E_INVALID;
+    if (!counters || !nccl_comm) ENG_FAIL(h, OFDM_E_INVALID, "stats allreduce: bad arguments");
+    NcclAllReduceFn ar = nccl_allreduce_fn();
+    if (!ar) ENG_FAIL(h, OFDM_E_INVALID, "stats allreduce: no NCCL library in this process (libnccl.so.2 not found)");
+    CU(h, cudaSetDevice(h->device));
+    constexpr int kNcclUint64 = 5, kNcclSum = 0;                           // ncclDataType_t / ncclRedOp_t (nccl.h)
+    if (mem == OFDM_MEM_DEVICE) {
+        const int rc = ar(counters, counters, 4, kNcclUint64, kNcclSum, nccl_comm, (cudaStream_t)stream);
+        if (rc != 0) ENG_FAIL(h, OFDM_E_CUDA, "ncclAllReduce failed (ncclResult_t %d)", rc);
+        return 0;
+    }
+    cudaStream_t st = h->own_stream;
+    CU(h, cudaMemcpyAsync(h->counters.p, counters, 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const int rc = ar(h->counters.p, h->counters.p, 4, kNcclUint64, kNcclSum, nccl_comm, st);
+    if (rc != 0) ENG_FAIL(h, OFDM_E_CUDA, "ncclAllReduce failed (ncclResult_t %d)", rc);
+    CU(h, cudaMemcpyAsync(counters, h->counters.p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     return 0;
 }

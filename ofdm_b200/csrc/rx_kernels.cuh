@@ -648,6 +648,41 @@ __device__ __forceinline__ int ramp_argmax(const float2 *__restrict__ x, long n_
     return best > 0.0f ? bidx : (int)k_lo;
 }
 
+// The same arg-max for a short lag range (<= 2 NT - 1 lags) well inside the capture: a thread takes two adjacent lags K, K + 1
+// with K on a 16-byte boundary and slides over 16-byte sample pairs -- a quarter of the load requests of ramp_argmax.
+// Same products, same summation order (n ascending), same tie rule -> the same lag. Falls back to ramp_argmax otherwise.
+template <int NT>
+__device__ __forceinline__ int ramp_argmax_pairs(const float2 *__restrict__ x, long n_samples, long k_lo, long k_hi,
+                                                 const float *s_lock, float *s_val, int *s_idx)
+{
+    const long par = (long)((reinterpret_cast<uintptr_t>(x) >> 3) & 1);          // x + k is 16-byte aligned iff (k + par) is even
+    const long k_start = k_lo - ((k_lo + par) & 1);
+    if ((reinterpret_cast<uintptr_t>(x) & 7) != 0 || k_start < 0 || k_hi - k_start + 1 > 2 * NT || k_start + 2 * NT + kSym + 2 > n_samples)
+        return ramp_argmax<NT>(x, n_samples, k_lo, k_hi, s_lock, s_val, s_idx);
+    const long K = k_start + 2 * (long)threadIdx.x;
+    float best = 0.0f;
+    int bidx = 0x7fffffff;
+    if (K <= k_hi) {
+        const float4 *p = reinterpret_cast<const float4 *>(x + K);
+        float ar = 0.0f, ai = 0.0f, br = 0.0f, bi = 0.0f;
+        float4 cur = __ldg(p);
+#pragma unroll 4
+        for (int m = 0; m < kSym / 2; m++) {
+            const float4 nxt = __ldg(p + m + 1);
+            const float l0 = s_lock[2 * m], l1 = s_lock[2 * m + 1];
+            ar = fmaf(cur.x, l0, ar); ai = fmaf(cur.y, l0, ai);                 // lag K:     x[K + 2m], x[K + 2m + 1]
+            ar = fmaf(cur.z, l1, ar); ai = fmaf(cur.w, l1, ai);
+            br = fmaf(cur.z, l0, br); bi = fmaf(cur.w, l0, bi);                 // lag K + 1: x[K + 2m + 1], x[K + 2m + 2]
+            br = fmaf(nxt.x, l1, br); bi = fmaf(nxt.y, l1, bi);
+            cur = nxt;
+        }
+        if (K >= k_lo) { const float v = ar * ar + ai * ai; if (v > best) { best = v; bidx = (int)K; } }
+        if (K + 1 <= k_hi) { const float v = br * br + bi * bi; if (v > best) { best = v; bidx = (int)K + 1; } }
+    }
+    block_argmax<NT>(best, bidx, s_val, s_idx);
+    return best > 0.0f ? bidx : (int)k_lo;
+}
+
 template <int MOD, bool GUARD, int PHASE>
 __global__ void __launch_bounds__(kAcq64Threads, kAcq64Ctas) rx_acquire_kernel(const RxArgs a)
 {
@@ -700,10 +735,29 @@ __global__ void __launch_bounds__(kAcq64Threads, kAcq64Ctas) rx_acquire_kernel(c
             constexpr int RUN = (NE + kAcq64Threads - 1) / kAcq64Threads;   // consecutive samples per thread
             float qr[RUN], qi[RUN], ee[RUN];
             float tqr = 0.0f, tqi = 0.0f, te = 0.0f;
+            // The global-load path (L1 tag stage) is what limits this kernel: a thread's run is fetched with 16-byte loads
+            // when the capture allows it, and a[n + 80] is lane + 8's a[n] (RUN = 10 samples per lane) -- only lanes 24..31
+            // load it themselves.
+            static_assert(RUN * 8 == kSym && RUN % 2 == 0, "lane + 8 holds the sample 80 further on");
+            float2 v0s[RUN];
+            const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (base + (long)kAcq64Threads * RUN + kSym <= M);   // uniform
+            if (vec) {
+                const float4 *x4 = reinterpret_cast<const float4 *>(x + base + (long)tid * RUN);
+#pragma unroll
+                for (int q = 0; q < RUN / 2; q++) {
+                    const float4 pq = __ldg(x4 + q);
+                    v0s[2 * q] = make_float2(pq.x, pq.y); v0s[2 * q + 1] = make_float2(pq.z, pq.w);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RUN; r++) v0s[r] = ld_sample(x, base + (long)tid * RUN + r, M);
+            }
 #pragma unroll
             for (int r = 0; r < RUN; r++) {
                 long n = base + (long)tid * RUN + r;
-                float2 v0 = ld_sample(x, n, M), v1 = ld_sample(x, n + kSym, M);
+                const float2 v0 = v0s[r];
+                float2 v1 = make_float2(__shfl_down_sync(0xffffffffu, v0.x, 8), __shfl_down_sync(0xffffffffu, v0.y, 8));
+                if (lane >= 24) v1 = ld_sample(x, n + kSym, M);
                 // conj(v0) * v1
                 float pr = v0.x * v1.x + v0.y * v1.y, pi = v0.x * v1.y - v0.y * v1.x;
                 qr[r] = tqr; qi[r] = tqi; ee[r] = te;                   // exclusive within the run
@@ -745,7 +799,7 @@ __global__ void __launch_bounds__(kAcq64Threads, kAcq64Ctas) rx_acquire_kernel(c
         } else {
             long d0 = s_d0, k_lo = d0 - 176, k_hi = d0 + 16;
             if (k_lo < -(kSym - 1)) k_lo = -(kSym - 1);
-            offset = (long)ramp_argmax<kAcq64Threads>(x, M, k_lo, k_hi, s_lock, s_val, s_idx) - 1;
+            offset = (long)ramp_argmax_pairs<kAcq64Threads>(x, M, k_lo, k_hi, s_lock, s_val, s_idx) - 1;
         }
     }
     if (status == ST_OK && offset < 0) status = ST_NEG_OFFSET;                       // src/receiver.rs:25

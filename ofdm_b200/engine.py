@@ -27,7 +27,8 @@ EXPORTS = [
     "ofdm_last_error", "ofdm_get_tables", "ofdm_host_alloc", "ofdm_host_free", "ofdm_coded_len",
     "ofdm_frame_data_syms", "ofdm_frame_len", "ofdm_max_payload", "ofdm_tx_encode_batch", "ofdm_rx_decode_batch",
     "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches", "ofdm_profile_begin", "ofdm_profile_read",
-    "ofdm_sync_search", "ofdm_sync_counts", "ofdm_engine_reserve", "ofdm_rx_decode_capture",
+    "ofdm_sync_search", "ofdm_sync_counts", "ofdm_engine_reserve", "ofdm_rx_decode_capture", "ofdm_rx_decode_file",
+    "ofdm_stats_allreduce",
     "ofdm_rs_encoded_len", "ofdm_rs_decoded_len", "ofdm_rs_encode_batch", "ofdm_rs_decode_batch",
 ]
 
@@ -60,6 +61,7 @@ class CChannelParams(C.Structure):
 
 
 PEAK_DTYPE = np.dtype([("offset", np.uint64), ("f_delta", np.float32), ("metric", np.float32)])      # = ofdm_peak
+FRAME_DTYPE = np.dtype([("offset", np.uint64), ("f_delta", np.float32), ("metric", np.float32), ("status", np.int32), ("out_len", np.uint32)])   # = ofdm_frame_info
 
 _lib = None
 
@@ -107,6 +109,10 @@ def load_library(build: bool = False) -> C.CDLL:
     L.ofdm_profile_read.restype = i32
     L.ofdm_sync_search.argtypes = [vp, vp, u64, vp, u32, vp, i32, vp]
     L.ofdm_sync_search.restype = i32
+    L.ofdm_rx_decode_file.argtypes = [vp, C.c_char_p, u64, u64, u32, u32, vp, u32, vp, u32, vp]
+    L.ofdm_rx_decode_file.restype = i32
+    L.ofdm_stats_allreduce.argtypes = [vp, vp, vp, i32, vp]
+    L.ofdm_stats_allreduce.restype = i32
     L.ofdm_sync_counts.argtypes = [vp, vp, vp]
     L.ofdm_sync_counts.restype = i32
     L.ofdm_engine_reserve.argtypes = [vp, u32, u64]
@@ -362,6 +368,24 @@ class Engine:
     def sync_search_device(self, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, stream=0):
         self._check(self.lib.ofdm_sync_search(self._h, iq_ptr, n_samples, peaks_ptr, max_peaks, n_peaks_ptr, MEM_DEVICE, stream or None),
                     "ofdm_sync_search")
+
+    def decode_file(self, path: str, start: int = 0, stop: int = 0, chunk_samples: int = 0, max_frame_samples: int = 1 << 18,
+                    out_stride: int = 1 << 16, max_frames: int = 4096):
+        """ofdm_rx_decode_file: every frame of an fc32 capture file (examples/lab3c.rs:57-74 for any length / frame count).
+        Returns (frame records [offset, f_delta, metric, status, out_len], list of payload bytes)."""
+        frames = np.zeros(max_frames, FRAME_DTYPE)
+        out = np.zeros((max_frames, out_stride), np.uint8)
+        n = C.c_uint32(0)
+        self._check(self.lib.ofdm_rx_decode_file(self._h, os.fsencode(path), start, stop, chunk_samples, max_frame_samples, _ptr(out),
+                                                 out_stride, _ptr(frames), max_frames, C.byref(n)), "ofdm_rx_decode_file")
+        k = n.value
+        return frames[:k].copy(), [bytes(out[i, : frames["out_len"][i]]) if frames["status"][i] == OK else b"" for i in range(k)]
+
+    def stats_allreduce(self, counters: np.ndarray, nccl_comm: int) -> np.ndarray:
+        """ofdm_stats_allreduce on host counters (4 x uint64); nccl_comm is the raw ncclComm_t."""
+        c = np.ascontiguousarray(counters, np.uint64)
+        self._check(self.lib.ofdm_stats_allreduce(self._h, _ptr(c), C.c_void_p(nccl_comm), MEM_HOST, None), "ofdm_stats_allreduce")
+        return c
 
     def sync_counts(self, stream=0):
         """(threshold crossings, frames detected, entries written to peaks[], overflowed tiles) of the last sync search;

@@ -74,6 +74,16 @@ pub struct ofdm_channel_params {
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
+pub struct ofdm_frame_info {
+    pub offset: u64,
+    pub f_delta: f32,
+    pub metric: f32,
+    pub status: i32,
+    pub out_len: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
 pub struct ofdm_peak {
     pub offset: u64,
     pub f_delta: f32,
@@ -112,6 +122,10 @@ extern "C" {
     pub fn ofdm_rx_decode_capture(h: *mut ofdm_engine, iq: *const ofdm_fc32, n_samples: u64, peaks: *const ofdm_peak, n_frames: u32,
                                   max_frame_samples: u32, out: *mut u8, out_stride: u32, out_len: *mut u32, status: *mut i32,
                                   mem: c_int, stream: *mut c_void) -> c_int;
+    pub fn ofdm_rx_decode_file(h: *mut ofdm_engine, path: *const c_char, start: u64, stop: u64, chunk_samples: u32,
+                               max_frame_samples: u32, out: *mut u8, out_stride: u32, frames: *mut ofdm_frame_info,
+                               max_frames: u32, n_frames: *mut u32) -> c_int;
+    pub fn ofdm_stats_allreduce(h: *mut ofdm_engine, counters: *mut u64, nccl_comm: *mut c_void, mem: c_int, stream: *mut c_void) -> c_int;
     pub fn ofdm_rs_encoded_len(data_len: usize) -> usize;
     pub fn ofdm_rs_decoded_len(coded_len: usize) -> usize;
     pub fn ofdm_rs_encode_batch(h: *mut ofdm_engine, data: *const u8, data_len: *const u32, n_streams: u32, data_stride: u32,

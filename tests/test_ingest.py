@@ -103,3 +103,32 @@ def test_stream_receiver_push_in_odd_blocks(oo):
     rx.close()
     assert rx.samples_in == cap.size
     assert [(f.offset, f.status, f.data) for f in frames] == [(p, 0, pay) for p, pay in sent]
+
+
+@pytest.mark.gpu
+def test_c_abi_decode_file_equals_python_ingest(tmp_path, oo):
+    """ofdm_rx_decode_file (the C entry a Rust caller binds) against the Python ingest and the transmitted payloads: chunked,
+    whole, and [start..stop]-sliced (examples/lab3c.rs:57-74)."""
+    import ofdm_b200 as ob
+    cfg = ob.Config(modulation=2, guard_bands=True, fec=True, cfo_mode=1, phase_mode=1)
+    ocfg = oo.make_cfg(True, 2, True, oo.SYNC_REFERENCE, 1, 1)
+    rng = np.random.default_rng(15)
+    cap, sent = _capture(oo, rng, 700_000, ocfg, 5000)
+    assert len(sent) > 20
+    path = tmp_path / "rx.dat"
+    path.write_bytes(ob.sig_to_bytes(cap))
+    eng = ob.Engine(cfg, 0)
+    for chunk in (90_000, 1 << 20):
+        rec, data = eng.decode_file(str(path), chunk_samples=chunk, max_frame_samples=30_000, out_stride=5008, max_frames=256)
+        assert [int(x) for x in rec["offset"]] == [p for p, _ in sent] and (rec["status"] == 0).all()
+        assert data == [pay for _, pay in sent] and [int(x) for x in rec["out_len"]] == [len(pay) for _, pay in sent]
+        assert (rec["metric"] > 0.5).all()
+    start, stop = sent[2][0] - 700, sent[7][0] + 200
+    rec, data = eng.decode_file(str(path), start=start, stop=stop, chunk_samples=90_000, max_frame_samples=30_000, out_stride=5008, max_frames=64)
+    good = rec["status"] == 0
+    assert [(int(o) + start, d) for o, d, g in zip(rec["offset"], data, good) if g] == [(p, pay) for p, pay in sent[2:7]]
+    with pytest.raises(ob.EngineError, match="max_frames"):
+        eng.decode_file(str(path), chunk_samples=90_000, max_frame_samples=30_000, out_stride=5008, max_frames=5)
+    with pytest.raises(ob.EngineError, match="cannot open"):
+        eng.decode_file(str(tmp_path / "missing.dat"))
+    eng.close()
