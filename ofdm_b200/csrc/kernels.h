@@ -36,6 +36,7 @@ DecodeKernel pick_decode(const ofdm_cfg &c, bool points);
 AcquireKernel pick_acquire(const ofdm_cfg &c);
 // tx64.cu
 TxKernel pick_tx(const ofdm_cfg &c, bool write);
+TxKernel pick_tx_frame(const ofdm_cfg &c);      // one-pass cluster kernel
 ChanKernel channel_conv_fn();
 ChanKernel channel_noise_fn();
 BerKernel ber_fn();

@@ -20,6 +20,21 @@ static TxKernel pick_tx_w(const ofdm_cfg &c)
 }
 TxKernel pick_tx(const ofdm_cfg &c, bool write) { return write ? pick_tx_w<true>(c) : pick_tx_w<false>(c); }
 
+template <int MOD>
+static TxKernel pick_txf_mod(bool guard, bool fec)
+{
+    if (guard) return fec ? (TxKernel)tx_frame_kernel<MOD, true, true> : (TxKernel)tx_frame_kernel<MOD, true, false>;
+    return fec ? (TxKernel)tx_frame_kernel<MOD, false, true> : (TxKernel)tx_frame_kernel<MOD, false, false>;
+}
+TxKernel pick_tx_frame(const ofdm_cfg &c)
+{
+    switch (c.modulation) {
+    case 0: return pick_txf_mod<0>(c.guard_bands, c.fec);
+    case 1: return pick_txf_mod<1>(c.guard_bands, c.fec);
+    default: return pick_txf_mod<2>(c.guard_bands, c.fec);
+    }
+}
+
 ChanKernel channel_conv_fn() { return channel_conv_kernel<>; }
 ChanKernel channel_noise_fn() { return channel_noise_kernel<>; }
 BerKernel ber_fn() { return ber_kernel<>; }

@@ -275,6 +275,242 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// One-pass TX: a frame per thread-block cluster
+// ------------------------------------------------------------------------------------------------------------------
+// `normalize` (src/transmitter.rs:183-194) needs the frame's maximum before a single sample can be written, which is why
+// tx_tile_kernel runs twice. Here a frame belongs to a CLUSTER of up to 16 CTAs: CTA r of the cluster transforms symbols
+// [133 r - tile_shift, 133 (r + 1) - tile_shift) of the frame ONCE, keeps their 64 time-domain samples each (68 kB, un-normalised,
+// cyclic prefixes not duplicated) in its own shared memory, publishes its maximum with one atomicMax, the cluster meets at
+// ONE hardware cluster barrier, and every CTA then scales its symbols and streams them out (CP included) with coalesced
+// 16-byte stores -- 8 B/sample of HBM traffic and one transform per symbol. Used for small batches (one wave of clusters,
+// e.g. the reference's one-frame `encode`: 17 us instead of 22 us for a 163 840-sample frame); with thousands of frames the
+// cluster barrier keeps the co-resident CTAs of an SM in lock step (all transform, then all store) and the two-pass kernel,
+// whose store pass overlaps the two inside every SM, is faster (ofdm_engine.cu: tx_device). Frames longer than 16 x 133
+// symbols always take the two-pass kernel.
+constexpr int kTxfWarps = 7;
+constexpr int kTxfThreads = kTxfWarps * 32;
+constexpr int kTxfChunk = 133;                      // symbols per CTA (multiple of 7: Hamming byte alignment of the chunk boundaries)
+constexpr int kTxfIters = (kTxfChunk + 4 * kTxfWarps - 1) / (4 * kTxfWarps);      // 5 warp iterations of 4 symbols
+constexpr int kTxfMaxCluster = 16;
+template <int MOD, bool GUARD> constexpr size_t txf_smem_bytes()
+{
+    return sizeof(float2) * (kTxfChunk * kNfft + kTxfWarps * kTrWarp) + (size_t)kTxfIters * 4 * kTxfWarps * (GUARD ? 48 : 64) + 64 +
+           sizeof(float2) * 16 * ((1 << ModTraits<MOD>::kBpc) + 2) + 16 + 512;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int MOD, bool GUARD, bool FEC>
+__global__ void __launch_bounds__(kTxfThreads, 2) tx_frame_kernel(const TxArgs a)
+{
+    constexpr int BPC = ModTraits<MOD>::kBpc;
+    constexpr int D = GUARD ? 48 : 64;
+    constexpr int BPS = BPC * D;
+    constexpr int NE = 1 << BPC;
+    constexpr int SLOTS = kTxfIters * 4 * kTxfWarps;                             // symbol slots of a CTA (>= kTxfChunk)
+    extern __shared__ __align__(128) uint8_t txf_smem[];
+    float2 *s_out = reinterpret_cast<float2 *>(txf_smem);                        // [kTxfChunk][64]: un-normalised time-domain symbols
+    float2 *s_tr = s_out + kTxfChunk * kNfft;
+    uint8_t *s_bits = reinterpret_cast<uint8_t *>(s_tr);                         // aliases s_tr: consumed before the first transform
+    uint8_t *s_car = reinterpret_cast<uint8_t *>(s_tr + kTxfWarps * kTrWarp);
+    float2 *s_lut = reinterpret_cast<float2 *>(s_car + SLOTS * D + 64);
+    uint8_t *s_enc = reinterpret_cast<uint8_t *>(s_lut + 16 * (NE + 2));
+    uint16_t *s_enc14 = reinterpret_cast<uint16_t *>(s_enc + 16);
+    static_assert(SLOTS * BPS / 8 + 32 <= (int)sizeof(float2) * kTxfWarps * kTrWarp, "the packed bit stream must fit the transpose scratch");
+
+    const uint32_t stream = blockIdx.y + a.stream0;
+    const uint32_t rank = cluster_ctarank();                                     // = blockIdx.x: the grid's x extent is the cluster size
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
+    const uint32_t n = a.payload_len[stream];
+    const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;
+    const uint64_t nbits = kHeaderBits + 8 * coded_len;
+    const uint64_t ncar = (nbits + BPC - 1) / BPC;
+    const int S = (int)((ncar + D - 1) / D);
+    const uint32_t frame_len = (kHeadSyms + (uint32_t)S) * kSym;
+    if (a.frame_len && rank == 0 && tid == 0) a.frame_len[stream] = frame_len;
+    const bool fits = frame_len <= a.iq_stride;
+    float2 *out = a.iq + (size_t)stream * a.iq_stride;
+    int t0 = (int)rank * kTxfChunk - a.tile_shift, t1 = t0 + kTxfChunk;
+    if (t0 < 0) t0 = 0;
+    if (t1 > S) t1 = S;
+    const bool work = fits && t0 < t1;
+    float mx = 0.0f;
+
+    if (work) {
+        for (int e = tid; e < 16 * (NE + 2); e += kTxfThreads) {                 // constellation table, see tx_tile_kernel
+            const int idx = e >> 4;
+            float re = 0.0f, im = 0.0f;
+            if (idx == NE + 1) re = 1.0f;
+            else if (idx == NE) { }
+            else if (MOD == 0) { re = (idx & 1) ? 1.0f : -1.0f; }
+            else if (MOD == 1) { re = (idx & 1) ? 1.0f : -1.0f; im = (idx & 2) ? 1.0f : -1.0f; }
+            else {
+                const uint32_t ci = idx & 7u, cq = (uint32_t)idx >> 3;
+                const uint32_t li = ci ^ (ci >> 1) ^ (ci >> 2), lq = cq ^ (cq >> 1) ^ (cq >> 2);
+                re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
+                im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
+            }
+            s_lut[e] = make_float2(im, re);
+        }
+        if (tid < 16) s_enc[tid] = (uint8_t)ham74_encode_nibble(tid);
+        if (FEC) for (int e = tid; e < 256; e += kTxfThreads) s_enc14[e] = (uint16_t)(ham74_encode_nibble(e & 15) | (ham74_encode_nibble(e >> 4) << 7));
+        __syncthreads();
+
+        // ---- chunk bit stream (same construction as a tile of tx_tile_kernel) -------------------------------------------
+        const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+        const uint32_t byte0 = (uint32_t)((long)t0 * BPS / 8), nbyte = (uint32_t)((long)(t1 - t0) * BPS / 8);
+        if (FEC) {
+            const uint32_t hdr = byte0 < 16 ? 16 - byte0 : 0;
+            if (tid < (int)hdr) s_bits[tid] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + tid, s_enc);
+            const uint32_t c0 = byte0 + hdr - 16;
+            const uint32_t ngrp = ((nbyte + 2 - hdr + 6) / 7 + 3) / 4;
+            const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
+            for (uint32_t u = tid; u < ngrp; u += kTxfThreads) {
+                const uint32_t pb = (c0 / 7) * 4 + 16 * u;
+                uint32_t v[4] = { 0, 0, 0, 0 };
+                if (pay_aligned && pb + 16 <= n) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) v[q] = __ldg(reinterpret_cast<const uint32_t *>(pay + pb) + q);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) if (pb + q < n) v[q >> 2] |= (uint32_t)pay[pb + q] << (8 * (q & 3));
+                }
+                uint64_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t lo = (uint32_t)s_enc14[v[q] & 255u] | ((uint32_t)s_enc14[(v[q] >> 8) & 255u] << 14);
+                    const uint32_t hi = (uint32_t)s_enc14[(v[q] >> 16) & 255u] | ((uint32_t)s_enc14[v[q] >> 24] << 14);
+                    w[q] = (uint64_t)lo | ((uint64_t)hi << 28);
+                }
+                uint32_t *dst = reinterpret_cast<uint32_t *>(s_bits + hdr + 28 * u);
+                dst[0] = (uint32_t)w[0];
+                dst[1] = (uint32_t)(w[0] >> 32) | ((uint32_t)w[1] << 24);
+                dst[2] = (uint32_t)(w[1] >> 8);
+                dst[3] = (uint32_t)(w[1] >> 40) | ((uint32_t)w[2] << 16);
+                dst[4] = (uint32_t)(w[2] >> 16);
+                dst[5] = (uint32_t)(w[2] >> 48) | ((uint32_t)w[3] << 8);
+                dst[6] = (uint32_t)(w[3] >> 24);
+            }
+        } else {
+            for (uint32_t b = tid; b < nbyte + 2; b += kTxfThreads) s_bits[b] = (uint8_t)frame_byte<FEC>(pay, n, coded_len, byte0 + b, s_enc);
+        }
+        __syncthreads();
+        {
+            const long ncar_local = (long)ncar - (long)t0 * D;
+            long have = (long)(t1 - t0) * D;
+            if (ncar_local < have) have = ncar_local;
+            const int ncar_have = (int)have;
+            const uint32_t *bits32 = reinterpret_cast<const uint32_t *>(s_bits);
+            for (int c4 = 4 * tid; c4 < SLOTS * D; c4 += 4 * kTxfThreads) {
+                const uint32_t bit = (uint32_t)c4 * BPC, wi = bit >> 5, sh = bit & 31;
+                const uint32_t v = __funnelshift_r(bits32[wi], bits32[wi + 1], sh);
+                constexpr uint32_t M = (uint32_t)(NE - 1);
+                uint32_t packed = (v & M) | (((v >> BPC) & M) << 8) | (((v >> (2 * BPC)) & M) << 16) | (((v >> (3 * BPC)) & M) << 24);
+                if (c4 + 4 > ncar_have) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) if (c4 + q >= ncar_have) packed = (packed & ~(0xFFu << (8 * q))) | ((uint32_t)NE << (8 * q));
+                }
+                *reinterpret_cast<uint32_t *>(s_car + c4) = packed;
+            }
+        }
+        __syncthreads();
+
+        // ---- transforms: each symbol once, results stay in shared memory --------------------------------------------------
+        cpx tw[8];
+#pragma unroll
+        for (int ka = 0; ka < 8; ka++) tw[ka] = c_from(__ldg(a.tables->w64 + ((l * ka) & 63)));
+        int d3 = 24 - (l >= 2), d4 = 31 - (l >= 1);
+        uint32_t fix0 = 0xFFu, fix3 = 0xFFu, fix4 = 0xFFu, fix7 = 0xFFu;
+        if (GUARD) {
+            if (data_rank<GUARD>(l) < 0) fix0 = is_pilot_bin(l) ? NE + 1 : NE;
+            if (data_rank<GUARD>(l + 24) < 0) fix3 = is_pilot_bin(l + 24) ? NE + 1 : NE;
+            if (data_rank<GUARD>(l + 32) < 0) fix4 = is_pilot_bin(l + 32) ? NE + 1 : NE;
+            if (data_rank<GUARD>(l + 56) < 0) fix7 = is_pilot_bin(l + 56) ? NE + 1 : NE;
+        }
+        asm volatile("" : "+r"(d3), "+r"(d4), "+r"(fix0), "+r"(fix3), "+r"(fix4), "+r"(fix7));
+        float2 *tr = s_tr + warp * kTrWarp + g * kTrGroup;
+        const unsigned long long *lut = reinterpret_cast<const unsigned long long *>(s_lut) + (lane & 15);
+#pragma unroll 1
+        for (int it = 0; it < kTxfIters; it++) {
+            const int sl = it * (4 * kTxfWarps) + 4 * warp + g;                   // symbol slot inside the chunk (the tail slots are unused)
+            const bool valid = t0 + sl < t1;
+            const uint8_t *rowp = s_car + sl * D + (GUARD ? l - 7 : l);
+            cpx x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t idx;
+                if (!GUARD) idx = rowp[8 * j];
+                else if (j == 1 || j == 2) idx = rowp[8 * j];
+                else if (j == 5 || j == 6) idx = rowp[8 * j - 3];
+                else if (j == 3) idx = fix3 != 0xFFu ? fix3 : rowp[d3];
+                else if (j == 4) idx = fix4 != 0xFFu ? fix4 : rowp[d4];
+                else if (j == 0) idx = fix0 != 0xFFu ? fix0 : rowp[0];
+                else idx = fix7 != 0xFFu ? fix7 : rowp[53];
+                x[j].v = lut[idx * 16];
+            }
+            fft64_group_p(x, tw, tr, l);
+            if (valid) {
+                unsigned long long *o = reinterpret_cast<unsigned long long *>(s_out + sl * kNfft + l);
+#pragma unroll
+                for (int kb = 0; kb < 8; kb++) {
+                    float re, im;
+                    c_split(x[kb], im, re);                                       // un-swap
+                    mx = fmaxf(mx, fmaxf(re, im));
+                    o[8 * kb] = c_make(re, im).v;                                 // time index l + 8 kb
+                }
+            }
+        }
+        mx *= 1.0f / 64.0f;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        if (lane == 0 && mx > 0.0f) atomicMax(a.stream_max + stream, __float_as_int(mx));
+        __threadfence();
+    }
+    // ---- the frame's maximum: every CTA of the cluster has published its own ---------------------------------------------
+    cluster_barrier();
+    const float fmx = fmaxf(__int_as_float(*reinterpret_cast<volatile int *>(a.stream_max + stream)), a.tables->head_max);
+    const float scale = (1.0f / 64.0f) / fmx;
+    if (rank == 0)
+        for (uint32_t i = tid; i < (uint32_t)(kHeadSyms * kSym) && i < a.iq_stride; i += kTxfThreads) {
+            float2 v = make_float2(0.0f, 0.0f);
+            if (fits) { v = a.tables->head[i]; v.x = v.x / fmx; v.y = v.y / fmx; }
+            out[i] = v;
+        }
+    if (rank == gridDim.x - 1) {
+        const uint32_t z0 = fits ? frame_len : (uint32_t)(kHeadSyms * kSym);
+        for (uint32_t i = z0 + tid; i < a.iq_stride; i += kTxfThreads) out[i] = make_float2(0.0f, 0.0f);
+    }
+    if (!work) return;
+    // ---- scale + copy out, cyclic prefix included (prefix_block, src/transmitter.rs:168-181: x[48..64] ++ x[0..64]) ------------
+    float2 *dst = out + (size_t)(kHeadSyms + t0) * kSym;
+    const int n_out = (t1 - t0) * kSym;
+    const cpx sc = c_make(scale, scale);
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int i = 2 * tid; i < n_out; i += 2 * kTxfThreads) {                  // two samples per thread: t even, so both come from one 16-byte read
+            const int sym = i / kSym, t = i - sym * kSym;
+            const int src = sym * kNfft + (t < kCp ? kNfft - kCp + t : t - kCp);
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s_out + src);
+            cpx p0, p1;
+            p0.v = v.x; p1.v = v.y;
+            ulonglong2 w;
+            w.x = c_mul2(p0, sc).v; w.y = c_mul2(p1, sc).v;
+            *reinterpret_cast<ulonglong2 *>(dst + i) = w;
+        }
+    } else {
+        for (int i = tid; i < n_out; i += kTxfThreads) {
+            const int sym = i / kSym, t = i - sym * kSym;
+            cpx p0;
+            p0.v = *reinterpret_cast<const unsigned long long *>(s_out + sym * kNfft + (t < kCp ? kNfft - kCp + t : t - kCp));
+            *reinterpret_cast<unsigned long long *>(dst + i) = c_mul2(p0, sc).v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // channel harness
 // ------------------------------------------------------------------------------------------------------------------
 struct ChanArgs {
