@@ -66,7 +66,7 @@ struct ofdm_engine {
     DevBuf rs_tables;                   // RsTables, built on first use
     // host-mode staging
     DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
     int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
     // per-kernel timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE): 3 events per call (start, after acquire, end)
@@ -262,6 +262,7 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
                        cudaMemcpy(h->d_wtables, wt, sizeof(wide::WideTables), cudaMemcpyHostToDevice) == cudaSuccess)) &&
               cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_copied[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_copied[1], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_done[0], cudaEventDisableTiming) == cudaSuccess &&
@@ -290,6 +291,7 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     for (void *p : h->pin) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
@@ -404,6 +406,9 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         tiles = (tiles + tpc - 1) / tpc;
     }
     const size_t tx_smem = sizeof(float2) * kTxWarps * kTrWarp + (size_t)kTxTileSyms * h->dcar + 64 + sizeof(float2) * 16 * ((1u << h->bpc) + 2) + 16 + 512;
+    // (Running the maximum pass of frame batch i+1 concurrently with the store pass of batch i on two streams, each kernel held
+    // to two CTAs per SM, was measured: 1.82 vs 1.77 ms -- together the passes are bound by the shared-memory pipe and the issue
+    // slots, which both of them use for the same transforms, so overlapping them buys nothing.)
     for (int pass = 0; pass < 2; pass++) {
         TxKernel k = pick_tx(h->cfg, pass == 1);
         if (h->smem_configured.insert((const void *)k).second)
@@ -598,9 +603,9 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
         if (n_samples[s] > mx) mx = n_samples[s];
     }
     // Host path: the capture is streamed through two device staging buffers in chunks of whole streams; the H2D copy of
-    // chunk c+1 (copy_stream) overlaps the kernels of chunk c (own_stream). Outputs are gathered on the device and
-    // copied back once.
-    cudaStream_t st = h->own_stream, cs = h->copy_stream;
+    // chunk c+1 (copy_stream) overlaps the kernels of chunk c (own_stream), and the payloads of chunk c go back on a third
+    // stream as soon as its kernels are done (PCIe is full duplex: the D2H traffic hides behind the H2D feed).
+    cudaStream_t st = h->own_stream, cs = h->copy_stream, os = h->d2h_stream;
     const size_t stream_bytes = (size_t)iq_stride * sizeof(float2);
     uint32_t chunk = (uint32_t)((256u << 20) / stream_bytes);
     if (chunk < 1) chunk = 1;
@@ -647,8 +652,9 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
                            out_stride, d_ol + s0, h->s_status.as<int32_t>() + s0, diag ? &dc : nullptr, st, s0, n_streams);
         if (rc) return rc;
         CU(h, cudaEventRecord(h->ev_done[b], st));
+        CU(h, cudaStreamWaitEvent(os, h->ev_done[b], 0));
+        CU(h, cudaMemcpyAsync(out + (size_t)s0 * out_stride, h->s_bytes.as<uint8_t>() + (size_t)s0 * out_stride, (size_t)ns * out_stride, cudaMemcpyDeviceToHost, os));
     }
-    CU(h, cudaMemcpyAsync(out, h->s_bytes.p, ob, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(out_len, d_ol, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
     CU(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int32_t) * (size_t)n_streams, cudaMemcpyDeviceToHost, st));
     if (diag) {
@@ -659,6 +665,7 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
         if (dd.points) CU(h, cudaMemcpyAsync(diag->points, dd.points, sizeof(float2) * (size_t)diag->points_stride * n_streams, cudaMemcpyDeviceToHost, st));
     }
     CU(h, cudaStreamSynchronize(st));
+    CU(h, cudaStreamSynchronize(os));
     return 0;
 }
 
