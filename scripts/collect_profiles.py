@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """Copy the bench lines scripts/refresh_profiles.sh left in gpurun_out/ into profiles/ and condense the ncu launch list."""
-import collections, csv, json, os, re, shutil
+import collections, csv, json, os, re, shutil, sys
+
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"          # round prefix of the artefacts
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC, DST = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 for f in sorted(os.listdir(SRC)):
-    if f.startswith("r1_bench") and f.endswith(".json"):
-        line = open(os.path.join(SRC, f)).read().strip()
-        json.loads(line)                                  # must be one valid JSON line
+    if (f.startswith(TAG + "_bench") and f.endswith(".json")) or (f.startswith(TAG + "_ncu_") and f.endswith(".txt")) or f == TAG + "_pytest_gpu.txt":
+        if f.endswith(".json"):
+            json.loads(open(os.path.join(SRC, f)).read().strip())      # must be one valid JSON line
         shutil.copy(os.path.join(SRC, f), os.path.join(DST, f))
         print("copied", f)
 path = os.path.join(SRC, "launches.csv")
@@ -20,7 +22,7 @@ if os.path.exists(path):
         name = re.sub(r"\(.*", "", r[ik])[:80]
         n, t = agg.get(name, (0, 0.0))
         agg[name] = (n + 1, t + float(r[iv].replace(",", "")) / 1e3)
-    with open(os.path.join(DST, "r1_launches_summary.csv"), "w") as f:
+    with open(os.path.join(DST, TAG + "_launches_summary.csv"), "w") as f:
         f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none) of `python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu`\n")
         f.write("# cold-cache, serialised per-launch times: compare SHARES, not absolutes\n")
         f.write("kernel,launches,total_us,avg_us\n")
