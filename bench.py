@@ -194,6 +194,8 @@ def read_traffic(workload: str):
         e = t.get(workload)
         if e:
             return e.get("dram_bytes_per_launch")
+        if workload.startswith("capture_") and "capture" in t:               # capture_<n samples>: per-sample figure x n
+            return int(t["capture"]["dram_bytes_per_sample"] * int(workload.split("_")[1]))
     return None
 
 
@@ -648,7 +650,7 @@ def capture_bench(args, rank, local_rank, world, steps=None):
                             "sharding": "one capture, contiguous ranges, overlap 2L + frame_len, de-duplicated by offset ownership" if world > 1 else "none",
                             "l2": "input (%.1f GB/GPU) larger than L2" % (8 * n / 1e9)},
                  "roofline": {"bound": "hbm", "kernel": "sync_scan_kernel (+select, refine)", "achieved": round(achieved, 1), "peak": peak,
-                              "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": src,
+                              "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": read_traffic(f"capture_{n}"), "peak_source": src,
                               "algorithmic_bytes_per_launch": 8 * n, "kernel_ms": round(ms, 4)},
                  "all_offsets_exact": exact_all, "max_cfo_abs_err": cfo_err, "peaks_found": frames_once,
                  "each_frame_found_once": bool(exact_all and frames_once == len(positions)), "detections_before_dedup": detections_raw,
@@ -738,8 +740,8 @@ def tx_bench(args, rank, local_rank, world, steps=None):
                       "config": {"workload": f"tx_{n}x64QAM_S{S}", "streams_per_gpu": n, "data_syms_per_frame": S, "frame_samples": frame_len,
                                  "payload_bytes": plen_b, "l2": "output (%.2f GB) larger than L2" % (8 * samples / 1e9)},
                       "roofline": {"bound": "hbm", "kernel": "tx_tile_kernel (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
-                                   "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
-                                   "peak_source": src, "algorithmic_bytes_per_launch": by},
+                                   "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": read_traffic(f"tx_{n}x64QAM_S{S}"),
+                                   "peak_source": src, "algorithmic_bytes_per_launch": by, "kernel_ms": round(ms, 4)},
                       "max_component": round(mx, 6), "frames_ok": frames_ok,
                       "gpu_launches": launches, "clocks": clocks})
 
