@@ -131,14 +131,29 @@ impl Drop for Engine {
     }
 }
 
+thread_local! {
+    /// One engine per (guard_bands, modulation) and thread: the reference's call-per-frame style (`encode!` / `decode!` in every
+    /// example) must not pay for cudaMalloc + stream + event set-up on each call. Handles are not thread-safe, hence thread-local.
+    static ENGINES: std::cell::RefCell<std::collections::HashMap<(bool, u32), Engine>> = std::cell::RefCell::new(std::collections::HashMap::new());
+}
+
+fn with_engine<T>(guard_bands: Option<bool>, modulation: Option<ModulationScheme>, f: impl FnOnce(&mut Engine) -> Result<T>) -> Result<T> {
+    let (g, m) = (guard_bands.unwrap_or(false), modulation.unwrap_or(ModulationScheme::Bpsk));
+    ENGINES.with(|cell| {
+        let mut map = cell.borrow_mut();
+        if !map.contains_key(&(g, m as u32)) {
+            map.insert((g, m as u32), Engine::new(g, m, false, 0)?);
+        }
+        f(map.get_mut(&(g, m as u32)).unwrap())
+    })
+}
+
 /// src/transmitter.rs:10-15 -- same signature (the `#[optargs::optfn]` attribute can be kept on this function).
 pub fn encode(data: &[u8], guard_bands: Option<bool>, modulation: Option<ModulationScheme>) -> Vec<Complex64> {
-    let mut e = Engine::new(guard_bands.unwrap_or(false), modulation.unwrap_or(ModulationScheme::Bpsk), false, 0).expect("engine");
-    e.encode_batch(&[data]).expect("encode").pop().unwrap()
+    with_engine(guard_bands, modulation, |e| Ok(e.encode_batch(&[data])?.pop().unwrap())).expect("encode")
 }
 
 /// src/receiver.rs:8-13 -- same signature and error behaviour.
 pub fn decode(samples: Vec<Complex64>, guard_bands: Option<bool>, modulation: Option<ModulationScheme>) -> Result<Vec<u8>> {
-    let mut e = Engine::new(guard_bands.unwrap_or(false), modulation.unwrap_or(ModulationScheme::Bpsk), false, 0)?;
-    e.decode_batch(&[&samples])?.pop().unwrap()
+    with_engine(guard_bands, modulation, |e| e.decode_batch(&[&samples])?.pop().unwrap())
 }
