@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "rx_kernels.cuh"
 #include "tx_kernels.cuh"
+#include "tx_resident.cuh"
 #include "sync_kernels.cuh"
 #include "wide_kernels.cuh"
 #include "rs_kernels.cuh"
@@ -37,6 +38,9 @@ AcquireKernel pick_acquire(const ofdm_cfg &c);
 // tx64.cu
 TxKernel pick_tx(const ofdm_cfg &c, bool write);
 TxKernel pick_tx_frame(const ofdm_cfg &c);      // one-pass cluster kernel
+// tx64r.cu
+TxKernel pick_tx_resident(const ofdm_cfg &c, int warps);   // one-pass persistent kernel, frames resident in tensor memory (warps per CTA: 8, 16, 32)
+size_t tx_resident_smem(const ofdm_cfg &c, int warps);
 ChanKernel channel_conv_fn();
 ChanKernel channel_noise_fn();
 BerKernel ber_fn();

@@ -69,6 +69,9 @@ struct ofdm_engine {
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
     int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
+    int n_sm = 0;                       // multiprocessors of the device (grid of the persistent TX kernel)
+    int tx_warps = 32;                  // OFDM_TX_WARPS=8|16|32: warps per CTA of the resident TX kernel
+    int tx_path = 0;                    // 0 = automatic; OFDM_TX_PATH=twopass|cluster|resident pins one (A/B measurements)
     // per-kernel timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE): 3 events per call (start, after acquire, end)
     std::vector<cudaEvent_t> prof_ev;
     uint32_t prof_cap = 0, prof_n = 0;
@@ -191,6 +194,10 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     h->device = device;
     h->bpc = cfg_bpc(cfg);
     h->dcar = cfg_dcar(cfg);
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char *tp = getenv("OFDM_TX_PATH"))
+        h->tx_path = !strcmp(tp, "twopass") ? 1 : !strcmp(tp, "cluster") ? 2 : !strcmp(tp, "resident") ? 3 : 0;
+    if (const char *tw = getenv("OFDM_TX_WARPS")) { const int w = atoi(tw); if (w == 8 || w == 16 || w == 32) h->tx_warps = w; }
     h->bps_sym = h->bpc * h->dcar;
     h->tile_shift = 0;
     if (cfg->fec) {                          // tile boundaries on Hamming byte boundaries: BPS*s == 128 (mod 14)
@@ -305,7 +312,7 @@ extern "C" int ofdm_engine_reserve(ofdm_engine *h, uint32_t max_streams, uint64_
     CU(h, cudaSetDevice(h->device));
     if (max_streams) {
         CU(h, h->state.ensure((h->wide ? sizeof(wide::StreamStateW) : sizeof(StreamState)) * (size_t)max_streams));
-        CU(h, h->scratch_u32.ensure(2 * sizeof(uint32_t) * (size_t)max_streams));
+        CU(h, h->scratch_u32.ensure(3 * sizeof(uint32_t) * (size_t)max_streams));
         CU(h, h->scratch_f32.ensure(5 * sizeof(double) * (size_t)max_streams));
         CU(h, h->cap_base.ensure((sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)max_streams));
     }
@@ -338,10 +345,11 @@ extern "C" uint64_t ofdm_kernel_launches(const ofdm_engine *h) { return h ? h->l
 static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *payload_len, uint32_t payload_stride,
                      uint32_t n_streams, ofdm_fc32 *iq, uint32_t iq_stride, uint32_t *frame_len_out, cudaStream_t st)
 {
-    CU(h, h->scratch_u32.ensure(2 * sizeof(uint32_t) * (size_t)n_streams));
+    CU(h, h->scratch_u32.ensure(3 * sizeof(uint32_t) * (size_t)n_streams));
     uint32_t *d_flen = h->scratch_u32.as<uint32_t>();
     int *d_max = reinterpret_cast<int *>(d_flen + n_streams);
-    CU(h, cudaMemsetAsync(d_flen, 0, 2 * sizeof(uint32_t) * (size_t)n_streams, st));
+    uint32_t *d_cnt = d_flen + 2 * (size_t)n_streams;
+    CU(h, cudaMemsetAsync(d_flen, 0, 3 * sizeof(uint32_t) * (size_t)n_streams, st));
     if (h->wide) {
         wide::WideTxArgs w{};
         w.payload = payload; w.payload_len = payload_len; w.payload_stride = payload_stride; w.n_streams = n_streams;
@@ -359,12 +367,36 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     a.iq = reinterpret_cast<float2 *>(iq); a.iq_stride = iq_stride; a.frame_len = d_flen; a.stream_max = d_max; a.tables = h->d_tables;
     a.tile_shift = h->tile_shift;
     const long max_syms = (long)iq_stride / 80 - 10;
+    // Large batches: ONE pass with the frames resident on chip (tx_resident.cuh). A frame is shared by a group of C persistent
+    // CTAs (one per SM), its un-normalised symbols wait in tensor memory for the frame maximum, and the stores of frame k-1
+    // overlap the transforms of frame k in every warp. C = the smallest group whose rings hold the longest frame iq_stride admits.
+    if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 3)) {
+        const int W = h->tx_warps;                                            // warps per CTA; 32 / W CTAs per SM
+        const int chunk_max = 7 * ((16 * W) / 7);
+        const int C = (int)((max_syms + h->tile_shift + chunk_max - 1) / chunk_max);
+        const int ctas = (32 / W) * h->n_sm;
+        int G = C <= ctas ? ctas / C : 0;
+        if (G > 0 && (uint32_t)G > n_streams) G = (int)n_streams;
+        // worth it once every group pipelines a few frames (the first transform and the last store of a group do not overlap)
+        if (G > 0 && (h->tx_path == 3 || n_streams >= 4u * (uint32_t)G)) {
+            TxKernel k = pick_tx_resident(h->cfg, W);
+            const size_t smem = tx_resident_smem(h->cfg, W);
+            if (h->smem_configured.insert((const void *)k).second)
+                CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            a.stream_cnt = d_cnt; a.group_ctas = C; a.n_groups = G;
+            k<<<dim3((unsigned)(G * C)), 32 * W, smem, st>>>(a);
+            h->launches++;
+            CU(h, cudaGetLastError());
+            if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        }
+    }
     // Small batches (the reference's one-frame `encode` call): one pass, a frame per thread-block cluster (<= 16 CTAs x 133
     // symbols held in shared memory, every symbol transformed once and written once), as long as all frames of the call are
     // in flight as ONE wave of clusters -- measured 17 vs 22 us for 1..8 frames of 163 840 samples. For larger batches the
     // cluster barrier keeps the two CTAs of an SM in the same phase (transform, then store) and the two-pass kernel wins
     // (1.77 vs 2.69 ms for 4096 frames): its store pass overlaps transforms and stores inside every SM.
-    if (max_syms > 0 && max_syms + h->tile_shift <= (long)kTxfMaxCluster * kTxfChunk) {
+    if (h->tx_path != 1 && max_syms > 0 && max_syms + h->tile_shift <= (long)kTxfMaxCluster * kTxfChunk) {
         unsigned cs = 1;
         while ((long)cs * kTxfChunk < max_syms + h->tile_shift) cs <<= 1;
         TxKernel k = pick_tx_frame(h->cfg);
@@ -381,7 +413,7 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         lc.blockDim = dim3(kTxfThreads); lc.dynamicSmemBytes = smem; lc.stream = st; lc.attrs = at; lc.numAttrs = 1;
         lc.gridDim = dim3(cs, n_streams < 65535u ? n_streams : 65535u);
         int max_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)k, &lc) == cudaSuccess && max_clusters > 0 && n_streams <= (uint32_t)max_clusters) {
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)k, &lc) == cudaSuccess && max_clusters > 0 && (n_streams <= (uint32_t)max_clusters || h->tx_path == 2)) {
             for (uint32_t s0 = 0; s0 < n_streams; s0 += 65535u) {
                 a.stream0 = s0;
                 lc.gridDim = dim3(cs, n_streams - s0 < 65535u ? n_streams - s0 : 65535u);

@@ -20,6 +20,9 @@ struct TxArgs {
     int32_t         tiles_per_cta;  // consecutive tiles of one frame handled by one CTA
     const RxTables *tables;
     uint32_t        stream0;        // first stream of this launch (gridDim.y <= 65535 streams per launch)
+    uint32_t       *stream_cnt;     // tx_resident_kernel: per stream, compute warps that have published their maximum
+    int32_t         group_ctas;     // tx_resident_kernel: CTAs sharing one frame
+    int32_t         n_groups;       // tx_resident_kernel: groups of the (persistent) grid
 };
 
 // byte `B` of the frame byte stream [header 16 B | (Hamming-coded) payload ...] (src/transmitter.rs:37-47, docs/SPEC.md 3)
