@@ -39,8 +39,8 @@ AcquireKernel pick_acquire(const ofdm_cfg &c);
 TxKernel pick_tx(const ofdm_cfg &c, bool write);
 TxKernel pick_tx_frame(const ofdm_cfg &c);      // one-pass cluster kernel
 // tx64r.cu
-TxKernel pick_tx_resident(const ofdm_cfg &c, int warps);   // one-pass persistent kernel, frames resident in tensor memory (warps per CTA: 8, 16, 32)
-size_t tx_resident_smem(const ofdm_cfg &c, int warps);
+TxKernel pick_tx_resident(const ofdm_cfg &c);   // one-pass persistent kernel, frames resident in tensor memory
+size_t tx_resident_smem(const ofdm_cfg &c);
 ChanKernel channel_conv_fn();
 ChanKernel channel_noise_fn();
 BerKernel ber_fn();

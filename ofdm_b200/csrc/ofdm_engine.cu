@@ -70,7 +70,6 @@ struct ofdm_engine {
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
     int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
     int n_sm = 0;                       // multiprocessors of the device (grid of the persistent TX kernel)
-    int tx_warps = 32;                  // OFDM_TX_WARPS=8|16|32: warps per CTA of the resident TX kernel
     int tx_path = 0;                    // 0 = automatic; OFDM_TX_PATH=twopass|cluster|resident pins one (A/B measurements)
     // per-kernel timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE): 3 events per call (start, after acquire, end)
     std::vector<cudaEvent_t> prof_ev;
@@ -197,7 +196,6 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char *tp = getenv("OFDM_TX_PATH"))
         h->tx_path = !strcmp(tp, "twopass") ? 1 : !strcmp(tp, "cluster") ? 2 : !strcmp(tp, "resident") ? 3 : 0;
-    if (const char *tw = getenv("OFDM_TX_WARPS")) { const int w = atoi(tw); if (w == 8 || w == 16 || w == 32) h->tx_warps = w; }
     h->bps_sym = h->bpc * h->dcar;
     h->tile_shift = 0;
     if (cfg->fec) {                          // tile boundaries on Hamming byte boundaries: BPS*s == 128 (mod 14)
@@ -371,16 +369,17 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     // CTAs (one per SM), its un-normalised symbols wait in tensor memory for the frame maximum, and the stores of frame k-1
     // overlap the transforms of frame k in every warp. C = the smallest group whose rings hold the longest frame iq_stride admits.
     if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 3)) {
-        const int W = h->tx_warps;                                            // warps per CTA; 32 / W CTAs per SM
+        const int W = kTrsWarpsPerCta;                                        // warps per CTA; 32 / W CTAs per SM
         const int chunk_max = 7 * ((16 * W) / 7);
         const int C = (int)((max_syms + h->tile_shift + chunk_max - 1) / chunk_max);
         const int ctas = (32 / W) * h->n_sm;
         int G = C <= ctas ? ctas / C : 0;
         if (G > 0 && (uint32_t)G > n_streams) G = (int)n_streams;
-        // worth it once every group pipelines a few frames (the first transform and the last store of a group do not overlap)
-        if (G > 0 && (h->tx_path == 3 || n_streams >= 4u * (uint32_t)G)) {
-            TxKernel k = pick_tx_resident(h->cfg, W);
-            const size_t smem = tx_resident_smem(h->cfg, W);
+        // worth it once every group has two frames to pipeline (measured: ahead of the two-pass kernel from 2 frames per group on,
+        // 0.050 vs 0.053 ms for 74 frames of 163 840 samples, 0.87 vs 1.02 ms for 2368); smaller batches take the cluster kernel
+        if (G > 0 && (h->tx_path == 3 || n_streams >= 2u * (uint32_t)(ctas / C))) {
+            TxKernel k = pick_tx_resident(h->cfg);
+            const size_t smem = tx_resident_smem(h->cfg);
             if (h->smem_configured.insert((const void *)k).second)
                 CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             a.stream_cnt = d_cnt; a.group_ctas = C; a.n_groups = G;

@@ -23,6 +23,7 @@
 namespace ofdm {
 
 // W warps per CTA, 32 / W CTAs per SM (each allocates 16 W of the SM's 512 tensor-memory columns)
+constexpr int kTrsWarpsPerCta = 32;                                           // the instantiated W
 constexpr int kTrsSlots = 4;                                                   // slots per warp, 16 columns each
 template <int W> struct TrsShape {
     static constexpr int kThreads = 32 * W;
@@ -44,13 +45,17 @@ template <int MOD, bool GUARD, int W> struct TrsSmem {
     static constexpr size_t kLut = kPay + kPayBytes;
     static constexpr size_t kEnc = kLut + sizeof(float2) * 16 * (NE + 2);
     static constexpr size_t kMisc = kEnc + 16 + 512;                                           // tensor-memory base address, payload mbarrier
-    static constexpr size_t kTotal = kMisc + 64;
+    static constexpr size_t kGeom = kMisc + 64;                                                // TrsGeom[2]
+    static constexpr size_t kTotal = kGeom + 256;
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+// Strong (L2) load without acquire semantics: an acquire load is followed by an invalidation of the whole L1 (CCTL.IVALL), once
+// per poll and warp. Nothing weak is read on the strength of the counter -- the only dependent read is the frame maximum,
+// itself a strong load issued after the polling loop has exited -- so the invalidation buys nothing.
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p)
 {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // Publish a warp's maximum and count its arrival WITHOUT a fence (a release would wait for every output store the thread
@@ -137,9 +142,12 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(trs_smem + L::kMisc);
     uint64_t *s_paybar = reinterpret_cast<uint64_t *>(trs_smem + L::kMisc + 8);
     uint8_t *s_pay = trs_smem + L::kPay;
-    __shared__ TrsGeom s_geom[2];                                               // this CTA's share of the current / the next frame (thread 0 works it out)
+    TrsGeom *s_geom = reinterpret_cast<TrsGeom *>(trs_smem + L::kGeom);         // [2]: this CTA's share of the current / the next frame (thread 0 works it out)
+    static_assert(2 * sizeof(TrsGeom) <= 256, "TrsGeom[2] must fit its slot");
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
+    int tid = threadIdx.x;
+    asm volatile("" : "+r"(tid));                                               // keep it in a register: under pressure ptxas re-reads SR_TID.X (S2R, an MIO instruction) inside the loops
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     const int C = a.group_ctas, G = a.n_groups;
     const int group = (int)blockIdx.x / C, rank = (int)blockIdx.x - group * C;
     const uint32_t arrivals = (uint32_t)(C * kTrsWarps);                        // per frame: every warp of the group, once
@@ -198,7 +206,9 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
         const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
         const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
         const bool pf = q.pf_on != 0;
-        if (pf) { mbar_wait(s_paybar, (uint32_t)q.pf_par); pay = s_pay - q.pf_off; }      // payload byte i of the chunk's span is s_pay[i - pf_off]
+        const int pf_off = q.pf_off;                                           // payload byte i of the chunk's span is s_pay[i - pf_off]
+        if (pf) mbar_wait(s_paybar, (uint32_t)q.pf_par);
+        auto pay_byte = [&](uint32_t i) -> uint32_t { return pf ? (uint32_t)s_pay[(int)i - pf_off] : (uint32_t)pay[i]; };
         const uint32_t n = q.n;
         const uint32_t byte0 = (uint32_t)((long)q.t0 * BPS / 8), nbyte = (uint32_t)((long)(q.t1 - q.t0) * BPS / 8);
         if (FEC) {
@@ -212,14 +222,14 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
                 if (pay_aligned && pb + 16 <= n) {
                     if (pf) {
 #pragma unroll
-                        for (int w = 0; w < 4; w++) v[w] = *reinterpret_cast<const uint32_t *>(s_pay + ((int)pb - q.pf_off) + 4 * w);
+                        for (int w = 0; w < 4; w++) v[w] = *reinterpret_cast<const uint32_t *>(s_pay + ((int)pb - pf_off) + 4 * w);
                     } else {
 #pragma unroll
                         for (int w = 0; w < 4; w++) v[w] = __ldg(reinterpret_cast<const uint32_t *>(pay + pb) + w);
                     }
                 } else {
 #pragma unroll
-                    for (int w = 0; w < 16; w++) if (pb + w < n) v[w >> 2] |= (uint32_t)pay[pb + w] << (8 * (w & 3));
+                    for (int w = 0; w < 16; w++) if (pb + w < n) v[w >> 2] |= pay_byte(pb + w) << (8 * (w & 3));
                 }
                 uint64_t w[4];
 #pragma unroll
@@ -238,7 +248,10 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
                 dst[6] = (uint32_t)(w[3] >> 24);
             }
         } else {
-            for (uint32_t b = tid; b < nbyte + 2; b += kTrsThreads) s_bits[b] = (uint8_t)frame_byte<FEC>(pay, n, q.coded_len, byte0 + b, s_enc);
+            for (uint32_t b = tid; b < nbyte + 2; b += kTrsThreads) {          // header, then the payload bytes as they are (src/transmitter.rs:37-47)
+                const uint32_t B = byte0 + b;
+                s_bits[b] = (uint8_t)(B < 16 ? (B < 8 ? (uint32_t)(q.coded_len >> (8 * B)) & 255u : 0u) : (B - 16 < n ? pay_byte(B - 16) : 0u));
+            }
         }
     };
     // (B2) bit stream -> one byte per data carrier (modulate, src/transmitter.rs:108-140); carriers past the frame's last
@@ -278,21 +291,15 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
     };
     // the frame's maximum, once every warp of the group has published its own (normalize, src/transmitter.rs:183-194)
     auto frame_max = [&](uint32_t stream) -> float {
-#ifndef TRS_ABL_NOWAIT
-        while (ld_acquire_gpu(a.stream_cnt + stream) < arrivals) __nanosleep(64);
-#endif
-        return fmaxf(__int_as_float((int)ld_acquire_gpu(reinterpret_cast<const uint32_t *>(a.stream_max) + stream)), head_max);
+        while (ld_relaxed_gpu(a.stream_cnt + stream) < arrivals) __nanosleep(64);
+        return fmaxf(__int_as_float((int)ld_relaxed_gpu(reinterpret_cast<const uint32_t *>(a.stream_max) + stream)), head_max);
     };
     // drain slot `it` of the previous frame: scale, store with the cyclic prefix (prefix_block, src/transmitter.rs:168-181)
     auto drain = [&](int it, int p_nsym, float2 *p_out, float p_scale) {
         cpx y[8];
         tmem_ld16(taddr0 + 16u * (uint32_t)it, y);
         const int sl = it * kTrsIterSyms + sym_in_iter;
-#ifdef TRS_ABL_NOSTORE
-        if (sl < p_nsym && p_scale == 123.0f) {
-#else
         if (sl < p_nsym) {
-#endif
             unsigned long long *sym = reinterpret_cast<unsigned long long *>(p_out + (size_t)sl * kSym + l);
             const cpx sc = c_make(p_scale, p_scale);
 #pragma unroll
@@ -402,18 +409,10 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
         if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
         // ---- (B) carrier bytes of frame k+1, head / zero fill of frame k-1 ----------------------------------------------------
         __syncthreads();                                                       // every warp is done with the carrier bytes of frame k
-#ifdef TRS_ABL_NOPROD
-        if (more && a.n_streams == 1) build_bits(qn, next);
-#else
         if (more) build_bits(qn, next);
-#endif
         if (have_prev) write_head(p_stream, p_fits, p_flen, p_fmx);
         __syncthreads();
-#ifdef TRS_ABL_NOPROD
-        if (more && a.n_streams == 1) unpack_carriers(qn);
-#else
         if (more) unpack_carriers(qn);
-#endif
         __syncthreads();
         have_prev = true; p_nit = n_it; p_nsym = nsym; p_stream = stream; p_flen = q.frame_len; p_fits = q.fits;
         p_out = a.iq + (size_t)stream * a.iq_stride + (size_t)(kHeadSyms + q.t0) * kSym;

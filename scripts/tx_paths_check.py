@@ -44,6 +44,8 @@ def main():
              ("qpsk_fec", dict(modulation=1, fec=1), 150, 1500, True), ("64qam_noguard", dict(guard_bands=0), 64, 5000, True)]
     if os.environ.get("TXCHECK_QUICK"):
         cases = cases[:1]
+    if os.environ.get("TXCHECK_SWEEP"):      # where does the one-pass kernel overtake the two-pass one? frames per group = n / (148 / C)
+        cases = [(f"sweep{k}", dict(), k, sy, False) for sy in (2038, 500) for k in (74, 148, 296, 444, 592, 888, 1184, 2368)]
     for name, over, ns, syms, ragged in cases:
         import dataclasses
         cfg = dataclasses.replace(bench.workload_cfg(), **over)
@@ -59,15 +61,11 @@ def main():
             plen = torch.full((ns,), plen_b, dtype=torch.int32, device=dev)
         t0 = time.time()
         a, fa, ms_a = run("twopass", cfg, payload, plen, pstride, ns, stride, 10)
-        for W in (32, 16, 8):
-            os.environ["OFDM_TX_WARPS"] = str(W)
-            b, fb, ms_b = run("resident", cfg, payload, plen, pstride, ns, stride, 10)
-            same = bool(torch.equal(a, b)) and bool(torch.equal(fa, fb))
-            nbad = int((a != b).sum().item())
-            ok &= same
-            print(f"{name}: n={ns} S={syms} stride={stride} twopass {ms_a:.4f} ms resident(W={W}) {ms_b:.4f} ms identical={same} diff_elems={nbad} ({time.time() - t0:.1f}s)", flush=True)
-            if W != 8:
-                del b
+        b, fb, ms_b = run("resident", cfg, payload, plen, pstride, ns, stride, 10)
+        same = bool(torch.equal(a, b)) and bool(torch.equal(fa, fb))
+        nbad = int((a != b).sum().item())
+        ok &= same
+        print(f"{name}: n={ns} S={syms} stride={stride} twopass {ms_a:.4f} ms resident {ms_b:.4f} ms identical={same} diff_elems={nbad} ({time.time() - t0:.1f}s)", flush=True)
         if not same:
             d = (a != b).any(dim=2)
             rows = d.any(dim=1).nonzero().flatten()[:5].tolist()

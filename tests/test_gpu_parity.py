@@ -683,3 +683,51 @@ def test_wideband_1024_parity(ob, oo, mod, guard, fec, modes):
     assert short.status[0] in (ob.TOO_SHORT, ob.NO_SYNC, ob.NEG_OFFSET) and short.out_len[0] == 0
     assert oo.decode(batch[0, :9000].astype(np.complex128), ocfg).status == short.status[0]
     eng.close()
+
+
+@pytest.mark.parametrize("mod,guard,fec", [(2, True, True), (2, False, False), (1, True, True), (0, False, True), (0, True, False)])
+def test_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
+    """The one-pass TX kernel (frames resident in tensor memory, tx_resident.cuh) is what large batches run; here it is forced
+    for a ragged batch: every frame against the oracle's encode (src/transmitter.rs:11-58), zero fill past the frame, and
+    bit-for-bit against the two-pass kernel. Lengths include the empty payload, one byte, and frames of 1, 2 and several CTAs'
+    worth of symbols; iq_stride admits frames that need a group of 3 CTAs."""
+    rng = np.random.default_rng(77 + 10 * mod + 2 * guard + fec)
+    cfg = ob.Config(modulation=mod, guard_bands=guard, fec=fec)
+    longest = cfg.max_payload(1300)
+    lens = [0, 1, 2, 15, 16, 17, 100, 333, 1000, longest // 3, longest // 2, longest - 1, longest] + [int(v) for v in rng.integers(0, longest + 1, 40)]
+    pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    out = {}
+    for path in ("resident", "twopass"):
+        monkeypatch.setenv("OFDM_TX_PATH", path)
+        eng = ob.Engine(cfg, 0)
+        out[path] = eng.tx_encode(pays)
+        eng.close()
+    iq, flen = out["resident"]
+    ocfg = oo.make_cfg(guard, mod, fec, 0, 0, 0, 0)
+    for i, p in enumerate(pays):
+        ref = oo.tx(p, ocfg)
+        assert ref.size == flen[i]
+        np.testing.assert_allclose(iq[i, : flen[i]], ref, atol=2e-6)
+        assert not iq[i, flen[i]:].any()
+    assert np.array_equal(flen, out["twopass"][1])
+    assert np.array_equal(iq.view(np.uint32), out["twopass"][0].view(np.uint32))
+
+
+def test_tx_resident_kernel_is_the_large_batch_path(ob, oo):
+    """A batch of a few hundred frames takes the one-pass kernel by itself (one launch instead of two); spot-check frames
+    against the oracle and the normalisation of every frame (max positive component 1, src/transmitter.rs:183-194)."""
+    cfg = ob.Config(modulation=2, guard_bands=True, fec=True)
+    rng = np.random.default_rng(5)
+    n = 600
+    plen = cfg.max_payload(64)
+    pays = [rng.integers(0, 256, plen - (i % 7), dtype=np.uint8).tobytes() for i in range(n)]
+    eng = ob.Engine(cfg, 0)
+    l0 = eng.kernel_launches
+    iq, flen = eng.tx_encode(pays)
+    assert eng.kernel_launches - l0 == 1
+    eng.close()
+    ocfg = oo.make_cfg(True, 2, True, 0, 0, 0, 0)
+    for i in (0, 1, 147, 148, 299, 599):
+        np.testing.assert_allclose(iq[i, : flen[i]], oo.tx(pays[i], ocfg), atol=2e-6)
+    mx = np.maximum(iq.real.max(axis=1), iq.imag.max(axis=1))
+    np.testing.assert_allclose(mx, 1.0, atol=1e-6)
