@@ -69,16 +69,15 @@ __device__ __forceinline__ void publish_max_and_arrive(int *mx_addr, int mx_bits
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" :: "l"(cnt_addr), "r"(one) : "memory");
 }
 // tensor memory: a warp reads / writes 32 lanes x 16 columns = its 16 registers of one slot (32x32b shape: thread i <-> lane i
-// of the warp's quadrant). The store takes the halves of every value in the other order: the inverse FFT leaves (im, re) in
-// the registers (swap . FFT . swap), the slot holds (re, im) -- the un-swap costs nothing.
-__device__ __forceinline__ void tmem_st16_swapped(uint32_t taddr, const cpx (&x)[8])
+// of the warp's quadrant)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const cpx (&x)[8])
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                  :: "r"(taddr),
-                    "r"((uint32_t)(x[0].v >> 32)), "r"((uint32_t)x[0].v), "r"((uint32_t)(x[1].v >> 32)), "r"((uint32_t)x[1].v),
-                    "r"((uint32_t)(x[2].v >> 32)), "r"((uint32_t)x[2].v), "r"((uint32_t)(x[3].v >> 32)), "r"((uint32_t)x[3].v),
-                    "r"((uint32_t)(x[4].v >> 32)), "r"((uint32_t)x[4].v), "r"((uint32_t)(x[5].v >> 32)), "r"((uint32_t)x[5].v),
-                    "r"((uint32_t)(x[6].v >> 32)), "r"((uint32_t)x[6].v), "r"((uint32_t)(x[7].v >> 32)), "r"((uint32_t)x[7].v)
+                    "r"((uint32_t)x[0].v), "r"((uint32_t)(x[0].v >> 32)), "r"((uint32_t)x[1].v), "r"((uint32_t)(x[1].v >> 32)),
+                    "r"((uint32_t)x[2].v), "r"((uint32_t)(x[2].v >> 32)), "r"((uint32_t)x[3].v), "r"((uint32_t)(x[3].v >> 32)),
+                    "r"((uint32_t)x[4].v), "r"((uint32_t)(x[4].v >> 32)), "r"((uint32_t)x[5].v), "r"((uint32_t)(x[5].v >> 32)),
+                    "r"((uint32_t)x[6].v), "r"((uint32_t)(x[6].v >> 32)), "r"((uint32_t)x[7].v), "r"((uint32_t)(x[7].v >> 32))
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, cpx (&x)[8])
@@ -103,7 +102,7 @@ struct TrsGeom {
     uint32_t frame_len;
     bool     fits;
     // payload bytes of the chunk, prefetched into shared memory by one TMA bulk copy while the previous frame is transformed
-    int      pf_on, pf_off, pf_par;     // pf_off: payload byte index of the buffer's first byte (16-byte aligned superset)
+    int      pf_on, pf_off;             // pf_off: payload byte index of the buffer's first byte (16-byte aligned superset)
 };
 template <int BPC, int D, bool FEC, int CHUNK_MAX>
 __device__ __forceinline__ TrsGeom trs_geometry(const TxArgs &a, uint32_t stream, int rank)
@@ -116,7 +115,7 @@ __device__ __forceinline__ TrsGeom trs_geometry(const TxArgs &a, uint32_t stream
     q.S = (int)((q.ncar + D - 1) / D);                              // OFDM data symbols (src/transmitter.rs:49-54)
     q.frame_len = (kHeadSyms + (uint32_t)q.S) * kSym;
     q.fits = q.frame_len <= a.iq_stride;
-    q.pf_on = 0; q.pf_off = 0; q.pf_par = 0;
+    q.pf_on = 0; q.pf_off = 0;
     const int C = a.group_ctas;
     q.chunk = 7 * ((q.S + a.tile_shift + 7 * C - 1) / (7 * C));
     q.lo = rank * q.chunk - a.tile_shift;
@@ -153,7 +152,11 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
     const uint32_t arrivals = (uint32_t)(C * kTrsWarps);                        // per frame: every warp of the group, once
 
     // ---- set-up: tables, tensor memory ------------------------------------------------------------------------------------
-    for (int e = tid; e < 16 * (NE + 2); e += kTrsThreads) {                     // constellation table, see tx_tile_kernel
+    // Constellation table as in tx_tile_kernel, but CONJUGATED: the inverse transform runs as conj . FFT . conj here instead
+    // of swap . FFT . swap. The two are the same numbers bit for bit (swap(x) = j conj(x), and the packed FFT commutes with a
+    // multiplication by j exactly: every add / multiply / fma is sign-symmetric), but the closing conj is free -- the
+    // scaling multiplies by (s, -s) -- whereas the closing swap costs a register move per value around the tensor-memory slot.
+    for (int e = tid; e < 16 * (NE + 2); e += kTrsThreads) {
         const int idx = e >> 4;
         float re = 0.0f, im = 0.0f;
         if (idx == NE + 1) re = 1.0f;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
             re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
             im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
         }
-        s_lut[e] = make_float2(im, re);
+        s_lut[e] = make_float2(re, -im);
     }
     if (tid < 16) s_enc[tid] = (uint8_t)ham74_encode_nibble(tid);
     if (FEC && tid < 256) s_enc14[tid] = (uint16_t)(ham74_encode_nibble(tid & 15) | (ham74_encode_nibble(tid >> 4) << 7));
@@ -197,17 +200,18 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
     const unsigned long long *lut = reinterpret_cast<const unsigned long long *>(s_lut) + (lane & 15);
     // tensor-memory slots of this warp: lane quadrant warp % 4, columns 64 (warp / 4) + 16 slot
     const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
-    const int sym_in_iter = 4 * warp + g;
+    uint32_t taddr_w = taddr0;
+    int sym_in_iter = 4 * warp + g;
+    asm volatile("" : "+r"(taddr_w), "+r"(sym_in_iter));                        // otherwise re-derived from tid in every iteration (7 instructions per symbol, measured)
     const uint8_t *car = s_car + (GUARD ? l - 7 : l);
 
     // (B1) coded bit stream of this CTA's chunk of a frame (same construction as a tile of tx_tile_kernel, the chunk is the tile)
     auto build_bits = [&](const TrsGeom &q, uint32_t stream) {
-        if (q.t0 >= q.t1) return;
+        if (q.t0 >= q.t1) return;                                              // (also when the frame does not fit iq_stride)
         const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
         const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
         const bool pf = q.pf_on != 0;
         const int pf_off = q.pf_off;                                           // payload byte i of the chunk's span is s_pay[i - pf_off]
-        if (pf) mbar_wait(s_paybar, (uint32_t)q.pf_par);
         auto pay_byte = [&](uint32_t i) -> uint32_t { return pf ? (uint32_t)s_pay[(int)i - pf_off] : (uint32_t)pay[i]; };
         const uint32_t n = q.n;
         const uint32_t byte0 = (uint32_t)((long)q.t0 * BPS / 8), nbyte = (uint32_t)((long)(q.t1 - q.t0) * BPS / 8);
@@ -263,16 +267,35 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
         if (ncar_local < have) have = ncar_local;
         const int ncar_have = (int)have;
         const uint32_t *bits32 = reinterpret_cast<const uint32_t *>(s_bits);
-        for (int c4 = 4 * tid; c4 < total; c4 += 4 * kTrsThreads) {
-            const uint32_t bit = (uint32_t)c4 * BPC, wi = bit >> 5, sh = bit & 31;
-            const uint32_t v = __funnelshift_r(bits32[wi], bits32[wi + 1], sh);
-            constexpr uint32_t M = (uint32_t)(NE - 1);
-            uint32_t packed = (v & M) | (((v >> BPC) & M) << 8) | (((v >> (2 * BPC)) & M) << 16) | (((v >> (3 * BPC)) & M) << 24);
+        constexpr uint32_t M = (uint32_t)(NE - 1);
+        auto spread4 = [&](uint32_t v) -> uint32_t {                           // 4 x BPC bits -> 4 carrier bytes
+            return (v & M) | (((v >> BPC) & M) << 8) | (((v >> (2 * BPC)) & M) << 16) | (((v >> (3 * BPC)) & M) << 24);
+        };
+        auto pad4 = [&](uint32_t packed, int c4) -> uint32_t {                 // the frame's last carriers / padding rows (rare)
             if (c4 + 4 > ncar_have) {
 #pragma unroll
                 for (int w = 0; w < 4; w++) if (c4 + w >= ncar_have) packed = (packed & ~(0xFFu << (8 * w))) | ((uint32_t)NE << (8 * w));
             }
-            *reinterpret_cast<uint32_t *>(s_car + c4) = packed;
+            return packed;
+        };
+        if (BPC == 6) {
+            // 16 carriers = 96 bits = 3 aligned words in, 4 words (one 16-byte store) out
+            for (int c16 = 16 * tid; c16 < total; c16 += 16 * kTrsThreads) {
+                const uint32_t *bw = bits32 + (c16 >> 4) * 3;
+                const uint32_t b0 = bw[0], b1 = bw[1], b2 = bw[2];
+                uint4 o;
+                o.x = pad4(spread4(b0), c16);
+                o.y = pad4(spread4(__funnelshift_r(b0, b1, 24)), c16 + 4);
+                o.z = pad4(spread4(__funnelshift_r(b1, b2, 16)), c16 + 8);
+                o.w = pad4(spread4(b2 >> 8), c16 + 12);
+                *reinterpret_cast<uint4 *>(s_car + c16) = o;                   // (total is a multiple of 16: D = 48 or 64 carriers per symbol)
+            }
+        } else {
+            for (int c4 = 4 * tid; c4 < total; c4 += 4 * kTrsThreads) {          // 4 carriers = 4 BPC bits from bit 4 BPC (c4 / 4)
+                const uint32_t bit = (uint32_t)c4 * BPC, wi = bit >> 5, sh = bit & 31;
+                const uint32_t v = __funnelshift_r(bits32[wi], bits32[wi + 1], sh);
+                *reinterpret_cast<uint32_t *>(s_car + c4) = pad4(spread4(v), c4);
+            }
         }
     };
     // frame head (lock | preamble x4 | training x5) and zero fill past the frame, once the frame maximum is known
@@ -297,11 +320,11 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
     // drain slot `it` of the previous frame: scale, store with the cyclic prefix (prefix_block, src/transmitter.rs:168-181)
     auto drain = [&](int it, int p_nsym, float2 *p_out, float p_scale) {
         cpx y[8];
-        tmem_ld16(taddr0 + 16u * (uint32_t)it, y);
+        tmem_ld16(taddr_w + 16u * (uint32_t)it, y);
         const int sl = it * kTrsIterSyms + sym_in_iter;
         if (sl < p_nsym) {
             unsigned long long *sym = reinterpret_cast<unsigned long long *>(p_out + (size_t)sl * kSym + l);
-            const cpx sc = c_make(p_scale, p_scale);
+            const cpx sc = c_make(p_scale, -p_scale);                          // conj and scale in one
 #pragma unroll
             for (int kb = 0; kb < 8; kb++) {
                 const unsigned long long v = c_mul2(y[kb], sc).v;              // time index l + 8 kb
@@ -316,7 +339,6 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
     float2 *p_out = nullptr;
     uint32_t p_stream = 0, p_flen = 0;
     bool p_fits = false, have_prev = false;
-    uint32_t pf_count = 0;                                                     // payload prefetches issued so far (thread 0): mbarrier phase
 
     uint32_t stream = (uint32_t)group;                                         // (the launcher guarantees group < n_streams)
     if (tid == 0) s_geom[0] = trs_geometry<BPC, D, FEC, TrsShape<W>::kChunkMax>(a, stream, rank);
@@ -327,16 +349,23 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
     __syncthreads();
 
     for (int k = 0; ; k++) {
+        // Frame k's geometry was published at least one CTA barrier ago; everything this iteration needs of it goes into
+        // registers now, because thread 0 is about to put frame k+1's geometry into the other slot, and the slot after that
+        // -- this one -- is rewritten an iteration later, possibly while a slow warp is still at the end of this iteration.
         const TrsGeom &q = s_geom[k & 1];
         TrsGeom &qn = s_geom[(k + 1) & 1];
-        if (rank == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = q.frame_len;
-        const int nsym = q.t1 - q.t0;
+        const int q_t0 = q.t0, nsym = q.t1 - q.t0;
+        const uint32_t q_flen = q.frame_len;
+        const bool q_fits = q.fits;
+        if (rank == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = q_flen;
         int n_it = nsym - 4 * warp;                                            // iterations in which this warp has at least one symbol
         n_it = n_it > 0 ? (n_it + kTrsIterSyms - 1) / kTrsIterSyms : 0;
         // ---- the next frame of the group: its geometry, and its payload bytes on their way into shared memory -----------------
         const uint32_t next = stream + (uint32_t)G;
         const bool more = next < a.n_streams;
         if (more && tid == 0) {
+            uint32_t pf_bytes = 0;
+            uintptr_t pf_src = 0;
             TrsGeom g2 = trs_geometry<BPC, D, FEC, TrsShape<W>::kChunkMax>(a, next, rank);
             if (g2.t0 < g2.t1) {
                 const long byte0 = (long)g2.t0 * BPS / 8, nbyte = (long)(g2.t1 - g2.t0) * BPS / 8;
@@ -356,13 +385,15 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
                     s1 <= reinterpret_cast<uintptr_t>(a.payload + (size_t)a.n_streams * a.payload_stride)) {
                     g2.pf_on = 1;
                     g2.pf_off = (int)((long)s0 - (long)reinterpret_cast<uintptr_t>(pay));
-                    g2.pf_par = (int)(pf_count & 1u);
-                    pf_count++;
-                    mbar_arrive_expect_tx(s_paybar, (uint32_t)(s1 - s0));
-                    tma_bulk_g2s(s_pay, reinterpret_cast<const void *>(s0), (uint32_t)(s1 - s0), s_paybar);
+                    pf_bytes = (uint32_t)(s1 - s0);
+                    pf_src = s0;
                 }
             }
             qn = g2;
+            // one mbarrier phase per frame: its completion publishes the geometry (release / acquire) and, when the payload
+            // bytes are prefetched, also means that they have landed
+            mbar_arrive_expect_tx(s_paybar, pf_bytes);
+            if (pf_bytes) tma_bulk_g2s(s_pay, reinterpret_cast<const void *>(pf_src), pf_bytes, s_paybar);
         }
         // ---- (A) drain frame k-1, transform frame k ------------------------------------------------------------------------
         float p_fmx = 1.0f, p_scale = 0.0f;
@@ -395,11 +426,11 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
 #pragma unroll
                     for (int kb = 0; kb < 8; kb++) {
                         float re, im;
-                        c_split(x[kb], im, re);
-                        mx = fmaxf(mx, fmaxf(re, im));
+                        c_split(x[kb], re, im);                                // the frame's sample is (re, -im)
+                        mx = fmaxf(mx, fmaxf(re, -im));
                     }
                 }
-                tmem_st16_swapped(taddr0 + 16u * (uint32_t)it, x);
+                tmem_st16(taddr_w + 16u * (uint32_t)it, x);
             }
         }
         // ---- publish this warp's maximum of frame k, count the arrival -------------------------------------------------------
@@ -408,14 +439,14 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
         for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
         if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
         // ---- (B) carrier bytes of frame k+1, head / zero fill of frame k-1 ----------------------------------------------------
-        __syncthreads();                                                       // every warp is done with the carrier bytes of frame k
-        if (more) build_bits(qn, next);
+        // (a warp starts on the bit stream as soon as its own transforms are done: s_bits and s_pay are not touched by phase A)
+        if (more) { mbar_wait(s_paybar, (uint32_t)(k & 1)); build_bits(qn, next); }
         if (have_prev) write_head(p_stream, p_fits, p_flen, p_fmx);
-        __syncthreads();
+        __syncthreads();                                                       // every warp is done with the carrier bytes of frame k; the bit stream is complete
         if (more) unpack_carriers(qn);
         __syncthreads();
-        have_prev = true; p_nit = n_it; p_nsym = nsym; p_stream = stream; p_flen = q.frame_len; p_fits = q.fits;
-        p_out = a.iq + (size_t)stream * a.iq_stride + (size_t)(kHeadSyms + q.t0) * kSym;
+        have_prev = true; p_nit = n_it; p_nsym = nsym; p_stream = stream; p_flen = q_flen; p_fits = q_fits;
+        p_out = a.iq + (size_t)stream * a.iq_stride + (size_t)(kHeadSyms + q_t0) * kSym;
         if (!more) break;
         stream = next;
     }
