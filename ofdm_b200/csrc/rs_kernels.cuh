@@ -320,6 +320,88 @@ static __device__ __noinline__ int rs_correct_from_remainder(uint8_t *data, cons
     return nerr;
 }
 
+// The same correction with the 32 lanes of a warp working on ONE block (all lanes call it together; `w` holds the block's
+// remainder, the same in every lane). One thread per block is the right shape while every lane has a block to repair (the
+// SIMT lanes are the parallelism); at an operating point where most blocks are clean, a warp would instead wait for its one
+// or two erroneous lanes to run ~45 000 instructions each on their own. Here lane i holds syndrome S_i, coefficient i of
+// the Berlekamp-Massey polynomials and Omega_i, takes 8 of the 255 Chien positions, and the sums over i are warp
+// reductions: ~2 000 warp instructions per block. Same bounded-distance semantics and counts as rs_correct_from_remainder.
+static __device__ __noinline__ int rs_correct_warp(uint8_t *data, const uint32_t (&w)[8], const RsGf gf, const int lane)
+{
+    constexpr unsigned kFull = 0xffffffffu;
+    uint32_t S = 0;                                                 // S_lane = rem(alpha^lane), Horner over the 32 remainder bytes
+#pragma unroll
+    for (int j = 0; j < kRsT2; j++) S = gf.mul_pow(S, (uint32_t)lane) ^ ((w[j >> 2] >> (8 * (j & 3))) & 255u);
+    // Berlekamp-Massey: C_lane, B_lane (coefficients beyond 31 only ever feed a locator of degree > 16, which fails anyway)
+    uint32_t C = lane == 0 ? 1u : 0u, B = C, b = 1;
+    int L = 0, m = 1;
+    for (int r = 0; r < kRsT2; r++) {
+        const uint32_t s = __shfl_sync(kFull, S, (r - lane) & 31);
+        uint32_t d = (lane <= r && lane <= L) ? gf.mul(C, s) : 0u;
+#pragma unroll
+        for (int k = 16; k >= 1; k >>= 1) d ^= __shfl_xor_sync(kFull, d, k);
+        if (d == 0) { m++; continue; }
+        const uint32_t coef = gf.div(d, b);
+        const uint32_t Bs = __shfl_sync(kFull, B, (lane - m) & 31);
+        const uint32_t Cn = C ^ (lane >= m ? gf.mul(coef, Bs) : 0u);
+        if (2 * L <= r) { B = C; L = r + 1 - L; b = d; m = 1; } else m++;
+        C = Cn;
+    }
+    if (2 * L > kRsT2) return -1;
+    // Chien search: this lane evaluates Lambda at the 8 positions e = lane + 32 k (locator X = alpha^e, byte 254 - e)
+    uint32_t y[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { y[k] = 1; acc[k] = 0; }          // C_0 = 1; acc = i e mod 255
+    for (int i = 1; i <= L; i++) {
+        const uint32_t ci = __shfl_sync(kFull, C, i);
+        const int lgc = ci ? (int)gf.lg[ci] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            acc[k] += (uint32_t)(lane + 32 * k);
+            if (acc[k] >= 255u) acc[k] -= 255u;
+            int idx = lgc - (int)acc[k];
+            if (idx < 0) idx += 255;
+            if (ci) y[k] ^= gf.ex[idx];
+        }
+    }
+    int nerr = 0;
+    unsigned roots[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        roots[k] = __ballot_sync(kFull, y[k] == 0 && lane + 32 * k < kRsN);
+        nerr += __popc(roots[k]);
+    }
+    if (nerr != L) return -1;
+    // Forney: Omega = S Lambda mod x^32 (lane i: Omega_i); e = X Omega(X^-1) / Lambda'(X^-1), one root at a time, sums by reduction
+    uint32_t Om = 0;
+    for (int j = 0; j <= L; j++) {
+        const uint32_t cj = __shfl_sync(kFull, C, j), s = __shfl_sync(kFull, S, (lane - j) & 31);
+        if (j <= lane) Om ^= gf.mul(cj, s);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned mask = roots[k];
+        while (mask) {
+            const uint32_t e = (uint32_t)(__ffs(mask) - 1 + 32 * k), einv = (255u - e) % 255u;
+            mask &= mask - 1;
+            uint32_t t = gf.mul_pow(Om, (einv * (uint32_t)lane) % 255u);
+            if ((lane & 1) && lane <= L) t |= gf.mul_pow(C, (einv * (uint32_t)(lane - 1)) % 255u) << 8;
+#pragma unroll
+            for (int q = 16; q >= 1; q >>= 1) t ^= __shfl_xor_sync(kFull, t, q);
+            const uint32_t om = t & 255u, dl = t >> 8;
+            if (dl == 0) return -1;
+            const uint32_t p = (uint32_t)(kRsN - 1) - e;
+            if (p < (uint32_t)kRsK && lane == 0) data[p] ^= (uint8_t)gf.mul_pow(gf.div(om, dl), e);
+        }
+    }
+    return nerr;
+}
+
+#ifndef RS_COOP_MAX_LANES
+#define RS_COOP_MAX_LANES 16
+#endif
+constexpr int kRsCoopMaxLanes = RS_COOP_MAX_LANES;     // erroneous lanes per warp up to which the warp repairs them one by one together
+
 template <int = 0>
 __global__ void __launch_bounds__(kRsThreads) rs_decode_kernel(const RsArgs a)
 {
@@ -331,52 +413,81 @@ __global__ void __launch_bounds__(kRsThreads) rs_decode_kernel(const RsArgs a)
     __syncthreads();
     const uint64_t task = (uint64_t)blockIdx.x * kRsThreads + tid;         // one block of one stream
     const uint32_t stream = (uint32_t)(task / a.blocks_per_stream), b = (uint32_t)(task - (uint64_t)stream * a.blocks_per_stream);
-    if (stream >= a.n_streams) return;
-    const uint32_t n = a.in_len[stream];
-    const uint32_t nb = n / kRsN + 1;                                      // src/utils.rs:160-176
-    const uint32_t need = nb * kRsK;
-    if (b == 0) a.out_len[stream] = need;
-    if (b >= nb || need > a.out_stride) return;
-
-    RsReader rd;
-    rd.init(a.in + (size_t)stream * a.in_stride + (size_t)b * kRsN, n > b * kRsN ? min((uint32_t)kRsN, n - b * kRsN) : 0u);
-    uint8_t *data = a.out + (size_t)stream * a.out_stride + (size_t)b * kRsK;
-    RsWriter wr;
-    wr.init(data);
-    RsLfsr L;
-    L.init((uint32_t)__cvta_generic_to_shared(s_lfsr), lane);
-    uint32_t dw[4];
-#pragma unroll 1
-    for (uint32_t g = 0; g < 13; g++) {                                    // data words 0..51
-        rd.next4(g, dw);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { L.step4(dw[i]); wr.put(4 * g + i, dw[i]); }
+    // (no early return: all 32 lanes of a warp stay for the cooperative repair below)
+    bool live = stream < a.n_streams;
+    uint32_t n = 0, nb = 0;
+    if (live) {
+        n = a.in_len[stream];
+        nb = n / kRsN + 1;                                                 // src/utils.rs:160-176
+        const uint32_t need = nb * kRsK;
+        if (b == 0) a.out_len[stream] = need;
+        live = b < nb && need <= a.out_stride;
     }
-    rd.next4(13, dw);                                                      // words 52..54, bytes 220..222 | received parity byte 0
+    uint8_t *data = nullptr;
+    uint32_t any = 0, rw[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if (live) {
+        RsReader rd;
+        rd.init(a.in + (size_t)stream * a.in_stride + (size_t)b * kRsN, n > b * kRsN ? min((uint32_t)kRsN, n - b * kRsN) : 0u);
+        data = a.out + (size_t)stream * a.out_stride + (size_t)b * kRsK;
+        RsWriter wr;
+        wr.init(data);
+        RsLfsr L;
+        L.init((uint32_t)__cvta_generic_to_shared(s_lfsr), lane);
+        uint32_t dw[4];
+#pragma unroll 1
+        for (uint32_t g = 0; g < 13; g++) {                                // data words 0..51
+            rd.next4(g, dw);
 #pragma unroll
-    for (int i = 0; i < 3; i++) { L.step4(dw[i]); wr.put(52 + i, dw[i]); }
-    uint32_t d = dw[3];
-    L.step(d); L.step(d >> 8); L.step(d >> 16);
-    wr.put_last(55, d, 3);
-    // remainder = computed parity ^ received parity (bytes 223..254 = byte 3 of word 55 and words 56..63)
-    uint32_t any = 0, rw[8];
+            for (int i = 0; i < 4; i++) { L.step4(dw[i]); wr.put(4 * g + i, dw[i]); }
+        }
+        rd.next4(13, dw);                                                  // words 52..54, bytes 220..222 | received parity byte 0
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        rd.next4(14 + h, dw);
+        for (int i = 0; i < 3; i++) { L.step4(dw[i]); wr.put(52 + i, dw[i]); }
+        uint32_t d = dw[3];
+        L.step(d); L.step(d >> 8); L.step(d >> 16);
+        wr.put_last(55, d, 3);
+        // remainder = computed parity ^ received parity (bytes 223..254 = byte 3 of word 55 and words 56..63)
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            rw[4 * h + i] = L.word(4 * h + i) ^ __funnelshift_r(d, dw[i], 24);
-            any |= rw[4 * h + i];
-            d = dw[i];
+        for (int h = 0; h < 2; h++) {
+            rd.next4(14 + h, dw);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                rw[4 * h + i] = L.word(4 * h + i) ^ __funnelshift_r(d, dw[i], 24);
+                any |= rw[4 * h + i];
+                d = dw[i];
+            }
         }
     }
-    if (any) {
-        uint8_t rem[kRsT2];
+    __syncwarp();
+    unsigned pend = __ballot_sync(0xffffffffu, any != 0);
+    if (pend == 0) return;
+    const RsGf gf{ s_exp, s_log };
+    if (__popc(pend) > kRsCoopMaxLanes) {
+        // most lanes have a block to repair: each on its own
+        if (any) {
+            uint8_t rem[kRsT2];
 #pragma unroll
-        for (int i = 0; i < kRsT2; i++) rem[i] = (uint8_t)(rw[i >> 2] >> (8 * (i & 3)));
-        const int r = rs_correct_from_remainder(data, rem, RsGf{ s_exp, s_log });
-        if (r < 0) atomicAdd(a.n_failed + stream, 1u);
-        else atomicAdd(a.n_corrected + stream, (uint32_t)r);
+            for (int i = 0; i < kRsT2; i++) rem[i] = (uint8_t)(rw[i >> 2] >> (8 * (i & 3)));
+            const int r = rs_correct_from_remainder(data, rem, gf);
+            if (r < 0) atomicAdd(a.n_failed + stream, 1u);
+            else atomicAdd(a.n_corrected + stream, (uint32_t)r);
+        }
+        return;
+    }
+    // few lanes: the warp repairs their blocks one after the other, all lanes on one block (the data bytes a lane has just
+    // written are patched by lane 0: the warp barrier above orders them)
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = __shfl_sync(0xffffffffu, rw[i], src);
+        const unsigned long long dp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(data), src);
+        const int r = rs_correct_warp(reinterpret_cast<uint8_t *>((uintptr_t)dp), w, gf, lane);
+        if (lane == src) {
+            if (r < 0) atomicAdd(a.n_failed + stream, 1u);
+            else atomicAdd(a.n_corrected + stream, (uint32_t)r);
+        }
     }
 }
 

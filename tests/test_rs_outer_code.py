@@ -132,6 +132,37 @@ def test_rs_decode_matches_oracle_with_errors(oo, eng):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("frac", [0.02, 0.15, 0.45])
+def test_rs_decode_sparse_errors_warp_cooperative_path(oo, eng, frac):
+    """At a realistic operating point most blocks are clean; a warp with at most 16 erroneous blocks among its 32 repairs them
+    one by one with all lanes on one block (rs_correct_warp). Bytes / corrected / failed must equal the oracle's, including
+    blocks beyond repair (17, 18 errors) and errors in the parity bytes only."""
+    rng = np.random.default_rng(int(1000 * frac))
+    coded_list = []
+    for n in (223 * 400, 223 * 97 + 5, 223 * 33):
+        c = oo.rs_encode(rng.integers(0, 256, n, dtype=np.uint8))
+        for b in range(c.size // 255):
+            if rng.random() < frac:
+                ne = int(rng.integers(1, 19))
+                lo, hi = (223, 255) if rng.random() < 0.1 else (0, 255)     # sometimes parity bytes only
+                pos = rng.choice(np.arange(lo, hi), min(ne, hi - lo), replace=False) + 255 * b
+                c[pos] ^= rng.integers(1, 256, pos.size, dtype=np.uint8)
+        coded_list.append(c)
+    stride = max(c.size for c in coded_list) + 1
+    coded = np.zeros((len(coded_list), stride), np.uint8)
+    clen = np.zeros(len(coded_list), np.uint32)
+    for i, c in enumerate(coded_list):
+        coded[i, :c.size] = c
+        clen[i] = c.size
+    data, data_len, n_corr, n_fail = eng.rs_decode(coded, clen)
+    for i, c in enumerate(coded_list):
+        want, wc, wf = oo.rs_decode(c)
+        assert int(data_len[i]) == want.size
+        assert (int(n_corr[i]), int(n_fail[i])) == (wc, wf), f"stream {i}"
+        assert (data[i, :want.size] == want).all(), f"stream {i}"
+
+
+@pytest.mark.gpu
 def test_rs_truncated_and_ragged_tail(oo, eng):
     # a stream cut inside a block: the missing bytes read as zeros (src/utils.rs:157,167) and count as errors
     rng = np.random.default_rng(9)
