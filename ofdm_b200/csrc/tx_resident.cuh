@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(32 * W, 32 / W) tx_resident_kernel(const TxArg
 
     // ---- set-up: tables, tensor memory ------------------------------------------------------------------------------------
     // Constellation table as in tx_tile_kernel, but CONJUGATED: the inverse transform runs as conj . FFT . conj here instead
-    // of swap . FFT . swap. The two are the same numbers bit for bit (swap(x) = j conj(x), and the packed FFT commutes with a
-    // multiplication by j exactly: every add / multiply / fma is sign-symmetric), but the closing conj is free -- the
+    // of swap . FFT . swap. The two give the same numbers, bit for bit except the sign of an exact zero (swap(x) = j conj(x),
+    // and the packed FFT commutes with a multiplication by j exactly: every add / multiply / fma is sign-symmetric; only an
+    // exact cancellation, which rounds to +0 on either side, breaks the symmetry), but the closing conj is free -- the
     // scaling multiplies by (s, -s) -- whereas the closing swap costs a register move per value around the tensor-memory slot.
     for (int e = tid; e < 16 * (NE + 2); e += kTrsThreads) {
         const int idx = e >> 4;

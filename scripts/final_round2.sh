@@ -30,7 +30,8 @@ python bench.py --workload capture --capture-samples 400000000 --steps 2 --no-cp
   $N -k regex:sync_scan -c 1 -o $O/scan python bench.py --workload capture --capture-samples 400000000 --steps 2 --no-cpu > $O/n2.log 2>&1
 python tools/ncu_summary.py $O/scan.ncu-rep > $O/r2_ncu_scan.txt 2>&1
 python bench.py --workload tx --steps 2 > $O/p3.log 2>&1 && \
-  $N -k regex:tx_tile -c 2 -o $O/tx python bench.py --workload tx --steps 2 > $O/n3.log 2>&1
+  $N -k regex:"tx_resident|tx_tile" -c 1 -o $O/tx python bench.py --workload tx --steps 2 > $O/n3.log 2>&1
 python tools/ncu_summary.py $O/tx.ncu-rep > $O/r2_ncu_tx.txt 2>&1
+python tools/sass_by_line.py $O/tx.ncu-rep ofdm_b200/libofdm_b200.so tx_resident_kernelILi2ELb1ELb1E 8347648 > $O/r2_ncu_tx_by_line.txt 2>&1
 rm -f $O/*.ncu-rep
 cat $O/r2_pytest_gpu.txt; head -c 700 $O/r2_bench.json; echo; wc -c $O/r2_*.json $O/r2_ncu_*.txt $O/launches.csv

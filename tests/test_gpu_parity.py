@@ -689,7 +689,7 @@ def test_wideband_1024_parity(ob, oo, mod, guard, fec, modes):
 def test_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
     """The one-pass TX kernel (frames resident in tensor memory, tx_resident.cuh) is what large batches run; here it is forced
     for a ragged batch: every frame against the oracle's encode (src/transmitter.rs:11-58), zero fill past the frame, and
-    bit-for-bit against the two-pass kernel. Lengths include the empty payload, one byte, and frames of 1, 2 and several CTAs'
+    value-for-value against the two-pass kernel. Lengths include the empty payload, one byte, and frames of 1, 2 and several CTAs'
     worth of symbols; iq_stride admits frames that need a group of 3 CTAs."""
     rng = np.random.default_rng(77 + 10 * mod + 2 * guard + fec)
     cfg = ob.Config(modulation=mod, guard_bands=guard, fec=fec)
@@ -710,7 +710,7 @@ def test_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
         np.testing.assert_allclose(iq[i, : flen[i]], ref, atol=2e-6)
         assert not iq[i, flen[i]:].any()
     assert np.array_equal(flen, out["twopass"][1])
-    assert np.array_equal(iq.view(np.uint32), out["twopass"][0].view(np.uint32))
+    assert np.array_equal(iq, out["twopass"][0])            # the same values (an exact zero may carry the other sign: conj vs swap transform)
 
 
 def test_tx_resident_kernel_is_the_large_batch_path(ob, oo):
