@@ -731,6 +731,20 @@ def tx_bench(args, rank, local_rank, world, steps=None):
     peak, src = read_peaks()
     mx = float(tx.max().item())
     frames_ok = bool((flen == frame_len).all().item())
+    # two frames of the batch against the CPU oracle's `encode` (the checker, outside the timed region): fp32 IFFT vs f64
+    oracle_ok = None
+    if rank == 0:
+        try:
+            import numpy as np
+            from oracle import oracle as oo
+            ocfg = oracle_cfg()
+            oracle_ok = True
+            for i in (0, n - 1):
+                ref = oo.tx(payload[i, :plen_b].cpu().numpy().tobytes(), ocfg)
+                got = tx[i].cpu().numpy().view(np.complex64).reshape(-1)
+                oracle_ok &= bool(ref.size == frame_len and np.allclose(got, ref, atol=2e-6))
+        except Exception as e:          # noqa: BLE001
+            oracle_ok = f"unchecked: {e}"
     launches = int(eng.kernel_launches - l0)
     eng.close()
     del tx
@@ -742,7 +756,7 @@ def tx_bench(args, rank, local_rank, world, steps=None):
                       "roofline": {"bound": "hbm", "kernel": "tx_resident_kernel (one pass, frames resident in tensor memory)" if launches == steps else "tx_tile_kernel (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
                                    "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": read_traffic(f"tx_{n}x64QAM_S{S}"),
                                    "peak_source": src, "algorithmic_bytes_per_launch": by, "kernel_ms": round(ms, 4)},
-                      "max_component": round(mx, 6), "frames_ok": frames_ok,
+                      "max_component": round(mx, 6), "frames_ok": frames_ok, "frames_match_oracle_on_sample": oracle_ok,
                       "gpu_launches": launches, "clocks": clocks})
 
 

@@ -132,6 +132,11 @@ uint32_t ofdm_max_payload(const ofdm_cfg *cfg, uint32_t n_data_syms);     /* lar
  * TX: replaces `encode` (src/transmitter.rs:11-58) for a batch of frames.
  * payload[s*payload_stride ..][payload_len[s]] -> iq_out[s*iq_stride ..][frame_len]; samples past the
  * frame up to iq_stride are zero-filled. frame_len_out (optional) receives each frame's length.
+ * Every frame is normalised by its own maximum positive component (`normalize`, src/transmitter.rs:183-194). Batches take the
+ * one-pass kernel that keeps a frame on chip until that maximum is known (a cooperative launch: it needs the device's SMs to
+ * itself for the ~ms it runs, and waits for them otherwise); a handful of frames, or frames too long for it, take the
+ * cluster / two-pass kernels. The results are the same values whichever kernel runs. (Measurement aid, read once at
+ * ofdm_engine_create: the environment variable OFDM_TX_PATH = twopass | cluster | resident pins one of them.)
  */
 int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, const uint32_t *payload_len,
                          uint32_t payload_stride, uint32_t n_streams,

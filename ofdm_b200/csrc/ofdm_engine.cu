@@ -383,7 +383,11 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
             if (h->smem_configured.insert((const void *)k).second)
                 CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             a.stream_cnt = d_cnt; a.group_ctas = C; a.n_groups = G;
-            k<<<dim3((unsigned)(G * C)), 32 * W, smem, st>>>(a);
+            // The CTAs of a group wait for one another (frame maximum through global memory), so the whole grid has to be
+            // resident at once: a cooperative launch is what guarantees that -- the grid (<= one CTA per SM) is scheduled only
+            // when all of it fits, also next to other work and next to a second kernel of this kind from another handle.
+            void *kargs[] = { (void *)&a };
+            CU(h, cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)(G * C)), dim3(32 * W), kargs, smem, st));
             h->launches++;
             CU(h, cudaGetLastError());
             if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
