@@ -818,6 +818,16 @@ __global__ void __launch_bounds__(kThreads, 3) wide_acquire_kernel(const WideRxA
         } else {
             long d0 = s_d0, k_lo = d0 - (11 * kL) / 5, k_hi = d0 + kL / 5;
             if (k_lo < -(kL - 1)) k_lo = -(kL - 1);
+            // The kernel is latency bound (one CTA per stream, a dozen dependent trips to DRAM). Whatever the refinement
+            // decides, the CFO rows, the training rows and the header symbol lie between k_lo + 2 L and k_hi + 11 L: ask
+            // for those lines now (L2 prefetch, no registers, no shared memory), while the ramp search runs.
+            {
+                long p0 = k_lo + 2 * kL, p1 = k_hi + 11 * kL;
+                if (p0 < 0) p0 = 0;
+                if (p1 > M) p1 = M;
+                const char *b = reinterpret_cast<const char *>(x + p0), *e = reinterpret_cast<const char *>(x + p1);
+                for (const char *q = b + 128 * (long)tid; q < e; q += 128 * kThreads) asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+            }
             offset = (a.lock_is_ramp ? ramp_argmax_closed_w(x, M, k_lo, k_hi, s_val, s_idx) : ramp_argmax_w(x, M, k_lo, k_hi, s_lock, s_val, s_idx)) - 1;
         }
     }
