@@ -561,7 +561,7 @@ def capture_bench(args, rank, local_rank, world, steps=None):
     stride, S = 1_000_003, args.syms
     payload_len = cfg.max_payload(S)
     frame_len = cfg.frame_len(payload_len)
-    shard = od.capture_shards(n_total, world, frame_len)[rank]
+    shard = od.capture_shards(n_total, world, frame_len, sym_len=cfg.sym_len, guard=od.CAPTURE_GUARD * (cfg.sym_len // 80))[rank]
     n = shard.read_hi - shard.read_lo                                          # samples this rank reads
     g = torch.Generator(device=dev)
     g.manual_seed(0x0FD3 + rank)
@@ -580,7 +580,7 @@ def capture_bench(args, rank, local_rank, world, steps=None):
     cap.normal_(0.0, 0.01, generator=g)
     capc = torch.view_as_complex(cap)
     positions = np.arange(5000, n_total - frame_len - 200, stride, dtype=np.int64)              # global frame starts
-    cfo_all = ((positions * 2654435761 % (1 << 32)) / float(1 << 32) * 2 - 1) * (0.9 * np.pi / 80)       # per frame, the same on every rank
+    cfo_all = ((positions * 2654435761 % (1 << 32)) / float(1 << 32) * 2 - 1) * (0.9 * np.pi / cfg.sym_len)   # per frame, the same on every rank
     t = torch.arange(frame_len, device=dev, dtype=torch.float32)
     touching = np.flatnonzero((positions + frame_len > shard.read_lo) & (positions < shard.read_hi))
     for i in touching:                                                         # frames cut by the range's ends are added in part
@@ -645,11 +645,11 @@ def capture_bench(args, rank, local_rank, world, steps=None):
         line = ({"metric": "sync_search_msamples_per_s", "value": round(n_total / (ms * 1e-3) / 1e6, 1), "unit": "Msamples/s",
                  "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4),
                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                 "config": {"workload": f"capture_{n_total}", "samples": n_total, "samples_read_per_gpu": n, "frames": int(len(positions)),
+                 "config": {"workload": f"capture_{n_total}" + ("" if NFFT == 64 else f"_N{NFFT}"), "samples": n_total, "samples_read_per_gpu": n, "frames": int(len(positions)),
                             "frame_stride": stride, "frame_samples": frame_len, "noise_sigma": 0.01,
                             "sharding": "one capture, contiguous ranges, overlap 2L + frame_len, de-duplicated by offset ownership" if world > 1 else "none",
                             "l2": "input (%.1f GB/GPU) larger than L2" % (8 * n / 1e9)},
-                 "roofline": {"bound": "hbm", "kernel": "sync_scan_kernel (+select, refine)", "achieved": round(achieved, 1), "peak": peak,
+                 "roofline": {"bound": "hbm", "kernel": "sync_scan_kernel (+select, refine)" if NFFT == 64 else "wide_scan_kernel (+select, refine)", "achieved": round(achieved, 1), "peak": peak,
                               "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": read_traffic(f"capture_{n}"), "peak_source": src,
                               "algorithmic_bytes_per_launch": 8 * n, "kernel_ms": round(ms, 4)},
                  "all_offsets_exact": exact_all, "max_cfo_abs_err": cfo_err, "peaks_found": frames_once,
@@ -670,7 +670,7 @@ def capture_cpu_baseline(cap, args):
     on one host thread (the reference is single-threaded), windows taken from the start of this run's capture."""
     from oracle import oracle as oo
     M = 2_000_000
-    lock = oo.locking_signal(80)
+    lock = oo.locking_signal(80 if NFFT == 64 else 1280)
     win = cap[:M].cpu().numpy().view(np.complex64).reshape(-1).astype(np.complex128)
     oo.xcorr_fft(win[:4096], lock)                                             # warm-up
     reps, t0 = 0, time.perf_counter()

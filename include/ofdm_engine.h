@@ -177,6 +177,8 @@ int ofdm_channel_apply_batch(ofdm_engine *h, const ofdm_fc32 *tx, const uint32_t
  * scan recorded, counts[1] = frames detected after the hold-off, counts[2] = entries written to peaks[], counts[3] = 3928-lag
  * tiles that held more than 12 threshold crossings (their surplus is dropped; a capture made of frames never does that --
  * OFDM_MEM_HOST turns it into an error). counts[1] > counts[2] means peaks[] was too small.
+ * nfft = 1024 engines run the same search with every length scaled by 16 (docs/SPEC.md 9; 4096-lag tiles), and so do
+ * ofdm_rx_decode_capture and ofdm_rx_decode_file below.
  */
 typedef struct {
     uint64_t offset;

@@ -12,6 +12,7 @@
 #include "tx_resident.cuh"
 #include "sync_kernels.cuh"
 #include "wide_kernels.cuh"
+#include "wide_sync_kernels.cuh"
 #include "rs_kernels.cuh"
 
 namespace ofdm {
@@ -49,6 +50,8 @@ SyncScanKernel sync_scan_fn(bool tma);
 SyncKernel sync_select_fn();
 SyncKernel sync_refine_fn();
 CapturePrepKernel capture_prep_fn();
+SyncKernel wide_scan_fn();             // nfft = 1024
+SyncKernel wide_sync_refine_fn();
 // rs.cu
 RsKernel rs_encode_fn();
 RsKernel rs_decode_fn();

@@ -314,8 +314,9 @@ extern "C" int ofdm_engine_reserve(ofdm_engine *h, uint32_t max_streams, uint64_
         CU(h, h->scratch_f32.ensure(5 * sizeof(double) * (size_t)max_streams));
         CU(h, h->cap_base.ensure((sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)max_streams));
     }
-    if (max_capture_samples >= 2 * (uint64_t)kSym) {                       // same layout as sync_plan
-        const uint64_t T = (max_capture_samples - 2 * kSym + 1 + kScanD - 1) / kScanD;
+    if (max_capture_samples >= 2 * (uint64_t)h->sym_len) {                 // same layout as sync_plan
+        const uint64_t tl = h->wide ? (uint64_t)kWScanD : (uint64_t)kScanD;
+        const uint64_t T = (max_capture_samples - 2 * (uint64_t)h->sym_len + 1 + tl - 1) / tl;
         CU(h, h->sync_scratch.ensure(((32 + 4 * T + 7) & ~(size_t)7) + (size_t)T * kTileCand * 19 + 16));
     }
     return 0;
@@ -498,14 +499,14 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
     cudaEvent_t *pe = prof ? &h->prof_ev[3 * (size_t)h->prof_n] : nullptr;
     if (prof) { h->prof_n++; CU(h, cudaEventRecord(pe[0], st)); }
     if (h->wide) {
-        if (stream_base) ENG_FAIL(h, OFDM_E_INVALID, "capture decode is not implemented for nfft = 1024");
         wide::WideRxArgs w{};
         w.iq = reinterpret_cast<const float2 *>(iq); w.n_samples = n_samples; w.iq_stride = iq_stride; w.n_streams = n_streams;
         w.state = h->state.as<wide::StreamStateW>() + state_offset; w.tables = h->d_wtables;
         w.out = out; w.out_stride = out_stride; w.out_len = out_len; w.status = status;
         w.sync_window = h->cfg.sync_window; w.tile_shift = h->tile_shift;
-        w.sync_mode = (int)h->cfg.sync_mode; w.cfo_mode = (int)h->cfg.cfo_mode; w.fec = (int)h->cfg.fec;
+        w.sync_mode = stream_base ? 2 : (int)h->cfg.sync_mode; w.cfo_mode = (int)h->cfg.cfo_mode; w.fec = (int)h->cfg.fec;
         w.lock_is_ramp = h->lock_is_ramp ? 1 : 0;
+        w.stream_base = stream_base;
         bool wpoints = false;
         if (diag) {
             w.d_offset = diag->offset; w.d_f_delta = diag->f_delta; w.d_h = reinterpret_cast<float2 *>(diag->h_k);
@@ -528,7 +529,6 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
             uint32_t tpc = (uint32_t)(((uint64_t)tiles * n_streams) / (8u * 148u * 2u));
             if (tpc < 1) tpc = 1;
             if (tpc > tiles) tpc = tiles;
-            if (const char *e = getenv("OFDM_WIDE_TPC")) { tpc = (uint32_t)atoi(e); if (tpc < 1) tpc = 1; if (tpc > tiles) tpc = tiles; }   // TEMP tuning knob
             tpc = (tiles + (tiles + tpc - 1) / tpc - 1) / ((tiles + tpc - 1) / tpc);
             w.tiles_per_cta = (int)tpc;
             tiles = (tiles + tpc - 1) / tpc;
@@ -786,8 +786,12 @@ static int sync_plan(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak 
     SyncArgs &a = p.a;
     a.iq = reinterpret_cast<const float2 *>(iq); a.n = n;
     a.tables = h->d_tables; a.peaks = reinterpret_cast<SyncPeak *>(peaks); a.max_peaks = max_peaks;
-    const uint64_t lags = n >= 2 * (uint64_t)kSym ? n - 2 * kSym + 1 : 0;
-    const uint64_t T = (lags + kScanD - 1) / kScanD;
+    a.wtables = h->d_wtables; a.lock_is_ramp = h->lock_is_ramp ? 1 : 0;
+    const uint64_t LS = (uint64_t)h->sym_len;                              // 80 or 1280
+    a.tile_lags = h->wide ? (uint32_t)kWScanD : (uint32_t)kScanD;
+    a.holdoff = (uint32_t)(10 * LS);
+    const uint64_t lags = n >= 2 * LS ? n - 2 * LS + 1 : 0;
+    const uint64_t T = (lags + a.tile_lags - 1) / a.tile_lags;
     if (T > 0xFFFFFFFFull) ENG_FAIL(h, OFDM_E_INVALID, "sync: capture too long");
     a.n_tiles = (uint32_t)T;
     const size_t C = (size_t)T * kTileCand;
@@ -804,8 +808,14 @@ static int sync_plan(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     p.grid = (uint32_t)(2 * sms);                                          // persistent: 2 CTAs per SM
-    // TMA staging needs a 16-byte aligned capture and at least one full 8-sample row
     p.tma = false;
+    if (h->wide) {
+        SyncKernel kw = wide_scan_fn();
+        if (h->smem_configured.insert((const void *)kw).second)
+            CU(h, cudaFuncSetAttribute((const void *)kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_scan_smem_bytes()));
+        return 0;
+    }
+    // TMA staging needs a 16-byte aligned capture and at least one full 8-sample row
     if ((reinterpret_cast<uintptr_t>(iq) & 15) == 0 && n / kScanT >= 1 && n / kScanT < 0x7FFFFF00ull && encode_tiled_fn()) {
         const cuuint64_t dims[2] = { 16, (cuuint64_t)(n / kScanT) };        // [rows][16 floats = 8 fc32 samples]
         const cuuint64_t strides[1] = { 64 };
@@ -826,6 +836,12 @@ static int sync_scan_range(ofdm_engine *h, SyncPlan &p, uint32_t tile_first, uin
 {
     if (tile_count == 0) return 0;
     p.a.tile_first = tile_first; p.a.tile_count = tile_count;
+    if (h->wide) {                                                         // one CTA per 4096-lag tile
+        wide_scan_fn()<<<tile_count, kWScanThreads, wide_scan_smem_bytes(), st>>>(p.a);
+        h->launches += 1;
+        CU(h, cudaGetLastError());
+        return 0;
+    }
     const uint32_t grid = tile_count < p.grid ? tile_count : p.grid;
     sync_scan_fn(p.tma)<<<grid, kScanRows, sync_scan_smem_bytes(p.tma), st>>>(p.a, p.tmap);
     h->launches += 1;
@@ -841,7 +857,8 @@ static int sync_finish(ofdm_engine *h, SyncPlan &p, uint32_t *n_peaks, cudaStrea
         // one CTA per detection; the launch is sized by max_peaks (in chunks), CTAs beyond the detection count exit at once
         const uint32_t worst = p.a.n_tiles > 0xFFFFFFFFu / kTileCand ? 0xFFFFFFFFu : p.a.n_tiles * kTileCand;
         const uint32_t rg = p.a.max_peaks < worst ? p.a.max_peaks : worst;
-        if (rg) sync_refine_fn()<<<rg, kAcqThreads, 0, st>>>(p.a);
+        if (rg && h->wide) wide_sync_refine_fn()<<<rg, wide::kThreads, 0, st>>>(p.a);
+        else if (rg) sync_refine_fn()<<<rg, kAcqThreads, 0, st>>>(p.a);
         h->launches += 2;
     }
     CU(h, cudaGetLastError());
@@ -862,7 +879,6 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
 {
     if (!h) return OFDM_E_INVALID;
     if (!iq || !peaks || !n_peaks || max_peaks == 0) ENG_FAIL(h, OFDM_E_INVALID, "sync: bad arguments");
-    if (h->wide) ENG_FAIL(h, OFDM_E_INVALID, "sync search is not implemented for nfft = 1024");
     CU(h, cudaSetDevice(h->device));
     if (mem == OFDM_MEM_DEVICE) return sync_device(h, iq, n_samples, peaks, max_peaks, n_peaks, (cudaStream_t)stream);
 
@@ -884,7 +900,9 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
         CU(h, cudaStreamWaitEvent(st, h->ev_copied[ev], 0));
         ev ^= 1;
         // tile k reads samples [3928 k - 8, 3928 k - 8 + 4096): complete once s1 covers them (or the capture ends)
-        uint64_t ready = s1 >= n_samples ? p.a.n_tiles : (s1 + kScanT >= (uint64_t)kScanRows * kScanT ? (s1 + kScanT - (uint64_t)kScanRows * kScanT) / kScanD + 1 : 0);
+        // (nfft = 1024: tile k reads samples [4096 k - 8, 4096 k - 8 + kWScanSamples))
+        const uint64_t t_span = h->wide ? (uint64_t)kWScanSamples : (uint64_t)kScanRows * kScanT, t_lags = p.a.tile_lags;
+        uint64_t ready = s1 >= n_samples ? p.a.n_tiles : (s1 + kScanT >= t_span ? (s1 + kScanT - t_span) / t_lags + 1 : 0);
         if (ready > p.a.n_tiles) ready = p.a.n_tiles;
         if (ready > tiles_done) {
             if (int rc = sync_scan_range(h, p, tiles_done, (uint32_t)ready - tiles_done, st)) return rc;
@@ -896,7 +914,7 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
     uint32_t cnt[4] = { 0, 0, 0, 0 };
     CU(h, cudaMemcpyAsync(cnt, p.a.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
-    if (cnt[3]) ENG_FAIL(h, OFDM_E_INVALID, "sync: %u tile(s) of %d lags hold more than %d threshold crossings (the capture is not a sequence of frames)", cnt[3], kScanD, kTileCand);
+    if (cnt[3]) ENG_FAIL(h, OFDM_E_INVALID, "sync: %u tile(s) of %u lags hold more than %d threshold crossings (the capture is not a sequence of frames)", cnt[3], p.a.tile_lags, kTileCand);
     const uint32_t m = cnt[1];
     std::vector<ofdm_peak> tmp(m);
     if (m) CU(h, cudaMemcpy(tmp.data(), h->s_points.p, sizeof(ofdm_peak) * m, cudaMemcpyDeviceToHost));
@@ -992,7 +1010,6 @@ extern "C" int ofdm_rx_decode_file(ofdm_engine *h, const char *path, uint64_t st
     if (!h) return OFDM_E_INVALID;
     if (!path || !out || !frames || !n_frames || max_frames == 0 || out_stride == 0 || max_frame_samples == 0)
         ENG_FAIL(h, OFDM_E_INVALID, "decode file: bad arguments");
-    if (h->wide) ENG_FAIL(h, OFDM_E_INVALID, "decode file is not implemented for nfft = 1024");
     *n_frames = 0;
     const uint64_t chunk = chunk_samples ? chunk_samples : (1u << 25);
     const uint64_t overlap = max_frame_samples;
@@ -1048,7 +1065,7 @@ extern "C" int ofdm_rx_decode_file(ofdm_engine *h, const char *path, uint64_t st
         const uint64_t cn = plan[i].second - plan[i].first;
         const bool final = i + 1 == plan.size();
         auto drain = [&]() { if (ahead.valid()) ahead.wait(); };                            // never leave a reader running on an error path
-        if (cn < (uint64_t)kHeadSyms * kSym) continue;
+        if (cn < (uint64_t)kHeadSyms * (uint64_t)h->sym_len) continue;
 #define FCU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { drain(); ENG_FAIL(h, OFDM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
         FCU(cudaMemcpyAsync(h->s_iq.p, h->pin[i & 1], cn * 8, cudaMemcpyHostToDevice, st));
         if (int rc = sync_device(h, h->s_iq.as<ofdm_fc32>(), cn, h->s_points.as<ofdm_peak>(), max_peaks, d_npk, st)) { drain(); return rc; }
@@ -1076,7 +1093,7 @@ extern "C" int ofdm_rx_decode_file(ofdm_engine *h, const char *path, uint64_t st
             if (pk[j].metric < 0.0f) continue;                             // frame head cut by the chunk end
             if (!final && pk[j].offset >= cn - overlap) continue;          // owned by the next chunk
             const uint64_t absolute = plan[i].first + pk[j].offset;
-            if (have_last && absolute < last + (uint64_t)kSyncHoldoff) continue;           // already reported from the previous chunk's body
+            if (have_last && absolute < last + 10ull * (uint64_t)h->sym_len) continue;    // already reported from the previous chunk's body
             have_last = true; last = absolute;
             if (count >= max_frames) { drain(); ENG_FAIL(h, OFDM_E_INVALID, "decode file: more than max_frames = %u frames", max_frames); }
             ofdm_frame_info &f = frames[count];

@@ -1,4 +1,4 @@
-// sync.cu -- instantiates the capture search / streaming receiver kernels (sync_kernels.cuh).
+// sync.cu -- instantiates the capture search / streaming receiver kernels (sync_kernels.cuh, wide_sync_kernels.cuh).
 #include "kernels.h"
 
 namespace ofdm {
@@ -7,5 +7,7 @@ SyncScanKernel sync_scan_fn(bool tma) { return tma ? (SyncScanKernel)sync_scan_k
 SyncKernel sync_select_fn() { return sync_select_kernel<>; }
 SyncKernel sync_refine_fn() { return sync_refine_kernel<>; }
 CapturePrepKernel capture_prep_fn() { return capture_prep_kernel<>; }
+SyncKernel wide_scan_fn() { return wide_scan_kernel<>; }
+SyncKernel wide_sync_refine_fn() { return wide_sync_refine_kernel<>; }
 
 }  // namespace ofdm

@@ -54,6 +54,10 @@ struct SyncArgs {
     uint32_t max_peaks;
     uint32_t n_tiles;        // 3928-lag tiles of the capture
     uint32_t tile_first, tile_count;   // tiles this scan launch covers (the grid is persistent and strides over them)
+    uint32_t tile_lags;      // lags per tile: kScanD (nfft = 64) or kWScanD (nfft = 1024, wide_sync_kernels.cuh)
+    uint32_t holdoff;        // lock + preamble + training = 10 symbol lengths: one detection per frame
+    const void *wtables;     // wide::WideTables (nfft = 1024)
+    int32_t  lock_is_ramp;   // nfft = 1024: the built-in locking ramp (closed-form ramp correlation)
 };
 
 // generic path: padded rows | row totals | energy windows | masks.  TMA path: 2 x 32 KB swizzled tiles (1024-byte aligned) + the same
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(kSelThreads) sync_select_kernel(const SyncArgs
             while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; j--; }
             v[j] = x;
         }
-        for (uint32_t k = 0; k < c; k++) a.ordered[pos++] = (unsigned long long)tile * kScanD + v[k];
+        for (uint32_t k = 0; k < c; k++) a.ordered[pos++] = (unsigned long long)tile * a.tile_lags + v[k];
     }
     const unsigned long long cr_before = block_exclusive_scan(crossings);
     (void)cr_before;
@@ -348,15 +352,16 @@ __global__ void __launch_bounds__(kSelThreads) sync_select_kernel(const SyncArgs
     __threadfence_block();
     __syncthreads();
     // ---- (2) hold-off: chains ---------------------------------------------------------------------------------------------
+    const unsigned long long holdoff = a.holdoff;
     for (unsigned long long i = tid; i < M; i += kSelThreads) {
-        const bool head = i == 0 || a.ordered[i] - a.ordered[i - 1] >= (unsigned long long)kSyncHoldoff;
+        const bool head = i == 0 || a.ordered[i] - a.ordered[i - 1] >= holdoff;
         if (!head) continue;
         unsigned long long last = a.ordered[i];
         a.keep[i] = 1;
         for (unsigned long long j = i + 1; j < M; j++) {
             const unsigned long long d = a.ordered[j];
-            if (d - a.ordered[j - 1] >= (unsigned long long)kSyncHoldoff) break;       // the next chain's head
-            const bool k = d >= last + (unsigned long long)kSyncHoldoff;
+            if (d - a.ordered[j - 1] >= holdoff) break;                                // the next chain's head
+            const bool k = d >= last + holdoff;
             a.keep[j] = k ? 1 : 0;
             if (k) last = d;
         }

@@ -78,6 +78,7 @@ struct WideRxArgs {
     float2   *d_points;
     uint32_t  points_stride;
     uint32_t  stream0;          // decode kernel: first stream of this launch (gridDim.y <= 65535)
+    const uint64_t *stream_base;    // optional: sample index of every stream's capture inside iq (NULL: stream * iq_stride)
 };
 
 // ---- block FFT: 1024 points, 256 threads, radix-4 Stockham autosort -------------------------------------------------
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(kWDecThreads, 2) wide_decode_kernel(const Wide
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t fstep = st->fstep;
     const uint32_t offset = (uint32_t)st->offset;
-    const float2 *x0 = a.iq + (size_t)stream * a.iq_stride + offset;
+    const float2 *x0 = a.iq + (a.stream_base ? (size_t)a.stream_base[stream] : (size_t)stream * a.iq_stride) + offset;
     const uint32_t n_avail = a.n_samples[stream] - offset;
     auto tile_t0 = [&](int tile) { int t = tile * kTileSymsW - a.tile_shift; return t < 0 ? 0 : t; };
     auto tile_t1 = [&](int tile) { int t = (tile + 1) * kTileSymsW - a.tile_shift; return t > S ? S : t; };
@@ -758,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 3) wide_acquire_kernel(const WideRxA
     const bool FEC = a.fec != 0;
     StreamStateW *st = a.state + stream;
     const long M = (long)a.n_samples[stream];
-    const float2 *x = a.iq + (size_t)stream * a.iq_stride;
+    const float2 *x = a.iq + (a.stream_base ? (size_t)a.stream_base[stream] : (size_t)stream * a.iq_stride);
     for (int i = tid; i < kL; i += kThreads) s_lock[i] = a.tables->lock[i].x;
     if (tid == 0) s_d0 = 0x7fffffff;
     __syncthreads();
@@ -767,7 +768,9 @@ __global__ void __launch_bounds__(kThreads, 3) wide_acquire_kernel(const WideRxA
     if (W > M) W = M;
     int status = ST_OK;
     long offset = 0;
-    if (SYNC == 0) {
+    if (SYNC == 2) {
+        offset = 0;                                    // frame start already known (ofdm_rx_decode_capture)
+    } else if (SYNC == 0) {
         offset = (a.lock_is_ramp ? ramp_argmax_closed_w(x, M, -(kL - 1), W - 1, s_val, s_idx) : ramp_argmax_w(x, M, -(kL - 1), W - 1, s_lock, s_val, s_idx)) - 1;
     } else {
         long d_end = W;

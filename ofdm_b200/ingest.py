@@ -73,7 +73,7 @@ class StreamReceiver:
     decoded payload."""
 
     def __init__(self, cfg: _e.Config, device: int = 0, chunk_samples: int = 1 << 25, max_frame_samples: int = 1 << 18,
-                 out_stride: int = 1 << 16, max_peaks: int = 4096, hold_off: int = 800):
+                 out_stride: int = 1 << 16, max_peaks: int = 4096, hold_off: Optional[int] = None):
         import torch
         if not torch.cuda.is_available():
             raise _e.EngineError("StreamReceiver needs a CUDA device (there is no CPU fallback)")
@@ -82,6 +82,8 @@ class StreamReceiver:
         self.torch = torch
         self.cfg, self.dev = cfg, torch.device("cuda", device)
         self.eng = _e.Engine(cfg, device)
+        if hold_off is None:
+            hold_off = 10 * cfg.sym_len                                   # lock + preamble + training: one detection per frame
         self.chunk, self.overlap, self.out_stride, self.max_peaks, self.hold_off = chunk_samples, max_frame_samples, out_stride, max_peaks, hold_off
         with torch.cuda.device(self.dev):
             self.h_bufs = [torch.empty((chunk_samples, 2), dtype=torch.float32).pin_memory() for _ in range(2)]

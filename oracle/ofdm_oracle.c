@@ -704,7 +704,6 @@ static long ramp_argmax_n(const oo_c64 *a, size_t n, long k_lo, long k_hi, const
     }
     return kbest;
 }
-static long ramp_argmax(const oo_c64 *a, size_t n, long k_lo, long k_hi, const oo_c64 *lock) { return ramp_argmax_n(a, n, k_lo, k_hi, lock, NSYM); }
 
 static int find_offset(const oo_c64 *a, size_t n, const oo_cfg *cfg, long *offset)
 {
@@ -872,67 +871,79 @@ int oo_decode(const oo_c64 *samples, size_t n, const oo_cfg *cfg,
 
 /* docs/SPEC.md section 4 (capture search). The reference's equivalent is the whole-capture xcorr_fft of
  * src/receiver.rs:20-21, which finds only the single strongest frame of a buffer (examples/jetson_rx.rs:84). */
-size_t oo_sync_search(const oo_c64 *a, size_t n, oo_peak *peaks, size_t max_peaks)
+/* L = symbol length (80 for nfft = 64, 1280 for nfft = 1024): every length of section 4 scales with it -- correlation lag and
+ * window L, hold-off and minimum post-offset length 10 L (lock + preamble + training), refinement window [d - 11 L / 5, d + L / 5]. */
+static size_t sync_search_len(const oo_c64 *a, size_t n, oo_peak *peaks, size_t max_peaks, int LS)
 {
-    if (n < 2 * NSYM) return 0;
-    oo_c64 lock[NSYM];
-    oo_locking_signal(lock, NSYM);
+    if (n < 2 * (size_t)LS) return 0;
+    oo_c64 *lock = (oo_c64 *)malloc(sizeof(oo_c64) * (size_t)LS);
+    oo_locking_signal(lock, LS);
+    const long HEAD = 10L * LS;
     size_t np = 0;
-    long d_last = (long)n - 2 * NSYM;
-    long last_acc = -800;
+    long d_last = (long)n - 2 * LS;
+    long last_acc = -HEAD;
     int prev_above = 0;
     oo_c64 P = c_make(0.0, 0.0);
     double R1 = 0.0, R2 = 0.0;
     for (long d = 0; d <= d_last; d++) {
         if ((d & 1023) == 0) {                    /* exact re-sum periodically: no drift */
             P = c_make(0.0, 0.0); R1 = 0.0; R2 = 0.0;
-            for (int m = 0; m < NSYM; m++) {
-                P = c_add(P, c_mul(c_conj(a[d + m]), a[d + m + NSYM]));
+            for (int m = 0; m < LS; m++) {
+                P = c_add(P, c_mul(c_conj(a[d + m]), a[d + m + LS]));
                 R1 += c_norm_sqr(a[d + m]);
-                R2 += c_norm_sqr(a[d + m + NSYM]);
+                R2 += c_norm_sqr(a[d + m + LS]);
             }
         } else {
-            P = c_sub(P, c_mul(c_conj(a[d - 1]), a[d - 1 + NSYM]));
-            P = c_add(P, c_mul(c_conj(a[d - 1 + NSYM]), a[d - 1 + 2 * NSYM]));
-            R1 += c_norm_sqr(a[d - 1 + NSYM]) - c_norm_sqr(a[d - 1]);
-            R2 += c_norm_sqr(a[d - 1 + 2 * NSYM]) - c_norm_sqr(a[d - 1 + NSYM]);
+            P = c_sub(P, c_mul(c_conj(a[d - 1]), a[d - 1 + LS]));
+            P = c_add(P, c_mul(c_conj(a[d - 1 + LS]), a[d - 1 + 2 * LS]));
+            R1 += c_norm_sqr(a[d - 1 + LS]) - c_norm_sqr(a[d - 1]);
+            R2 += c_norm_sqr(a[d - 1 + 2 * LS]) - c_norm_sqr(a[d - 1 + LS]);
         }
         int above = c_norm_sqr(P) > 0.5 * R1 * R2;
-        if (above && !prev_above && d >= last_acc + 800) {
+        if (above && !prev_above && d >= last_acc + HEAD) {
             last_acc = d;
-            long k_lo = d - 176, k_hi = d + 16;
-            if (k_lo < -(NSYM - 1)) k_lo = -(NSYM - 1);
-            long offset = ramp_argmax(a, n, k_lo, k_hi, lock) - 1;
-            if (offset >= 0 && (size_t)offset + 800 <= n && np < max_peaks) {
+            long k_lo = d - (11L * LS) / 5, k_hi = d + LS / 5;
+            if (k_lo < -(LS - 1)) k_lo = -(LS - 1);
+            long offset = ramp_argmax_n(a, n, k_lo, k_hi, lock, LS) - 1;
+            if (offset >= 0 && (size_t)offset + (size_t)HEAD <= n && np < max_peaks) {
                 const oo_c64 *x = a + offset;
                 oo_c64 s = c_make(0.0, 0.0);
-                for (int i = 0; i < NSYM; i++) {
-                    s = c_add(s, c_mul(c_conj(x[2 * NSYM + i]), x[3 * NSYM + i]));
-                    s = c_add(s, c_mul(c_conj(x[3 * NSYM + i]), x[4 * NSYM + i]));
+                for (int i = 0; i < LS; i++) {
+                    s = c_add(s, c_mul(c_conj(x[2 * LS + i]), x[3 * LS + i]));
+                    s = c_add(s, c_mul(c_conj(x[3 * LS + i]), x[4 * LS + i]));
                 }
                 oo_c64 p0 = c_make(0.0, 0.0);
                 double r1 = 0.0, r2 = 0.0;
-                for (int m = 0; m < NSYM; m++) {
-                    p0 = c_add(p0, c_mul(c_conj(a[d + m]), a[d + m + NSYM]));
+                for (int m = 0; m < LS; m++) {
+                    p0 = c_add(p0, c_mul(c_conj(a[d + m]), a[d + m + LS]));
                     r1 += c_norm_sqr(a[d + m]);
-                    r2 += c_norm_sqr(a[d + m + NSYM]);
+                    r2 += c_norm_sqr(a[d + m + LS]);
                 }
                 peaks[np].offset = (uint64_t)offset;
-                peaks[np].f_delta = oo_angle(s) / 80.0;
+                peaks[np].f_delta = oo_angle(s) / (double)LS;
                 peaks[np].metric = c_norm_sqr(p0) / (r1 * r2);
                 np++;
             }
         }
         prev_above = above;
     }
+    free(lock);
     return np;
 }
 
+size_t oo_sync_search(const oo_c64 *a, size_t n, oo_peak *peaks, size_t max_peaks) { return sync_search_len(a, n, peaks, max_peaks, NSYM); }
+
 size_t oo_sync_search_fc32(const float *iq, size_t n, oo_peak *peaks, size_t max_peaks)
+{
+    return oo_sync_search_fc32_n(iq, n, peaks, max_peaks, NFFT);
+}
+
+/* the same for the layout with `nfft` subcarriers (64 or 1024; docs/SPEC.md 9) */
+size_t oo_sync_search_fc32_n(const float *iq, size_t n, oo_peak *peaks, size_t max_peaks, int nfft)
 {
     oo_c64 *x = (oo_c64 *)malloc(sizeof(oo_c64) * (n + 1));
     oo_fc32_to_sig(iq, n, x);
-    size_t r = oo_sync_search(x, n, peaks, max_peaks);
+    size_t r = sync_search_len(x, n, peaks, max_peaks, nfft == 1024 ? 1280 : NSYM);
     free(x);
     return r;
 }

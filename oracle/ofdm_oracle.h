@@ -126,6 +126,7 @@ int oo_decode(const oo_c64 *samples, size_t n, const oo_cfg *cfg,
 typedef struct { uint64_t offset; double f_delta; double metric; } oo_peak;
 size_t oo_sync_search(const oo_c64 *a, size_t n, oo_peak *peaks, size_t max_peaks);
 size_t oo_sync_search_fc32(const float *iq, size_t n, oo_peak *peaks, size_t max_peaks);
+size_t oo_sync_search_fc32_n(const float *iq, size_t n, oo_peak *peaks, size_t max_peaks, int nfft);   /* nfft = 64 or 1024: every length scales with the symbol length */
 
 /* fc32 batch front end used by the CPU baseline: threads = OpenMP threads (0 = default). */
 int oo_decode_batch_fc32(const float *iq, const uint32_t *n_samples, uint32_t n_streams, size_t iq_stride,

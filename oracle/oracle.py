@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
     L.oo_max_threads.restype = i32
     L.oo_sync_search_fc32.argtypes = [vp, sz, vp, sz]
     L.oo_sync_search_fc32.restype = sz
+    L.oo_sync_search_fc32_n.argtypes = [vp, sz, vp, sz, C.c_int]
+    L.oo_sync_search_fc32_n.restype = sz
     L.oo_angle.argtypes = [C.c_double * 2]
     _lib = L
     return L
@@ -379,9 +381,10 @@ def max_threads() -> int:
 PEAK_DTYPE = np.dtype([("offset", np.uint64), ("f_delta", np.float64), ("metric", np.float64)])
 
 
-def sync_search(iq_c64: np.ndarray, max_peaks: int = 4096) -> np.ndarray:
-    """Capture search (docs/SPEC.md 4). iq_c64: complex64 capture. Returns a structured array (offset, f_delta, metric)."""
+def sync_search(iq_c64: np.ndarray, max_peaks: int = 4096, nfft: int = 64) -> np.ndarray:
+    """Capture search (docs/SPEC.md 4; nfft = 1024: section 9, every length scaled by 16). iq_c64: complex64 capture.
+    Returns a structured array (offset, f_delta, metric)."""
     x = np.ascontiguousarray(iq_c64, dtype=np.complex64)
     peaks = np.zeros(max_peaks, PEAK_DTYPE)
-    n = lib().oo_sync_search_fc32(_p(x), x.size, _p(peaks), max_peaks)
+    n = lib().oo_sync_search_fc32_n(_p(x), x.size, _p(peaks), max_peaks, int(nfft))
     return peaks[:n].copy()
