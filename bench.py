@@ -18,7 +18,8 @@ its own 4096 streams, no data-path collective; the BER counters are sum-reduced 
   roofline : decode kernel, algorithmic bytes (8 B/sample in + payload bytes out) / its CUDA-event duration.
   cpu_baseline : the CPU oracle (C port of the reference algorithm; the Rust reference cannot be built here).
   secondary (N=1, after the headline's timed region): the other BASELINE.json configs on the same box --
-          snr30 (config 2 at 30 dB), capture (config 3), wide (config 4, nfft 1024), tx -- each with value, kernel_ms, roofline.
+          snr30 (config 2 at 30 dB), capture (config 3), wide (config 4, nfft 1024), capture_wide (config 3 for the nfft 1024
+          layout), tx, rs (the RS(255,223) outer code) -- each with value, kernel_ms, roofline and its checks.
 """
 from __future__ import annotations
 
@@ -58,7 +59,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the snr30 / wide / capture / tx legs after the headline")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the snr30 / wide / capture / capture_wide / tx / rs legs after the headline")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --streams per GPU; strong: --streams in total, split evenly over the ranks")
     ap.add_argument("--workload", default="streams", choices=["streams", "capture", "rs", "ingest", "tx"],
@@ -481,12 +482,16 @@ def main():
         for name, fn in (("snr30", lambda: snr30_leg(args, sec_steps, barrier, local_rank)),
                          ("wide", lambda: wide_leg(args, sec_steps, barrier, local_rank)),
                          ("capture", lambda: capture_bench(args, 0, local_rank, 1, steps=sec_steps)),
-                         ("tx", lambda: tx_bench(args, 0, local_rank, 1, steps=sec_steps))):
+                         ("capture_wide", lambda: capture_wide_leg(args, sec_steps, local_rank)),
+                         ("tx", lambda: tx_bench(args, 0, local_rank, 1, steps=sec_steps)),
+                         ("rs", lambda: rs_bench(args, 0, local_rank, 1))):
             try:
                 full = fn()
                 secondary[name] = {k: full[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "config", "roofline", "clocks",
                                                         "gpu_launches", "ber", "all_offsets_exact", "max_cfo_abs_err", "peaks_found",
-                                                        "frames_ok", "decoded_gbit_per_s", "credited") if k in full}
+                                                        "frames_ok", "decoded_gbit_per_s", "credited", "each_frame_found_once",
+                                                        "frames_match_oracle_on_sample", "encode_ms", "decode_clean_ms",
+                                                        "decode_8_errors_per_block_ms", "decode_2pct_blocks_with_errors_ms", "checks") if k in full}
             except Exception as e:       # noqa: BLE001 -- a secondary leg must never take the headline line down
                 secondary[name] = {"error": repr(e)[:300]}
             NFFT = args.nfft
@@ -538,6 +543,19 @@ def snr30_leg(args, steps, barrier, local_rank):
 def wide_leg(args, steps, barrier, local_rank):
     """BASELINE.json configs[3]: the 1024-subcarrier variant, 4096 streams x 128 data symbols."""
     return _streams_leg(args, 1024, 50.0, 128, steps, barrier, local_rank)
+
+
+def capture_wide_leg(args, steps, local_rank):
+    """The capture search for the 1024-subcarrier layout (docs/SPEC.md 9): 4e8 samples, one 128-symbol frame every 1 000 003."""
+    global NFFT
+    import copy
+    a = copy.copy(args)
+    a.syms, a.capture_samples, a.no_cpu = 128, 4e8, True
+    NFFT = 1024
+    try:
+        return capture_bench(a, 0, local_rank, 1, steps=steps)
+    finally:
+        NFFT = args.nfft
 
 
 def capture_bench(args, rank, local_rank, world, steps=None):
