@@ -51,6 +51,7 @@ SyncKernel sync_select_fn();
 SyncKernel sync_refine_fn();
 CapturePrepKernel capture_prep_fn();
 SyncKernel wide_scan_fn();             // nfft = 1024
+SyncScanKernel wide_scan_tma_fn();     // ... tile staged by TMA tensor copies (16-byte aligned captures)
 SyncKernel wide_sync_refine_fn();
 // rs.cu
 RsKernel rs_encode_fn();

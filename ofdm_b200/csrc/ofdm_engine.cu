@@ -315,7 +315,7 @@ extern "C" int ofdm_engine_reserve(ofdm_engine *h, uint32_t max_streams, uint64_
         CU(h, h->cap_base.ensure((sizeof(uint64_t) + sizeof(uint32_t)) * (size_t)max_streams));
     }
     if (max_capture_samples >= 2 * (uint64_t)h->sym_len) {                 // same layout as sync_plan
-        const uint64_t tl = h->wide ? (uint64_t)kWScanD : (uint64_t)kScanD;
+        const uint64_t tl = h->wide ? (uint64_t)kWTD : (uint64_t)kScanD;          // the smaller of the two wide tile sizes
         const uint64_t T = (max_capture_samples - 2 * (uint64_t)h->sym_len + 1 + tl - 1) / tl;
         CU(h, h->sync_scratch.ensure(((32 + 4 * T + 7) & ~(size_t)7) + (size_t)T * kTileCand * 19 + 16));
     }
@@ -787,8 +787,20 @@ static int sync_plan(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak 
     a.iq = reinterpret_cast<const float2 *>(iq); a.n = n;
     a.tables = h->d_tables; a.peaks = reinterpret_cast<SyncPeak *>(peaks); a.max_peaks = max_peaks;
     a.wtables = h->d_wtables; a.lock_is_ramp = h->lock_is_ramp ? 1 : 0;
+    p.tma = false;
+    // TMA staging needs a 16-byte aligned capture and at least one full 8-sample row
+    if ((reinterpret_cast<uintptr_t>(iq) & 15) == 0 && n / kScanT >= 1 && n / kScanT < 0x7FFFFF00ull && encode_tiled_fn() &&
+        !(h->wide && getenv("OFDM_WIDE_SCAN_GENERIC"))) {
+        const cuuint64_t dims[2] = { 16, (cuuint64_t)(n / kScanT) };        // [rows][16 floats = 8 fc32 samples]
+        const cuuint64_t strides[1] = { 64 };
+        const cuuint32_t box[2] = { 16, 256 }, estr[2] = { 1, 1 };
+        const CUresult r = encode_tiled_fn()(reinterpret_cast<CUtensorMap *>(&p.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<ofdm_fc32 *>(iq),
+                                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        p.tma = r == CUDA_SUCCESS;
+    }
     const uint64_t LS = (uint64_t)h->sym_len;                              // 80 or 1280
-    a.tile_lags = h->wide ? (uint32_t)kWScanD : (uint32_t)kScanD;
+    a.tile_lags = h->wide ? (p.tma ? (uint32_t)kWTD : (uint32_t)kWScanD) : (uint32_t)kScanD;
     a.holdoff = (uint32_t)(10 * LS);
     const uint64_t lags = n >= 2 * LS ? n - 2 * LS + 1 : 0;
     const uint64_t T = (lags + a.tile_lags - 1) / a.tile_lags;
@@ -808,22 +820,17 @@ static int sync_plan(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     p.grid = (uint32_t)(2 * sms);                                          // persistent: 2 CTAs per SM
-    p.tma = false;
     if (h->wide) {
-        SyncKernel kw = wide_scan_fn();
-        if (h->smem_configured.insert((const void *)kw).second)
-            CU(h, cudaFuncSetAttribute((const void *)kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_scan_smem_bytes()));
+        if (p.tma) {
+            SyncScanKernel kw = wide_scan_tma_fn();
+            if (h->smem_configured.insert((const void *)kw).second)
+                CU(h, cudaFuncSetAttribute((const void *)kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_scan_tma_smem_bytes()));
+        } else {
+            SyncKernel kw = wide_scan_fn();
+            if (h->smem_configured.insert((const void *)kw).second)
+                CU(h, cudaFuncSetAttribute((const void *)kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_scan_smem_bytes()));
+        }
         return 0;
-    }
-    // TMA staging needs a 16-byte aligned capture and at least one full 8-sample row
-    if ((reinterpret_cast<uintptr_t>(iq) & 15) == 0 && n / kScanT >= 1 && n / kScanT < 0x7FFFFF00ull && encode_tiled_fn()) {
-        const cuuint64_t dims[2] = { 16, (cuuint64_t)(n / kScanT) };        // [rows][16 floats = 8 fc32 samples]
-        const cuuint64_t strides[1] = { 64 };
-        const cuuint32_t box[2] = { 16, 256 }, estr[2] = { 1, 1 };
-        const CUresult r = encode_tiled_fn()(reinterpret_cast<CUtensorMap *>(&p.tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<ofdm_fc32 *>(iq),
-                                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        p.tma = r == CUDA_SUCCESS;
     }
     SyncScanKernel k = sync_scan_fn(p.tma);
     if (h->smem_configured.insert((const void *)k).second)
@@ -836,8 +843,9 @@ static int sync_scan_range(ofdm_engine *h, SyncPlan &p, uint32_t tile_first, uin
 {
     if (tile_count == 0) return 0;
     p.a.tile_first = tile_first; p.a.tile_count = tile_count;
-    if (h->wide) {                                                         // one CTA per 4096-lag tile
-        wide_scan_fn()<<<tile_count, kWScanThreads, wide_scan_smem_bytes(), st>>>(p.a);
+    if (h->wide) {                                                         // one CTA per tile (3576 lags staged by TMA, or 4096)
+        if (p.tma) wide_scan_tma_fn()<<<tile_count, kWTThreads, wide_scan_tma_smem_bytes(), st>>>(p.a, p.tmap);
+        else wide_scan_fn()<<<tile_count, kWScanThreads, wide_scan_smem_bytes(), st>>>(p.a);
         h->launches += 1;
         CU(h, cudaGetLastError());
         return 0;
@@ -901,7 +909,7 @@ extern "C" int ofdm_sync_search(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n_
         ev ^= 1;
         // tile k reads samples [3928 k - 8, 3928 k - 8 + 4096): complete once s1 covers them (or the capture ends)
         // (nfft = 1024: tile k reads samples [4096 k - 8, 4096 k - 8 + kWScanSamples))
-        const uint64_t t_span = h->wide ? (uint64_t)kWScanSamples : (uint64_t)kScanRows * kScanT, t_lags = p.a.tile_lags;
+        const uint64_t t_span = h->wide ? (p.tma ? (uint64_t)kWTRows * 8 : (uint64_t)kWScanSamples) : (uint64_t)kScanRows * kScanT, t_lags = p.a.tile_lags;
         uint64_t ready = s1 >= n_samples ? p.a.n_tiles : (s1 + kScanT >= t_span ? (s1 + kScanT - t_span) / t_lags + 1 : 0);
         if (ready > p.a.n_tiles) ready = p.a.n_tiles;
         if (ready > tiles_done) {

@@ -42,6 +42,10 @@ def test_wide_sync_search_matches_oracle(oo):
     # unaligned capture pointer, a frame cut by the capture end, nothing / too little to search
     got, ref = eng.sync_search(cap[3:700_001]), oo.sync_search(cap[3:700_001], nfft=1024)
     assert [int(x) for x in got["offset"]] == [int(x) for x in ref["offset"]] and len(got) > 5
+    # aligned capture whose length is not a multiple of 8 (the tail samples are patched into the TMA-staged tile), ending inside a frame head
+    for cut in (sent[9][0] + 12_801, sent[9][0] + 12_799, sent[15][0] + 2563):
+        got, ref = eng.sync_search(cap[:cut]), oo.sync_search(cap[:cut], nfft=1024)
+        assert [int(x) for x in got["offset"]] == [int(x) for x in ref["offset"]], cut
     noise = cap[:4000].copy()
     assert len(eng.sync_search(noise)) == len(oo.sync_search(noise, nfft=1024)) == 0
     assert len(eng.sync_search(noise[:2000])) == 0                      # shorter than two symbol lengths
