@@ -140,3 +140,31 @@ def test_wideband_1024_oracle_loopback(oo, mod):
     data = [k for k in used if k not in set(pilots)]
     assert len(data) == 768
     np.testing.assert_allclose(sym[data][16 * 8:] / sym[pilots][0], -1.0, atol=1e-9)
+
+
+def test_oracle_capture_search_scales_with_the_symbol_length(oo):
+    """docs/SPEC.md 4 / 9: the capture search of the nfft = 1024 layout is the nfft = 64 one with every length scaled by 16.
+    Planted frames are found at `start - 1` (lag - 1 rule) with their CFO, in both layouts; the hold-off keeps one detection
+    per frame; a frame head cut by the end of the capture is not reported."""
+    rng = np.random.default_rng(12)
+    for nfft, gap in ((64, 900), (1024, 14_000)):
+        cfg = oo.make_cfg(True, oo.QAM64, True, oo.SYNC_SCHMIDL_COX, oo.CFO_ANGLE_OF_SUM, oo.PHASE_ANGLE_OF_SUM, 0, nfft=nfft)
+        L = nfft + nfft // 4
+        parts, want, pos = [], [], 0
+        for k in range(6):
+            g = int(rng.integers(gap, 3 * gap))
+            parts.append(1e-3 * (rng.standard_normal(g) + 1j * rng.standard_normal(g)))
+            pos += g
+            tx = oo.tx(rng.integers(0, 256, int(rng.integers(1, 800)), dtype=np.uint8).tobytes(), cfg)
+            f = float(rng.uniform(-0.5, 0.5) * np.pi / L)
+            parts.append(tx * np.exp(1j * f * np.arange(tx.size)))
+            want.append((pos - 1, f))
+            pos += tx.size
+        cap = np.concatenate(parts).astype(np.complex64)
+        pk = oo.sync_search(cap, nfft=nfft)
+        assert [int(x) for x in pk["offset"]] == [p for p, _ in want]
+        np.testing.assert_allclose(pk["f_delta"], [f for _, f in want], atol=2e-4 / (L / 80))
+        assert (pk["metric"] > 0.5).all()
+        cut = want[-1][0] + 10 * L                                         # the last frame's head just fits: offset + 10 L <= M
+        assert len(oo.sync_search(cap[:cut - 1], nfft=nfft)) == len(want) - 1
+        assert len(oo.sync_search(cap[:cut], nfft=nfft)) == len(want)
