@@ -58,6 +58,7 @@ struct SyncArgs {
     uint32_t holdoff;        // lock + preamble + training = 10 symbol lengths: one detection per frame
     const void *wtables;     // wide::WideTables (nfft = 1024)
     int32_t  lock_is_ramp;   // nfft = 1024: the built-in locking ramp (closed-form ramp correlation)
+    uint32_t prefetch_ahead; // wide_scan_tma_kernel: L2-prefetch the tile this many tiles ahead (0: off)
 };
 
 // generic path: padded rows | row totals | energy windows | masks.  TMA path: 2 x 32 KB swizzled tiles (1024-byte aligned) + the same

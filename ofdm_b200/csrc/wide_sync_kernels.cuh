@@ -208,6 +208,17 @@ __global__ void __launch_bounds__(kWTThreads, 3) wide_scan_tma_kernel(const Sync
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                          :: "r"(tile_sa + (uint32_t)h * (256 * 64)), "l"(&tmap), "r"(0), "r"((int)(origin / 8 + 256 * h)), "r"(bar_sa) : "memory");
     }
+    // One tile per CTA and no second buffer: what hides the next tile's trip to DRAM is an L2 prefetch of the tile this SM slot
+    // will most likely run next (CTAs are dispatched in order, 3 per SM), issued while this one's boxes are still in flight.
+    if (tid == 32 && a.prefetch_ahead) {
+        const long long nxt = tile + a.prefetch_ahead;
+        if (nxt < (long long)a.tile_first + a.tile_count) {
+#pragma unroll
+            for (int h = 0; h < 3; h++)
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                             :: "l"(&tmap), "r"(0), "r"((int)(nxt * kWTLagRows - 1 + 256 * h)) : "memory");
+        }
+    }
     mbar_wait(s_bar, 0);
     {   // the capture's last n % 8 samples lie past the tensor map's last full row: patch them into the staged tile
         const long long n_rows_full = n / 8, row_tail = n_rows_full - origin / 8;
