@@ -916,6 +916,19 @@ def ingest_bench(args, rank, local_rank, world):
             frames = ingest.decode_file(path, cfg, receiver=rx)
             runs.append(time.perf_counter() - t0)
         rx.close()
+        # the same file through the C entry a Rust / C caller binds (ofdm_rx_decode_file: parallel pread into two pinned
+        # buffers one chunk ahead of the GPU)
+        eng.decode_file(path, stop=1 << 26, chunk_samples=kw["chunk_samples"], max_frame_samples=kw["max_frame_samples"],
+                        out_stride=kw["out_stride"], max_frames=2048)
+        c_runs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rec, data = eng.decode_file(path, chunk_samples=kw["chunk_samples"], max_frame_samples=kw["max_frame_samples"],
+                                        out_stride=kw["out_stride"], max_frames=2048)
+            c_runs.append(time.perf_counter() - t0)
+        c_sec = sorted(c_runs)[1]
+        c_exact = [int(x) for x in rec["offset"]] == [p - 1 for p in positions] and all(d == want for d in data)
+    eng.close()
     sec = sorted(runs)[1]
     ok = [f for f in frames if f.status == 0 and f.data == want]
     exact = [f.offset for f in frames] == [p - 1 for p in positions]
@@ -925,6 +938,8 @@ def ingest_bench(args, rank, local_rank, world):
                       "config": {"workload": "fc32_file_2^27_samples", "file_bytes": 8 * n, "frames": len(positions), "frame_samples": frame_len,
                                  "chunk_samples": kw["chunk_samples"], "source": "page cache (/dev/shm)", "timing": "host wall clock, median of 3"},
                       "file_gbyte_per_s": round(8 * n / sec / 1e9, 2), "frames_found": len(frames), "frames_decoded_exact": len(ok),
+                      "c_abi": {"entry": "ofdm_rx_decode_file", "ms": round(c_sec * 1e3, 2), "msamples_per_s": round(n / c_sec / 1e6, 1),
+                                "file_gbyte_per_s": round(8 * n / c_sec / 1e9, 2), "all_frames_exact": bool(c_exact)},
                       "all_offsets_exact": exact})
 
 

@@ -1060,7 +1060,11 @@ extern "C" int ofdm_rx_decode_file(ofdm_engine *h, const char *path, uint64_t st
         if (b >= n) break;
         a = b - overlap;
     }
-    auto load = [&](size_t i) { return pread_parallel(fd, 8 * (start + plan[i].first), (uint8_t *)h->pin[i & 1], 8 * (plan[i].second - plan[i].first), 8); };
+    // page cache -> pinned memory is a kernel-side copy, a few GB/s per thread: as many readers as the host has threads (<= 32)
+    int readers = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("OFDM_FILE_READERS")) readers = atoi(e);
+    readers = readers < 1 ? 8 : (readers > 32 ? 32 : readers);
+    auto load = [&](size_t i) { return pread_parallel(fd, 8 * (start + plan[i].first), (uint8_t *)h->pin[i & 1], 8 * (plan[i].second - plan[i].first), readers); };
     std::future<bool> ahead = std::async(std::launch::async, load, (size_t)0);
     std::vector<ofdm_peak> pk(max_peaks);
     std::vector<uint32_t> lens(max_peaks);
