@@ -484,6 +484,7 @@ def main():
                          ("capture", lambda: capture_bench(args, 0, local_rank, 1, steps=sec_steps)),
                          ("capture_wide", lambda: capture_wide_leg(args, sec_steps, local_rank)),
                          ("tx", lambda: tx_bench(args, 0, local_rank, 1, steps=sec_steps)),
+                         ("tx_wide", lambda: tx_wide_leg(args, sec_steps, local_rank)),
                          ("rs", lambda: rs_bench(args, 0, local_rank, 1))):
             try:
                 full = fn()
@@ -543,6 +544,19 @@ def snr30_leg(args, steps, barrier, local_rank):
 def wide_leg(args, steps, barrier, local_rank):
     """BASELINE.json configs[3]: the 1024-subcarrier variant, 4096 streams x 128 data symbols."""
     return _streams_leg(args, 1024, 50.0, 128, steps, barrier, local_rank)
+
+
+def tx_wide_leg(args, steps, local_rank):
+    """TX half of BASELINE.json configs[3]: 4096 frames of 128 data symbols x 1024 subcarriers (the frames the wide leg receives)."""
+    global NFFT
+    import copy
+    a = copy.copy(args)
+    a.syms = 128
+    NFFT = 1024
+    try:
+        return tx_bench(a, 0, local_rank, 1, steps=steps)
+    finally:
+        NFFT = args.nfft
 
 
 def capture_wide_leg(args, steps, local_rank):
@@ -769,10 +783,10 @@ def tx_bench(args, rank, local_rank, world, steps=None):
     return ({"metric": "tx_msamples_per_s", "value": round(samples / (ms * 1e-3) / 1e6, 1), "unit": "Msamples/s", "n_gpus": 1,
                       "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"tx_{n}x64QAM_S{S}", "streams_per_gpu": n, "data_syms_per_frame": S, "frame_samples": frame_len,
+                      "config": {"workload": f"tx_{n}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}"), "streams_per_gpu": n, "nfft": NFFT, "data_syms_per_frame": S, "frame_samples": frame_len,
                                  "payload_bytes": plen_b, "l2": "output (%.2f GB) larger than L2" % (8 * samples / 1e9)},
-                      "roofline": {"bound": "hbm", "kernel": "tx_resident_kernel (one pass, frames resident in tensor memory)" if launches == steps else "tx_tile_kernel (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
-                                   "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": read_traffic(f"tx_{n}x64QAM_S{S}"),
+                      "roofline": {"bound": "hbm", "kernel": (("wide_tx_resident_kernel" if NFFT == 1024 else "tx_resident_kernel") + " (one pass, frames resident in tensor memory)") if launches == steps else ("wide_tx_kernel" if NFFT == 1024 else "tx_tile_kernel") + " (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
+                                   "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": read_traffic(f"tx_{n}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}")),
                                    "peak_source": src, "algorithmic_bytes_per_launch": by, "kernel_ms": round(ms, 4)},
                       "max_component": round(mx, 6), "frames_ok": frames_ok, "frames_match_oracle_on_sample": oracle_ok,
                       "gpu_launches": launches, "clocks": clocks})

@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-diag-suppress", "177",
 ]
 # one translation unit per kernel family (csrc/kernels.h) + the C ABI; compiled in parallel, linked into one library
-UNITS = ["rx64_m2", "wide_rx_m2", "rx64_m0", "rx64_m1", "wide_rx_m0", "wide_rx_m1", "wide_tx", "tx64", "tx64r", "rx64", "wide_rx",
+UNITS = ["rx64_m2", "wide_rx_m2", "rx64_m0", "rx64_m1", "wide_rx_m0", "wide_rx_m1", "wide_tx", "wide_txr", "tx64", "tx64r", "rx64", "wide_rx",
          "rs", "sync", "ofdm_engine"]
 OBJ_DIR = os.path.join(_HERE, "build")
 
@@ -35,10 +35,18 @@ def engine_is_stale() -> bool:
 
 
 def _unit_deps(unit: str):
-    """Headers a unit really includes (every unit sees kernels.h, which pulls in all .cuh files)."""
-    deps = [os.path.join(CSRC, unit + ".cu"), os.path.join(ROOT, "include", "ofdm_engine.h")]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
-    return deps
+    """Files a unit really includes: its .cu and, recursively, every quoted #include that lives in csrc/ or include/."""
+    import re
+    seen, todo = set(), [os.path.join(CSRC, unit + ".cu")]
+    while todo:
+        f = os.path.normpath(todo.pop())
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.add(f)
+        with open(f, "r", encoding="utf-8", errors="replace") as fh:
+            for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', fh.read(), flags=re.M):
+                todo.append(os.path.join(os.path.dirname(f), inc))
+    return sorted(seen)
 
 
 def build_engine(force: bool = False, verbose: bool = False, units=None) -> str:

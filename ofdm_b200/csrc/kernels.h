@@ -64,5 +64,10 @@ template <> WDecodeKernel wpick_decode_mod<2>(bool, bool, int, bool);
 WDecodeKernel wpick_decode(const ofdm_cfg &c, bool points);
 WDecodeKernel wpick_acquire(const ofdm_cfg &c);
 WTxKernel wpick_tx(const ofdm_cfg &c, bool write);
+// wide_txr.cu
+WTxKernel wpick_tx_resident(const ofdm_cfg &c);  // one-pass persistent kernel, frames resident in tensor memory (wide_tx_resident.cuh)
+size_t wide_tx_resident_smem(const ofdm_cfg &c);
+int wide_tx_resident_syms_per_cta();
+int wide_tx_resident_threads();
 
 }  // namespace ofdm

@@ -354,6 +354,27 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         w.payload = payload; w.payload_len = payload_len; w.payload_stride = payload_stride; w.n_streams = n_streams;
         w.iq = reinterpret_cast<float2 *>(iq); w.iq_stride = iq_stride; w.frame_len = d_flen; w.stream_max = d_max; w.tables = h->d_wtables;
         const long max_syms = (long)iq_stride / wide::kL - 10;
+        // Large batches: ONE pass, frames resident in tensor memory (wide_tx_resident.cuh): groups of C persistent CTAs (one per SM,
+        // 32 symbols each) per frame, launched cooperatively because the CTAs of a group wait for one another's frame maximum.
+        if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 3)) {
+            const int per = wide_tx_resident_syms_per_cta();
+            const int C = (int)((max_syms + per - 1) / per);
+            int G = C <= h->n_sm ? h->n_sm / C : 0;
+            if (G > 0 && (uint32_t)G > n_streams) G = (int)n_streams;
+            if (G > 0 && (h->tx_path == 3 || n_streams >= 2u * (uint32_t)(h->n_sm / C))) {
+                WTxKernel k = wpick_tx_resident(h->cfg);
+                const size_t smem = wide_tx_resident_smem(h->cfg);
+                if (h->smem_configured.insert((const void *)k).second)
+                    CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                w.stream_cnt = d_cnt; w.group_ctas = C; w.n_groups = G;
+                void *kargs[] = { (void *)&w };
+                CU(h, cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)(G * C)), dim3((unsigned)wide_tx_resident_threads()), kargs, smem, st));
+                h->launches++;
+                CU(h, cudaGetLastError());
+                if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+                return 0;
+            }
+        }
         const uint32_t tiles = max_syms > 0 ? (uint32_t)((max_syms + 7) / 8) : 1;
         launch_streams(wpick_tx(h->cfg, false), w, tiles, n_streams, wide::kThreads, 0, st, h->launches);
         launch_streams(wpick_tx(h->cfg, true), w, tiles, n_streams, wide::kThreads, 0, st, h->launches);

@@ -972,6 +972,9 @@ struct WideTxArgs {
     int            *stream_max;
     const WideTables *tables;
     uint32_t        stream0;        // first stream of this launch
+    uint32_t       *stream_cnt;     // wide_tx_resident_kernel: per stream, warps that have published their maximum
+    int32_t         group_ctas;     // wide_tx_resident_kernel: CTAs sharing one frame
+    int32_t         n_groups;       // wide_tx_resident_kernel: groups of the (persistent) grid
 };
 
 template <int MOD, bool GUARD, bool FEC, bool WRITE>

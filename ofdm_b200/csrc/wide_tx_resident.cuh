@@ -1,0 +1,341 @@
+// wide_tx_resident.cuh -- one-pass transmit kernel of the 1024-subcarrier variant for large batches (BASELINE.json configs[3],
+// docs/SPEC.md 9): `encode` (src/transmitter.rs:11-58) with every OFDM symbol transformed ONCE.
+//
+// `normalize` (src/transmitter.rs:183-194) divides the frame by its maximum positive component, so nothing can be stored
+// before the whole frame has been transformed; wide_tx_kernel therefore runs every inverse FFT twice (maximum pass, store
+// pass). Here a frame belongs to a GROUP of C persistent CTAs (one per SM; formed by block index like tx_resident_kernel's,
+// launched cooperatively so that the whole grid is resident), and the un-normalised symbols wait in the SMs' TENSOR MEMORY
+// (tcgen05.st / tcgen05.ld, SASS STTM / LDTM): 512 columns x 128 lanes x 4 B = 256 kB = exactly 32 symbols of 1024 complex
+// samples per SM, so the 128-symbol frames of the bench workload take C = 4.
+//
+// One OFDM symbol per WARP, as in wide_decode_kernel: the inverse transform is conj . FFT . conj with the register-resident
+// 32 x 32 split (lane l holds bins l + 32 j; 32-point DFT in registers, twiddle W1024^(l k1), one 32 x 32 exchange through a
+// warp-private shared-memory buffer, second 32-point DFT -> lane t1 holds the samples t1 + 32 t2). The constellation table
+// is stored conjugated, the closing conj rides on the scaling (multiply by (s, -s)). A warp's 64 result registers go to its
+// own tensor-memory slot (its lane quadrant x 64 columns): a slot is only ever touched by the warp that wrote it, and NOTHING
+// in the frame loop needs a CTA barrier -- a warp builds the coded bit stream of its own symbols (Hamming(7,4) over 16-byte
+// payload groups, docs/SPEC.md 3), looks the carriers up, transforms, and later drains its slot with coalesced 256-byte
+// row stores (cyclic prefix = the last 8 rows once more). Per frame k a warp runs:
+//   wait for the maximum of frame k-1 | 2 x { drain slot i of frame k-1 | transform its symbol i of frame k into slot i } |
+//   publish its maximum of frame k (atomicMax + arrival counter, fence-free as in tx_resident.cuh) |
+//   bit streams of its symbols of frame k+1, its share of the head / zero fill of frame k-1
+// -- the last step is also the time the maximum of frame k needs to travel between the SMs of the group.
+#pragma once
+
+#include "wide_kernels.cuh"
+#include "tx_resident.cuh"
+
+namespace ofdm {
+namespace wide {
+
+constexpr int kWTrsWarps = 16;                                   // 128 registers per thread x 512 threads = the register file
+constexpr int kWTrsThreads = 32 * kWTrsWarps;
+constexpr int kWTrsSlots = 2;                                    // symbols per warp and frame (64 tensor-memory columns each)
+constexpr int kWTrsSyms = kWTrsWarps * kWTrsSlots;               // 32 symbols per CTA = all 512 columns
+constexpr int kWTrsBitsBuf = 832;                                // per slot: header 16 + 28 groups x 28 coded bytes (+ slack), multiple of 64
+
+template <int MOD> struct WTrsSmem {
+    static constexpr int NE = 1 << ModTraits<MOD>::kBpc;
+    static constexpr size_t kBuf = 0;                                                      // [warp][kWBuf]: 32 x 32 exchange
+    static constexpr size_t kTw = kBuf + sizeof(float2) * kWTrsWarps * kWBuf;              // [l][kWPitch]: W1024^(l k1)
+    static constexpr size_t kOff = kTw + sizeof(float2) * kWBuf;                           // [j][l]: bit offset of bin l + 32 j | (override entry + 1) << 16
+    static constexpr size_t kLut = kOff + sizeof(uint32_t) * kN;                           // [entry][lane & 15] conjugated constellation, null, pilot
+    static constexpr size_t kEnc = kLut + sizeof(float2) * 16 * (NE + 2);                  // Hamming byte table (256 x u16), tensor-memory base address
+    static constexpr size_t kBits = kEnc + 512 + 64;                                       // [warp][slot][kWTrsBitsBuf]
+    static constexpr size_t kTotal = kBits + (size_t)kWTrsWarps * kWTrsSlots * kWTrsBitsBuf;
+};
+
+// this CTA's share of frame `stream`: symbols [t0, t1) of its S data symbols (an even split over the group)
+struct WTrsGeom {
+    uint32_t n;
+    uint64_t coded_len, ncar;
+    int      S, t0, t1;
+    uint32_t frame_len;
+    bool     fits;
+};
+template <int BPC, int D, bool FEC>
+__device__ __forceinline__ WTrsGeom wtrs_geometry(const WideTxArgs &a, uint32_t stream, int rank)
+{
+    WTrsGeom q;
+    q.n = __ldg(a.payload_len + stream);
+    q.coded_len = FEC ? (14ull * q.n + 7) / 8 : q.n;
+    const uint64_t nbits = kHeaderBits + 8 * q.coded_len;
+    q.ncar = (nbits + BPC - 1) / BPC;                               // constellation symbols (src/transmitter.rs:108-140)
+    const uint64_t S64 = (q.ncar + D - 1) / D;                      // OFDM data symbols (src/transmitter.rs:49-54)
+    q.S = (int)S64;
+    q.frame_len = (10u + (uint32_t)q.S) * kL;
+    q.fits = (10ull + S64) * kL <= (uint64_t)a.iq_stride;
+    const int C = a.group_ctas;
+    const int chunk = (q.S + C - 1) / C;
+    q.t0 = rank * chunk;
+    q.t1 = q.t0 + chunk < q.S ? q.t0 + chunk : q.S;
+    if (!q.fits || q.t1 < q.t0 || chunk > kWTrsSyms) q.t1 = q.t0;   // (the launcher sizes C so that a fitting frame's chunk never exceeds the slots)
+    return q;
+}
+
+// Stream bytes [s BPSB, (s + 1) BPSB + 2) of the frame byte stream [header 16 B | (Hamming-coded) payload] into a warp-private
+// buffer; returns the buffer's BIT index of the symbol's first bit. With FEC the buffer starts on a 7-byte unit of the coded
+// stream (7 coded bytes = 8 nibbles = 4 payload bytes); lane u encodes payload bytes [16 u, 16 u + 16) into 28 coded bytes.
+template <int BPSB, bool FEC>
+__device__ __forceinline__ uint32_t wtrs_build_bits(uint8_t *bits, const uint8_t *__restrict__ pay, bool pay_aligned, uint32_t n, uint64_t coded_len,
+                                                    int s, const uint16_t *s_enc14, int lane)
+{
+    const uint32_t B0 = (uint32_t)s * BPSB;
+    constexpr uint32_t nbyte = BPSB + 2;
+    if (FEC) {
+        const uint32_t hdr = B0 < 16 ? 16 - B0 : 0;                  // header bytes inside this symbol (symbol 0 only: BPSB >= 96)
+        if ((uint32_t)lane < hdr) bits[lane] = (uint8_t)(B0 + lane < 8 ? (uint32_t)(coded_len >> (8 * (B0 + lane))) & 255u : 0u);
+        const uint32_t c0 = B0 + hdr - 16;                           // first coded byte of the symbol
+        const uint32_t u0 = c0 / 7, skip = c0 - 7 * u0;
+        const uint32_t ngrp = ((nbyte - hdr + skip + 6) / 7 + 3) / 4;
+        for (uint32_t u = lane; u < ngrp; u += 32) {
+            const uint32_t pb = 4 * u0 + 16 * u;
+            uint32_t v[4] = { 0, 0, 0, 0 };
+            if (pay_aligned && pb + 16 <= n) {
+#pragma unroll
+                for (int w = 0; w < 4; w++) v[w] = __ldg(reinterpret_cast<const uint32_t *>(pay + pb) + w);
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; w++) if (pb + w < n) v[w >> 2] |= (uint32_t)pay[pb + w] << (8 * (w & 3));
+            }
+            uint64_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t lo = (uint32_t)s_enc14[v[i] & 255u] | ((uint32_t)s_enc14[(v[i] >> 8) & 255u] << 14);
+                const uint32_t hi = (uint32_t)s_enc14[(v[i] >> 16) & 255u] | ((uint32_t)s_enc14[v[i] >> 24] << 14);
+                w[i] = (uint64_t)lo | ((uint64_t)hi << 28);
+            }
+            uint32_t *dst = reinterpret_cast<uint32_t *>(bits + hdr + 28 * u);
+            dst[0] = (uint32_t)w[0];
+            dst[1] = (uint32_t)(w[0] >> 32) | ((uint32_t)w[1] << 24);
+            dst[2] = (uint32_t)(w[1] >> 8);
+            dst[3] = (uint32_t)(w[1] >> 40) | ((uint32_t)w[2] << 16);
+            dst[4] = (uint32_t)(w[2] >> 16);
+            dst[5] = (uint32_t)(w[2] >> 48) | ((uint32_t)w[3] << 8);
+            dst[6] = (uint32_t)(w[3] >> 24);
+        }
+        return 8u * (hdr ? 0u : skip);
+    } else {
+        for (uint32_t b = lane; b < nbyte; b += 32) {                // header, then the payload bytes as they are (src/transmitter.rs:37-47)
+            const uint32_t B = B0 + b;
+            bits[b] = (uint8_t)(B < 16 ? (B < 8 ? (uint32_t)(coded_len >> (8 * B)) & 255u : 0u) : (B - 16 < n ? (uint32_t)pay[B - 16] : 0u));
+        }
+        return 0u;
+    }
+}
+
+template <int MOD, bool GUARD, bool FEC>
+__global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const WideTxArgs a)
+{
+    typedef WTrsSmem<MOD> L;
+    constexpr int BPC = ModTraits<MOD>::kBpc, NE = 1 << BPC, D = GUARD ? 768 : 1024, BPSB = BPC * D / 8;
+    static_assert(16 + 28 * (((BPSB + 2 + 6 + 6) / 7 + 3) / 4) <= kWTrsBitsBuf, "bit-stream buffer of one symbol");
+    extern __shared__ __align__(128) uint8_t wtrs_smem[];
+    float2 *s_buf = reinterpret_cast<float2 *>(wtrs_smem + L::kBuf);
+    float2 *s_tw = reinterpret_cast<float2 *>(wtrs_smem + L::kTw);
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(wtrs_smem + L::kOff);
+    float2 *s_lut = reinterpret_cast<float2 *>(wtrs_smem + L::kLut);
+    uint16_t *s_enc14 = reinterpret_cast<uint16_t *>(wtrs_smem + L::kEnc);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(wtrs_smem + L::kEnc + 512);
+    uint8_t *s_bits = wtrs_smem + L::kBits;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = a.group_ctas, G = a.n_groups;
+    const int group = (int)blockIdx.x / C, rank = (int)blockIdx.x - group * C;
+    const uint32_t arrivals = (uint32_t)(C * kWTrsWarps);                       // per frame: every warp of the group, once
+
+    // ---- set-up: tables, tensor memory ------------------------------------------------------------------------------------
+    for (int e = tid; e < 16 * (NE + 2); e += kWTrsThreads) {                   // conjugated constellation (conj . FFT . conj), null, pilot
+        const int idx = e >> 4;
+        float re = 0.0f, im = 0.0f;
+        if (idx == NE + 1) re = 1.0f;
+        else if (idx == NE) { }
+        else if (MOD == 0) { re = (idx & 1) ? 1.0f : -1.0f; }
+        else if (MOD == 1) { re = (idx & 1) ? 1.0f : -1.0f; im = (idx & 2) ? 1.0f : -1.0f; }
+        else {
+            const uint32_t ci = idx & 7u, cq = (uint32_t)idx >> 3;
+            const uint32_t li = ci ^ (ci >> 1) ^ (ci >> 2), lq = cq ^ (cq >> 1) ^ (cq >> 2);
+            re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
+            im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
+        }
+        s_lut[e] = make_float2(re, -im);
+    }
+    for (int e = tid; e < kN; e += kWTrsThreads) {                              // e = 32 j + l <-> bin l + 32 j = e (encode_block, src/transmitter.rs:144-165)
+        const int rk = w_rank<GUARD>(e);
+        s_off[e] = rk >= 0 ? (uint32_t)(rk * BPC) : ((GUARD && w_is_pilot(e)) ? (uint32_t)(NE + 2) << 16 : (uint32_t)(NE + 1) << 16);
+        const int r = e >> 5, c = e & 31;
+        s_tw[r * kWPitch + c] = __ldg(a.tables->w1024 + ((r * c) & (kN - 1)));
+    }
+    if (FEC && tid < 256) s_enc14[tid] = (uint16_t)(ham74_encode_nibble(tid & 15) | (ham74_encode_nibble(tid >> 4) << 7));
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_addr(s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(s_tmem);
+    const float head_max = a.tables->head_max;
+
+    // this warp's tensor-memory slots: lane quadrant warp % 4, columns 128 (warp / 4) + 64 slot
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * (warp >> 2));
+    float2 *buf = s_buf + warp * kWBuf;
+    unsigned long long *wr = reinterpret_cast<unsigned long long *>(buf + lane);
+    const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(buf + lane * kWPitch);
+    const ulonglong2 *tw_row = reinterpret_cast<const ulonglong2 *>(s_tw + lane * kWPitch);
+    const unsigned long long *lut = reinterpret_cast<const unsigned long long *>(s_lut) + (lane & 15);
+    const uint32_t *off_col = s_off + lane;
+    uint8_t *mybits = s_bits + (size_t)warp * kWTrsSlots * kWTrsBitsBuf;
+
+    float mx = 0.0f;
+    // carriers -> inverse FFT of symbol s into slot `slot` (prefix_block's IFFT, src/transmitter.rs:168-181)
+    auto transform = [&](int slot, int s, uint64_t ncar, uint32_t bit0) {
+        const uint8_t *bits = mybits + slot * kWTrsBitsBuf;
+        // carriers past the frame's last constellation symbol are padding (encode_block's exhausted iterator): the null entry
+        const long left = (long)ncar - (long)s * D;
+        const uint32_t lim_bits = left >= D ? 0xFFFFFFFFu : (uint32_t)(left > 0 ? left : 0) * BPC;
+        cpx x[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (!w_row_used<GUARD>(j)) { x[j] = c_make(0.0f, 0.0f); continue; }
+            const uint32_t t = off_col[32 * j];
+            const uint32_t o = t & 0xFFFFu, bit = bit0 + o, bb = bit >> 3;
+            const uint32_t w = ((uint32_t)bits[bb] | ((uint32_t)bits[bb + 1] << 8)) >> (bit & 7u);
+            uint32_t idx = w & (uint32_t)(NE - 1);
+            if (o >= lim_bits) idx = NE;
+            if (t >> 16) idx = (t >> 16) - 1u;
+            x[j].v = lut[idx * 16];
+        }
+        dft32_p(x);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const ulonglong2 ww = tw_row[q];
+            cpx w0, w1;
+            w0.v = ww.x; w1.v = ww.y;
+            x[2 * q] = c_mul(x[2 * q], w0); x[2 * q + 1] = c_mul(x[2 * q + 1], w1);
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) wr[k1 * kWPitch] = x[k1].v;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 16; q++) { const ulonglong2 v = row[q]; x[2 * q].v = v.x; x[2 * q + 1].v = v.y; }
+        __syncwarp();
+        dft32_p(x);
+#pragma unroll
+        for (int t2 = 0; t2 < 32; t2++) {
+            float re, im;
+            c_split(x[t2], re, im);                                            // the frame's sample is (re, -im) / 1024
+            mx = fmaxf(mx, fmaxf(re, -im));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            cpx y[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) y[i] = x[8 * c + i];
+            tmem_st16(taddr + (uint32_t)(64 * slot + 16 * c), y);
+        }
+    };
+    // drain a slot: scale, store with the cyclic prefix (prefix_block, src/transmitter.rs:168-181)
+    auto drain = [&](int slot, int s, float2 *fout, float scale) {
+        unsigned long long *sym = reinterpret_cast<unsigned long long *>(fout + (size_t)(10 + s) * kL) + lane;
+        const cpx sc = c_make(scale, -scale);                                  // conj and scale in one
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            cpx y[8];
+            tmem_ld16(taddr + (uint32_t)(64 * slot + 16 * c), y);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int t2 = 8 * c + i;
+                const unsigned long long v = c_mul2(y[i], sc).v;               // time index lane + 32 t2
+                sym[kCpW + 32 * t2] = v;
+                if (t2 >= 24) sym[32 * (t2 - 24)] = v;                         // cyclic prefix = last 256 samples
+            }
+        }
+    };
+    // frame head (lock | preamble x4 | training x5) and zero fill past the frame, spread over all threads of the group
+    auto write_head = [&](uint32_t stream, bool fits, uint32_t frame_len, float fmx) {
+        float2 *out = a.iq + (size_t)stream * a.iq_stride;
+        const uint32_t gthreads = (uint32_t)(C * kWTrsThreads), gt = (uint32_t)(rank * kWTrsThreads + tid);
+        const uint32_t hw = a.iq_stride < (uint32_t)kHeadW ? a.iq_stride : (uint32_t)kHeadW;
+        for (uint32_t i = gt; i < hw; i += gthreads) {
+            float2 v = make_float2(0.0f, 0.0f);
+            if (fits) { v = __ldg(a.tables->head + i); v.x = v.x / fmx; v.y = v.y / fmx; }
+            out[i] = v;
+        }
+        const uint32_t z0 = fits ? frame_len : (uint32_t)kHeadW;
+        for (uint32_t i = z0 + gt; i < a.iq_stride; i += gthreads) out[i] = make_float2(0.0f, 0.0f);
+    };
+    auto frame_max = [&](uint32_t stream) -> float {
+        while (ld_relaxed_gpu(a.stream_cnt + stream) < arrivals) __nanosleep(64);
+        return fmaxf(__int_as_float((int)ld_relaxed_gpu(reinterpret_cast<const uint32_t *>(a.stream_max) + stream)), head_max);
+    };
+    auto build = [&](const WTrsGeom &q, uint32_t stream, uint32_t (&bit0)[kWTrsSlots]) {
+        const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+        const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
+#pragma unroll
+        for (int i = 0; i < kWTrsSlots; i++) {
+            const int s = q.t0 + warp + kWTrsWarps * i;
+            bit0[i] = 0;
+            if (s < q.t1) bit0[i] = wtrs_build_bits<BPSB, FEC>(mybits + i * kWTrsBitsBuf, pay, pay_aligned, q.n, q.coded_len, s, s_enc14, lane);
+        }
+        __syncwarp();
+    };
+
+    uint32_t stream = (uint32_t)group;                                         // (the launcher guarantees group < n_streams)
+    WTrsGeom q = wtrs_geometry<BPC, D, FEC>(a, stream, rank);
+    uint32_t bit0[kWTrsSlots];
+    build(q, stream, bit0);
+    bool have_prev = false, p_fits = false;
+    int p_t0 = 0, p_t1 = 0;
+    uint32_t p_stream = 0, p_flen = 0;
+
+    for (;;) {
+        if (rank == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = q.frame_len;
+        // ---- drain frame k-1, transform frame k -----------------------------------------------------------------------------
+        float p_fmx = 1.0f, p_scale = 0.0f;
+        if (have_prev) { p_fmx = frame_max(p_stream); p_scale = (1.0f / (float)kN) * (1.0f / p_fmx); }
+        tmem_wait_st();                                                        // the slots of frame k-1 were written an iteration ago
+        float2 *p_out = a.iq + (size_t)p_stream * a.iq_stride;
+        mx = 0.0f;
+#pragma unroll 1
+        for (int i = 0; i < kWTrsSlots; i++) {
+            const int ps = p_t0 + warp + kWTrsWarps * i, s = q.t0 + warp + kWTrsWarps * i;
+            if (have_prev && ps < p_t1) drain(i, ps, p_out, p_scale);
+            if (s < q.t1) transform(i, s, q.ncar, bit0[i]);
+        }
+        // ---- publish this warp's maximum of frame k, count the arrival -------------------------------------------------------
+        mx *= 1.0f / (float)kN;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
+        // ---- bit streams of frame k+1, head / zero fill of frame k-1 ---------------------------------------------------------
+        const uint32_t next = stream + (uint32_t)G;
+        const bool more = next < a.n_streams;
+        WTrsGeom qn = q;
+        __syncwarp();                                                          // every lane has read its carriers of frame k
+        if (more) { qn = wtrs_geometry<BPC, D, FEC>(a, next, rank); build(qn, next, bit0); }
+        if (have_prev) write_head(p_stream, p_fits, p_flen, p_fmx);
+        have_prev = true; p_t0 = q.t0; p_t1 = q.t1; p_stream = stream; p_flen = q.frame_len; p_fits = q.fits;
+        if (!more) break;
+        stream = next;
+        q = qn;
+    }
+    // ---- the group's last frame ---------------------------------------------------------------------------------------------
+    {
+        const float p_fmx = frame_max(p_stream), p_scale = (1.0f / (float)kN) * (1.0f / p_fmx);
+        tmem_wait_st();
+        float2 *p_out = a.iq + (size_t)p_stream * a.iq_stride;
+#pragma unroll 1
+        for (int i = 0; i < kWTrsSlots; i++) {
+            const int ps = p_t0 + warp + kWTrsWarps * i;
+            if (ps < p_t1) drain(i, ps, p_out, p_scale);
+        }
+        write_head(p_stream, p_fits, p_flen, p_fmx);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+}
+
+}  // namespace wide
+}  // namespace ofdm

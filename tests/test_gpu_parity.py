@@ -713,6 +713,64 @@ def test_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
     assert np.array_equal(iq, out["twopass"][0])            # the same values (an exact zero may carry the other sign: conj vs swap transform)
 
 
+@pytest.mark.parametrize("mod,guard,fec", [(2, True, True), (2, False, False), (1, True, True), (0, False, True), (2, True, False)])
+def test_wide_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
+    """nfft = 1024: the one-pass TX kernel (frames resident in tensor memory, wide_tx_resident.cuh) forced for a ragged batch:
+    every frame against the oracle's encode (src/transmitter.rs:11-58 scaled by 16, docs/SPEC.md 9), zero fill past the frame,
+    frame lengths and (to rounding: the two kernels use different FFT factorisations) the two-pass kernel. Lengths include the
+    empty payload, one byte, the header-only symbol, and frames of 1, 2 and 3 CTAs' worth of symbols (32 symbols per CTA)."""
+    rng = np.random.default_rng(177 + 10 * mod + 2 * guard + fec)
+    cfg = ob.Config(modulation=mod, guard_bands=guard, fec=fec, nfft=1024, cp=256)
+    longest = cfg.max_payload(70)
+    lens = [0, 1, 2, 15, 16, 17, 100, 333, 577, cfg.max_payload(1), cfg.max_payload(1) + 1, cfg.max_payload(32), cfg.max_payload(33),
+            longest // 2, longest - 1, longest] + [int(v) for v in rng.integers(0, longest + 1, 12)]
+    pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+    out = {}
+    for path in ("resident", "twopass"):
+        monkeypatch.setenv("OFDM_TX_PATH", path)
+        eng = ob.Engine(cfg, 0)
+        l0 = eng.kernel_launches
+        out[path] = eng.tx_encode(pays)
+        assert eng.kernel_launches - l0 == (1 if path == "resident" else 2)
+        eng.close()
+    iq, flen = out["resident"]
+    ocfg = oo.make_cfg(guard, mod, fec, 0, 0, 0, 0, nfft=1024)
+    for i, p in enumerate(pays):
+        ref = oo.tx(p, ocfg)
+        assert ref.size == flen[i]
+        np.testing.assert_allclose(iq[i, : flen[i]], ref, atol=2e-6)
+        assert not iq[i, flen[i]:].any()
+        assert abs(max(iq[i].real.max(), iq[i].imag.max()) - 1.0) < 1e-6          # normalize, src/transmitter.rs:183-194
+    assert np.array_equal(flen, out["twopass"][1])
+    np.testing.assert_allclose(iq, out["twopass"][0], atol=2e-6)
+
+
+def test_wide_tx_resident_kernel_is_the_large_batch_path(ob, oo):
+    """nfft = 1024: a batch of a few hundred frames takes the one-pass kernel by itself (one launch); frames that do not fit
+    iq_stride come back zeroed with their required length, as from the two-pass kernel; RX decodes what TX produced."""
+    cfg = ob.Config(modulation=2, guard_bands=True, fec=True, sync_mode=ob.SYNC_SCHMIDL_COX, cfo_mode=ob.CFO_ANGLE_OF_SUM,
+                    phase_mode=ob.PHASE_ANGLE_OF_SUM, sync_window=4096, nfft=1024, cp=256)
+    rng = np.random.default_rng(6)
+    n = 330
+    plen = cfg.max_payload(40)
+    pays = [rng.integers(0, 256, plen - (i % 9) * 311, dtype=np.uint8).tobytes() for i in range(n)]
+    eng = ob.Engine(cfg, 0)
+    l0 = eng.kernel_launches
+    iq, flen = eng.tx_encode(pays)
+    assert eng.kernel_launches - l0 == 1
+    ocfg = oo.make_cfg(True, 2, True, oo.SYNC_SCHMIDL_COX, oo.CFO_ANGLE_OF_SUM, oo.PHASE_ANGLE_OF_SUM, 4096, nfft=1024)
+    for i in (0, 1, 36, 37, 147, 148, 329):
+        np.testing.assert_allclose(iq[i, : flen[i]], oo.tx(pays[i], ocfg), atol=2e-6)
+    mx = np.maximum(iq.real.max(axis=1), iq.imag.max(axis=1))
+    np.testing.assert_allclose(mx, 1.0, atol=1e-6)
+    pick = list(range(0, n, 10))
+    lead = 1e-4 * (rng.standard_normal(60) + 1j * rng.standard_normal(60))
+    batch, ns = _batch([np.concatenate([lead, iq[i, : flen[i]]]) for i in pick])
+    res = eng.rx_decode(batch, ns)
+    assert all(res.status[j] == 0 and res.data[j] == pays[i] for j, i in enumerate(pick))
+    eng.close()
+
+
 def test_tx_resident_kernel_is_the_large_batch_path(ob, oo):
     """A batch of a few hundred frames takes the one-pass kernel by itself (one launch instead of two); spot-check frames
     against the oracle and the normalisation of every frame (max positive component 1, src/transmitter.rs:183-194)."""
