@@ -65,9 +65,9 @@ WDecodeKernel wpick_decode(const ofdm_cfg &c, bool points);
 WDecodeKernel wpick_acquire(const ofdm_cfg &c);
 WTxKernel wpick_tx(const ofdm_cfg &c, bool write);
 // wide_txr.cu
-WTxKernel wpick_tx_resident(const ofdm_cfg &c);  // one-pass persistent kernel, frames resident in tensor memory (wide_tx_resident.cuh)
+WTxKernel wpick_tx_resident(const ofdm_cfg &c, bool double_buffered);  // one-pass persistent kernel, frames resident in tensor memory (wide_tx_resident.cuh)
 size_t wide_tx_resident_smem(const ofdm_cfg &c);
-int wide_tx_resident_syms_per_cta();
+int wide_tx_resident_syms_per_cta(bool double_buffered);
 int wide_tx_resident_threads();
 
 }  // namespace ofdm

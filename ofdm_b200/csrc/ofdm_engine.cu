@@ -357,12 +357,14 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         // Large batches: ONE pass, frames resident in tensor memory (wide_tx_resident.cuh): groups of C persistent CTAs (one per SM,
         // 32 symbols each) per frame, launched cooperatively because the CTAs of a group wait for one another's frame maximum.
         if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 3)) {
-            const int per = wide_tx_resident_syms_per_cta();
+            bool db = false;
+            if (const char *e = getenv("OFDM_WTX_DB")) db = atoi(e) != 0;
+            const int per = wide_tx_resident_syms_per_cta(db);
             const int C = (int)((max_syms + per - 1) / per);
             int G = C <= h->n_sm ? h->n_sm / C : 0;
             if (G > 0 && (uint32_t)G > n_streams) G = (int)n_streams;
             if (G > 0 && (h->tx_path == 3 || n_streams >= 2u * (uint32_t)(h->n_sm / C))) {
-                WTxKernel k = wpick_tx_resident(h->cfg);
+                WTxKernel k = wpick_tx_resident(h->cfg, db);
                 const size_t smem = wide_tx_resident_smem(h->cfg);
                 if (h->smem_configured.insert((const void *)k).second)
                     CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -32,17 +32,19 @@ constexpr int kWTrsWarps = 16;                                   // 128 register
 constexpr int kWTrsThreads = 32 * kWTrsWarps;
 constexpr int kWTrsSlots = 2;                                    // symbols per warp and frame (64 tensor-memory columns each)
 constexpr int kWTrsSyms = kWTrsWarps * kWTrsSlots;               // 32 symbols per CTA = all 512 columns
-constexpr int kWTrsBitsBuf = 832;                                // per slot: header 16 + 28 groups x 28 coded bytes (+ slack), multiple of 64
+constexpr int kWTrsBitsBuf = 832;                                // per warp: header 16 + 28 groups x 28 coded bytes (+ slack), multiple of 64
+constexpr int kWTrsCarBuf = 1024 + 64;                           // per slot: one byte per data carrier | null entry | pilot entry (+ slack)
 
 template <int MOD> struct WTrsSmem {
     static constexpr int NE = 1 << ModTraits<MOD>::kBpc;
     static constexpr size_t kBuf = 0;                                                      // [warp][kWBuf]: 32 x 32 exchange
     static constexpr size_t kTw = kBuf + sizeof(float2) * kWTrsWarps * kWBuf;              // [l][kWPitch]: W1024^(l k1)
-    static constexpr size_t kOff = kTw + sizeof(float2) * kWBuf;                           // [j][l]: bit offset of bin l + 32 j | (override entry + 1) << 16
-    static constexpr size_t kLut = kOff + sizeof(uint32_t) * kN;                           // [entry][lane & 15] conjugated constellation, null, pilot
+    static constexpr size_t kOff = kTw + sizeof(float2) * kWBuf;                           // [j][l]: index of bin l + 32 j in the carrier bytes (D: null, D + 1: pilot)
+    static constexpr size_t kLut = kOff + sizeof(uint16_t) * kN;                           // [entry][lane & 15] conjugated constellation, null, pilot
     static constexpr size_t kEnc = kLut + sizeof(float2) * 16 * (NE + 2);                  // Hamming byte table (256 x u16), tensor-memory base address
-    static constexpr size_t kBits = kEnc + 512 + 64;                                       // [warp][slot][kWTrsBitsBuf]
-    static constexpr size_t kTotal = kBits + (size_t)kWTrsWarps * kWTrsSlots * kWTrsBitsBuf;
+    static constexpr size_t kBits = kEnc + 512 + 64;                                       // [warp][kWTrsBitsBuf]: coded bit stream of the symbol being prepared
+    static constexpr size_t kCar = kBits + (size_t)kWTrsWarps * kWTrsBitsBuf;              // [warp][slot][kWTrsCarBuf]
+    static constexpr size_t kTotal = kCar + (size_t)kWTrsWarps * kWTrsSlots * kWTrsCarBuf;
 };
 
 // this CTA's share of frame `stream`: symbols [t0, t1) of its S data symbols (an even split over the group)
@@ -53,7 +55,7 @@ struct WTrsGeom {
     uint32_t frame_len;
     bool     fits;
 };
-template <int BPC, int D, bool FEC>
+template <int BPC, int D, bool FEC, int PER>
 __device__ __forceinline__ WTrsGeom wtrs_geometry(const WideTxArgs &a, uint32_t stream, int rank)
 {
     WTrsGeom q;
@@ -69,7 +71,7 @@ __device__ __forceinline__ WTrsGeom wtrs_geometry(const WideTxArgs &a, uint32_t 
     const int chunk = (q.S + C - 1) / C;
     q.t0 = rank * chunk;
     q.t1 = q.t0 + chunk < q.S ? q.t0 + chunk : q.S;
-    if (!q.fits || q.t1 < q.t0 || chunk > kWTrsSyms) q.t1 = q.t0;   // (the launcher sizes C so that a fitting frame's chunk never exceeds the slots)
+    if (!q.fits || q.t1 < q.t0 || chunk > PER) q.t1 = q.t0;         // (the launcher sizes C so that a fitting frame's chunk never exceeds the slots)
     return q;
 }
 
@@ -124,20 +126,49 @@ __device__ __forceinline__ uint32_t wtrs_build_bits(uint8_t *bits, const uint8_t
     }
 }
 
-template <int MOD, bool GUARD, bool FEC>
+// bit stream -> one byte per data carrier (modulate, src/transmitter.rs:108-140); carriers past the frame's last constellation
+// symbol are padding (encode_block's exhausted iterator, src/transmitter.rs:144-165): the null entry, which is also car[D];
+// car[D + 1] is the pilot entry -- the bin table points there, so the transform needs no special cases
+template <int BPC, int D>
+__device__ __forceinline__ void wtrs_unpack_carriers(uint8_t *car, const uint8_t *bits, uint32_t bit0, long left, int lane)
+{
+    constexpr uint32_t NE = 1u << BPC, M = NE - 1u;
+    const int have = left >= D ? D : (left > 0 ? (int)left : 0);
+    const uint32_t *bits32 = reinterpret_cast<const uint32_t *>(bits);
+#pragma unroll 2
+    for (int c4 = 4 * lane; c4 < D; c4 += 128) {                               // 4 carriers = 4 BPC bits
+        const uint32_t bit = bit0 + (uint32_t)c4 * BPC, wi = bit >> 5, sh = bit & 31u;
+        const uint32_t v = __funnelshift_r(bits32[wi], bits32[wi + 1], sh);
+        uint32_t packed = (v & M) | (((v >> BPC) & M) << 8) | (((v >> (2 * BPC)) & M) << 16) | (((v >> (3 * BPC)) & M) << 24);
+        if (c4 + 4 > have) {
+#pragma unroll
+            for (int w = 0; w < 4; w++) if (c4 + w >= have) packed = (packed & ~(0xFFu << (8 * w))) | (NE << (8 * w));
+        }
+        *reinterpret_cast<uint32_t *>(car + c4) = packed;
+    }
+    if (lane == 0) *reinterpret_cast<uint16_t *>(car + D) = (uint16_t)(NE | ((NE + 1u) << 8));
+}
+
+// DB = false: a warp holds TWO symbols of a frame (32 symbols per CTA); a frame's slots are drained while the next frame is
+//             transformed into them, so every warp waits for the frame maximum right after the group's last transform.
+// DB = true : a warp holds ONE symbol of each of TWO consecutive frames (16 symbols per CTA and frame, twice the CTAs per
+//             group): frame k is transformed into slot k & 1 BEFORE frame k-1 is drained from the other slot -- the maximum of
+//             frame k-1 has had a whole transform's time to arrive, and the warps of a group drift apart by up to a frame
+//             instead of marching in phase (all storing, then all transforming).
+template <int MOD, bool GUARD, bool FEC, bool DB>
 __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const WideTxArgs a)
 {
     typedef WTrsSmem<MOD> L;
     constexpr int BPC = ModTraits<MOD>::kBpc, NE = 1 << BPC, D = GUARD ? 768 : 1024, BPSB = BPC * D / 8;
-    static_assert(16 + 28 * (((BPSB + 2 + 6 + 6) / 7 + 3) / 4) <= kWTrsBitsBuf, "bit-stream buffer of one symbol");
+    constexpr int SPW = DB ? 1 : kWTrsSlots;                                    // symbols per warp and frame
+    static_assert(16 + 28 * (((BPSB + 2 + 6 + 6) / 7 + 3) / 4) <= kWTrsBitsBuf - 8, "bit-stream buffer of one symbol");
     extern __shared__ __align__(128) uint8_t wtrs_smem[];
     float2 *s_buf = reinterpret_cast<float2 *>(wtrs_smem + L::kBuf);
     float2 *s_tw = reinterpret_cast<float2 *>(wtrs_smem + L::kTw);
-    uint32_t *s_off = reinterpret_cast<uint32_t *>(wtrs_smem + L::kOff);
+    uint16_t *s_off = reinterpret_cast<uint16_t *>(wtrs_smem + L::kOff);
     float2 *s_lut = reinterpret_cast<float2 *>(wtrs_smem + L::kLut);
     uint16_t *s_enc14 = reinterpret_cast<uint16_t *>(wtrs_smem + L::kEnc);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(wtrs_smem + L::kEnc + 512);
-    uint8_t *s_bits = wtrs_smem + L::kBits;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = a.group_ctas, G = a.n_groups;
@@ -162,7 +193,7 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
     }
     for (int e = tid; e < kN; e += kWTrsThreads) {                              // e = 32 j + l <-> bin l + 32 j = e (encode_block, src/transmitter.rs:144-165)
         const int rk = w_rank<GUARD>(e);
-        s_off[e] = rk >= 0 ? (uint32_t)(rk * BPC) : ((GUARD && w_is_pilot(e)) ? (uint32_t)(NE + 2) << 16 : (uint32_t)(NE + 1) << 16);
+        s_off[e] = (uint16_t)(rk >= 0 ? rk : ((GUARD && w_is_pilot(e)) ? D + 1 : D));
         const int r = e >> 5, c = e & 31;
         s_tw[r * kWPitch + c] = __ldg(a.tables->w1024 + ((r * c) & (kN - 1)));
     }
@@ -184,27 +215,19 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
     const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(buf + lane * kWPitch);
     const ulonglong2 *tw_row = reinterpret_cast<const ulonglong2 *>(s_tw + lane * kWPitch);
     const unsigned long long *lut = reinterpret_cast<const unsigned long long *>(s_lut) + (lane & 15);
-    const uint32_t *off_col = s_off + lane;
-    uint8_t *mybits = s_bits + (size_t)warp * kWTrsSlots * kWTrsBitsBuf;
+    const uint16_t *off_col = s_off + lane;
+    uint8_t *mybits = wtrs_smem + L::kBits + (size_t)warp * kWTrsBitsBuf;
+    uint8_t *mycar = wtrs_smem + L::kCar + (size_t)warp * kWTrsSlots * kWTrsCarBuf;
 
     float mx = 0.0f;
-    // carriers -> inverse FFT of symbol s into slot `slot` (prefix_block's IFFT, src/transmitter.rs:168-181)
-    auto transform = [&](int slot, int s, uint64_t ncar, uint32_t bit0) {
-        const uint8_t *bits = mybits + slot * kWTrsBitsBuf;
-        // carriers past the frame's last constellation symbol are padding (encode_block's exhausted iterator): the null entry
-        const long left = (long)ncar - (long)s * D;
-        const uint32_t lim_bits = left >= D ? 0xFFFFFFFFu : (uint32_t)(left > 0 ? left : 0) * BPC;
+    // carriers -> inverse FFT into tensor-memory slot `slot` (prefix_block's IFFT, src/transmitter.rs:168-181)
+    auto transform = [&](int slot) {
+        const uint8_t *car = mycar + slot * kWTrsCarBuf;
         cpx x[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             if (!w_row_used<GUARD>(j)) { x[j] = c_make(0.0f, 0.0f); continue; }
-            const uint32_t t = off_col[32 * j];
-            const uint32_t o = t & 0xFFFFu, bit = bit0 + o, bb = bit >> 3;
-            const uint32_t w = ((uint32_t)bits[bb] | ((uint32_t)bits[bb + 1] << 8)) >> (bit & 7u);
-            uint32_t idx = w & (uint32_t)(NE - 1);
-            if (o >= lim_bits) idx = NE;
-            if (t >> 16) idx = (t >> 16) - 1u;
-            x[j].v = lut[idx * 16];
+            x[j].v = lut[(uint32_t)car[off_col[32 * j]] * 16u];
         }
         dft32_p(x);
 #pragma unroll
@@ -257,64 +280,110 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
         float2 *out = a.iq + (size_t)stream * a.iq_stride;
         const uint32_t gthreads = (uint32_t)(C * kWTrsThreads), gt = (uint32_t)(rank * kWTrsThreads + tid);
         const uint32_t hw = a.iq_stride < (uint32_t)kHeadW ? a.iq_stride : (uint32_t)kHeadW;
-        for (uint32_t i = gt; i < hw; i += gthreads) {
-            float2 v = make_float2(0.0f, 0.0f);
-            if (fits) { v = __ldg(a.tables->head + i); v.x = v.x / fmx; v.y = v.y / fmx; }
-            out[i] = v;
+        for (uint32_t i0 = gt; i0 < hw; i0 += 4 * gthreads) {                  // four table loads in flight per thread
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + u * gthreads;
+                v[u] = make_float2(0.0f, 0.0f);
+                if (fits && i < hw) v[u] = __ldg(a.tables->head + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + u * gthreads;
+                if (i < hw) out[i] = make_float2(v[u].x / fmx, v[u].y / fmx);
+            }
         }
         const uint32_t z0 = fits ? frame_len : (uint32_t)kHeadW;
         for (uint32_t i = z0 + gt; i < a.iq_stride; i += gthreads) out[i] = make_float2(0.0f, 0.0f);
     };
     auto frame_max = [&](uint32_t stream) -> float {
-        while (ld_relaxed_gpu(a.stream_cnt + stream) < arrivals) __nanosleep(64);
+        while (ld_relaxed_gpu(a.stream_cnt + stream) < arrivals) __nanosleep(32);
         return fmaxf(__int_as_float((int)ld_relaxed_gpu(reinterpret_cast<const uint32_t *>(a.stream_max) + stream)), head_max);
     };
-    auto build = [&](const WTrsGeom &q, uint32_t stream, uint32_t (&bit0)[kWTrsSlots]) {
+    // the carrier bytes of this warp's symbols of frame `stream` (geometry q), symbol i -> carrier buffer slot0 + i
+    auto build = [&](const WTrsGeom &q, uint32_t stream, int slot0) {
         const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
         const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
 #pragma unroll
-        for (int i = 0; i < kWTrsSlots; i++) {
+        for (int i = 0; i < SPW; i++) {
             const int s = q.t0 + warp + kWTrsWarps * i;
-            bit0[i] = 0;
-            if (s < q.t1) bit0[i] = wtrs_build_bits<BPSB, FEC>(mybits + i * kWTrsBitsBuf, pay, pay_aligned, q.n, q.coded_len, s, s_enc14, lane);
+            if (s < q.t1) {
+                const uint32_t bit0 = wtrs_build_bits<BPSB, FEC>(mybits, pay, pay_aligned, q.n, q.coded_len, s, s_enc14, lane);
+                __syncwarp();
+                wtrs_unpack_carriers<BPC, D>(mycar + (slot0 + i) * kWTrsCarBuf, mybits, bit0, (long)q.ncar - (long)s * D, lane);
+                __syncwarp();
+            }
         }
-        __syncwarp();
+    };
+    // bring the payload bytes the next build() will read towards the SM (the build comes an iteration's work later)
+    auto prefetch = [&](const WTrsGeom &q, uint32_t stream) {
+        const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+#pragma unroll
+        for (int i = 0; i < SPW; i++) {
+            const int s = q.t0 + warp + kWTrsWarps * i;
+            if (s < q.t1) {
+                const uint32_t B0 = (uint32_t)s * BPSB, c0 = B0 < 16 ? 0 : B0 - 16;
+                const uint32_t pb = FEC ? 4 * (c0 / 7) + 16 * lane : c0 + 32 * lane;
+                constexpr uint32_t span = FEC ? (BPSB * 4) / 7 + 32 : BPSB + 32;
+                if ((FEC ? 16u : 32u) * lane < span && pb < q.n)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pay + pb));
+            }
+        }
     };
 
     uint32_t stream = (uint32_t)group;                                         // (the launcher guarantees group < n_streams)
-    WTrsGeom q = wtrs_geometry<BPC, D, FEC>(a, stream, rank);
-    uint32_t bit0[kWTrsSlots];
-    build(q, stream, bit0);
+    WTrsGeom q = wtrs_geometry<BPC, D, FEC, kWTrsWarps * SPW>(a, stream, rank);
+    build(q, stream, 0);
     bool have_prev = false, p_fits = false;
     int p_t0 = 0, p_t1 = 0;
     uint32_t p_stream = 0, p_flen = 0;
 
-    for (;;) {
+    for (int k = 0; ; k++) {
         if (rank == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = q.frame_len;
-        // ---- drain frame k-1, transform frame k -----------------------------------------------------------------------------
-        float p_fmx = 1.0f, p_scale = 0.0f;
-        if (have_prev) { p_fmx = frame_max(p_stream); p_scale = (1.0f / (float)kN) * (1.0f / p_fmx); }
-        tmem_wait_st();                                                        // the slots of frame k-1 were written an iteration ago
-        float2 *p_out = a.iq + (size_t)p_stream * a.iq_stride;
-        mx = 0.0f;
-#pragma unroll 1
-        for (int i = 0; i < kWTrsSlots; i++) {
-            const int ps = p_t0 + warp + kWTrsWarps * i, s = q.t0 + warp + kWTrsWarps * i;
-            if (have_prev && ps < p_t1) drain(i, ps, p_out, p_scale);
-            if (s < q.t1) transform(i, s, q.ncar, bit0[i]);
-        }
-        // ---- publish this warp's maximum of frame k, count the arrival -------------------------------------------------------
-        mx *= 1.0f / (float)kN;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-        if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
-        // ---- bit streams of frame k+1, head / zero fill of frame k-1 ---------------------------------------------------------
         const uint32_t next = stream + (uint32_t)G;
         const bool more = next < a.n_streams;
         WTrsGeom qn = q;
-        __syncwarp();                                                          // every lane has read its carriers of frame k
-        if (more) { qn = wtrs_geometry<BPC, D, FEC>(a, next, rank); build(qn, next, bit0); }
-        if (have_prev) write_head(p_stream, p_fits, p_flen, p_fmx);
+        if (more) { qn = wtrs_geometry<BPC, D, FEC, kWTrsWarps * SPW>(a, next, rank); prefetch(qn, next); }
+        float p_fmx = 1.0f;
+        mx = 0.0f;
+        if (DB) {
+            // ---- transform frame k into slot k & 1, publish, prepare frame k+1, THEN drain frame k-1 from the other slot -----
+            const int s = q.t0 + warp;
+            if (s < q.t1) transform(k & 1);
+            mx *= 1.0f / (float)kN;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+            if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
+            if (more) build(qn, next, (k + 1) & 1);
+            if (have_prev) {
+                p_fmx = frame_max(p_stream);
+                tmem_wait_st();
+                const int ps = p_t0 + warp;
+                if (ps < p_t1) drain((k + 1) & 1, ps, a.iq + (size_t)p_stream * a.iq_stride, (1.0f / (float)kN) * (1.0f / p_fmx));
+                write_head(p_stream, p_fits, p_flen, p_fmx);
+            }
+        } else {
+            // ---- drain frame k-1, transform frame k ---------------------------------------------------------------------------
+            float p_scale = 0.0f;
+            if (have_prev) { p_fmx = frame_max(p_stream); p_scale = (1.0f / (float)kN) * (1.0f / p_fmx); }
+            tmem_wait_st();                                                    // the slots of frame k-1 were written an iteration ago
+            float2 *p_out = a.iq + (size_t)p_stream * a.iq_stride;
+#pragma unroll 1
+            for (int i = 0; i < SPW; i++) {
+                const int ps = p_t0 + warp + kWTrsWarps * i, s = q.t0 + warp + kWTrsWarps * i;
+                if (have_prev && ps < p_t1) drain(i, ps, p_out, p_scale);
+                if (s < q.t1) transform(i);
+            }
+            mx *= 1.0f / (float)kN;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+            if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
+            // ---- carrier bytes of frame k+1, head / zero fill of frame k-1 (also the time the maximum of frame k needs to travel) ----
+            __syncwarp();                                                      // every lane has read its carriers of frame k
+            if (more) build(qn, next, 0);
+            if (have_prev) write_head(p_stream, p_fits, p_flen, p_fmx);
+        }
         have_prev = true; p_t0 = q.t0; p_t1 = q.t1; p_stream = stream; p_flen = q.frame_len; p_fits = q.fits;
         if (!more) break;
         stream = next;
@@ -325,10 +394,17 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
         const float p_fmx = frame_max(p_stream), p_scale = (1.0f / (float)kN) * (1.0f / p_fmx);
         tmem_wait_st();
         float2 *p_out = a.iq + (size_t)p_stream * a.iq_stride;
+        if (DB) {
+            // p_stream was frame number (streams of this group so far) - 1; its slot parity is tracked by have_prev's loop index:
+            // recomputed from the stream index
+            const int kk = (int)((p_stream - (uint32_t)group) / (uint32_t)G);
+            if (p_t0 + warp < p_t1) drain(kk & 1, p_t0 + warp, p_out, p_scale);
+        } else {
 #pragma unroll 1
-        for (int i = 0; i < kWTrsSlots; i++) {
-            const int ps = p_t0 + warp + kWTrsWarps * i;
-            if (ps < p_t1) drain(i, ps, p_out, p_scale);
+            for (int i = 0; i < SPW; i++) {
+                const int ps = p_t0 + warp + kWTrsWarps * i;
+                if (ps < p_t1) drain(i, ps, p_out, p_scale);
+            }
         }
         write_head(p_stream, p_fits, p_flen, p_fmx);
     }

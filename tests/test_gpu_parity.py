@@ -713,8 +713,9 @@ def test_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
     assert np.array_equal(iq, out["twopass"][0])            # the same values (an exact zero may carry the other sign: conj vs swap transform)
 
 
+@pytest.mark.parametrize("db", [0, 1])
 @pytest.mark.parametrize("mod,guard,fec", [(2, True, True), (2, False, False), (1, True, True), (0, False, True), (2, True, False)])
-def test_wide_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
+def test_wide_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec, db):
     """nfft = 1024: the one-pass TX kernel (frames resident in tensor memory, wide_tx_resident.cuh) forced for a ragged batch:
     every frame against the oracle's encode (src/transmitter.rs:11-58 scaled by 16, docs/SPEC.md 9), zero fill past the frame,
     frame lengths and (to rounding: the two kernels use different FFT factorisations) the two-pass kernel. Lengths include the
@@ -726,6 +727,7 @@ def test_wide_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
             longest // 2, longest - 1, longest] + [int(v) for v in rng.integers(0, longest + 1, 12)]
     pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
     out = {}
+    monkeypatch.setenv("OFDM_WTX_DB", str(db))          # 0: two symbols of a frame per warp; 1: one symbol of two frames in flight
     for path in ("resident", "twopass"):
         monkeypatch.setenv("OFDM_TX_PATH", path)
         eng = ob.Engine(cfg, 0)
