@@ -64,6 +64,7 @@ struct ofdm_engine {
     DevBuf sync_scratch;                // candidate list + counters of ofdm_sync_search
     DevBuf cap_base;                    // per-frame base / length of ofdm_rx_decode_capture
     DevBuf rs_tables;                   // RsTables, built on first use
+    DevBuf wtx_slots;                   // wide_tx_resident_kernel: one word per warp of a group and frame (frame maximum exchange)
     // host-mode staging
     DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
@@ -291,7 +292,7 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_wtables) cudaFree(h->d_wtables);
     DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
-                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base, &h->rs_tables };
+                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base, &h->rs_tables, &h->wtx_slots };
     for (DevBuf *b : bufs) b->release();
     for (void *p : h->pin) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -368,7 +369,11 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
                 const size_t smem = wide_tx_resident_smem(h->cfg);
                 if (h->smem_configured.insert((const void *)k).second)
                     CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                w.stream_cnt = d_cnt; w.group_ctas = C; w.n_groups = G;
+                // one flagged word per warp of a group and frame (the frame maximum travels through them), zeroed per call
+                const size_t slot_words = (size_t)n_streams * (size_t)C * (size_t)(wide_tx_resident_threads() / 32);
+                CU(h, h->wtx_slots.ensure(sizeof(uint32_t) * slot_words));
+                CU(h, cudaMemsetAsync(h->wtx_slots.p, 0, sizeof(uint32_t) * slot_words, st));
+                w.stream_cnt = h->wtx_slots.as<uint32_t>(); w.group_ctas = C; w.n_groups = G;
                 void *kargs[] = { (void *)&w };
                 CU(h, cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)(G * C)), dim3((unsigned)wide_tx_resident_threads()), kargs, smem, st));
                 h->launches++;

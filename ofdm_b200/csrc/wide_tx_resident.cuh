@@ -17,7 +17,7 @@
 // payload groups, docs/SPEC.md 3), looks the carriers up, transforms, and later drains its slot with coalesced 256-byte
 // row stores (cyclic prefix = the last 8 rows once more). Per frame k a warp runs:
 //   wait for the maximum of frame k-1 | 2 x { drain slot i of frame k-1 | transform its symbol i of frame k into slot i } |
-//   publish its maximum of frame k (atomicMax + arrival counter, fence-free as in tx_resident.cuh) |
+//   publish its maximum of frame k (one flagged word per warp, collected by the others in one L2 round trip) |
 //   bit streams of its symbols of frame k+1, its share of the head / zero fill of frame k-1
 // -- the last step is also the time the maximum of frame k needs to travel between the SMs of the group.
 #pragma once
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
         float2 *out = a.iq + (size_t)stream * a.iq_stride;
         const uint32_t gthreads = (uint32_t)(C * kWTrsThreads), gt = (uint32_t)(rank * kWTrsThreads + tid);
         const uint32_t hw = a.iq_stride < (uint32_t)kHeadW ? a.iq_stride : (uint32_t)kHeadW;
+        const float rfmx = 1.0f / fmx;
         for (uint32_t i0 = gt; i0 < hw; i0 += 4 * gthreads) {                  // four table loads in flight per thread
             float2 v[4];
 #pragma unroll
@@ -291,15 +292,39 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const uint32_t i = i0 + u * gthreads;
-                if (i < hw) out[i] = make_float2(v[u].x / fmx, v[u].y / fmx);
+                if (i < hw) out[i] = make_float2(v[u].x * rfmx, v[u].y * rfmx);
             }
         }
         const uint32_t z0 = fits ? frame_len : (uint32_t)kHeadW;
         for (uint32_t i = z0 + gt; i < a.iq_stride; i += gthreads) out[i] = make_float2(0.0f, 0.0f);
     };
+    // The frame maximum (normalize, src/transmitter.rs:183-194) travels through one 32-bit word per warp of the group,
+    // stream_cnt[stream][rank * 16 + warp] = float bits of the warp's maximum (>= 0) | 0x80000000 as the "written" flag
+    // (the array is zeroed before the launch): a plain store to publish, ONE round trip to the L2 to collect -- every lane
+    // loads two of the words, the warp votes on the flags and reduces the values (no atomics, no second dependent load).
+    const uint32_t n_words = arrivals;
+    auto publish_max = [&](uint32_t stream, float m) {
+        if (lane == 0)
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(a.stream_cnt + (size_t)stream * n_words + (uint32_t)(rank * kWTrsWarps + warp)),
+                         "r"(__float_as_uint(fmaxf(m, 0.0f)) | 0x80000000u) : "memory");
+    };
     auto frame_max = [&](uint32_t stream) -> float {
-        while (ld_relaxed_gpu(a.stream_cnt + stream) < arrivals) __nanosleep(32);
-        return fmaxf(__int_as_float((int)ld_relaxed_gpu(reinterpret_cast<const uint32_t *>(a.stream_max) + stream)), head_max);
+        const uint32_t *sl = a.stream_cnt + (size_t)stream * n_words;
+        float m;
+        for (;;) {
+            uint32_t all = 0x80000000u;
+            m = 0.0f;
+            for (uint32_t w = lane; w < n_words; w += 32) {
+                const uint32_t v = ld_relaxed_gpu(sl + w);
+                all &= v;
+                m = fmaxf(m, __uint_as_float(v & 0x7FFFFFFFu));
+            }
+            if (__all_sync(0xffffffffu, (all >> 31) != 0u)) break;
+            __nanosleep(32);
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+        return fmaxf(m, head_max);
     };
     // the carrier bytes of this warp's symbols of frame `stream` (geometry q), symbol i -> carrier buffer slot0 + i
     auto build = [&](const WTrsGeom &q, uint32_t stream, int slot0) {
@@ -354,7 +379,7 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
             mx *= 1.0f / (float)kN;
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-            if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
+            publish_max(stream, mx);
             if (more) build(qn, next, (k + 1) & 1);
             if (have_prev) {
                 p_fmx = frame_max(p_stream);
@@ -378,7 +403,7 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
             mx *= 1.0f / (float)kN;
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-            if (lane == 0) publish_max_and_arrive(a.stream_max + stream, __float_as_int(fmaxf(mx, 0.0f)), a.stream_cnt + stream);
+            publish_max(stream, mx);
             // ---- carrier bytes of frame k+1, head / zero fill of frame k-1 (also the time the maximum of frame k needs to travel) ----
             __syncwarp();                                                      // every lane has read its carriers of frame k
             if (more) build(qn, next, 0);
