@@ -47,6 +47,25 @@ template <int MOD> struct WTrsSmem {
     static constexpr size_t kTotal = kCar + (size_t)kWTrsWarps * kWTrsSlots * kWTrsCarBuf;
 };
 
+// a warp reads / writes one whole symbol slot: 32 lanes x 64 columns = its 64 registers (ONE tensor-memory access and one wait
+// instead of four of each)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, cpx (&x)[32])
+{
+    uint32_t r[64];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) x[i].v = (unsigned long long)r[2 * i] | ((unsigned long long)r[2 * i + 1] << 32);
+}
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const cpx (&x)[32])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};"
+                 :: "r"(taddr), "r"((uint32_t)x[0].v), "r"((uint32_t)(x[0].v >> 32)), "r"((uint32_t)x[1].v), "r"((uint32_t)(x[1].v >> 32)), "r"((uint32_t)x[2].v), "r"((uint32_t)(x[2].v >> 32)), "r"((uint32_t)x[3].v), "r"((uint32_t)(x[3].v >> 32)), "r"((uint32_t)x[4].v), "r"((uint32_t)(x[4].v >> 32)), "r"((uint32_t)x[5].v), "r"((uint32_t)(x[5].v >> 32)), "r"((uint32_t)x[6].v), "r"((uint32_t)(x[6].v >> 32)), "r"((uint32_t)x[7].v), "r"((uint32_t)(x[7].v >> 32)), "r"((uint32_t)x[8].v), "r"((uint32_t)(x[8].v >> 32)), "r"((uint32_t)x[9].v), "r"((uint32_t)(x[9].v >> 32)), "r"((uint32_t)x[10].v), "r"((uint32_t)(x[10].v >> 32)), "r"((uint32_t)x[11].v), "r"((uint32_t)(x[11].v >> 32)), "r"((uint32_t)x[12].v), "r"((uint32_t)(x[12].v >> 32)), "r"((uint32_t)x[13].v), "r"((uint32_t)(x[13].v >> 32)), "r"((uint32_t)x[14].v), "r"((uint32_t)(x[14].v >> 32)), "r"((uint32_t)x[15].v), "r"((uint32_t)(x[15].v >> 32)), "r"((uint32_t)x[16].v), "r"((uint32_t)(x[16].v >> 32)), "r"((uint32_t)x[17].v), "r"((uint32_t)(x[17].v >> 32)), "r"((uint32_t)x[18].v), "r"((uint32_t)(x[18].v >> 32)), "r"((uint32_t)x[19].v), "r"((uint32_t)(x[19].v >> 32)), "r"((uint32_t)x[20].v), "r"((uint32_t)(x[20].v >> 32)), "r"((uint32_t)x[21].v), "r"((uint32_t)(x[21].v >> 32)), "r"((uint32_t)x[22].v), "r"((uint32_t)(x[22].v >> 32)), "r"((uint32_t)x[23].v), "r"((uint32_t)(x[23].v >> 32)), "r"((uint32_t)x[24].v), "r"((uint32_t)(x[24].v >> 32)), "r"((uint32_t)x[25].v), "r"((uint32_t)(x[25].v >> 32)), "r"((uint32_t)x[26].v), "r"((uint32_t)(x[26].v >> 32)), "r"((uint32_t)x[27].v), "r"((uint32_t)(x[27].v >> 32)), "r"((uint32_t)x[28].v), "r"((uint32_t)(x[28].v >> 32)), "r"((uint32_t)x[29].v), "r"((uint32_t)(x[29].v >> 32)), "r"((uint32_t)x[30].v), "r"((uint32_t)(x[30].v >> 32)), "r"((uint32_t)x[31].v), "r"((uint32_t)(x[31].v >> 32))
+                 : "memory");
+}
+
 // this CTA's share of frame `stream`: symbols [t0, t1) of its S data symbols (an even split over the group)
 struct WTrsGeom {
     uint32_t n;
@@ -250,29 +269,19 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
             c_split(x[t2], re, im);                                            // the frame's sample is (re, -im) / 1024
             mx = fmaxf(mx, fmaxf(re, -im));
         }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            cpx y[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) y[i] = x[8 * c + i];
-            tmem_st16(taddr + (uint32_t)(64 * slot + 16 * c), y);
-        }
+        tmem_st64(taddr + (uint32_t)(64 * slot), x);
     };
     // drain a slot: scale, store with the cyclic prefix (prefix_block, src/transmitter.rs:168-181)
     auto drain = [&](int slot, int s, float2 *fout, float scale) {
         unsigned long long *sym = reinterpret_cast<unsigned long long *>(fout + (size_t)(10 + s) * kL) + lane;
         const cpx sc = c_make(scale, -scale);                                  // conj and scale in one
+        cpx y[32];
+        tmem_ld64(taddr + (uint32_t)(64 * slot), y);
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            cpx y[8];
-            tmem_ld16(taddr + (uint32_t)(64 * slot + 16 * c), y);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int t2 = 8 * c + i;
-                const unsigned long long v = c_mul2(y[i], sc).v;               // time index lane + 32 t2
-                sym[kCpW + 32 * t2] = v;
-                if (t2 >= 24) sym[32 * (t2 - 24)] = v;                         // cyclic prefix = last 256 samples
-            }
+        for (int t2 = 0; t2 < 32; t2++) {
+            const unsigned long long v = c_mul2(y[t2], sc).v;                  // time index lane + 32 t2
+            sym[kCpW + 32 * t2] = v;
+            if (t2 >= 24) sym[32 * (t2 - 24)] = v;                             // cyclic prefix = last 256 samples
         }
     };
     // frame head (lock | preamble x4 | training x5) and zero fill past the frame, spread over all threads of the group
