@@ -64,6 +64,8 @@ def build_engine(force: bool = False, verbose: bool = False, units=None) -> str:
         if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(d) for d in _unit_deps(unit)):
             return unit, 0, ""
         cmd = [nvcc, *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-c", "-o", obj, os.path.join(CSRC, unit + ".cu")]
+        if os.environ.get("OFDM_NVCC_EXTRA"):
+            cmd += os.environ["OFDM_NVCC_EXTRA"].split()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         r = subprocess.run(cmd, capture_output=True, text=True)

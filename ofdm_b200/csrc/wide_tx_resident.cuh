@@ -33,7 +33,8 @@ constexpr int kWTrsThreads = 32 * kWTrsWarps;
 constexpr int kWTrsSlots = 2;                                    // symbols per warp and frame (64 tensor-memory columns each)
 constexpr int kWTrsSyms = kWTrsWarps * kWTrsSlots;               // 32 symbols per CTA = all 512 columns
 constexpr int kWTrsBitsBuf = 832;                                // per warp: header 16 + 28 groups x 28 coded bytes (+ slack), multiple of 64
-constexpr int kWTrsCarBuf = 1024 + 64;                           // per slot: one byte per data carrier | null entry | pilot entry (+ slack)
+constexpr int kWTrsHeadPer = 6;                                  // head samples per thread held in shared memory (a group of 4 CTAs: 12 800 / 2048 = 6.25; the rest is read through the cache)
+constexpr int kWTrsCarBuf = 1024 + 16;                           // per slot: one byte per data carrier | null entry | pilot entry (+ slack)
 
 template <int MOD> struct WTrsSmem {
     static constexpr int NE = 1 << ModTraits<MOD>::kBpc;
@@ -44,7 +45,8 @@ template <int MOD> struct WTrsSmem {
     static constexpr size_t kEnc = kLut + sizeof(float2) * 16 * (NE + 2);                  // Hamming byte table (256 x u16), tensor-memory base address
     static constexpr size_t kBits = kEnc + 512 + 64;                                       // [warp][kWTrsBitsBuf]: coded bit stream of the symbol being prepared
     static constexpr size_t kCar = kBits + (size_t)kWTrsWarps * kWTrsBitsBuf;              // [warp][slot][kWTrsCarBuf]
-    static constexpr size_t kTotal = kCar + (size_t)kWTrsWarps * kWTrsSlots * kWTrsCarBuf;
+    static constexpr size_t kHead = kCar + (size_t)kWTrsWarps * kWTrsSlots * kWTrsCarBuf;  // [kWTrsHeadPer][thread]: this CTA's share of the frame head
+    static constexpr size_t kTotal = kHead + sizeof(float2) * kWTrsHeadPer * kWTrsThreads;
 };
 
 // a warp reads / writes one whole symbol slot: 32 lanes x 64 columns = its 64 registers (ONE tensor-memory access and one wait
@@ -285,18 +287,39 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
         }
     };
     // frame head (lock | preamble x4 | training x5) and zero fill past the frame, spread over all threads of the group
+    // A thread writes the same head samples of every frame: groups of >= 4 CTAs keep their share of the (un-normalised) head
+    // table in shared memory (no L2 round trip per frame), smaller groups read the table through the cache.
+    const uint32_t gthreads = (uint32_t)(C * kWTrsThreads), gt = (uint32_t)(rank * kWTrsThreads + tid);
+    const uint32_t hw = a.iq_stride < (uint32_t)kHeadW ? a.iq_stride : (uint32_t)kHeadW;
+    const bool head_cached = C >= 4;
+    float2 *s_head = reinterpret_cast<float2 *>(wtrs_smem + L::kHead) + tid;
+    if (head_cached) {
+#pragma unroll
+        for (int u = 0; u < kWTrsHeadPer; u++) {
+            const uint32_t i = gt + u * gthreads;
+            s_head[u * kWTrsThreads] = i < (uint32_t)kHeadW ? __ldg(a.tables->head + i) : make_float2(0.0f, 0.0f);
+        }
+    }
     auto write_head = [&](uint32_t stream, bool fits, uint32_t frame_len, float fmx) {
         float2 *out = a.iq + (size_t)stream * a.iq_stride;
-        const uint32_t gthreads = (uint32_t)(C * kWTrsThreads), gt = (uint32_t)(rank * kWTrsThreads + tid);
-        const uint32_t hw = a.iq_stride < (uint32_t)kHeadW ? a.iq_stride : (uint32_t)kHeadW;
-        const float rfmx = 1.0f / fmx;
-        for (uint32_t i0 = gt; i0 < hw; i0 += 4 * gthreads) {                  // four table loads in flight per thread
+        const float rfmx = fits ? 1.0f / fmx : 0.0f;                           // a frame that does not fit iq_stride comes back zeroed
+        uint32_t i0 = gt;
+        if (head_cached) {
+#pragma unroll
+            for (int u = 0; u < kWTrsHeadPer; u++) {
+                const uint32_t i = gt + u * gthreads;
+                const float2 v = s_head[u * kWTrsThreads];
+                if (i < hw) out[i] = make_float2(v.x * rfmx, v.y * rfmx);
+            }
+            i0 = gt + kWTrsHeadPer * gthreads;
+        }
+        for (; i0 < hw; i0 += 4 * gthreads) {                                  // four table loads in flight per thread
             float2 v[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const uint32_t i = i0 + u * gthreads;
                 v[u] = make_float2(0.0f, 0.0f);
-                if (fits && i < hw) v[u] = __ldg(a.tables->head + i);
+                if (i < hw) v[u] = __ldg(a.tables->head + i);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -329,6 +352,9 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
                 m = fmaxf(m, __uint_as_float(v & 0x7FFFFFFFu));
             }
             if (__all_sync(0xffffffffu, (all >> 31) != 0u)) break;
+#ifdef WTRS_EXPERIMENT_NO_WAIT
+            break;
+#endif
             __nanosleep(32);
         }
 #pragma unroll
@@ -361,7 +387,7 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
                 const uint32_t pb = FEC ? 4 * (c0 / 7) + 16 * lane : c0 + 32 * lane;
                 constexpr uint32_t span = FEC ? (BPSB * 4) / 7 + 32 : BPSB + 32;
                 if ((FEC ? 16u : 32u) * lane < span && pb < q.n)
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pay + pb));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(pay + pb));
             }
         }
     };

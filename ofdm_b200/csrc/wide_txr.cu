@@ -33,3 +33,4 @@ int wide_tx_resident_syms_per_cta(bool double_buffered) { return double_buffered
 int wide_tx_resident_threads() { return wide::kWTrsThreads; }
 
 }  // namespace ofdm
+static_assert(ofdm::wide::WTrsSmem<2>::kTotal <= 232448, "wide_tx_resident_kernel: dynamic shared memory of one CTA");
