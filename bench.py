@@ -443,8 +443,12 @@ def main():
         same = bool((out_host.to(dev) == wl.out).all().item())
         ceil = h2d_ceiling(torch, rx_host, dev, barrier)
         ceil = float(allreduce(torch.tensor([ceil], dtype=torch.float64, device=dev), "MIN").item())
-        h2d_rate = n_streams * iq_stride * 8 / dt / 1e9
-        e2e = {"value": round(job_samples / dt / 1e6, 1), "unit": "Msamples/s", "h2d_bytes_per_step": int(n_streams * iq_stride * 8 + n_streams * 4),
+        h2d_moved = int(eng.last_h2d_bytes)                    # what the engine really copied: the cyclic prefixes stay on the host
+        h2d_rate = h2d_moved / dt / 1e9
+        e2e = {"value": round(job_samples / dt / 1e6, 1), "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d_moved + n_streams * 4),
+               "host_capture_bytes_per_step": int(n_streams * iq_stride * 8),
+               "h2d_note": "head region of every stream, then -- once the acquisition has located the frame -- the useful nfft samples of each "
+                           "data symbol (2-D copies); the capture-equivalent rate is host_capture_bytes_per_step / ms_per_step",
                "d2h_bytes_per_step": int(n_streams * out_stride + n_streams * 8), "ms_per_step": round(dt * 1e3, 3),
                "decoded_gbit_per_s": round(job_streams * payload_len * 8 / dt / 1e9, 2),
                "h2d_gb_per_s_per_gpu": round(h2d_rate, 1), "h2d_ceiling_gb_per_s": round(ceil, 1),

@@ -272,6 +272,15 @@ int ofdm_profile_read(ofdm_engine *h, float *acquire_ms, float *decode_ms, uint3
 /* how many kernels this handle has launched so far (bench.py's gpu_launches) */
 uint64_t ofdm_kernel_launches(const ofdm_engine *h);
 
+/*
+ * Host -> device bytes the last ofdm_rx_decode_batch(OFDM_MEM_HOST) call moved (bench.py's e2e.h2d_bytes_per_step). With
+ * sync_window > 0 and captures much longer than the window the host path fetches the frame head region of every stream,
+ * lets the acquisition locate the frame, and then copies only the useful nfft samples of the data symbols the header asks
+ * for: the cyclic prefixes that `unprefix_block` (src/receiver.rs:104-118) discards never cross PCIe. Otherwise the whole
+ * capture is copied. OFDM_RX_FEED=full|skipcp in the environment pins one of the two for A/B measurements.
+ */
+uint64_t ofdm_last_h2d_bytes(const ofdm_engine *h);
+
 #ifdef __cplusplus
 }
 #endif

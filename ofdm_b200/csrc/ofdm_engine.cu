@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <set>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -66,9 +67,18 @@ struct ofdm_engine {
     DevBuf rs_tables;                   // RsTables, built on first use
     DevBuf wtx_slots;                   // wide_tx_resident_kernel: one word per warp of a group and frame (frame maximum exchange)
     // host-mode staging
+    DevBuf s_iq3, s_plan, s_moved;
     DevBuf s_iq, s_iq2, s_bytes, s_bytes2, s_len, s_len2, s_status, s_aux, s_points, s_h;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
+    // host path of ofdm_rx_decode_batch that leaves the cyclic prefixes on the host (rx_host_skip_cp)
+    cudaEvent_t ev_feed[3][3] = {};                 // per staging buffer: head copied, plan on the host, decode done
+    cudaStream_t feed_streams[4] = {};              // the per-stream 2-D copies of a chunk are spread over several streams (copy engines)
+    cudaEvent_t ev_lane[4] = {};
+    void *pin_plan = nullptr;                       // pinned: per stream (offset, data symbols to fetch), 3 chunks
+    size_t pin_plan_cap = 0;
+    uint64_t h2d_bytes_last = 0;                    // host -> device bytes of the last host-mode RX call
+    int rx_feed = 0;                                // 0 = automatic; OFDM_RX_FEED=full|skipcp|gather pins one (A/B measurements)
     int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
     int n_sm = 0;                       // multiprocessors of the device (grid of the persistent TX kernel)
     int tx_path = 0;                    // 0 = automatic; OFDM_TX_PATH=twopass|cluster|resident pins one (A/B measurements)
@@ -195,6 +205,7 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     h->bpc = cfg_bpc(cfg);
     h->dcar = cfg_dcar(cfg);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char *rf = getenv("OFDM_RX_FEED")) h->rx_feed = !strcmp(rf, "full") ? 1 : !strcmp(rf, "skipcp") ? 2 : !strcmp(rf, "gather") ? 3 : 0;
     if (const char *tp = getenv("OFDM_TX_PATH"))
         h->tx_path = !strcmp(tp, "twopass") ? 1 : !strcmp(tp, "cluster") ? 2 : !strcmp(tp, "resident") ? 3 : 0;
     h->bps_sym = h->bpc * h->dcar;
@@ -292,13 +303,16 @@ extern "C" void ofdm_engine_destroy(ofdm_engine *h)
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_wtables) cudaFree(h->d_wtables);
     DevBuf *bufs[] = { &h->state, &h->scratch_u32, &h->scratch_f32, &h->counters, &h->s_iq, &h->s_iq2, &h->s_bytes, &h->s_bytes2,
-                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base, &h->rs_tables, &h->wtx_slots };
+                       &h->s_len, &h->s_len2, &h->s_status, &h->s_aux, &h->s_points, &h->s_h, &h->sync_scratch, &h->cap_base, &h->rs_tables, &h->wtx_slots, &h->s_iq3, &h->s_plan, &h->s_moved };
     for (DevBuf *b : bufs) b->release();
     for (void *p : h->pin) if (p) cudaFreeHost(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) if (h->ev_feed[i][j]) cudaEventDestroy(h->ev_feed[i][j]);
+    if (h->pin_plan) cudaFreeHost(h->pin_plan);
+    for (int i = 0; i < 4; i++) { if (h->feed_streams[i]) cudaStreamDestroy(h->feed_streams[i]); if (h->ev_lane[i]) cudaEventDestroy(h->ev_lane[i]); }
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     delete h;
 }
@@ -518,8 +532,10 @@ extern "C" int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, cons
 static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples, uint32_t n_streams, uint32_t iq_stride,
                      uint32_t max_n_samples, uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
                      const ofdm_rx_diag *diag, cudaStream_t st, size_t state_offset = 0, size_t state_total = 0,
-                     const uint64_t *stream_base = nullptr)
+                     const uint64_t *stream_base = nullptr, int phase = 0)
 {
+    // phase: 0 = acquisition + decode; 1 = acquisition only, 2 = decode only (the host path runs them apart: the data symbols
+    // are fetched from the host only once the acquisition has said where they are)
     if (state_total < n_streams) state_total = n_streams;
     const size_t state_sz = h->wide ? sizeof(wide::StreamStateW) : sizeof(StreamState);
     if (state_offset == 0) CU(h, h->state.ensure(state_sz * state_total));
@@ -544,13 +560,12 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
         WDecodeKernel ka = wpick_acquire(h->cfg);
         if (h->smem_configured.insert((const void *)ka).second)
             CU(h, cudaFuncSetAttribute((const void *)ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide::wide_acquire_smem()));
-        ka<<<n_streams, wide::kThreads, wide::wide_acquire_smem(), st>>>(w);
+        if (phase != 2) { ka<<<n_streams, wide::kThreads, wide::wide_acquire_smem(), st>>>(w); h->launches += 1; }
         if (prof) CU(h, cudaEventRecord(pe[1], st));
-        h->launches += 1;
         uint32_t mxs = max_n_samples ? max_n_samples : iq_stride;
         if (mxs > iq_stride) mxs = iq_stride;
         const long S = ((long)mxs + wide::kL - 1) / wide::kL - 10;
-        if (S > 0) {
+        if (S > 0 && phase != 1) {
             uint32_t tiles = (uint32_t)((S + h->tile_shift + wide::kTileSymsW - 1) / wide::kTileSymsW);
             // several consecutive tiles per CTA (per-stream tables and the prefetch pipeline are reused), but keep >= ~8 waves
             // of CTAs (148 SMs x 2 CTAs) and split a stream's tiles evenly over its CTAs
@@ -586,13 +601,12 @@ static int rx_device(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samp
     AcquireKernel kacq = pick_acquire(h->cfg);
     if (h->smem_configured.insert((const void *)kacq).second)       // kAcq64Ctas CTAs x ~19 kB static smem must fit the carve-out
         CU(h, cudaFuncSetAttribute((const void *)kacq, cudaFuncAttributePreferredSharedMemoryCarveout, 80));
-    kacq<<<n_streams, kAcq64Threads, 0, st>>>(a);
+    if (phase != 2) { kacq<<<n_streams, kAcq64Threads, 0, st>>>(a); h->launches += 1; }
     if (prof) CU(h, cudaEventRecord(pe[1], st));
     uint32_t mx = max_n_samples ? max_n_samples : iq_stride;
     if (mx > iq_stride) mx = iq_stride;
     long rows = ((long)mx + 79) / 80, S = rows - 10;
-    h->launches += 1;
-    if (S > 0) {
+    if (S > 0 && phase != 1) {
         uint32_t tiles = (uint32_t)((S + h->tile_shift + kTileSyms - 1) / kTileSyms);
         // several consecutive tiles per CTA (lane constants and the prefetch pipeline are reused across them), but keep
         // >= ~32 waves of CTAs (148 SMs x 4 CTAs) so the tail stays small, and split a stream's tiles evenly over its CTAs
@@ -648,6 +662,219 @@ extern "C" int ofdm_profile_read(ofdm_engine *h, float *acquire_ms, float *decod
     return 0;
 }
 
+// per stream: where the acquisition put the frame and how many data symbols the header asks for (0 unless status OK)
+template <class State>
+__global__ void rx_plan_kernel(const State *__restrict__ state, uint32_t n, uint32_t *__restrict__ plan)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool ok = state[i].status == ST_OK;
+    plan[2 * i] = ok ? (uint32_t)state[i].offset : 0u;
+    plan[2 * i + 1] = ok ? state[i].n_syms : 0u;
+}
+
+// Pull the useful samples of the wanted data symbols of a chunk of streams straight out of (pinned, device-mapped) HOST memory:
+// the SMs issue the PCIe reads themselves -- thousands of 8-byte loads in flight, one 512-byte (nfft 64) row per two warp
+// requests -- so neither a copy-engine descriptor per stream nor a trip of the plan to the host is needed. Only samples
+// below n_samples exist (a last, cut-off symbol is fetched as far as it goes). blockIdx.y = stream, blockIdx.x strides its rows.
+template <int N>
+__global__ void __launch_bounds__(256) rx_gather_kernel(const float2 *__restrict__ host_iq, float2 *__restrict__ dev, const uint32_t *__restrict__ plan,
+                                                        const uint32_t *__restrict__ n_samples, uint32_t iq_stride, uint32_t head_len,
+                                                        unsigned long long *__restrict__ moved)
+{
+    constexpr uint32_t L = N + N / 4, CP = N / 4;
+    const uint32_t i = blockIdx.y;
+    const uint64_t off = plan[2 * i], want = plan[2 * i + 1], M = n_samples[i];
+    if (want == 0) return;
+    uint64_t r0 = head_len > off ? (head_len - off) / L : 0;                     // data symbols below r0 lie wholly inside the head copy
+    r0 = r0 > 10 ? r0 - 10 : 0;
+    if (r0 >= want) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                   // bytes this stream's CTAs pull (for e2e.h2d_bytes_per_step)
+        uint64_t r_full = M >= off + L ? (M - off) / L : 0;
+        r_full = r_full > 10 ? r_full - 10 : 0;
+        if (r_full > want) r_full = want;
+        uint64_t n = r_full > r0 ? (r_full - r0) * N : 0;
+        const uint64_t rp = r_full > r0 ? r_full : r0;
+        if (rp < want) { const uint64_t t = off + (10 + rp) * L + CP; if (t < M) n += M - t < N ? M - t : N; }
+        atomicAdd(moved, (unsigned long long)(n * sizeof(float2)));
+    }
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(host_iq + (size_t)i * iq_stride);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(dev + (size_t)i * iq_stride);
+    const uint64_t total = (want - r0) * N;
+    constexpr int U = 8;
+    for (uint64_t e0 = (uint64_t)blockIdx.x * (256 * U) + threadIdx.x; e0 < total; e0 += (uint64_t)gridDim.x * (256 * U)) {
+        unsigned long long v[U];
+        uint64_t idx[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t e = e0 + (uint64_t)u * 256;
+            idx[u] = off + (10 + r0 + e / N) * L + CP + (e % N);
+            v[u] = 0ull;
+            if (e < total && idx[u] < M) v[u] = src[idx[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (e0 + (uint64_t)u * 256 < total && idx[u] < M) dst[idx[u]] = v[u];
+    }
+}
+
+// Host path of ofdm_rx_decode_batch that never moves a cyclic prefix over PCIe. `unprefix_block` (src/receiver.rs:104-118)
+// throws the prefix of every data symbol away, and past the frame head the prefixes are a fifth of the capture -- but where
+// they are is only known after synchronisation. So per chunk of streams: (1) ONE 2-D copy brings the first
+// sync_window + 13 symbols of every stream (everything the acquisition can touch: search window, refinement, CFO rows,
+// training rows, header symbol); (2) the acquisition kernel runs on that, and (offset, data symbols wanted) of every stream
+// goes back to the host; (3) per stream ONE 2-D copy (width nfft, pitch nfft + cp samples) fetches the useful part of exactly
+// the data symbols the header asks for, to the very place they have in the capture -- the device image is the capture with
+// holes where the prefixes (and whatever follows the frame) would be, so the decode kernel runs on it unchanged; (4) decode,
+// payload bytes back on the third stream. The head copy of chunk c + 1 is queued before the symbol copies of chunk c, so the
+// copy engine is never idle while the host waits for an acquisition; three staging buffers rotate.
+static int rx_host_skip_cp(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples, uint32_t n_streams, uint32_t iq_stride, uint32_t mx,
+                           uint32_t head_len, uint8_t *out, uint32_t out_stride, const ofdm_rx_diag *dd, bool have_diag,
+                           uint32_t *d_ns, uint32_t *d_ol, const ofdm_fc32 *iq_mapped)
+{
+    // iq_mapped: device-side address of the (pinned) host capture, or NULL -- then step (3) is one 2-D copy per stream issued by
+    // the host after it has read the plan, instead of the gather kernel
+    cudaStream_t st = h->own_stream, cs = h->copy_stream, os = h->d2h_stream;
+    const size_t stream_bytes = (size_t)iq_stride * sizeof(float2);
+    const uint32_t L = (uint32_t)h->sym_len, N = (uint32_t)h->nfft, CP = L - N;
+    uint32_t chunk = (uint32_t)((128u << 20) / stream_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_streams) chunk = n_streams;
+    DevBuf *stage[3] = { &h->s_iq, &h->s_iq2, &h->s_iq3 };
+    for (DevBuf *b : stage) CU(h, b->ensure(chunk * stream_bytes));
+    CU(h, h->s_plan.ensure(3 * 2 * sizeof(uint32_t) * (size_t)chunk));
+    CU(h, h->s_moved.ensure(16));
+    CU(h, cudaMemsetAsync(h->s_moved.p, 0, 16, cs));
+    if (h->pin_plan_cap < 3 * 2 * sizeof(uint32_t) * (size_t)chunk) {
+        if (h->pin_plan) cudaFreeHost(h->pin_plan);
+    for (int i = 0; i < 4; i++) { if (h->feed_streams[i]) cudaStreamDestroy(h->feed_streams[i]); if (h->ev_lane[i]) cudaEventDestroy(h->ev_lane[i]); }
+        h->pin_plan = nullptr; h->pin_plan_cap = 0;
+        CU(h, cudaHostAlloc(&h->pin_plan, 3 * 2 * sizeof(uint32_t) * (size_t)chunk, cudaHostAllocDefault));
+        h->pin_plan_cap = 3 * 2 * sizeof(uint32_t) * (size_t)chunk;
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+        if (!h->ev_feed[i][j]) CU(h, cudaEventCreateWithFlags(&h->ev_feed[i][j], cudaEventDisableTiming));
+    const uint32_t n_chunks = (n_streams + chunk - 1) / chunk;
+    uint64_t moved = 0;
+    double submit_s = 0.0;
+    int n_lanes = 4;
+    if (const char *e = getenv("OFDM_RX_FEED_LANES")) { n_lanes = atoi(e); n_lanes = n_lanes < 1 ? 1 : (n_lanes > 4 ? 4 : n_lanes); }
+    for (int i = 0; i < n_lanes && !iq_mapped; i++) {
+        if (!h->feed_streams[i]) CU(h, cudaStreamCreateWithFlags(&h->feed_streams[i], cudaStreamNonBlocking));
+        if (!h->ev_lane[i]) CU(h, cudaEventCreateWithFlags(&h->ev_lane[i], cudaEventDisableTiming));
+    }
+
+    auto diag_at = [&](uint32_t s0) {
+        ofdm_rx_diag dc = *dd;
+        if (dc.offset) dc.offset += s0;
+        if (dc.f_delta) dc.f_delta += s0;
+        if (dc.n_data_syms) dc.n_data_syms += s0;
+        if (dc.h_k) dc.h_k += (size_t)s0 * h->nfft;
+        if (dc.points) dc.points += (size_t)s0 * dc.points_stride;
+        return dc;
+    };
+    // (1) + (2) of chunk c
+    auto feed_head = [&](uint32_t c) -> int {
+        const uint32_t s0 = c * chunk, ns = n_streams - s0 < chunk ? n_streams - s0 : chunk;
+        const int b = (int)(c % 3);
+        if (c >= 3) CU(h, cudaStreamWaitEvent(cs, h->ev_feed[b][2], 0));         // staging buffer free again (decode of chunk c - 3)
+        CU(h, cudaMemcpy2DAsync(stage[b]->p, stream_bytes, iq + (size_t)s0 * iq_stride, stream_bytes, (size_t)head_len * sizeof(float2), ns,
+                                cudaMemcpyHostToDevice, cs));
+        moved += (uint64_t)ns * head_len * sizeof(float2);
+        CU(h, cudaEventRecord(h->ev_feed[b][0], cs));
+        CU(h, cudaStreamWaitEvent(st, h->ev_feed[b][0], 0));
+        ofdm_rx_diag dc = diag_at(s0);
+        int rc = rx_device(h, stage[b]->as<ofdm_fc32>(), d_ns + s0, ns, iq_stride, mx, h->s_bytes.as<uint8_t>() + (size_t)s0 * out_stride,
+                           out_stride, d_ol + s0, h->s_status.as<int32_t>() + s0, have_diag ? &dc : nullptr, st, s0, n_streams, nullptr, 1);
+        if (rc) return rc;
+        uint32_t *d_plan = h->s_plan.as<uint32_t>() + (size_t)b * 2 * chunk;
+        if (h->wide) rx_plan_kernel<<<(ns + 127) / 128, 128, 0, st>>>(h->state.as<wide::StreamStateW>() + s0, ns, d_plan);
+        else rx_plan_kernel<<<(ns + 127) / 128, 128, 0, st>>>(h->state.as<StreamState>() + s0, ns, d_plan);
+        h->launches++;
+        CU(h, cudaMemcpyAsync(reinterpret_cast<uint32_t *>(h->pin_plan) + (size_t)b * 2 * chunk, d_plan, 2 * sizeof(uint32_t) * (size_t)ns, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaEventRecord(h->ev_feed[b][1], st));
+        return 0;
+    };
+    if (int rc = feed_head(0)) return rc;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t s0 = c * chunk, ns = n_streams - s0 < chunk ? n_streams - s0 : chunk;
+        const int b = (int)(c % 3);
+        if (c + 1 < n_chunks) { if (int rc = feed_head(c + 1)) return rc; }
+        if (iq_mapped) {
+            CU(h, cudaStreamWaitEvent(cs, h->ev_feed[b][1], 0));
+            const uint32_t *d_plan = h->s_plan.as<uint32_t>() + (size_t)b * 2 * chunk;
+            const float2 *src = reinterpret_cast<const float2 *>(iq_mapped) + (size_t)s0 * iq_stride;
+            const dim3 grid(8, ns);
+            if (h->wide) rx_gather_kernel<1024><<<grid, 256, 0, cs>>>(src, stage[b]->as<float2>(), d_plan, d_ns + s0, iq_stride, head_len, h->s_moved.as<unsigned long long>());
+            else rx_gather_kernel<64><<<grid, 256, 0, cs>>>(src, stage[b]->as<float2>(), d_plan, d_ns + s0, iq_stride, head_len, h->s_moved.as<unsigned long long>());
+            h->launches++;
+        } else
+            CU(h, cudaEventSynchronize(h->ev_feed[b][1]));
+        // (3) the useful samples of the data symbols that are not already inside the head copy
+        const uint32_t *plan = reinterpret_cast<const uint32_t *>(h->pin_plan) + (size_t)b * 2 * chunk;
+        if (!iq_mapped) {                                                        // the lanes start once the head copy (and the buffer) is theirs
+            CU(h, cudaEventRecord(h->ev_copied[b & 1], cs));
+            for (int l = 0; l < n_lanes; l++) CU(h, cudaStreamWaitEvent(h->feed_streams[l], h->ev_copied[b & 1], 0));
+        }
+        const auto t_sub0 = std::chrono::steady_clock::now();
+        for (uint32_t i = 0; i < ns && !iq_mapped; i++) {
+            cudaStream_t cs = h->feed_streams[i % (uint32_t)n_lanes];
+            const uint64_t off = plan[2 * i], want = plan[2 * i + 1], M = n_samples[s0 + i];
+            if (want == 0) continue;
+            uint64_t r0 = head_len > off ? (head_len - off) / L : 0;             // data symbols r < r0 - 10 lie wholly inside the head copy
+            r0 = r0 > 10 ? r0 - 10 : 0;
+            // symbol r is whole in the capture when off + (10 + r) L + L <= M ... only its useful part [CP, L) matters: off + (10 + r) L + L <= M
+            uint64_t r_full = M >= off + L ? (M - off) / L : 0;                  // rows (of L samples, counted from the offset) that are whole
+            r_full = r_full > 10 ? r_full - 10 : 0;
+            if (r_full > want) r_full = want;
+            const float2 *src = reinterpret_cast<const float2 *>(iq) + (size_t)(s0 + i) * iq_stride;
+            float2 *dst = stage[b]->as<float2>() + (size_t)i * iq_stride;
+            if (r_full > r0) {
+                const uint64_t t = off + (10 + r0) * L + CP;
+                CU(h, cudaMemcpy2DAsync(dst + t, (size_t)L * sizeof(float2), src + t, (size_t)L * sizeof(float2), (size_t)N * sizeof(float2), (size_t)(r_full - r0),
+                                        cudaMemcpyHostToDevice, cs));
+                moved += (r_full - r0) * N * sizeof(float2);
+            }
+            const uint64_t rp = r_full > r0 ? r_full : r0;                       // a last, cut-off symbol (zero-padded tail row, src/receiver.rs:206-210)
+            if (rp < want) {
+                const uint64_t t = off + (10 + rp) * L + CP;
+                if (t < M) {
+                    CU(h, cudaMemcpyAsync(dst + t, src + t, (size_t)(M - t) * sizeof(float2), cudaMemcpyHostToDevice, cs));
+                    moved += (M - t) * sizeof(float2);
+                }
+            }
+        }
+        submit_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sub0).count();
+        if (!iq_mapped)
+            for (int l = 0; l < n_lanes; l++) {
+                CU(h, cudaEventRecord(h->ev_lane[l], h->feed_streams[l]));
+                CU(h, cudaStreamWaitEvent(st, h->ev_lane[l], 0));
+                CU(h, cudaStreamWaitEvent(cs, h->ev_lane[l], 0));                // later head copies into this buffer come after its symbol copies
+            }
+        CU(h, cudaEventRecord(h->ev_copied[b & 1], cs));
+        CU(h, cudaStreamWaitEvent(st, h->ev_copied[b & 1], 0));
+        // (4) decode, payload bytes back
+        ofdm_rx_diag dc = diag_at(s0);
+        int rc = rx_device(h, stage[b]->as<ofdm_fc32>(), d_ns + s0, ns, iq_stride, mx, h->s_bytes.as<uint8_t>() + (size_t)s0 * out_stride,
+                           out_stride, d_ol + s0, h->s_status.as<int32_t>() + s0, have_diag ? &dc : nullptr, st, s0, n_streams, nullptr, 2);
+        if (rc) return rc;
+        CU(h, cudaEventRecord(h->ev_feed[b][2], st));
+        CU(h, cudaStreamWaitEvent(os, h->ev_feed[b][2], 0));
+        CU(h, cudaMemcpyAsync(out + (size_t)s0 * out_stride, h->s_bytes.as<uint8_t>() + (size_t)s0 * out_stride, (size_t)ns * out_stride, cudaMemcpyDeviceToHost, os));
+    }
+    if (getenv("OFDM_DEBUG_FEED")) fprintf(stderr, "[ofdm] skip-cp feed: %u chunks, host time in the 2-D copy submissions %.2f ms\n", n_chunks, submit_s * 1e3);
+    if (iq_mapped) {                                                           // what the gather kernels pulled (counted on the device)
+        unsigned long long pulled = 0;
+        CU(h, cudaMemcpyAsync(&pulled, h->s_moved.p, sizeof(pulled), cudaMemcpyDeviceToHost, cs));
+        CU(h, cudaStreamSynchronize(cs));
+        moved += pulled;
+    }
+    h->h2d_bytes_last = moved;
+    return 0;
+}
+
+extern "C" uint64_t ofdm_last_h2d_bytes(const ofdm_engine *h) { return h ? h->h2d_bytes_last : 0; }
+
 extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const uint32_t *n_samples,
                                     uint32_t n_streams, uint32_t iq_stride, uint32_t max_n_samples,
                                     uint8_t *out, uint32_t out_stride, uint32_t *out_len, int32_t *status,
@@ -696,9 +923,37 @@ extern "C" int ofdm_rx_decode_batch(ofdm_engine *h, const ofdm_fc32 *iq, const u
         }
     }
     CU(h, cudaMemcpyAsync(d_ns, n_samples, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyHostToDevice, st));
+    // Everything the acquisition can touch lies in the first sync_window + 13 symbols of a stream (docs/SPEC.md 4-5: lags
+    // below the window, refinement up to a fifth of a symbol later, 10 head rows, the header symbol). When that is a small part
+    // of the capture the data symbols are fetched WITHOUT their cyclic prefixes once the acquisition has located them.
+    const uint64_t head_len64 = (uint64_t)h->cfg.sync_window + 13ull * (uint64_t)h->sym_len;
+    // Measured (B200, PCIe 5 x16, 55 GB/s copy ceiling; profiles/r2_feed_ab.txt): the gather kernel pulls 46 GB/s, and the GPU
+    // fetches host memory in 128-byte lines -- an nfft = 64 symbol's 512 useful bytes at an arbitrary 8-byte alignment touch the
+    // same five lines as the whole 640-byte symbol, so nothing is saved there (6 753 vs 6 857 Msamples/s); 2-D copies per stream
+    // run at 40 GB/s (a copy-engine cost per copy, not host time: 1.1 us per submission). With nfft = 1024 (8 KB useful of
+    // 10 KB) the gather path wins: 7 022 vs 6 695 Msamples/s. So: automatic = gather for symbols of >= 4 KB, else the whole copy.
+    bool skip_cp = h->rx_feed != 1 && h->cfg.sync_window > 0 &&
+                   (h->rx_feed >= 2 ? head_len64 <= iq_stride : (4 * head_len64 <= iq_stride && (size_t)h->nfft * sizeof(float2) >= 4096));
+    // the gather kernel reads the capture in place: only pinned (device-mapped) host memory qualifies; a pageable capture is
+    // copied whole (automatic mode) or fetched with 2-D copies (OFDM_RX_FEED=skipcp)
+    const ofdm_fc32 *iq_mapped = nullptr;
+    if (skip_cp && h->rx_feed != 2) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, iq) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+            iq_mapped = reinterpret_cast<const ofdm_fc32 *>(pa.devicePointer);
+        else {
+            (void)cudaGetLastError();
+            skip_cp = false;
+        }
+    }
+    h->h2d_bytes_last = (uint64_t)n_streams * stream_bytes;
+    if (skip_cp) {
+        int rc = rx_host_skip_cp(h, iq, n_samples, n_streams, iq_stride, mx, (uint32_t)head_len64, out, out_stride, &dd, diag != nullptr, d_ns, d_ol, iq_mapped);
+        if (rc) return rc;
+    }
     DevBuf *stage[2] = { &h->s_iq, &h->s_iq2 };
     uint32_t ci = 0;
-    for (uint32_t s0 = 0; s0 < n_streams; s0 += chunk, ci++) {
+    for (uint32_t s0 = 0; s0 < n_streams && !skip_cp; s0 += chunk, ci++) {
         const uint32_t ns = n_streams - s0 < chunk ? n_streams - s0 : chunk;
         const int b = ci & 1;
         if (ci >= 2) CU(h, cudaStreamWaitEvent(cs, h->ev_done[b], 0));           // staging buffer free again

@@ -28,7 +28,7 @@ EXPORTS = [
     "ofdm_frame_data_syms", "ofdm_frame_len", "ofdm_max_payload", "ofdm_tx_encode_batch", "ofdm_rx_decode_batch",
     "ofdm_channel_apply_batch", "ofdm_ber_accumulate", "ofdm_kernel_launches", "ofdm_profile_begin", "ofdm_profile_read",
     "ofdm_sync_search", "ofdm_sync_counts", "ofdm_engine_reserve", "ofdm_rx_decode_capture", "ofdm_rx_decode_file",
-    "ofdm_stats_allreduce",
+    "ofdm_stats_allreduce", "ofdm_last_h2d_bytes",
     "ofdm_rs_encoded_len", "ofdm_rs_decoded_len", "ofdm_rs_encode_batch", "ofdm_rs_decode_batch",
 ]
 
@@ -128,6 +128,8 @@ def load_library(build: bool = False) -> C.CDLL:
     L.ofdm_rs_decode_batch.restype = i32
     L.ofdm_kernel_launches.argtypes = [vp]
     L.ofdm_kernel_launches.restype = u64
+    L.ofdm_last_h2d_bytes.argtypes = [vp]
+    L.ofdm_last_h2d_bytes.restype = u64
     _lib = L
     return L
 
@@ -248,6 +250,11 @@ class Engine:
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.ofdm_kernel_launches(self._h))
+
+    @property
+    def last_h2d_bytes(self) -> int:
+        """Host -> device bytes of the last host-mode rx_decode call (the cyclic prefixes may have stayed on the host)."""
+        return int(self.lib.ofdm_last_h2d_bytes(self._h))
 
     def profile_begin(self, max_calls: int):
         self._check(self.lib.ofdm_profile_begin(self._h, max_calls), "ofdm_profile_begin")

@@ -136,4 +136,5 @@ extern "C" {
     pub fn ofdm_profile_begin(h: *mut ofdm_engine, max_calls: u32) -> c_int;
     pub fn ofdm_profile_read(h: *mut ofdm_engine, acquire_ms: *mut f32, decode_ms: *mut f32, n_calls: *mut u32) -> c_int;
     pub fn ofdm_kernel_launches(h: *const ofdm_engine) -> u64;
+    pub fn ofdm_last_h2d_bytes(h: *const ofdm_engine) -> u64;
 }

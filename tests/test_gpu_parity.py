@@ -791,3 +791,69 @@ def test_tx_resident_kernel_is_the_large_batch_path(ob, oo):
         np.testing.assert_allclose(iq[i, : flen[i]], oo.tx(pays[i], ocfg), atol=2e-6)
     mx = np.maximum(iq.real.max(axis=1), iq.imag.max(axis=1))
     np.testing.assert_allclose(mx, 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("nfft", [64, 1024])
+def test_host_feed_without_cyclic_prefixes_matches_full_copy(ob, oo, monkeypatch, nfft):
+    """Host-mode rx_decode fetches the head region of every stream, locates the frame, and then copies only the useful nfft
+    samples of the data symbols the header asks for (rx_host_skip_cp: `unprefix_block`, src/receiver.rs:104-118, discards the
+    prefixes anyway). Same status / lengths / bytes / offset / f_delta / h_k / points as the whole-capture copy, and as the
+    oracle, on a ragged batch: frames of different lengths and lead-ins, a capture cut in the middle of a data symbol (zero-padded
+    tail row, src/receiver.rs:206-210), one cut inside the head, pure noise, noise after the frame; several chunks of streams."""
+    L = nfft + nfft // 4
+    win = 2048 if nfft == 64 else 4096
+    cfg = ob.Config(modulation=2, guard_bands=True, fec=True, sync_mode=ob.SYNC_SCHMIDL_COX, cfo_mode=ob.CFO_ANGLE_OF_SUM,
+                    phase_mode=ob.PHASE_ANGLE_OF_SUM, sync_window=win, nfft=nfft, cp=nfft // 4)
+    ocfg = oo.make_cfg(True, 2, True, oo.SYNC_SCHMIDL_COX, oo.CFO_ANGLE_OF_SUM, oo.PHASE_ANGLE_OF_SUM, win, nfft=nfft)
+    rng = np.random.default_rng(900 + nfft)
+    syms = [400, 399, 250, 1, 2, 120] if nfft == 64 else [62, 61, 12, 1, 2, 25]
+    lens = [cfg.max_payload(s) - int(rng.integers(0, 40)) for s in syms] + [0]
+    pays = [rng.integers(0, 256, max(n, 0), dtype=np.uint8).tobytes() for n in lens]
+    caps = []
+    for i, p in enumerate(pays):
+        tx = oo.tx(p, ocfg)
+        lead = int(rng.integers(0, win - 200))
+        c = oo.channel(tx, 45.0 if nfft == 64 else 60.0, 0.0015 / (nfft // 64), 1, 300 + i)
+        noise = lambda k: 1e-4 * (rng.standard_normal(k) + 1j * rng.standard_normal(k))
+        caps.append(np.concatenate([noise(lead), c, noise(int(rng.integers(0, 5 * L)))]))
+    caps.append(caps[0][: caps[0].size - 3 * L - L // 3])      # cut in the middle of a data symbol: the header asks for more than is there
+    caps.append(caps[1][: 7 * L])                              # cut inside the head
+    caps.append(1e-3 * (rng.standard_normal(20 * L) + 1j * rng.standard_normal(20 * L)))       # nothing there
+    reps = 70 if nfft == 64 else 24                            # > one 128 MB chunk of streams
+    import torch
+    pageable, ns = _batch(caps * reps)
+    pinned = torch.empty(pageable.shape, dtype=torch.complex64, pin_memory=True)   # the gather kernel reads the capture in place
+    batch = pinned.numpy()
+    batch[:] = pageable
+    assert 4 * (win + 13 * L) <= batch.shape[1] and batch.nbytes > (160 << 20)
+    res = {}
+    for feed in ("full", "skipcp", "gather", "", "pageable"):
+        if feed in ("", "pageable"):
+            monkeypatch.delenv("OFDM_RX_FEED", raising=False)
+        else:
+            monkeypatch.setenv("OFDM_RX_FEED", feed)
+        eng = ob.Engine(cfg, 0)
+        res[feed] = eng.rx_decode(pageable if feed == "pageable" else batch, ns, points=True)
+        res[feed].moved = eng.last_h2d_bytes
+        eng.close()
+    full, skip = res["full"], res["skipcp"]
+    assert full.moved == batch.nbytes and skip.moved < 0.9 * batch.nbytes
+    assert res["gather"].moved == skip.moved
+    # pinned capture: the automatic choice is the gather kernel for symbols of >= 4 KB (nfft 1024); with nfft 64 the 128-byte
+    # fetch granularity of host memory eats the saving (measured), so the capture is copied whole
+    assert res[""].moved == (skip.moved if nfft == 1024 else batch.nbytes)
+    assert res["pageable"].moved == batch.nbytes                                      # pageable capture: copied whole
+    for r in (skip, res["gather"], res[""], res["pageable"]):
+        assert np.array_equal(r.status, full.status) and np.array_equal(r.out_len, full.out_len)
+        assert np.array_equal(r.offset, full.offset) and np.array_equal(r.f_delta, full.f_delta)
+        assert np.array_equal(r.h_k, full.h_k) and np.array_equal(r.n_data_syms, full.n_data_syms)
+        assert r.data == full.data
+        assert np.array_equal(r.points, full.points)
+    for i, c in enumerate(caps):
+        ref = oo.decode(batch[i, : ns[i]].astype(np.complex128), ocfg, want_points=False)
+        assert ref.status == skip.status[i], (i, ref.status, skip.status[i])
+        if ref.status == 0:
+            assert ref.offset == skip.offset[i] and skip.data[i] == ref.data.tobytes()
+            if i < len(pays):
+                assert skip.data[i] == pays[i]
+    assert (full.status[: len(pays)] == 0).sum() >= len(pays) - 1 and full.status[len(pays) + 2] == ob.NO_SYNC
