@@ -447,8 +447,9 @@ def main():
         h2d_rate = h2d_moved / dt / 1e9
         e2e = {"value": round(job_samples / dt / 1e6, 1), "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d_moved + n_streams * 4),
                "host_capture_bytes_per_step": int(n_streams * iq_stride * 8),
-               "h2d_note": "head region of every stream, then -- once the acquisition has located the frame -- the useful nfft samples of each "
-                           "data symbol (2-D copies); the capture-equivalent rate is host_capture_bytes_per_step / ms_per_step",
+               "h2d_note": ("whole capture copied (chunks of streams, double-buffered)" if h2d_moved >= n_streams * iq_stride * 8 else
+                            "head region of every stream, then -- once the acquisition has located the frame -- only the useful nfft samples of "
+                            "each wanted data symbol, pulled from the pinned capture by a gather kernel: the cyclic prefixes stay on the host"),
                "d2h_bytes_per_step": int(n_streams * out_stride + n_streams * 8), "ms_per_step": round(dt * 1e3, 3),
                "decoded_gbit_per_s": round(job_streams * payload_len * 8 / dt / 1e9, 2),
                "h2d_gb_per_s_per_gpu": round(h2d_rate, 1), "h2d_ceiling_gb_per_s": round(ceil, 1),

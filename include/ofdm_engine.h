@@ -137,6 +137,9 @@ uint32_t ofdm_max_payload(const ofdm_cfg *cfg, uint32_t n_data_syms);     /* lar
  * itself for the ~ms it runs, and waits for them otherwise); a handful of frames, or frames too long for it, take the
  * cluster / two-pass kernels. The results are the same values whichever kernel runs. (Measurement aid, read once at
  * ofdm_engine_create: the environment variable OFDM_TX_PATH = twopass | cluster | resident pins one of them.)
+ * nfft = 1024 has the same two large-batch choices: wide_tx_resident_kernel (one pass, a symbol per warp, frames resident in
+ * tensor memory; from two frames per group of CTAs on) and the two-pass wide_tx_kernel; they agree to fp32 rounding (different
+ * FFT factorisations), each within 2e-6 of the oracle's `encode`.
  */
 int ofdm_tx_encode_batch(ofdm_engine *h, const uint8_t *payload, const uint32_t *payload_len,
                          uint32_t payload_stride, uint32_t n_streams,

@@ -5,7 +5,7 @@
 use std::{env, fs, path::PathBuf, process::Command};
 
 const UNITS: [&str; 13] = ["rx64_m0", "rx64_m1", "rx64_m2", "rx64", "tx64", "wide_rx_m0", "wide_rx_m1", "wide_rx_m2", "wide_rx",
-                           "wide_tx", "sync", "rs", "ofdm_engine"];
+                           "wide_tx", "wide_txr", "sync", "rs", "ofdm_engine"];
 
 fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
