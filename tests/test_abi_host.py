@@ -185,3 +185,17 @@ int main() {
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert out[0] == "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
     assert out[1:] == ["10719222850664546238", "14064965282130556830"]
+
+
+def test_rust_build_script_compiles_every_translation_unit():
+    """rust/ofdm-sys/build.rs (cannot be run here: no cargo) must list exactly the units ofdm_b200/_build.py links, with the
+    array length Rust's type needs -- a unit missing there is an undefined symbol at the maintainer's first `cargo build`."""
+    import re
+    from ofdm_b200 import _build
+    src = open(os.path.join(ROOT, "rust", "ofdm-sys", "build.rs")).read()
+    m = re.search(r"const UNITS: \[&str; (\d+)\] = \[(.*?)\];", src, re.S)
+    units = re.findall(r'"(\w+)"', m.group(2))
+    assert int(m.group(1)) == len(units)
+    assert sorted(units) == sorted(_build.UNITS)
+    for u in units:
+        assert os.path.exists(os.path.join(ROOT, "ofdm_b200", "csrc", u + ".cu"))
