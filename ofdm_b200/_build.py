@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-diag-suppress", "177",
 ]
 # one translation unit per kernel family (csrc/kernels.h) + the C ABI; compiled in parallel, linked into one library
-UNITS = ["rx64_m2", "wide_rx_m2", "rx64_m0", "rx64_m1", "wide_rx_m0", "wide_rx_m1", "wide_tx", "wide_txr", "tx64", "tx64r", "rx64", "wide_rx",
+UNITS = ["rx64_m2", "wide_rx_m2", "rx64_m0", "rx64_m1", "wide_rx_m0", "wide_rx_m1", "wide_tx", "wide_txr", "tx64", "tx64r", "tx64w", "rx64", "wide_rx",
          "rs", "sync", "ofdm_engine"]
 OBJ_DIR = os.path.join(_HERE, "build")
 

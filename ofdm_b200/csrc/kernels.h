@@ -42,6 +42,11 @@ TxKernel pick_tx_frame(const ofdm_cfg &c);      // one-pass cluster kernel
 // tx64r.cu
 TxKernel pick_tx_resident(const ofdm_cfg &c);   // one-pass persistent kernel, frames resident in tensor memory
 size_t tx_resident_smem(const ofdm_cfg &c);
+// tx64w.cu
+TxKernel pick_tx_warp(const ofdm_cfg &c);       // one-pass persistent kernel without CTA barriers in the frame loop (tx_warp.cuh)
+size_t tx_warp_smem(const ofdm_cfg &c);
+int tx_warp_syms_per_cta();
+int tx_warp_threads();
 ChanKernel channel_conv_fn();
 ChanKernel channel_noise_fn();
 BerKernel ber_fn();

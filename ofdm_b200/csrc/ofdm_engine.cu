@@ -81,7 +81,7 @@ struct ofdm_engine {
     int rx_feed = 0;                                // 0 = automatic; OFDM_RX_FEED=full|skipcp|gather pins one (A/B measurements)
     int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
     int n_sm = 0;                       // multiprocessors of the device (grid of the persistent TX kernel)
-    int tx_path = 0;                    // 0 = automatic; OFDM_TX_PATH=twopass|cluster|resident pins one (A/B measurements)
+    int tx_path = 0;                    // 0 = automatic; OFDM_TX_PATH=twopass|cluster|resident|warp pins one (A/B measurements)
     // per-kernel timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE): 3 events per call (start, after acquire, end)
     std::vector<cudaEvent_t> prof_ev;
     uint32_t prof_cap = 0, prof_n = 0;
@@ -207,7 +207,7 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char *rf = getenv("OFDM_RX_FEED")) h->rx_feed = !strcmp(rf, "full") ? 1 : !strcmp(rf, "skipcp") ? 2 : !strcmp(rf, "gather") ? 3 : 0;
     if (const char *tp = getenv("OFDM_TX_PATH"))
-        h->tx_path = !strcmp(tp, "twopass") ? 1 : !strcmp(tp, "cluster") ? 2 : !strcmp(tp, "resident") ? 3 : 0;
+        h->tx_path = !strcmp(tp, "twopass") ? 1 : !strcmp(tp, "cluster") ? 2 : !strcmp(tp, "resident") ? 3 : !strcmp(tp, "warp") ? 4 : 0;
     h->bps_sym = h->bpc * h->dcar;
     h->tile_shift = 0;
     if (cfg->fec) {                          // tile boundaries on Hamming byte boundaries: BPS*s == 128 (mod 14)
@@ -411,7 +411,31 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     // Large batches: ONE pass with the frames resident on chip (tx_resident.cuh). A frame is shared by a group of C persistent
     // CTAs (one per SM), its un-normalised symbols wait in tensor memory for the frame maximum, and the stores of frame k-1
     // overlap the transforms of frame k in every warp. C = the smallest group whose rings hold the longest frame iq_stride admits.
-    if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 3)) {
+    // ... second version of it (tx_warp.cuh): a warp owns 16 consecutive symbols and prepares their carrier bytes itself, the
+    // frame maximum travels through one flagged word per warp -- no CTA barrier in the frame loop.
+    if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 4)) {
+        const int per = tx_warp_syms_per_cta();
+        const int C = (int)((max_syms + per - 1) / per);
+        int G = C <= h->n_sm ? h->n_sm / C : 0;
+        if (G > 0 && (uint32_t)G > n_streams) G = (int)n_streams;
+        if (G > 0 && (h->tx_path == 4 || n_streams >= 2u * (uint32_t)(h->n_sm / C))) {
+            TxKernel k = pick_tx_warp(h->cfg);
+            const size_t smem = tx_warp_smem(h->cfg);
+            if (h->smem_configured.insert((const void *)k).second)
+                CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const size_t slot_words = (size_t)n_streams * (size_t)C * (size_t)(tx_warp_threads() / 32);
+            CU(h, h->wtx_slots.ensure(sizeof(uint32_t) * slot_words));
+            CU(h, cudaMemsetAsync(h->wtx_slots.p, 0, sizeof(uint32_t) * slot_words, st));
+            a.stream_cnt = h->wtx_slots.as<uint32_t>(); a.group_ctas = C; a.n_groups = G;
+            void *kargs[] = { (void *)&a };
+            CU(h, cudaLaunchCooperativeKernel((const void *)k, dim3((unsigned)(G * C)), dim3((unsigned)tx_warp_threads()), kargs, smem, st));
+            h->launches++;
+            CU(h, cudaGetLastError());
+            if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        }
+    }
+    if (max_syms > 0 && h->n_sm > 0 && h->tx_path == 3) {
         const int W = kTrsWarpsPerCta;                                        // warps per CTA; 32 / W CTAs per SM
         const int chunk_max = 7 * ((16 * W) / 7);
         const int C = (int)((max_syms + h->tile_shift + chunk_max - 1) / chunk_max);

@@ -101,12 +101,14 @@ __device__ __forceinline__ WTrsGeom wtrs_geometry(const WideTxArgs &a, uint32_t 
 // stream (7 coded bytes = 8 nibbles = 4 payload bytes); lane u encodes payload bytes [16 u, 16 u + 16) into 28 coded bytes.
 template <int BPSB, bool FEC>
 __device__ __forceinline__ uint32_t wtrs_build_bits(uint8_t *bits, const uint8_t *__restrict__ pay, bool pay_aligned, uint32_t n, uint64_t coded_len,
-                                                    int s, const uint16_t *s_enc14, int lane)
+                                                    uint32_t B0, const uint16_t *s_enc14, int lane)
 {
-    const uint32_t B0 = (uint32_t)s * BPSB;
+    // B0 = first stream byte wanted
     constexpr uint32_t nbyte = BPSB + 2;
     if (FEC) {
-        const uint32_t hdr = B0 < 16 ? 16 - B0 : 0;                  // header bytes inside this symbol (symbol 0 only: BPSB >= 96)
+        const uint32_t hdr = B0 < 16 ? 16 - B0 : 0;                  // header bytes inside this span
+        const uint32_t pad = (0u - hdr) & 3u;                        // keeps the 28-byte groups behind them on 4-byte boundaries
+        bits += pad;
         if ((uint32_t)lane < hdr) bits[lane] = (uint8_t)(B0 + lane < 8 ? (uint32_t)(coded_len >> (8 * (B0 + lane))) & 255u : 0u);
         const uint32_t c0 = B0 + hdr - 16;                           // first coded byte of the symbol
         const uint32_t u0 = c0 / 7, skip = c0 - 7 * u0;
@@ -137,7 +139,7 @@ __device__ __forceinline__ uint32_t wtrs_build_bits(uint8_t *bits, const uint8_t
             dst[5] = (uint32_t)(w[2] >> 48) | ((uint32_t)w[3] << 8);
             dst[6] = (uint32_t)(w[3] >> 24);
         }
-        return 8u * (hdr ? 0u : skip);
+        return 8u * (hdr ? pad : skip);
     } else {
         for (uint32_t b = lane; b < nbyte; b += 32) {                // header, then the payload bytes as they are (src/transmitter.rs:37-47)
             const uint32_t B = B0 + b;
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
         for (int i = 0; i < SPW; i++) {
             const int s = q.t0 + warp + kWTrsWarps * i;
             if (s < q.t1) {
-                const uint32_t bit0 = wtrs_build_bits<BPSB, FEC>(mybits, pay, pay_aligned, q.n, q.coded_len, s, s_enc14, lane);
+                const uint32_t bit0 = wtrs_build_bits<BPSB, FEC>(mybits, pay, pay_aligned, q.n, q.coded_len, (uint32_t)s * BPSB, s_enc14, lane);
                 __syncwarp();
                 wtrs_unpack_carriers<BPC, D>(mycar + (slot0 + i) * kWTrsCarBuf, mybits, bit0, (long)q.ncar - (long)s * D, lane);
                 __syncwarp();

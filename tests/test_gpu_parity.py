@@ -697,20 +697,23 @@ def test_tx_resident_kernel_parity(ob, oo, monkeypatch, mod, guard, fec):
     lens = [0, 1, 2, 15, 16, 17, 100, 333, 1000, longest // 3, longest // 2, longest - 1, longest] + [int(v) for v in rng.integers(0, longest + 1, 40)]
     pays = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
     out = {}
-    for path in ("resident", "twopass"):
+    for path in ("resident", "warp", "twopass"):
         monkeypatch.setenv("OFDM_TX_PATH", path)
         eng = ob.Engine(cfg, 0)
+        l0 = eng.kernel_launches
         out[path] = eng.tx_encode(pays)
+        assert eng.kernel_launches - l0 == (2 if path == "twopass" else 1)
         eng.close()
-    iq, flen = out["resident"]
     ocfg = oo.make_cfg(guard, mod, fec, 0, 0, 0, 0)
-    for i, p in enumerate(pays):
-        ref = oo.tx(p, ocfg)
-        assert ref.size == flen[i]
-        np.testing.assert_allclose(iq[i, : flen[i]], ref, atol=2e-6)
-        assert not iq[i, flen[i]:].any()
-    assert np.array_equal(flen, out["twopass"][1])
-    assert np.array_equal(iq, out["twopass"][0])            # the same values (an exact zero may carry the other sign: conj vs swap transform)
+    for path in ("resident", "warp"):                       # "warp": the barrier-free second version (tx_warp.cuh), the large-batch default
+        iq, flen = out[path]
+        for i, p in enumerate(pays):
+            ref = oo.tx(p, ocfg)
+            assert ref.size == flen[i]
+            np.testing.assert_allclose(iq[i, : flen[i]], ref, atol=2e-6)
+            assert not iq[i, flen[i]:].any()
+        assert np.array_equal(flen, out["twopass"][1])
+        assert np.array_equal(iq, out["twopass"][0])        # the same values (an exact zero may carry the other sign: conj vs swap transform)
 
 
 @pytest.mark.parametrize("db", [0, 1])
