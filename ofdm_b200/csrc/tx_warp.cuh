@@ -202,32 +202,38 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
         if ((FEC ? 16u : 32u) * lane < span && pb < q.n) asm volatile("prefetch.global.L1 [%0];" :: "l"(pay + pb));
     };
 
+    // Only (first symbol of the warp, end of the CTA's chunk, frame length, fits) of a frame live across the loop: with 1024
+    // threads a thread has 64 registers, and the rest of the geometry is a few integer operations away when it is needed.
     uint32_t stream = (uint32_t)group;                                         // (the launcher guarantees group < n_streams)
-    TwGeom q = tw_geometry<BPC, D, FEC>(a, stream, rank);
-    build(q, stream);
+    int first, t1;
+    uint32_t flen;
+    bool fits;
+    {
+        const TwGeom q0 = tw_geometry<BPC, D, FEC>(a, stream, rank);
+        build(q0, stream);
+        first = q0.t0 + kTwWarpSyms * warp; t1 = q0.t1; flen = q0.frame_len; fits = q0.fits;
+    }
     bool have_prev = false, p_fits = false;
     int p_first = 0, p_t1 = 0;
     uint32_t p_stream = 0, p_flen = 0;
 
     for (;;) {
-        if (rank == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = q.frame_len;
+        if (rank == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = flen;
         const uint32_t next = stream + (uint32_t)G;
         const bool more = next < a.n_streams;
-        TwGeom qn = q;
-        if (more) { qn = tw_geometry<BPC, D, FEC>(a, next, rank); prefetch(qn, next); }
+        if (more) prefetch(tw_geometry<BPC, D, FEC>(a, next, rank), next);
         // ---- drain frame k-1, transform frame k -------------------------------------------------------------------------------
         float p_fmx = 1.0f, p_scale = 0.0f;
         if (have_prev) { p_fmx = frame_max(p_stream); p_scale = (1.0f / 64.0f) * (1.0f / p_fmx); }
         tmem_wait_st();                                                        // the slots of frame k-1 were written an iteration ago
         float2 *p_out = a.iq + (size_t)p_stream * a.iq_stride;
-        const int first = q.t0 + kTwWarpSyms * warp;
         float mx = 0.0f;
 #pragma unroll 1
         for (int it = 0; it < 4; it++) {
             if (have_prev && p_first + 4 * it < p_t1) drain(it, p_first, p_t1, p_out, p_scale);
-            if (first + 4 * it < q.t1) {
+            if (first + 4 * it < t1) {
                 const int sl = 4 * it + g;                                     // symbol inside the warp's span
-                const bool valid = first + sl < q.t1;
+                const bool valid = first + sl < t1;
                 const uint8_t *rowp = car + (valid ? sl : 0) * D;
                 uint32_t idx[8];
 #pragma unroll
@@ -262,12 +268,15 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
         publish_max(stream, mx);
         // ---- carrier bytes of frame k+1, head / zero fill of frame k-1 (also the time the maximum of frame k needs to travel) -------
         __syncwarp();                                                          // every lane has read its carriers of frame k
-        if (more) build(qn, next);
         if (have_prev) write_head(p_stream, p_fits, p_flen, p_fmx);
-        have_prev = true; p_first = first; p_t1 = q.t1; p_stream = stream; p_flen = q.frame_len; p_fits = q.fits;
+        have_prev = true; p_first = first; p_t1 = t1; p_stream = stream; p_flen = flen; p_fits = fits;
         if (!more) break;
+        {
+            const TwGeom qn = tw_geometry<BPC, D, FEC>(a, next, rank);
+            build(qn, next);
+            first = qn.t0 + kTwWarpSyms * warp; t1 = qn.t1; flen = qn.frame_len; fits = qn.fits;
+        }
         stream = next;
-        q = qn;
     }
     // ---- the group's last frame ---------------------------------------------------------------------------------------------
     {
