@@ -423,7 +423,7 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
             const size_t smem = tx_warp_smem(h->cfg);
             if (h->smem_configured.insert((const void *)k).second)
                 CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const size_t slot_words = (size_t)n_streams * (size_t)C * (size_t)(tx_warp_threads() / 32);
+            const size_t slot_words = (size_t)n_streams * (size_t)C;              // one flagged word per CTA of a group and frame
             CU(h, h->wtx_slots.ensure(sizeof(uint32_t) * slot_words));
             CU(h, cudaMemsetAsync(h->wtx_slots.p, 0, sizeof(uint32_t) * slot_words, st));
             a.stream_cnt = h->wtx_slots.as<uint32_t>(); a.group_ctas = C; a.n_groups = G;

@@ -30,7 +30,7 @@ template <int MOD> struct TwSmem {
     static constexpr size_t kTr = 0;                                                         // [warp][kTrWarp]: transpose scratch
     static constexpr size_t kLut = kTr + sizeof(float2) * kTwWarps * kTrWarp;                // [entry][lane & 15] conjugated constellation, null, pilot
     static constexpr size_t kEnc = kLut + sizeof(float2) * 16 * (NE + 2);                    // Hamming byte table (256 x u16), tensor-memory base address
-    static constexpr size_t kBits = kEnc + 512 + 64;                                         // [warp][kWTrsBitsBuf]: coded bit stream being prepared
+    static constexpr size_t kBits = kEnc + 512 + 16 + 256 + 48;                              // (tensor-memory address, arrival counters, warp maxima) | [warp][kWTrsBitsBuf]: coded bit stream being prepared
     static constexpr size_t kCar = kBits + (size_t)kTwWarps * wide::kWTrsBitsBuf;            // [warp][kTwCarBuf]
     static constexpr size_t kTotal = kCar + (size_t)kTwWarps * kTwCarBuf;
 };
@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     const int C = a.group_ctas, G = a.n_groups;
     const int group = (int)blockIdx.x / C, rank = (int)blockIdx.x - group * C;
-    const uint32_t n_words = (uint32_t)(C * kTwWarps);                          // per frame: one flagged word per warp of the group
 
     // ---- set-up: tables, tensor memory ------------------------------------------------------------------------------------
     for (int e = tid; e < 16 * (NE + 2); e += kTwThreads) {                     // conjugated constellation (conj . FFT . conj), null, pilot
@@ -99,6 +98,7 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
         s_lut[e] = make_float2(re, -im);
     }
     if (FEC && tid < 256) s_enc14[tid] = (uint16_t)(ham74_encode_nibble(tid & 15) | (ham74_encode_nibble(tid >> 4) << 7));
+    if (tid < 2) reinterpret_cast<uint32_t *>(tw_smem + L::kEnc + 512 + 8)[tid] = 0;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_addr(s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -158,10 +158,31 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
         const uint32_t z0 = fits ? frame_len : (uint32_t)(kHeadSyms * kSym);
         for (uint32_t i = z0 + gt; i < a.iq_stride; i += gthreads) out[i] = make_float2(0.0f, 0.0f);
     };
-    auto publish_max = [&](uint32_t stream, float m) {
-        if (lane == 0)
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(a.stream_cnt + (size_t)stream * n_words + (uint32_t)(rank * kTwWarps + warp)),
-                         "r"(__float_as_uint(fmaxf(m, 0.0f)) | 0x80000000u) : "memory");
+    // Frame maximum (normalize, src/transmitter.rs:183-194), two levels. Inside the CTA: every warp drops its maximum into shared
+    // memory and counts itself (shared-memory atomic); the LAST warp of a frame reduces the 32 values and publishes ONE flagged
+    // word for the CTA (float bits | 0x80000000; the array is zeroed before the launch). Between the CTAs of the group: a poll is
+    // one load by lane r < C of CTA r's word, a vote on the flags and a warp maximum -- a quarter of the instructions and of the
+    // L2 requests of polling one word per warp, which matters here: up to 31 spinning warps share the schedulers with the working ones.
+    float *s_wmax = reinterpret_cast<float *>(tw_smem + L::kEnc + 512 + 16);     // [2][32] (frame parity, warp)
+    uint32_t *s_arrived = reinterpret_cast<uint32_t *>(tw_smem + L::kEnc + 512 + 8);   // [2]
+    const uint32_t n_words = (uint32_t)C;
+    auto publish_max = [&](uint32_t stream, float m, int parity) {
+        if (lane == 0) s_wmax[32 * parity + warp] = fmaxf(m, 0.0f);
+        __syncwarp();
+        uint32_t seen = 0;
+        if (lane == 0) { __threadfence_block(); seen = atomicAdd(s_arrived + parity, 1u); }
+        seen = __shfl_sync(0xffffffffu, seen, 0);
+        if (seen == (uint32_t)(kTwWarps - 1)) {                                  // the CTA's last warp of this frame
+            __threadfence_block();
+            float v = s_wmax[32 * parity + lane];
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, sft));
+            if (lane == 0) {
+                s_arrived[parity] = 0;                                           // (parity is reused two frames later, after everybody has collected this one)
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(a.stream_cnt + (size_t)stream * n_words + (uint32_t)rank),
+                             "r"(__float_as_uint(v) | 0x80000000u) : "memory");
+            }
+        }
     };
     auto frame_max = [&](uint32_t stream) -> float {
         const uint32_t *sl = a.stream_cnt + (size_t)stream * n_words;
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
                 m = fmaxf(m, __uint_as_float(v & 0x7FFFFFFFu));
             }
             if (__all_sync(0xffffffffu, (all >> 31) != 0u)) break;
-            __nanosleep(32);
+            __nanosleep(64);
         }
 #pragma unroll
         for (int sft = 16; sft >= 1; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
@@ -217,7 +238,7 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
     int p_first = 0, p_t1 = 0;
     uint32_t p_stream = 0, p_flen = 0;
 
-    for (;;) {
+    for (int k = 0; ; k++) {
         if (rank == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = flen;
         const uint32_t next = stream + (uint32_t)G;
         const bool more = next < a.n_streams;
@@ -265,7 +286,7 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_warp_kernel(const TxArgs a)
         mx *= 1.0f / 64.0f;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-        publish_max(stream, mx);
+        publish_max(stream, mx, k & 1);
         // ---- carrier bytes of frame k+1, head / zero fill of frame k-1 (also the time the maximum of frame k needs to travel) -------
         __syncwarp();                                                          // every lane has read its carriers of frame k
         if (have_prev) write_head(p_stream, p_fits, p_flen, p_fmx);
