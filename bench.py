@@ -790,7 +790,7 @@ def tx_bench(args, rank, local_rank, world, steps=None):
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": f"tx_{n}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}"), "streams_per_gpu": n, "nfft": NFFT, "data_syms_per_frame": S, "frame_samples": frame_len,
                                  "payload_bytes": plen_b, "l2": "output (%.2f GB) larger than L2" % (8 * samples / 1e9)},
-                      "roofline": {"bound": "hbm", "kernel": (("wide_tx_resident_kernel" if NFFT == 1024 else "tx_resident_kernel") + " (one pass, frames resident in tensor memory)") if launches == steps else ("wide_tx_kernel" if NFFT == 1024 else "tx_tile_kernel") + " (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
+                      "roofline": {"bound": "hbm", "kernel": (("wide_tx_resident_kernel" if NFFT == 1024 else ("tx_resident_kernel" if os.environ.get("OFDM_TX_PATH") == "resident" else "tx_warp_kernel")) + " (one pass, frames resident in tensor memory)") if launches == steps else ("wide_tx_kernel" if NFFT == 1024 else "tx_tile_kernel") + " (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
                                    "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": read_traffic(f"tx_{n}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}")),
                                    "peak_source": src, "algorithmic_bytes_per_launch": by, "kernel_ms": round(ms, 4)},
                       "max_component": round(mx, 6), "frames_ok": frames_ok, "frames_match_oracle_on_sample": oracle_ok,
