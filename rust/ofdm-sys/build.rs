@@ -4,7 +4,7 @@
 // there; the identical C ABI is exercised through C++ (ofdm_b200/host) and Python ctypes (ofdm_b200/engine.py).
 use std::{env, fs, path::PathBuf, process::Command};
 
-const UNITS: [&str; 15] = ["rx64_m0", "rx64_m1", "rx64_m2", "rx64", "tx64", "wide_rx_m0", "wide_rx_m1", "wide_rx_m2", "wide_rx", "wide_tx", "wide_txr", "tx64r", "sync", "rs", "ofdm_engine"];
+const UNITS: [&str; 16] = ["rx64_m0", "rx64_m1", "rx64_m2", "rx64", "tx64", "wide_rx_m0", "wide_rx_m1", "wide_rx_m2", "wide_rx", "wide_tx", "wide_txr", "tx64r", "tx64w", "sync", "rs", "ofdm_engine"];
 
 fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
