@@ -1110,7 +1110,7 @@ static int sync_plan(ofdm_engine *h, const ofdm_fc32 *iq, uint64_t n, ofdm_peak 
     a.tile_lags = h->wide ? (p.tma ? (uint32_t)kWTD : (uint32_t)kWScanD) : (uint32_t)kScanD;
     a.holdoff = (uint32_t)(10 * LS);
     a.prefetch_ahead = 0;
-    if (h->wide && p.tma) a.prefetch_ahead = 3u * (uint32_t)h->n_sm;      // the tile that follows in the same SM slot (3 CTAs per SM)
+    if (h->wide && p.tma) a.prefetch_ahead = (uint32_t)kWTCtasPerSm * (uint32_t)h->n_sm;   // the tile that follows in the same SM slot
     const uint64_t lags = n >= 2 * LS ? n - 2 * LS + 1 : 0;
     const uint64_t T = (lags + a.tile_lags - 1) / a.tile_lags;
     if (T > 0xFFFFFFFFull) ENG_FAIL(h, OFDM_E_INVALID, "sync: capture too long");

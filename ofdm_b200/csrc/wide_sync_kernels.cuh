@@ -171,16 +171,23 @@ __global__ void __launch_bounds__(kWScanThreads) wide_scan_kernel(const SyncArgs
 // 256-row boxes = 768 rows: 447 rows of lags + 2 x 160 halo rows + the row that feeds above(d - 1). No register round trip,
 // no shared stores, and a thread reads a row as 4 conflict-free LDS.128 (scan_row<true>). Three CTAs per SM: while one waits
 // for its boxes the others reduce theirs.
-constexpr int kWTRows = 768;
+#ifndef WT_BOXES
+#define WT_BOXES 3
+#endif
+#ifndef WT_CTAS
+#define WT_CTAS 3
+#endif
+constexpr int kWTBoxes = WT_BOXES, kWTCtasPerSm = WT_CTAS;
+constexpr int kWTRows = 256 * kWTBoxes;
 constexpr int kWTLagRows = kWTRows - 2 * kWScanR - 1;           // 447
 constexpr int kWTD = kWTLagRows * 8;                            // 3576 lags per tile
-constexpr int kWTThreads = 448;                                 // >= kWTLagRows, whole warps
+constexpr int kWTThreads = (kWTLagRows + 31) / 32 * 32;         // >= kWTLagRows, whole warps (448 for three boxes)
 constexpr int kWTTileBytes = kWTRows * 64;
 constexpr int kWTPre = kWTRows + 3;
 constexpr size_t wide_scan_tma_smem_bytes() { return 1024 + (size_t)kWTTileBytes + 3 * sizeof(double) * kWTPre + 2 * sizeof(float) * kWTPre + 32; }
 
 template <int = 0>
-__global__ void __launch_bounds__(kWTThreads, 3) wide_scan_tma_kernel(const SyncArgs a, const __grid_constant__ ScanTensorMap tmap)
+__global__ void __launch_bounds__(kWTThreads, WT_CTAS) wide_scan_tma_kernel(const SyncArgs a, const __grid_constant__ ScanTensorMap tmap)
 {
     constexpr int L = wide::kL;
     extern __shared__ __align__(1024) uint8_t wscan_tma_smem[];
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(kWTThreads, 3) wide_scan_tma_kernel(const Sync
         const uint32_t bar_sa = smem_addr(s_bar);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_sa), "r"((uint32_t)kWTTileBytes) : "memory");
 #pragma unroll
-        for (int h = 0; h < 3; h++)
+        for (int h = 0; h < kWTBoxes; h++)
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                          :: "r"(tile_sa + (uint32_t)h * (256 * 64)), "l"(&tmap), "r"(0), "r"((int)(origin / 8 + 256 * h)), "r"(bar_sa) : "memory");
     }
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(kWTThreads, 3) wide_scan_tma_kernel(const Sync
         const long long nxt = tile + a.prefetch_ahead;
         if (nxt < (long long)a.tile_first + a.tile_count) {
 #pragma unroll
-            for (int h = 0; h < 3; h++)
+            for (int h = 0; h < kWTBoxes; h++)
                 asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
                              :: "l"(&tmap), "r"(0), "r"((int)(nxt * kWTLagRows - 1 + 256 * h)) : "memory");
         }
