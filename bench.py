@@ -724,6 +724,20 @@ def capture_cpu_baseline(cap, args):
             "argmax_index": idx}
 
 
+def tx_kernel_label(launches, steps):
+    """Which TX kernel ran, from OFDM_TX_PATH (the engine's A/B switch) and the launches per step."""
+    path = os.environ.get("OFDM_TX_PATH", "")
+    wide = NFFT == 1024
+    if path == "twopass" or (launches == 2 * steps and path not in ("", "spec")):
+        return ("wide_tx_kernel" if wide else "tx_tile_kernel") + " (max pass + store pass)"
+    if launches == 2 * steps:
+        return ("wide_tx_spec_kernel" if wide else "tx_spec_kernel") + (" (one pass: every symbol scaled with the head maximum and stored at once; frames whose "
+                                                                          "data beat it are redone) + redo-check launch")
+    if path == "resident" or wide:
+        return ("wide_tx_resident_kernel" if wide else "tx_resident_kernel") + " (one pass, frames resident in tensor memory)"
+    return "tx_warp_kernel (one pass, frames resident in tensor memory, barrier-free frame loop)"
+
+
 def tx_bench(args, rank, local_rank, world, steps=None):
     """TX side of the path: payload bytes -> Hamming -> 64QAM -> IFFT -> CP -> head -> normalise, for the
     headline workload's frames; the round trip against the RX path and the oracle is in tests/. 8 B/sample written once."""
@@ -790,7 +804,7 @@ def tx_bench(args, rank, local_rank, world, steps=None):
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": f"tx_{n}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}"), "streams_per_gpu": n, "nfft": NFFT, "data_syms_per_frame": S, "frame_samples": frame_len,
                                  "payload_bytes": plen_b, "l2": "output (%.2f GB) larger than L2" % (8 * samples / 1e9)},
-                      "roofline": {"bound": "hbm", "kernel": (("wide_tx_resident_kernel" if NFFT == 1024 else ("tx_resident_kernel" if os.environ.get("OFDM_TX_PATH") == "resident" else "tx_warp_kernel")) + " (one pass, frames resident in tensor memory)") if launches == steps else ("wide_tx_kernel" if NFFT == 1024 else "tx_tile_kernel") + " (max pass + store pass)", "achieved": round(by / (ms * 1e-3) / 1e9, 1),
+                      "roofline": {"bound": "hbm", "kernel": tx_kernel_label(launches, steps), "achieved": round(by / (ms * 1e-3) / 1e9, 1),
                                    "peak": peak, "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / peak, 4), "traffic": read_traffic(f"tx_{n}x64QAM_S{S}" + ("" if NFFT == 64 else f"_N{NFFT}")),
                                    "peak_source": src, "algorithmic_bytes_per_launch": by, "kernel_ms": round(ms, 4)},
                       "max_component": round(mx, 6), "frames_ok": frames_ok, "frames_match_oracle_on_sample": oracle_ok,

@@ -44,6 +44,7 @@ TxKernel pick_tx_resident(const ofdm_cfg &c);   // one-pass persistent kernel, f
 size_t tx_resident_smem(const ofdm_cfg &c);
 // tx64w.cu
 TxKernel pick_tx_warp(const ofdm_cfg &c);       // one-pass persistent kernel without CTA barriers in the frame loop (tx_warp.cuh)
+TxKernel pick_tx_spec(const ofdm_cfg &c);       // speculative one-pass kernel: scales with the head maximum at once, records the frames that beat it
 size_t tx_warp_smem(const ofdm_cfg &c);
 int tx_warp_syms_per_cta();
 int tx_warp_threads();
@@ -71,6 +72,7 @@ WDecodeKernel wpick_acquire(const ofdm_cfg &c);
 WTxKernel wpick_tx(const ofdm_cfg &c, bool write);
 // wide_txr.cu
 WTxKernel wpick_tx_resident(const ofdm_cfg &c, bool double_buffered);  // one-pass persistent kernel, frames resident in tensor memory (wide_tx_resident.cuh)
+WTxKernel wpick_tx_spec(const ofdm_cfg &c);      // speculative one-pass kernel (scales with the head maximum at once, records the frames that beat it)
 size_t wide_tx_resident_smem(const ofdm_cfg &c);
 int wide_tx_resident_syms_per_cta(bool double_buffered);
 int wide_tx_resident_threads();

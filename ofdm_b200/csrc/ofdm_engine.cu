@@ -81,7 +81,7 @@ struct ofdm_engine {
     int rx_feed = 0;                                // 0 = automatic; OFDM_RX_FEED=full|skipcp|gather pins one (A/B measurements)
     int bps_sym = 0, bpc = 0, dcar = 0, tile_shift = 0;
     int n_sm = 0;                       // multiprocessors of the device (grid of the persistent TX kernel)
-    int tx_path = 0;                    // 0 = automatic; OFDM_TX_PATH=twopass|cluster|resident|warp pins one (A/B measurements)
+    int tx_path = 0;                    // 0 = automatic; OFDM_TX_PATH=twopass|cluster|resident|warp|spec pins one (A/B measurements)
     // per-kernel timing of ofdm_rx_decode_batch(OFDM_MEM_DEVICE): 3 events per call (start, after acquire, end)
     std::vector<cudaEvent_t> prof_ev;
     uint32_t prof_cap = 0, prof_n = 0;
@@ -207,7 +207,7 @@ extern "C" int ofdm_engine_create(const ofdm_cfg *cfg, int device, ofdm_engine *
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (const char *rf = getenv("OFDM_RX_FEED")) h->rx_feed = !strcmp(rf, "full") ? 1 : !strcmp(rf, "skipcp") ? 2 : !strcmp(rf, "gather") ? 3 : 0;
     if (const char *tp = getenv("OFDM_TX_PATH"))
-        h->tx_path = !strcmp(tp, "twopass") ? 1 : !strcmp(tp, "cluster") ? 2 : !strcmp(tp, "resident") ? 3 : !strcmp(tp, "warp") ? 4 : 0;
+        h->tx_path = !strcmp(tp, "twopass") ? 1 : !strcmp(tp, "cluster") ? 2 : !strcmp(tp, "resident") ? 3 : !strcmp(tp, "warp") ? 4 : !strcmp(tp, "spec") ? 5 : 0;
     h->bps_sym = h->bpc * h->dcar;
     h->tile_shift = 0;
     if (cfg->fec) {                          // tile boundaries on Hamming byte boundaries: BPS*s == 128 (mod 14)
@@ -371,7 +371,25 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         const long max_syms = (long)iq_stride / wide::kL - 10;
         // Large batches: ONE pass, frames resident in tensor memory (wide_tx_resident.cuh): groups of C persistent CTAs (one per SM,
         // 32 symbols each) per frame, launched cooperatively because the CTAs of a group wait for one another's frame maximum.
-        if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 3)) {
+        // Speculative one pass (wide_tx_spec_kernel): bet that the frame maximum is the head's, store every symbol at once, redo the
+        // frames that lost the bet with the two-pass kernel (its store pass with redo_only). Large-batch default.
+        const int spw = wide_tx_resident_threads() / 32;                       // symbols per unit: one per warp
+        const uint64_t wspec_units = max_syms > 0 ? (uint64_t)n_streams * (uint64_t)((max_syms + spw - 1) / spw) : 0;
+        if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 5 || (h->tx_path == 0 && wspec_units >= 32ull * (uint64_t)h->n_sm))) {
+            WTxKernel k = wpick_tx_spec(h->cfg);
+            const size_t smem = wide_tx_resident_smem(h->cfg);
+            if (h->smem_configured.insert((const void *)k).second)
+                CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            w.group_ctas = (int32_t)((max_syms + spw - 1) / spw);
+            k<<<(unsigned)(wspec_units < (uint64_t)h->n_sm ? wspec_units : (uint64_t)h->n_sm), wide_tx_resident_threads(), smem, st>>>(w);
+            h->launches++;
+            w.redo_only = (int32_t)((max_syms + 7) / 8);                         // tiles of 8 symbols a redone frame walks
+            launch_streams(wpick_tx(h->cfg, true), w, 1, n_streams, wide::kThreads, 0, st, h->launches);
+            CU(h, cudaGetLastError());
+            if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+            return 0;
+        }
+        if (max_syms > 0 && h->n_sm > 0 && h->tx_path == 3) {
             bool db = false;
             if (const char *e = getenv("OFDM_WTX_DB")) db = atoi(e) != 0;
             const int per = wide_tx_resident_syms_per_cta(db);
@@ -411,9 +429,38 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
     // Large batches: ONE pass with the frames resident on chip (tx_resident.cuh). A frame is shared by a group of C persistent
     // CTAs (one per SM), its un-normalised symbols wait in tensor memory for the frame maximum, and the stores of frame k-1
     // overlap the transforms of frame k in every warp. C = the smallest group whose rings hold the longest frame iq_stride admits.
+    // Speculative one pass (tx_spec_kernel, tx_warp.cuh): bet that the frame maximum is the head's (true for scrambled payloads),
+    // scale and store every symbol at once, then redo the frames that lost the bet with the store pass of the two-pass kernel.
+    // Large-batch default (from two units of 512 symbols per SM on): 4096 frames 1.15 ms against 1.29 ms for the exact one-pass
+    // kernel below, which costs the same whatever the payloads are (OFDM_TX_PATH=warp) -- a frame that loses the bet costs a
+    // second store pass.
+    const uint64_t spec_units = max_syms > 0 ? (uint64_t)n_streams * (uint64_t)((max_syms + tx_warp_syms_per_cta() - 1) / tx_warp_syms_per_cta()) : 0;
+    if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 5 || (h->tx_path == 0 && spec_units >= 2ull * (uint64_t)h->n_sm))) {
+        const int per = tx_warp_syms_per_cta();
+        const uint32_t U = (uint32_t)((max_syms + per - 1) / per);
+        const uint64_t units = (uint64_t)n_streams * U;
+        TxKernel k = pick_tx_spec(h->cfg);
+        const size_t smem = tx_warp_smem(h->cfg);
+        if (h->smem_configured.insert((const void *)k).second)
+            CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a.group_ctas = (int32_t)U;
+        k<<<(unsigned)(units < (uint64_t)h->n_sm ? units : (uint64_t)h->n_sm), tx_warp_threads(), smem, st>>>(a);
+        h->launches++;
+        uint32_t tiles = (uint32_t)((max_syms + h->tile_shift + kTxTileSyms - 1) / kTxTileSyms);
+        a.tiles_per_cta = (int)tiles;                                          // one CTA per frame: it exits at once unless the frame has to be redone
+        a.redo_only = 1;
+        const size_t tx_smem = sizeof(float2) * kTxWarps * kTrWarp + (size_t)kTxTileSyms * h->dcar + 64 + sizeof(float2) * 16 * ((1u << h->bpc) + 2) + 16 + 512;
+        TxKernel k2 = pick_tx(h->cfg, true);
+        if (h->smem_configured.insert((const void *)k2).second)
+            CU(h, cudaFuncSetAttribute((const void *)k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tx_smem));
+        launch_streams(k2, a, 1, n_streams, kTxThreads, tx_smem, st, h->launches);
+        CU(h, cudaGetLastError());
+        if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     // ... second version of it (tx_warp.cuh): a warp owns 16 consecutive symbols and prepares their carrier bytes itself, the
     // frame maximum travels through one flagged word per warp -- no CTA barrier in the frame loop.
-    if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 0 || h->tx_path == 4)) {
+    if (max_syms > 0 && h->n_sm > 0 && h->tx_path == 4) {
         const int per = tx_warp_syms_per_cta();
         const int C = (int)((max_syms + per - 1) / per);
         int G = C <= h->n_sm ? h->n_sm / C : 0;

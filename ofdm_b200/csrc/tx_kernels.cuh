@@ -23,6 +23,7 @@ struct TxArgs {
     uint32_t       *stream_cnt;     // tx_resident_kernel: per stream, compute warps that have published their maximum
     int32_t         group_ctas;     // tx_resident_kernel: CTAs sharing one frame
     int32_t         n_groups;       // tx_resident_kernel: groups of the (persistent) grid
+    int32_t         redo_only;      // tx_tile_kernel<WRITE>: only frames whose stream_max is set (the speculative kernel lost its bet on them)
 };
 
 // byte `B` of the frame byte stream [header 16 B | (Hamming-coded) payload ...] (src/transmitter.rs:37-47, docs/SPEC.md 3)
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
     static_assert(kTxTileSyms * BPS / 8 + 32 <= (int)sizeof(float2) * kTxWarps * kTrWarp, "the packed bit stream must fit the transpose scratch");
 
     const uint32_t stream = blockIdx.y + a.stream0;
+    if (WRITE && a.redo_only && a.stream_max[stream] == 0) return;   // (tx_spec_kernel wrote this frame already, with the right maximum)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     const uint32_t n = a.payload_len[stream];
     const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;

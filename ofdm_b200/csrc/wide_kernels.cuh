@@ -975,10 +975,12 @@ struct WideTxArgs {
     uint32_t       *stream_cnt;     // wide_tx_resident_kernel: per stream, warps that have published their maximum
     int32_t         group_ctas;     // wide_tx_resident_kernel: CTAs sharing one frame
     int32_t         n_groups;       // wide_tx_resident_kernel: groups of the (persistent) grid
+    int32_t         redo_only;      // wide_tx_kernel<WRITE>: > 0 = redo pass, one CTA per frame walks this many tiles, and only when the frame's stream_max is set
 };
 
+// 8 symbols of one frame: tile `bx` of `nbx` (the kernel's blockIdx.x / gridDim.x, or the redo loop's counter)
 template <int MOD, bool GUARD, bool FEC, bool WRITE>
-__global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
+__device__ __forceinline__ void wide_tx_tile(const WideTxArgs &a, const uint32_t stream, const uint32_t bx, const uint32_t nbx)
 {
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 768 : 1024;
@@ -989,7 +991,6 @@ __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
     __shared__ __align__(8) float2 s_map[64];
     __shared__ uint8_t s_enc[16];
 
-    const uint32_t stream = blockIdx.y + a.stream0;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = a.payload_len[stream];
     const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;
@@ -997,22 +998,22 @@ __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
     const uint64_t ncar = (nbits + BPC - 1) / BPC;
     const int S = (int)((ncar + D - 1) / D);
     const uint32_t frame_len = (10u + (uint32_t)S) * kL;
-    if (a.frame_len && blockIdx.x == 0 && tid == 0) a.frame_len[stream] = frame_len;
+    if (a.frame_len && bx == 0 && tid == 0) a.frame_len[stream] = frame_len;
     const bool fits = frame_len <= a.iq_stride;
     float2 *out = a.iq + (size_t)stream * a.iq_stride;
-    int t0 = (int)blockIdx.x * TS, t1 = t0 + TS;
+    int t0 = (int)bx * TS, t1 = t0 + TS;
     if (t1 > S) t1 = S;
     float scale = 1.0f / (float)kN;
     if (WRITE) {
         const float mx = fmaxf(__int_as_float(a.stream_max[stream]), a.tables->head_max);
         scale *= 1.0f / mx;
-        if (blockIdx.x == 0)
+        if (bx == 0)
             for (uint32_t i = tid; i < (uint32_t)kHeadW && i < a.iq_stride; i += kThreads) {
                 float2 v = make_float2(0.0f, 0.0f);
                 if (fits) { v = a.tables->head[i]; v.x = v.x / mx; v.y = v.y / mx; }
                 out[i] = v;
             }
-        if (blockIdx.x == gridDim.x - 1) {
+        if (bx == nbx - 1) {
             const uint32_t z0 = fits ? frame_len : (uint32_t)kHeadW;
             for (uint32_t i = z0 + tid; i < a.iq_stride; i += kThreads) out[i] = make_float2(0.0f, 0.0f);
         }
@@ -1085,6 +1086,23 @@ __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
         for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
         if (lane == 0 && mx > 0.0f) atomicMax(a.stream_max + stream, __float_as_int(mx));
     }
+}
+
+template <int MOD, bool GUARD, bool FEC, bool WRITE>
+__global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
+{
+    const uint32_t stream = blockIdx.y + a.stream0;
+    if (WRITE && a.redo_only) {
+        // redo pass behind wide_tx_spec_kernel: one CTA per frame; it exits at once unless the frame's data beat the head maximum
+        // (stream_max set), else it rewrites the whole frame tile by tile with that maximum
+        if (a.stream_max[stream] == 0) return;
+        for (uint32_t bx = 0; bx < (uint32_t)a.redo_only; bx++) {
+            wide_tx_tile<MOD, GUARD, FEC, WRITE>(a, stream, bx, (uint32_t)a.redo_only);
+            __syncthreads();
+        }
+        return;
+    }
+    wide_tx_tile<MOD, GUARD, FEC, WRITE>(a, stream, blockIdx.x, gridDim.x);
 }
 
 }  // namespace wide

@@ -475,5 +475,161 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_resident_kernel(const
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
 }
 
+
+// ---- speculative one-pass kernel: no residency ----------------------------------------------------------------------------------
+// Same bet as tx_spec_kernel (tx_warp.cuh): the frame maximum `normalize` divides by is max(head_max, data maximum), head_max is
+// a constant, and at nfft = 1024 the data symbols of a scrambled payload reach about a fifth of it. Every symbol is transformed
+// once, scaled with head_max and stored at once -- no tensor memory, no exchange between SMs, no cooperative launch -- and a warp
+// whose data beat head_max records its maximum (atomicMax on stream_max[stream], 0 otherwise). Those frames are redone by the
+// two-pass kernel's store pass with the recorded maximum (wide_tx_kernel<WRITE>, redo_only: every other frame's CTAs exit at
+// once). Work unit = (frame, span of 16 symbols: one per warp), persistent CTAs stride over the units.
+template <int MOD, bool GUARD, bool FEC>
+__global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_spec_kernel(const WideTxArgs a)
+{
+    typedef WTrsSmem<MOD> L;
+    constexpr int BPC = ModTraits<MOD>::kBpc, NE = 1 << BPC, D = GUARD ? 768 : 1024, BPSB = BPC * D / 8;
+    extern __shared__ __align__(128) uint8_t wtrs_smem[];
+    float2 *s_buf = reinterpret_cast<float2 *>(wtrs_smem + L::kBuf);
+    float2 *s_tw = reinterpret_cast<float2 *>(wtrs_smem + L::kTw);
+    uint16_t *s_off = reinterpret_cast<uint16_t *>(wtrs_smem + L::kOff);
+    float2 *s_lut = reinterpret_cast<float2 *>(wtrs_smem + L::kLut);
+    uint16_t *s_enc14 = reinterpret_cast<uint16_t *>(wtrs_smem + L::kEnc);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < 16 * (NE + 2); e += kWTrsThreads) {                   // conjugated constellation (conj . FFT . conj), null, pilot
+        const int idx = e >> 4;
+        float re = 0.0f, im = 0.0f;
+        if (idx == NE + 1) re = 1.0f;
+        else if (idx == NE) { }
+        else if (MOD == 0) { re = (idx & 1) ? 1.0f : -1.0f; }
+        else if (MOD == 1) { re = (idx & 1) ? 1.0f : -1.0f; im = (idx & 2) ? 1.0f : -1.0f; }
+        else {
+            const uint32_t ci = idx & 7u, cq = (uint32_t)idx >> 3;
+            const uint32_t li = ci ^ (ci >> 1) ^ (ci >> 2), lq = cq ^ (cq >> 1) ^ (cq >> 2);
+            re = (2.0f * (float)li - 7.0f) * (1.0f / 7.0f);
+            im = (2.0f * (float)lq - 7.0f) * (1.0f / 7.0f);
+        }
+        s_lut[e] = make_float2(re, -im);
+    }
+    for (int e = tid; e < kN; e += kWTrsThreads) {                              // e = 32 j + l <-> bin l + 32 j = e (encode_block, src/transmitter.rs:144-165)
+        const int rk = w_rank<GUARD>(e);
+        s_off[e] = (uint16_t)(rk >= 0 ? rk : ((GUARD && w_is_pilot(e)) ? D + 1 : D));
+        const int r = e >> 5, c = e & 31;
+        s_tw[r * kWPitch + c] = __ldg(a.tables->w1024 + ((r * c) & (kN - 1)));
+    }
+    if (FEC && tid < 256) s_enc14[tid] = (uint16_t)(ham74_encode_nibble(tid & 15) | (ham74_encode_nibble(tid >> 4) << 7));
+    __syncthreads();
+    const float head_max = a.tables->head_max;
+    const float scale = (1.0f / (float)kN) * (1.0f / head_max);
+
+    float2 *buf = s_buf + warp * kWBuf;
+    unsigned long long *wr = reinterpret_cast<unsigned long long *>(buf + lane);
+    const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(buf + lane * kWPitch);
+    const ulonglong2 *tw_row = reinterpret_cast<const ulonglong2 *>(s_tw + lane * kWPitch);
+    const unsigned long long *lut = reinterpret_cast<const unsigned long long *>(s_lut) + (lane & 15);
+    const uint16_t *off_col = s_off + lane;
+    uint8_t *mybits = wtrs_smem + L::kBits + (size_t)warp * kWTrsBitsBuf;
+    uint8_t *car = wtrs_smem + L::kCar + (size_t)warp * kWTrsSlots * kWTrsCarBuf;
+
+    const uint32_t U = (uint32_t)a.group_ctas;                                  // spans of 16 symbols per frame (from iq_stride)
+    const uint64_t n_units = (uint64_t)a.n_streams * U;
+    auto prefetch_unit = [&](uint64_t u) {
+        if (u >= n_units) return;
+        const uint32_t st2 = n_units >> 32 ? (uint32_t)(u / U) : (uint32_t)u / U, j2 = (uint32_t)(u - (uint64_t)st2 * U);
+        const uint32_t B0 = (j2 * kWTrsWarps + (uint32_t)warp) * BPSB, c0 = B0 < 16 ? 0 : B0 - 16;
+        const uint32_t pb = FEC ? 4 * (c0 / 7) + 16 * lane : c0 + 32 * lane;
+        constexpr uint32_t span = FEC ? (BPSB * 4) / 7 + 32 : BPSB + 32;
+        if ((FEC ? 16u : 32u) * lane < span && pb < __ldg(a.payload_len + st2))
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(a.payload + (size_t)st2 * a.payload_stride + pb));
+    };
+    for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const uint32_t stream = n_units >> 32 ? (uint32_t)(unit / U) : (uint32_t)unit / U, j = (uint32_t)(unit - (uint64_t)stream * U);
+        prefetch_unit(unit + gridDim.x);                                       // the payload bytes of this warp's share of the CTA's next unit
+        const uint32_t n = __ldg(a.payload_len + stream);
+        const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;
+        const uint64_t ncar = (kHeaderBits + 8 * coded_len + BPC - 1) / BPC;    // constellation symbols (src/transmitter.rs:108-140)
+        const uint64_t S64 = (ncar + D - 1) / D;                                // OFDM data symbols (src/transmitter.rs:49-54)
+        const uint32_t flen = (10u + (uint32_t)S64) * kL;
+        const bool fits = (10ull + S64) * kL <= (uint64_t)a.iq_stride;
+        float2 *out = a.iq + (size_t)stream * a.iq_stride;
+        if (j == 0 && tid == 0 && a.frame_len) a.frame_len[stream] = flen;
+        {                                                                      // this unit's share of the frame head (12 800 samples over the U units), already divided by the bet
+            const float rh = fits ? 1.0f / head_max : 0.0f;
+            const uint32_t per = ((uint32_t)kHeadW + U - 1) / U, h_lo = j * per;
+            uint32_t h_hi = h_lo + per < (uint32_t)kHeadW ? h_lo + per : (uint32_t)kHeadW;
+            if (h_hi > a.iq_stride) h_hi = a.iq_stride;
+            for (uint32_t i0 = h_lo + tid; i0 < h_hi; i0 += 4 * kWTrsThreads) {  // four table loads in flight per thread
+                float2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + u * kWTrsThreads;
+                    v[u] = make_float2(0.0f, 0.0f);
+                    if (i < h_hi) v[u] = __ldg(a.tables->head + i);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + u * kWTrsThreads;
+                    if (i < h_hi) out[i] = make_float2(v[u].x * rh, v[u].y * rh);
+                }
+            }
+        }
+        {                                                                      // zero fill past the frame inside this unit's share of the row
+            const uint64_t u_lo = (uint64_t)(10 + (uint64_t)j * kWTrsWarps) * kL;
+            const uint64_t u_hi = j + 1 == U ? (uint64_t)a.iq_stride : (uint64_t)(10 + (uint64_t)(j + 1) * kWTrsWarps) * kL;
+            const uint64_t f_end = fits ? (uint64_t)flen : (uint64_t)kHeadW;
+            uint64_t z = f_end > u_lo ? f_end : u_lo;
+            const uint64_t hi = u_hi < (uint64_t)a.iq_stride ? u_hi : (uint64_t)a.iq_stride;
+            for (z += tid; z < hi; z += kWTrsThreads) out[z] = make_float2(0.0f, 0.0f);
+        }
+        const long s = (long)j * kWTrsWarps + warp;                            // this warp's symbol
+        if (!fits || s >= (long)S64) continue;
+        {
+            const uint8_t *pay = a.payload + (size_t)stream * a.payload_stride;
+            const bool pay_aligned = (reinterpret_cast<uintptr_t>(pay) & 3) == 0;
+            __syncwarp();
+            const uint32_t bit0 = wtrs_build_bits<BPSB, FEC>(mybits, pay, pay_aligned, n, coded_len, (uint32_t)s * BPSB, s_enc14, lane);
+            __syncwarp();
+            wtrs_unpack_carriers<BPC, D>(car, mybits, bit0, (long)ncar - s * D, lane);
+            __syncwarp();
+        }
+        cpx x[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) {
+            if (!w_row_used<GUARD>(jj)) { x[jj] = c_make(0.0f, 0.0f); continue; }
+            x[jj].v = lut[(uint32_t)car[off_col[32 * jj]] * 16u];
+        }
+        dft32_p(x);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const ulonglong2 ww = tw_row[q];
+            cpx w0, w1;
+            w0.v = ww.x; w1.v = ww.y;
+            x[2 * q] = c_mul(x[2 * q], w0); x[2 * q + 1] = c_mul(x[2 * q + 1], w1);
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) wr[k1 * kWPitch] = x[k1].v;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 16; q++) { const ulonglong2 v = row[q]; x[2 * q].v = v.x; x[2 * q + 1].v = v.y; }
+        __syncwarp();
+        dft32_p(x);
+        float mx = 0.0f;
+        unsigned long long *sym = reinterpret_cast<unsigned long long *>(out + (size_t)(10 + s) * kL) + lane;
+        const cpx sc = c_make(scale, -scale);                                  // conj and scale in one
+#pragma unroll
+        for (int t2 = 0; t2 < 32; t2++) {
+            float re, im;
+            c_split(x[t2], re, im);                                            // the frame's sample is (re, -im) / 1024
+            mx = fmaxf(mx, fmaxf(re, -im));
+            const unsigned long long v = c_mul2(x[t2], sc).v;                  // time index lane + 32 t2
+            sym[kCpW + 32 * t2] = v;
+            if (t2 >= 24) sym[32 * (t2 - 24)] = v;                             // cyclic prefix = last 256 samples
+        }
+        mx *= 1.0f / (float)kN;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        if (lane == 0 && mx > head_max) atomicMax(a.stream_max + stream, __float_as_int(mx));     // the bet is lost for this frame: it will be redone
+    }
+}
+
 }  // namespace wide
 }  // namespace ofdm

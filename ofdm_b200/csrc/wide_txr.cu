@@ -21,6 +21,20 @@ static WTxKernel wpick_txr_db(const ofdm_cfg &c)
 }
 // double_buffered: one symbol per warp and frame, two frames in flight per CTA (16 symbols per CTA and frame); else 32
 WTxKernel wpick_tx_resident(const ofdm_cfg &c, bool double_buffered) { return double_buffered ? wpick_txr_db<true>(c) : wpick_txr_db<false>(c); }
+template <int MOD>
+static WTxKernel wpick_txs_mod(bool guard, bool fec)
+{
+    if (guard) return fec ? (WTxKernel)wide::wide_tx_spec_kernel<MOD, true, true> : (WTxKernel)wide::wide_tx_spec_kernel<MOD, true, false>;
+    return fec ? (WTxKernel)wide::wide_tx_spec_kernel<MOD, false, true> : (WTxKernel)wide::wide_tx_spec_kernel<MOD, false, false>;
+}
+WTxKernel wpick_tx_spec(const ofdm_cfg &c)
+{
+    switch (c.modulation) {
+    case 0: return wpick_txs_mod<0>(c.guard_bands, c.fec);
+    case 1: return wpick_txs_mod<1>(c.guard_bands, c.fec);
+    default: return wpick_txs_mod<2>(c.guard_bands, c.fec);
+    }
+}
 size_t wide_tx_resident_smem(const ofdm_cfg &c)
 {
     switch (c.modulation) {

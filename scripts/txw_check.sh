@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tx_resident_kernel" > gpurun_out/txw_tests.log 2>&1
 tail -4 gpurun_out/txw_tests.log
-for pth in warp warp; do
+for pth in warp spec warp spec; do
 OFDM_TX_PATH=$pth timeout 300 python bench.py --workload tx --steps 30 > gpurun_out/txw_$pth.json 2> gpurun_out/txw_$pth.err
 python - <<P
 import json
