@@ -132,11 +132,15 @@ uint32_t ofdm_max_payload(const ofdm_cfg *cfg, uint32_t n_data_syms);     /* lar
  * TX: replaces `encode` (src/transmitter.rs:11-58) for a batch of frames.
  * payload[s*payload_stride ..][payload_len[s]] -> iq_out[s*iq_stride ..][frame_len]; samples past the
  * frame up to iq_stride are zero-filled. frame_len_out (optional) receives each frame's length.
- * Every frame is normalised by its own maximum positive component (`normalize`, src/transmitter.rs:183-194). Batches take the
- * one-pass kernel that keeps a frame on chip until that maximum is known (a cooperative launch: it needs the device's SMs to
- * itself for the ~ms it runs, and waits for them otherwise); a handful of frames, or frames too long for it, take the
- * cluster / two-pass kernels. The results are the same values whichever kernel runs. (Measurement aid, read once at
- * ofdm_engine_create: the environment variable OFDM_TX_PATH = twopass | cluster | resident pins one of them.)
+ * Every frame is normalised by its own maximum positive component (`normalize`, src/transmitter.rs:183-194). Batches take a
+ * speculative one-pass kernel: that maximum is max(maximum of the constant frame head, maximum of the data symbols), and for
+ * scrambled payloads it is the head's -- so every symbol is scaled with the head maximum and stored at once, and the (rare)
+ * frames whose data symbols beat it are redone with their own maximum by a second pass. The output does not depend on the bet,
+ * only the cost does (a frame that loses it is written twice). The exact one-pass kernels keep a frame on chip (tensor memory)
+ * until its maximum is known (cooperative launches: they need the device's SMs to themselves for the ~ms they run); a handful
+ * of frames, or frames too long for them, take the cluster / two-pass kernels. The results are the same values whichever kernel
+ * runs. (Measurement aid, read once at ofdm_engine_create: the environment variable
+ * OFDM_TX_PATH = twopass | cluster | resident | warp | spec pins one of them.)
  * nfft = 1024 has the same two large-batch choices: wide_tx_resident_kernel (one pass, a symbol per warp, frames resident in
  * tensor memory; from two frames per group of CTAs on) and the two-pass wide_tx_kernel; they agree to fp32 rounding (different
  * FFT factorisations), each within 2e-6 of the oracle's `encode`.
