@@ -23,7 +23,7 @@ struct TxArgs {
     uint32_t       *stream_cnt;     // tx_resident_kernel: per stream, compute warps that have published their maximum
     int32_t         group_ctas;     // tx_resident_kernel: CTAs sharing one frame
     int32_t         n_groups;       // tx_resident_kernel: groups of the (persistent) grid
-    int32_t         redo_only;      // tx_tile_kernel<WRITE>: only frames whose stream_max is set (the speculative kernel lost its bet on them)
+    int32_t         redo_only;      // tx_tile_kernel<WRITE>: > 0 = redo pass: a CTA checks this many consecutive frames and rewrites those whose stream_max is set
 };
 
 // byte `B` of the frame byte stream [header 16 B | (Hamming-coded) payload ...] (src/transmitter.rs:37-47, docs/SPEC.md 3)
@@ -66,8 +66,9 @@ template <int MOD, bool GUARD> constexpr size_t tx_smem_bytes()
 // WRITE = false: only the per-stream maximum positive component is produced (`normalize`, src/transmitter.rs:183-194);
 // WRITE = true : the symbols are recomputed and stored once, already normalised, together with the frame head and
 // the zero fill -- 8 B/sample of HBM traffic in total instead of write + read-modify-write.
+// the tiles [bx * tiles_per_cta, ...) of one frame; (bx, nbx) = the kernel's block index and grid extent in x, (0, 1) in the redo pass
 template <int MOD, bool GUARD, bool FEC, bool WRITE>
-__global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
+__device__ __forceinline__ void tx_tile_body(const TxArgs &a, const uint32_t stream, const uint32_t bx, const uint32_t nbx)
 {
     constexpr int BPC = ModTraits<MOD>::kBpc;
     constexpr int D = GUARD ? 48 : 64;
@@ -82,8 +83,6 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
     uint16_t *s_enc14 = reinterpret_cast<uint16_t *>(s_enc + 16);               // payload byte -> its two 7-bit codewords (low nibble first)
     static_assert(kTxTileSyms * BPS / 8 + 32 <= (int)sizeof(float2) * kTxWarps * kTrWarp, "the packed bit stream must fit the transpose scratch");
 
-    const uint32_t stream = blockIdx.y + a.stream0;
-    if (WRITE && a.redo_only && a.stream_max[stream] == 0) return;   // (tx_spec_kernel wrote this frame already, with the right maximum)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 3, l = lane & 7;
     const uint32_t n = a.payload_len[stream];
     const uint64_t coded_len = FEC ? (14ull * n + 7) / 8 : n;
@@ -91,12 +90,12 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
     const uint64_t ncar = (nbits + BPC - 1) / BPC;                 // constellation symbols (src/transmitter.rs:108-140)
     const int S = (int)((ncar + D - 1) / D);                       // OFDM data symbols (src/transmitter.rs:49-54)
     const uint32_t frame_len = (kHeadSyms + (uint32_t)S) * kSym;
-    if (a.frame_len && blockIdx.x == 0 && tid == 0) a.frame_len[stream] = frame_len;
+    if (a.frame_len && bx == 0 && tid == 0) a.frame_len[stream] = frame_len;
     const bool fits = frame_len <= a.iq_stride;
     float2 *out = a.iq + (size_t)stream * a.iq_stride;
 
     const int n_tiles = (S + a.tile_shift + kTxTileSyms - 1) / kTxTileSyms;
-    const int tile_first = (int)blockIdx.x * a.tiles_per_cta;
+    const int tile_first = (int)bx * a.tiles_per_cta;
     int tile_end = tile_first + a.tiles_per_cta;
     if (tile_end > n_tiles) tile_end = n_tiles;
     float scale = 1.0f / 64.0f;
@@ -105,13 +104,13 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
         const float inv = 1.0f / mx;
         scale *= inv;
         // frame head (lock | preamble x4 | training x5) and zero fill past the frame
-        if (blockIdx.x == 0)
+        if (bx == 0)
             for (uint32_t i = tid; i < (uint32_t)(kHeadSyms * kSym) && i < a.iq_stride; i += kTxThreads) {
                 float2 v = make_float2(0.0f, 0.0f);
                 if (fits) { v = a.tables->head[i]; v.x = v.x / mx; v.y = v.y / mx; }
                 out[i] = v;
             }
-        if (blockIdx.x == gridDim.x - 1) {
+        if (bx == nbx - 1) {
             const uint32_t z0 = fits ? frame_len : (uint32_t)(kHeadSyms * kSym);
             for (uint32_t i = z0 + tid; i < a.iq_stride; i += kTxThreads) out[i] = make_float2(0.0f, 0.0f);
         }
@@ -277,6 +276,23 @@ __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
         for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
         if (lane == 0 && mx > 0.0f) atomicMax(a.stream_max + stream, __float_as_int(mx));
     }
+}
+
+template <int MOD, bool GUARD, bool FEC, bool WRITE>
+__global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
+{
+    if (WRITE && a.redo_only) {
+        // redo pass behind tx_spec_kernel: a CTA looks at `redo_only` consecutive frames and rewrites, whole, those whose data
+        // beat the head maximum (stream_max set by the speculative kernel); for scrambled payloads that is none, and the CTA exits
+        const uint32_t s0 = a.stream0 + blockIdx.y * (uint32_t)a.redo_only;
+        for (uint32_t i = 0; i < (uint32_t)a.redo_only && s0 + i < a.n_streams; i++) {
+            if (a.stream_max[s0 + i] == 0) continue;
+            __syncthreads();                                        // (the previous frame's readers of the shared tables are done)
+            tx_tile_body<MOD, GUARD, FEC, WRITE>(a, s0 + i, 0u, 1u);
+        }
+        return;
+    }
+    tx_tile_body<MOD, GUARD, FEC, WRITE>(a, blockIdx.y + a.stream0, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -975,7 +975,8 @@ struct WideTxArgs {
     uint32_t       *stream_cnt;     // wide_tx_resident_kernel: per stream, warps that have published their maximum
     int32_t         group_ctas;     // wide_tx_resident_kernel: CTAs sharing one frame
     int32_t         n_groups;       // wide_tx_resident_kernel: groups of the (persistent) grid
-    int32_t         redo_only;      // wide_tx_kernel<WRITE>: > 0 = redo pass, one CTA per frame walks this many tiles, and only when the frame's stream_max is set
+    int32_t         redo_only;      // wide_tx_kernel<WRITE>: > 0 = redo pass: a CTA checks this many consecutive frames and rewrites those whose stream_max is set
+    int32_t         redo_tiles;     // ... walking this many tiles of 8 symbols each
 };
 
 // 8 symbols of one frame: tile `bx` of `nbx` (the kernel's blockIdx.x / gridDim.x, or the redo loop's counter)
@@ -1091,17 +1092,20 @@ __device__ __forceinline__ void wide_tx_tile(const WideTxArgs &a, const uint32_t
 template <int MOD, bool GUARD, bool FEC, bool WRITE>
 __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
 {
-    const uint32_t stream = blockIdx.y + a.stream0;
     if (WRITE && a.redo_only) {
-        // redo pass behind wide_tx_spec_kernel: one CTA per frame; it exits at once unless the frame's data beat the head maximum
-        // (stream_max set), else it rewrites the whole frame tile by tile with that maximum
-        if (a.stream_max[stream] == 0) return;
-        for (uint32_t bx = 0; bx < (uint32_t)a.redo_only; bx++) {
-            wide_tx_tile<MOD, GUARD, FEC, WRITE>(a, stream, bx, (uint32_t)a.redo_only);
-            __syncthreads();
+        // redo pass behind wide_tx_spec_kernel: a CTA looks at `redo_only` consecutive frames and rewrites, tile by tile, those whose
+        // data beat the head maximum (stream_max set); for scrambled payloads that is none, and the CTA exits
+        const uint32_t s0 = a.stream0 + blockIdx.y * (uint32_t)a.redo_only;
+        for (uint32_t i = 0; i < (uint32_t)a.redo_only && s0 + i < a.n_streams; i++) {
+            if (a.stream_max[s0 + i] == 0) continue;
+            for (uint32_t bx = 0; bx < (uint32_t)a.redo_tiles; bx++) {
+                __syncthreads();
+                wide_tx_tile<MOD, GUARD, FEC, WRITE>(a, s0 + i, bx, (uint32_t)a.redo_tiles);
+            }
         }
         return;
     }
+    const uint32_t stream = blockIdx.y + a.stream0;
     wide_tx_tile<MOD, GUARD, FEC, WRITE>(a, stream, blockIdx.x, gridDim.x);
 }
 

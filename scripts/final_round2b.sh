@@ -17,11 +17,11 @@ python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > $O/launch_plain.log 2>&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches.csv \
     python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > $O/launch_ncu.log 2>&1
 N="ncu --set full --clock-control none --import-source on -f"
-$N -k regex:"tx_warp" -c 1 -o $O/txw python bench.py --workload tx --steps 2 > $O/n3.log 2>&1
-python tools/ncu_summary.py $O/txw.ncu-rep > $O/r2_ncu_tx_warp.txt 2>&1
-python tools/sass_by_line.py $O/txw.ncu-rep ofdm_b200/libofdm_b200.so tx_warp_kernelILi2ELb1ELb1E 8347648 > $O/r2_ncu_tx_warp_by_line.txt 2>&1
-$N -k regex:"wide_tx_resident" -c 1 -o $O/wtxr python bench.py --workload tx --nfft 1024 --syms 128 --steps 2 > $O/n4.log 2>&1
-python tools/ncu_summary.py $O/wtxr.ncu-rep > $O/r2_ncu_wide_tx.txt 2>&1
-python tools/sass_by_line.py $O/wtxr.ncu-rep ofdm_b200/libofdm_b200.so wide_tx_resident_kernelILi2ELb1ELb1ELb0E 524288 > $O/r2_ncu_wide_tx_by_line.txt 2>&1
+$N -k regex:"tx_spec_kernel" -c 1 -o $O/txw python bench.py --workload tx --steps 2 > $O/n3.log 2>&1
+python tools/ncu_summary.py $O/txw.ncu-rep > $O/r2_ncu_tx_spec.txt 2>&1
+python tools/sass_by_line.py $O/txw.ncu-rep ofdm_b200/libofdm_b200.so tx_spec_kernelILi2ELb1ELb1E 8347648 > $O/r2_ncu_tx_spec_by_line.txt 2>&1
+$N -k regex:"wide_tx_spec" -c 1 -o $O/wtxr python bench.py --workload tx --nfft 1024 --syms 128 --steps 2 > $O/n4.log 2>&1
+python tools/ncu_summary.py $O/wtxr.ncu-rep > $O/r2_ncu_wide_tx_spec.txt 2>&1
+python tools/sass_by_line.py $O/wtxr.ncu-rep ofdm_b200/libofdm_b200.so wide_tx_spec_kernelILi2ELb1ELb1E 524288 > $O/r2_ncu_wide_tx_spec_by_line.txt 2>&1
 rm -f $O/*.ncu-rep
-cat $O/r2_pytest_gpu.txt $O/smoke.log; head -c 600 $O/r2_bench.json; echo; wc -c $O/r2_bench*.json $O/r2_ncu_tx_warp.txt $O/r2_ncu_wide_tx.txt $O/launches.csv
+cat $O/r2_pytest_gpu.txt $O/smoke.log; head -c 600 $O/r2_bench.json; echo; wc -c $O/r2_bench*.json $O/r2_ncu_tx_spec.txt $O/r2_ncu_wide_tx_spec.txt $O/launches.csv
