@@ -381,12 +381,13 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
             if (h->smem_configured.insert((const void *)k).second)
                 CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             w.group_ctas = (int32_t)((max_syms + spw - 1) / spw);
+            w.stream_cnt = d_cnt;                                                // [0]: warps whose data beat the head maximum (zeroed above)
             k<<<(unsigned)(wspec_units < (uint64_t)h->n_sm ? wspec_units : (uint64_t)h->n_sm), wide_tx_resident_threads(), smem, st>>>(w);
             h->launches++;
-            w.redo_only = (int32_t)std::max<uint32_t>(8u, (n_streams + 65534u) / 65535u);   // frames a CTA of the redo pass checks
+            w.redo_only = 1;
             w.redo_tiles = (int32_t)((max_syms + 7) / 8);                        // tiles of 8 symbols a redone frame walks
             w.stream0 = 0;
-            wpick_tx(h->cfg, true)<<<dim3(1, (n_streams + (uint32_t)w.redo_only - 1) / (uint32_t)w.redo_only), wide::kThreads, 0, st>>>(w);
+            wpick_tx(h->cfg, true)<<<dim3(1, std::min<uint32_t>(n_streams, 2u * (uint32_t)h->n_sm)), wide::kThreads, 0, st>>>(w);
             h->launches++;
             CU(h, cudaGetLastError());
             if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));
@@ -447,17 +448,18 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         if (h->smem_configured.insert((const void *)k).second)
             CU(h, cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         a.group_ctas = (int32_t)U;
+        a.stream_cnt = d_cnt;                                                  // [0]: warps whose data beat the head maximum (zeroed above)
         k<<<(unsigned)(units < (uint64_t)h->n_sm ? units : (uint64_t)h->n_sm), tx_warp_threads(), smem, st>>>(a);
         h->launches++;
         uint32_t tiles = (uint32_t)((max_syms + h->tile_shift + kTxTileSyms - 1) / kTxTileSyms);
         a.tiles_per_cta = (int)tiles;                                          // one CTA per frame: it exits at once unless the frame has to be redone
-        a.redo_only = (int32_t)std::max<uint32_t>(8u, (n_streams + 65534u) / 65535u);     // frames a CTA of the redo pass checks
+        a.redo_only = 1;
         const size_t tx_smem = sizeof(float2) * kTxWarps * kTrWarp + (size_t)kTxTileSyms * h->dcar + 64 + sizeof(float2) * 16 * ((1u << h->bpc) + 2) + 16 + 512;
         TxKernel k2 = pick_tx(h->cfg, true);
         if (h->smem_configured.insert((const void *)k2).second)
             CU(h, cudaFuncSetAttribute((const void *)k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tx_smem));
         a.stream0 = 0;
-        k2<<<dim3(1, (n_streams + (uint32_t)a.redo_only - 1) / (uint32_t)a.redo_only), kTxThreads, tx_smem, st>>>(a);
+        k2<<<dim3(1, std::min<uint32_t>(n_streams, 4u * (uint32_t)h->n_sm)), kTxThreads, tx_smem, st>>>(a);
         h->launches++;
         CU(h, cudaGetLastError());
         if (frame_len_out) CU(h, cudaMemcpyAsync(frame_len_out, d_flen, sizeof(uint32_t) * (size_t)n_streams, cudaMemcpyDeviceToDevice, st));

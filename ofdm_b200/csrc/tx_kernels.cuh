@@ -23,7 +23,7 @@ struct TxArgs {
     uint32_t       *stream_cnt;     // tx_resident_kernel: per stream, compute warps that have published their maximum
     int32_t         group_ctas;     // tx_resident_kernel: CTAs sharing one frame
     int32_t         n_groups;       // tx_resident_kernel: groups of the (persistent) grid
-    int32_t         redo_only;      // tx_tile_kernel<WRITE>: > 0 = redo pass: a CTA checks this many consecutive frames and rewrites those whose stream_max is set
+    int32_t         redo_only;      // tx_tile_kernel<WRITE>: redo pass behind tx_spec_kernel (frames whose stream_max is set, if stream_cnt[0] != 0)
 };
 
 // byte `B` of the frame byte stream [header 16 B | (Hamming-coded) payload ...] (src/transmitter.rs:37-47, docs/SPEC.md 3)
@@ -282,13 +282,14 @@ template <int MOD, bool GUARD, bool FEC, bool WRITE>
 __global__ void __launch_bounds__(kTxThreads, 4) tx_tile_kernel(const TxArgs a)
 {
     if (WRITE && a.redo_only) {
-        // redo pass behind tx_spec_kernel: a CTA looks at `redo_only` consecutive frames and rewrites, whole, those whose data
-        // beat the head maximum (stream_max set by the speculative kernel); for scrambled payloads that is none, and the CTA exits
-        const uint32_t s0 = a.stream0 + blockIdx.y * (uint32_t)a.redo_only;
-        for (uint32_t i = 0; i < (uint32_t)a.redo_only && s0 + i < a.n_streams; i++) {
-            if (a.stream_max[s0 + i] == 0) continue;
+        // redo pass behind tx_spec_kernel: nothing to do unless the speculative kernel counted a frame whose data beat the head
+        // maximum (stream_cnt[0]; for scrambled payloads: never) -- then the CTAs stride over the frames and rewrite, whole, those
+        // whose stream_max is set
+        if (a.stream_cnt[0] == 0) return;
+        for (uint32_t s = blockIdx.y; s < a.n_streams; s += gridDim.y) {
+            if (a.stream_max[s] == 0) continue;
             __syncthreads();                                        // (the previous frame's readers of the shared tables are done)
-            tx_tile_body<MOD, GUARD, FEC, WRITE>(a, s0 + i, 0u, 1u);
+            tx_tile_body<MOD, GUARD, FEC, WRITE>(a, s, 0u, 1u);
         }
         return;
     }

@@ -461,7 +461,10 @@ __global__ void __launch_bounds__(kTwThreads, 1) tx_spec_kernel(const TxArgs a)
         mx *= 1.0f / 64.0f;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-        if (lane == 0 && mx > head_max) atomicMax(a.stream_max + stream, __float_as_int(mx));     // the bet is lost for this frame: it will be redone
+        if (lane == 0 && mx > head_max) {                                      // the bet is lost for this frame: it will be redone
+            atomicMax(a.stream_max + stream, __float_as_int(mx));
+            atomicAdd(a.stream_cnt, 1u);                                       // (what the redo pass looks at first)
+        }
     }
 }
 

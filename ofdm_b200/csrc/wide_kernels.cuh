@@ -975,7 +975,7 @@ struct WideTxArgs {
     uint32_t       *stream_cnt;     // wide_tx_resident_kernel: per stream, warps that have published their maximum
     int32_t         group_ctas;     // wide_tx_resident_kernel: CTAs sharing one frame
     int32_t         n_groups;       // wide_tx_resident_kernel: groups of the (persistent) grid
-    int32_t         redo_only;      // wide_tx_kernel<WRITE>: > 0 = redo pass: a CTA checks this many consecutive frames and rewrites those whose stream_max is set
+    int32_t         redo_only;      // wide_tx_kernel<WRITE>: redo pass behind wide_tx_spec_kernel (frames whose stream_max is set, if stream_cnt[0] != 0)
     int32_t         redo_tiles;     // ... walking this many tiles of 8 symbols each
 };
 
@@ -1093,14 +1093,14 @@ template <int MOD, bool GUARD, bool FEC, bool WRITE>
 __global__ void __launch_bounds__(kThreads) wide_tx_kernel(const WideTxArgs a)
 {
     if (WRITE && a.redo_only) {
-        // redo pass behind wide_tx_spec_kernel: a CTA looks at `redo_only` consecutive frames and rewrites, tile by tile, those whose
-        // data beat the head maximum (stream_max set); for scrambled payloads that is none, and the CTA exits
-        const uint32_t s0 = a.stream0 + blockIdx.y * (uint32_t)a.redo_only;
-        for (uint32_t i = 0; i < (uint32_t)a.redo_only && s0 + i < a.n_streams; i++) {
-            if (a.stream_max[s0 + i] == 0) continue;
+        // redo pass behind wide_tx_spec_kernel: nothing to do unless the speculative kernel counted a frame whose data beat the head
+        // maximum (stream_cnt[0]) -- then the CTAs stride over the frames and rewrite, tile by tile, those whose stream_max is set
+        if (a.stream_cnt[0] == 0) return;
+        for (uint32_t s = blockIdx.y; s < a.n_streams; s += gridDim.y) {
+            if (a.stream_max[s] == 0) continue;
             for (uint32_t bx = 0; bx < (uint32_t)a.redo_tiles; bx++) {
                 __syncthreads();
-                wide_tx_tile<MOD, GUARD, FEC, WRITE>(a, s0 + i, bx, (uint32_t)a.redo_tiles);
+                wide_tx_tile<MOD, GUARD, FEC, WRITE>(a, s, bx, (uint32_t)a.redo_tiles);
             }
         }
         return;

@@ -627,7 +627,10 @@ __global__ void __launch_bounds__(kWTrsThreads, 1) wide_tx_spec_kernel(const Wid
         mx *= 1.0f / (float)kN;
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-        if (lane == 0 && mx > head_max) atomicMax(a.stream_max + stream, __float_as_int(mx));     // the bet is lost for this frame: it will be redone
+        if (lane == 0 && mx > head_max) {                                      // the bet is lost for this frame: it will be redone
+            atomicMax(a.stream_max + stream, __float_as_int(mx));
+            atomicAdd(a.stream_cnt, 1u);                                       // (what the redo pass looks at first)
+        }
     }
 }
 
