@@ -375,7 +375,7 @@ static int tx_device(ofdm_engine *h, const uint8_t *payload, const uint32_t *pay
         // frames that lost the bet with the two-pass kernel (its store pass with redo_only). Large-batch default.
         const int spw = wide_tx_resident_threads() / 32;                       // symbols per unit: one per warp
         const uint64_t wspec_units = max_syms > 0 ? (uint64_t)n_streams * (uint64_t)((max_syms + spw - 1) / spw) : 0;
-        if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 5 || (h->tx_path == 0 && wspec_units >= 32ull * (uint64_t)h->n_sm))) {
+        if (max_syms > 0 && h->n_sm > 0 && (h->tx_path == 5 || (h->tx_path == 0 && wspec_units >= 2ull * (uint64_t)h->n_sm))) {
             WTxKernel k = wpick_tx_spec(h->cfg);
             const size_t smem = wide_tx_resident_smem(h->cfg);
             if (h->smem_configured.insert((const void *)k).second)
