@@ -1,4 +1,5 @@
-// tx_warp.cuh -- nfft = 64 one-pass transmit kernel for large batches, second version: tx_resident_kernel's transform, tensor-
+// tx_warp.cuh -- nfft = 64 one-pass transmit kernels for large batches: tx_warp_kernel (exact; below) and, at the end of the file,
+// tx_spec_kernel (speculative on the constant head maximum, with a redo pass: the default). tx_warp_kernel is the second version: tx_resident_kernel's transform, tensor-
 // memory residency and groups of persistent CTAs (tx_resident.cuh), with the frame loop of wide_tx_resident_kernel -- NOTHING in
 // it is a CTA barrier.
 //
