@@ -326,7 +326,14 @@ __device__ __forceinline__ void rx_symbol_p(const RxLaneP &L, const ulonglong2 *
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kDecWarps = 7;
 constexpr int kDecThreads = kDecWarps * 32;      // 256
-constexpr int kDecIters = 8;                     // 4 symbols per warp iteration -> 32 symbols per warp
+#ifndef DEC_ITERS
+#define DEC_ITERS 8
+#endif
+#ifndef DEC_WARP_OUT
+#define DEC_WARP_OUT 0
+#endif
+constexpr int kDecIters = DEC_ITERS;             // 4 symbols per warp iteration -> 32 symbols per warp (28 with 7 iterations: a warp's span is then Hamming-aligned)
+constexpr bool kDecWarpOut = DEC_WARP_OUT != 0 && (4 * DEC_ITERS) % 7 == 0;   // warps turn their own carrier bytes into payload bytes: no CTA barrier (tiles > 0)
 constexpr int kDecBaseTiles = 8;                 // tiles per CTA whose start phasors are tabulated (tiles_per_cta <= 8, kDecBaseTiles * 4 * kDecWarps <= threads)
 constexpr int kTileSyms = kDecWarps * 4 * kDecIters;   // 224 OFDM symbols per CTA (multiple of 7: Hamming byte alignment)
 constexpr int kStageBytes = 4 * kSym * 8 + 16;       // 4 consecutive OFDM symbols (CPs included) + 1 leading / 1 trailing alignment sample
@@ -505,6 +512,75 @@ __global__ void __launch_bounds__(kDecThreads, GUARD ? 4 : 3) rx_decode_kernel(c
                 }
             }
             rowp += 4 * D;
+        }
+        if (kDecWarpOut && tile > 0) {
+            // ---- a warp's 28 symbols start on a payload-byte boundary (28 x BPS bits = whole bytes, Hamming or not, and the tile
+            // does): the warp converts its own carrier bytes, nobody waits for anybody. (Tile 0 starts at stream bit 0, its
+            // payload bytes at bit 128: there the boundaries between the warps cut through bytes -- CTA-wide conversion below.)
+            __syncwarp();
+            const int w_s1 = s_warp + 4 * kDecIters < t1 ? s_warp + 4 * kDecIters : t1;
+            if (s_warp < w_s1) {
+                const long wbit0 = (long)s_warp * BPS, wbit1 = (long)w_s1 * BPS;
+                const long wj0 = (wbit0 - kHeaderBits + NB - 1) / NB;
+                long wj1 = (wbit1 - kHeaderBits) / NB;
+                if (wj1 > (long)st->out_len) wj1 = (long)st->out_len;
+                const int wpbase = (int)(kHeaderBits + wj0 * NB - wbit0);
+                const int wnbytes = (int)(wj1 - wj0);
+                const uint8_t *wcar = s_car + (s_warp - t0) * D;
+                if (MOD == 2) {
+                    constexpr int NC = (3 * NB + 5) / 6 + 1;
+                    const int c0 = wpbase / 6, sh = wpbase - 6 * c0;
+                    const uint8_t *cp = wcar + c0 + (NB / 2) * lane;
+                    const uint32_t cp_s = (uint32_t)__cvta_generic_to_shared(cp);
+                    uint32_t wa = cp_s & ~3u;
+                    const uint32_t sel = 0x3210u + 0x1111u * (cp_s & 3u);
+                    static_assert(((NB / 2) * 32) % 4 == 0, "carrier stride per iteration must keep the word alignment");
+                    for (int u = 3 * lane; u < wnbytes; u += 3 * 32, cp += (NB / 2) * 32, wa += (NB / 2) * 32) {
+                        uint32_t lo, hi = 0;
+                        if (NC > 5) {
+                            uint32_t w0, w1, w2;
+                            asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                                         : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(wa));
+                            const uint32_t p0 = pack4x6(__byte_perm(w0, w1, sel)), p1 = pack4x6(__byte_perm(w1, w2, sel));
+                            lo = p0 | (p1 << 24);
+                            hi = p1 >> 8;
+                        } else {
+                            lo = cp[0] | (cp[1] << 6) | (cp[2] << 12) | (cp[3] << 18) | (cp[4] << 24);
+                        }
+                        lo = __funnelshift_r(lo, hi, sh);
+                        hi >>= sh;
+                        uint32_t w0, w1, w2;
+                        if (FEC) {
+                            w0 = lo & 0x3FFFu; w1 = (lo >> 14) & 0x3FFFu; w2 = __funnelshift_r(lo, hi, 28) & 0x3FFFu;
+                            w0 = s_ham[w0 & 127u] | (s_ham[w0 >> 7] << 4);
+                            w1 = s_ham[w1 & 127u] | (s_ham[w1 >> 7] << 4);
+                            w2 = s_ham[w2 & 127u] | (s_ham[w2 >> 7] << 4);
+                        } else {
+                            w0 = lo & 255u; w1 = (lo >> 8) & 255u; w2 = (lo >> 16) & 255u;
+                        }
+                        uint8_t *o = out + wj0 + u;
+                        o[0] = (uint8_t)w0;
+                        st_global_u8_if(o + 1, w1, u + 1 < wnbytes);
+                        st_global_u8_if(o + 2, w2, u + 2 < wnbytes);
+                    }
+                } else {
+                    for (int u = lane; u < wnbytes; u += 32) {
+                        const int p = wpbase + u * NB;
+                        const int c = p / BPC, sh = p - c * BPC;
+                        constexpr int NC = (NB + BPC - 1) / BPC + (BPC > 1 ? 1 : 0);
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int i = 0; i < NC; i++) v |= (uint32_t)wcar[c + i] << (BPC * i);
+                        v >>= sh;
+                        uint32_t byte;
+                        if (FEC) byte = (uint32_t)s_ham[v & 127u] | ((uint32_t)s_ham[(v >> 7) & 127u] << 4);
+                        else byte = v & 255u;
+                        out[wj0 + u] = (uint8_t)byte;
+                    }
+                }
+            }
+            __syncwarp();                                       // this warp's rows of s_car are rewritten by its next tile
+            continue;
         }
         __syncthreads();
 
